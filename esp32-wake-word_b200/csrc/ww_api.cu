@@ -1,0 +1,787 @@
+// libwwb200.so -- C ABI over the sm_100a kernels (see include/ww_b200.h for the contract).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ww_b200.h"
+#include "ww_cnn.cuh"
+#include "ww_ctc.cuh"
+#include "ww_mfcc.cuh"
+#include "ww_tables.h"
+#ifdef WW_WITH_TC
+#include "ww_cnn_tc.cuh"
+#endif
+
+using namespace ww;
+
+#define WW_VERSION_NUM 100
+
+struct FeatMode {
+    uint4* tables = nullptr;  // device blob
+    float dct[WW_N_MELS * WW_N_MFCC];
+    int origin_off;
+    int reflect;
+    float mode_pscale;  // multiplies 0.25 * input_scale^2
+    float log_floor, log_offset;
+};
+
+struct ww_ctx {
+    int device = 0;
+    int sm_count = 148;
+    std::string err;
+    FeatMode feat[2];
+    // weights (device)
+    float* wblob = nullptr;
+    CnnWeights w{};
+    bool have_weights = false;
+#ifdef WW_WITH_TC
+    TcWeights tcw{};
+#endif
+    // fused-path scratch
+    float* scratch = nullptr;          // [chunk][13][63]
+    long long scratch_clips = 0;
+    // host-buffer path
+    cudaStream_t hs[2] = {nullptr, nullptr};
+    cudaEvent_t hev[2] = {nullptr, nullptr};
+    void* h_pin[2] = {nullptr, nullptr};
+    void* d_pcm[2] = {nullptr, nullptr};
+    float* d_logits[2] = {nullptr, nullptr};
+    unsigned char* d_dec[2] = {nullptr, nullptr};
+    float* h_logits[2] = {nullptr, nullptr};
+    unsigned char* h_dec[2] = {nullptr, nullptr};
+    long long host_chunk = 0;
+    size_t host_chunk_bytes = 0;
+};
+
+static int fail(ww_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+static int cuda_fail(ww_ctx* c, cudaError_t e, const char* what) {
+    return fail(c, WW_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                              \
+    do {                                                      \
+        cudaError_t e_ = (call);                              \
+        if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// table construction
+// ------------------------------------------------------------------------------------------------
+struct HostTables {
+    std::vector<unsigned char> blob;
+    float dct[WW_N_MELS * WW_N_MFCC];
+};
+
+static void fill_common(HostTables& t, const float* window320, float preemph, const std::vector<int>& start,
+                        const std::vector<int>& len, const std::vector<int>& off, const std::vector<float>& w,
+                        const std::vector<float>& bias) {
+    t.blob.assign(TB_BYTES, 0);
+    float* win = reinterpret_cast<float*>(t.blob.data() + TB_WIN_OFF);
+    for (int i = 0; i < 160; ++i) {
+        const float w0 = window320[2 * i], w1 = window320[2 * i + 1];
+        win[4 * i + 0] = w0;
+        win[4 * i + 1] = preemph * w0;
+        win[4 * i + 2] = w1;
+        win[4 * i + 3] = preemph * w1;
+    }
+    float* tw1 = reinterpret_cast<float*>(t.blob.data() + TB_TW1_OFF);
+    for (int j = 0; j < 8; ++j)
+        for (int l = 0; l < 16; ++l)
+            for (int h = 0; h < 2; ++h) {
+                const double ang = -2.0 * M_PI * (double)(l * (2 * j + h)) / 256.0;
+                tw1[(16 * j + l) * 4 + 2 * h + 0] = (float)cos(ang);
+                tw1[(16 * j + l) * 4 + 2 * h + 1] = (float)sin(ang);
+            }
+    float* tw2 = reinterpret_cast<float*>(t.blob.data() + TB_TW2_OFF);
+    for (int k = 0; k <= 128; ++k) {
+        const double ang = -2.0 * M_PI * (double)k / 512.0;
+        tw2[2 * k] = (float)cos(ang);
+        tw2[2 * k + 1] = (float)sin(ang);
+    }
+    float* mw = reinterpret_cast<float*>(t.blob.data() + TB_MELW_OFF);
+    for (size_t i = 0; i < w.size(); ++i) mw[i] = w[i];
+    int* mm = reinterpret_cast<int*>(t.blob.data() + TB_MELM_OFF);
+    for (int j = 0; j < WW_N_MELS; ++j) {
+        mm[4 * j + 0] = start[j];
+        mm[4 * j + 1] = len[j];
+        mm[4 * j + 2] = off[j];
+        float b = bias[j];
+        memcpy(&mm[4 * j + 3], &b, 4);
+    }
+}
+
+// PY-MFCC: torchaudio's own fp32 tables (tools/gen_tables.py)
+static void build_py_tables(HostTables& t) {
+    std::vector<int> start(WW_PY_MEL_START, WW_PY_MEL_START + 40), len(WW_PY_MEL_LEN, WW_PY_MEL_LEN + 40),
+        off(WW_PY_MEL_OFF, WW_PY_MEL_OFF + 40);
+    std::vector<float> w(WW_PY_MEL_W, WW_PY_MEL_W + WW_PY_MEL_NNZ), bias(40, 0.f);
+    fill_common(t, WW_PY_WINDOW, 0.97f, start, len, off, w, bias);
+    memcpy(t.dct, WW_PY_DCT, sizeof(t.dct));
+}
+
+// C-MFCC: tables rebuilt with the float arithmetic of main/esp_mfcc/mfcc.c
+//   window  mfcc.c:110-131 (symmetric Hamming, alpha 0.53836)
+//   fbank   mfcc.c:133-234 (bin-index triangles, hz_to_mel(0) evaluated at 1 Hz)
+//   dct     mfcc.c:20-64   (n = 40 > 32: cos table, orthonormal scaling)
+static bool build_esp_tables(HostTables& t) {
+    const int frame_size = WW_WIN, n_fft = WW_N_FFT, n_filters = WW_N_MELS, sr = 16000;
+    float window[WW_WIN];
+    const float alpha = 0.53836f;
+    for (int i = 0; i < frame_size; ++i)
+        window[i] = alpha - (1.0f - alpha) * cosf((float)(2.0f * M_PI * i / (frame_size - 1)));
+    auto hz_to_mel = [](float f) {
+        if (f == 0) f = 1;
+        return 1127.0f * log1pf(f / 700.0f);
+    };
+    auto mel_to_hz = [](float m) { return 700.0f * (powf(10.0f, m / 2595.0f) - 1.0f); };
+    const int nb = n_fft / 2 + 1;
+    std::vector<float> fb((size_t)n_filters * nb, 0.f);
+    const float low_mel = hz_to_mel(0.f), high_mel = hz_to_mel((float)(sr / 2));
+    std::vector<int> bins(n_filters + 2);
+    const float bin_width = (float)sr / n_fft;
+    for (int i = 0; i < n_filters + 2; ++i) {
+        const float mel = low_mel + i * (high_mel - low_mel) / (n_filters + 1);
+        bins[i] = (int)floorf(mel_to_hz(mel) / bin_width);
+    }
+    for (int i = 0; i < n_filters; ++i) {
+        int left = bins[i], center = bins[i + 1], right = bins[i + 2];
+        left = left < 0 ? 0 : left;
+        center = center < 0 ? 0 : center;
+        right = right < 0 ? 0 : right;
+        left = left >= nb ? nb - 1 : left;
+        center = center >= nb ? nb - 1 : center;
+        right = right >= nb ? nb - 1 : right;
+        if (left >= center) center = left + 1;
+        if (center >= right) right = center + 1;
+        if (right >= nb) right = nb - 1;
+        if (center <= left || right <= center) return false;  // mfcc.c would divide by zero here
+        for (int j = left; j <= center; ++j)
+            if (j >= 0 && j < nb) fb[(size_t)i * nb + j] = (float)(j - left) / (center - left);
+        for (int j = center; j <= right; ++j)
+            if (j >= 0 && j < nb) fb[(size_t)i * nb + j] = (float)(right - j) / (right - center);
+    }
+    std::vector<int> start(n_filters), len(n_filters), off(n_filters);
+    std::vector<float> w, bias(n_filters);
+    for (int i = 0; i < n_filters; ++i) {
+        int lo = nb, hi = -1;
+        float sum = 0.f;
+        for (int j = 0; j < nb; ++j)
+            if (fb[(size_t)i * nb + j] != 0.f) {
+                lo = j < lo ? j : lo;
+                hi = j;
+                sum += fb[(size_t)i * nb + j];
+            }
+        if (hi < 0) { lo = 0; hi = 0; }
+        start[i] = lo;
+        len[i] = hi - lo + 1;
+        off[i] = (int)w.size();
+        for (int j = lo; j <= hi; ++j) w.push_back(fb[(size_t)i * nb + j]);
+        bias[i] = 1e-12f * sum;  // the per-bin "+ 1e-12f" of mfcc.c:266 carried through the filter
+    }
+    if ((int)w.size() > MEL_W_CAP) return false;
+    fill_common(t, window, 0.97f, start, len, off, w, bias);
+    const int n = n_filters;
+    for (int k = 0; k < WW_N_MFCC; ++k) {
+        const float scale = (k == 0) ? sqrtf(1.0f / n) : sqrtf(2.0f / n);
+        for (int i = 0; i < n; ++i) {
+            const float angle = (float)(M_PI * k * (2 * i + 1) / (2.0f * n));
+            t.dct[i * WW_N_MFCC + k] = scale * cosf(angle);
+        }
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+extern "C" int ww_version(void) { return WW_VERSION_NUM; }
+
+extern "C" const char* ww_last_error(const ww_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+static const long long kScratchClips = 16384;  // 16384 * 3276 B = 54 MB: stays in the 126 MB L2
+
+extern "C" int ww_create(ww_ctx** out, int device) {
+    if (!out) return WW_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+        fprintf(stderr, "ww_b200: no usable CUDA device (%s); there is no CPU fallback\n",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range");
+        return WW_ERR_CUDA;
+    }
+    ww_ctx* ctx = new (std::nothrow) ww_ctx();
+    if (!ctx) return WW_ERR_NOMEM;
+    ctx->device = device;
+    auto bail = [&](cudaError_t err, const char* what) {
+        fprintf(stderr, "ww_b200: %s: %s\n", what, cudaGetErrorString(err));
+        ww_destroy(ctx);
+        return WW_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+    if (prop.major < 10) {
+        fprintf(stderr, "ww_b200: device sm_%d%d is not Blackwell (sm_100a required)\n", prop.major, prop.minor);
+        ww_destroy(ctx);
+        return WW_ERR_UNSUPPORTED;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+
+    HostTables ht[2];
+    build_py_tables(ht[0]);
+    const bool esp_ok = build_esp_tables(ht[1]);
+    for (int m = 0; m < 2; ++m) {
+        if (m == 1 && !esp_ok) continue;
+        if ((e = cudaMalloc(&ctx->feat[m].tables, TB_BYTES)) != cudaSuccess) return bail(e, "cudaMalloc tables");
+        if ((e = cudaMemcpy(ctx->feat[m].tables, ht[m].blob.data(), TB_BYTES, cudaMemcpyHostToDevice)) != cudaSuccess)
+            return bail(e, "cudaMemcpy tables");
+        memcpy(ctx->feat[m].dct, ht[m].dct, sizeof(ht[m].dct));
+    }
+    ctx->feat[0].origin_off = -256;
+    ctx->feat[0].reflect = 1;
+    ctx->feat[0].mode_pscale = 1.0f;
+    ctx->feat[0].log_floor = 0.f;
+    ctx->feat[0].log_offset = 1e-6f;
+    ctx->feat[1].origin_off = -96;
+    ctx->feat[1].reflect = 0;
+    ctx->feat[1].mode_pscale = 1.0f / 512.0f;
+    ctx->feat[1].log_floor = 1e-12f;
+    ctx->feat[1].log_offset = 0.f;
+
+    // opt in to the dynamic shared memory the frontend needs
+    if ((e = cudaFuncSetAttribute(mfcc_kernel<int16_t, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  MfccSmem<int16_t, 64>::TOTAL)) != cudaSuccess)
+        return bail(e, "cudaFuncSetAttribute(mfcc s16)");
+    if ((e = cudaFuncSetAttribute(mfcc_kernel<float, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  MfccSmem<float, 32>::TOTAL)) != cudaSuccess)
+        return bail(e, "cudaFuncSetAttribute(mfcc f32)");
+#ifdef WW_WITH_TC
+    if ((e = tc_init()) != cudaSuccess) return bail(e, "tc_init");
+#endif
+    *out = ctx;
+    return WW_OK;
+}
+
+extern "C" void ww_destroy(ww_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (int m = 0; m < 2; ++m) cudaFree(ctx->feat[m].tables);
+    cudaFree(ctx->wblob);
+    cudaFree(ctx->scratch);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->hs[i]) cudaStreamDestroy(ctx->hs[i]);
+        if (ctx->hev[i]) cudaEventDestroy(ctx->hev[i]);
+        if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
+        cudaFree(ctx->d_pcm[i]);
+        cudaFree(ctx->d_logits[i]);
+        cudaFree(ctx->d_dec[i]);
+        if (ctx->h_logits[i]) cudaFreeHost(ctx->h_logits[i]);
+        if (ctx->h_dec[i]) cudaFreeHost(ctx->h_dec[i]);
+    }
+#ifdef WW_WITH_TC
+    tc_free_weights(ctx->tcw);
+#endif
+    delete ctx;
+}
+
+extern "C" int ww_load_weights(ww_ctx* ctx, const float* conv1, const float* conv2, const float* conv3,
+                               const float* fc1, const float* fc2, int num_classes) {
+    if (!ctx) return WW_ERR_INVALID;
+    if (!conv1 || !conv2 || !conv3 || !fc1 || !fc2 || num_classes < 1 || num_classes > 4096)
+        return fail(ctx, WW_ERR_INVALID, "ww_load_weights: null pointer or bad num_classes");
+    CK(cudaSetDevice(ctx->device));
+    const int n1 = 13 * 3 * 32, n2 = 32 * 3 * 64, n3 = 64 * 3 * 128, n4 = 64 * 128, n5 = num_classes * 64;
+    std::vector<float> h((size_t)n1 + n2 + n3 + n4 + n5);
+    // torch [O][I][3] -> [I][3][O] so that a warp reads one weight per lane, coalesced over O
+    auto tr = [](const float* src, float* dst, int O, int I) {
+        for (int o = 0; o < O; ++o)
+            for (int i = 0; i < I; ++i)
+                for (int r = 0; r < 3; ++r) dst[(i * 3 + r) * O + o] = src[(o * I + i) * 3 + r];
+    };
+    float* p = h.data();
+    tr(conv1, p, 32, 13);
+    tr(conv2, p + n1, 64, 32);
+    tr(conv3, p + n1 + n2, 128, 64);
+    memcpy(p + n1 + n2 + n3, fc1, sizeof(float) * n4);
+    memcpy(p + n1 + n2 + n3 + n4, fc2, sizeof(float) * n5);
+    cudaFree(ctx->wblob);
+    ctx->wblob = nullptr;
+    ctx->have_weights = false;
+    CK(cudaMalloc(&ctx->wblob, h.size() * sizeof(float)));
+    CK(cudaMemcpy(ctx->wblob, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    ctx->w.w1t = ctx->wblob;
+    ctx->w.w2t = ctx->wblob + n1;
+    ctx->w.w3t = ctx->wblob + n1 + n2;
+    ctx->w.fc1 = ctx->wblob + n1 + n2 + n3;
+    ctx->w.fc2 = ctx->wblob + n1 + n2 + n3 + n4;
+    ctx->w.num_classes = num_classes;
+#ifdef WW_WITH_TC
+    {
+        cudaError_t e = tc_load_weights(ctx->tcw, conv1, conv2, conv3, fc1, fc2, num_classes);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "tc_load_weights");
+    }
+#endif
+    ctx->have_weights = true;
+    return WW_OK;
+}
+
+extern "C" int ww_num_frames(int feat_mode, int n_samples) {
+    if (feat_mode == WW_FEAT_PY) return n_samples < 257 ? 0 : 1 + n_samples / WW_HOP;  // reflect pad needs n > 256
+    if (feat_mode == WW_FEAT_ESP) return n_samples < WW_WIN ? 0 : (n_samples - WW_WIN) / WW_HOP + 1;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// features
+// ------------------------------------------------------------------------------------------------
+static int launch_mfcc(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_signals, int n_samples,
+                       long long sig_stride, int feat_mode, float* out, long long oss, long long ocs, long long ofs,
+                       cudaStream_t st) {
+    if (!pcm || !out) return fail(ctx, WW_ERR_INVALID, "mfcc: null buffer");
+    if (feat_mode != WW_FEAT_PY && feat_mode != WW_FEAT_ESP) return fail(ctx, WW_ERR_INVALID, "mfcc: bad feat_mode");
+    if (pcm_type != WW_PCM_S16 && pcm_type != WW_PCM_F32) return fail(ctx, WW_ERR_INVALID, "mfcc: bad pcm_type");
+    if (n_signals < 0 || sig_stride < n_samples) return fail(ctx, WW_ERR_INVALID, "mfcc: bad sizes");
+    const FeatMode& fm = ctx->feat[feat_mode];
+    if (!fm.tables) return fail(ctx, WW_ERR_UNSUPPORTED, "mfcc: feature mode unavailable");
+    const int T = ww_num_frames(feat_mode, n_samples);
+    if (T <= 0) return fail(ctx, WW_ERR_INVALID, "mfcc: signal shorter than one frame");  // mfcc.c:434-437
+    if (n_signals == 0) return WW_OK;
+    const int frames = pcm_type == WW_PCM_S16 ? 64 : 32;
+    const size_t esz = pcm_type == WW_PCM_S16 ? 2 : 4;
+    MfccArgs a;
+    a.pcm = pcm;
+    a.sig_stride = sig_stride;
+    a.n_samples = n_samples;
+    a.n_frames = T;
+    a.blocks_per_sig = (T + frames - 1) / frames;
+    a.out = out;
+    a.out_sig_stride = oss;
+    a.out_coef_stride = ocs;
+    a.out_frame_stride = ofs;
+    a.tables = fm.tables;
+    a.origin_off = fm.origin_off;
+    a.reflect = fm.reflect;
+    a.use_bulk = (((uintptr_t)pcm % 16) == 0 && (sig_stride * esz) % 16 == 0 && ((size_t)n_samples * esz) % 16 == 0) ? 1 : 0;
+    const float in_scale = pcm_type == WW_PCM_S16 ? (1.0f / 32768.0f) : 1.0f;  // torchaudio.load normalisation
+    a.pscale = 0.25f * in_scale * in_scale * fm.mode_pscale;
+    a.log_floor = fm.log_floor;
+    a.log_offset = fm.log_offset;
+    a.preemph = 0.97f;
+    memcpy(a.dct, fm.dct, sizeof(a.dct));
+    const long long total_blocks = n_signals * a.blocks_per_sig;
+    if (total_blocks > 0x7fffffffLL) return fail(ctx, WW_ERR_INVALID, "mfcc: too many blocks for one launch");
+    if (pcm_type == WW_PCM_S16)
+        mfcc_kernel<int16_t, 64><<<(unsigned)total_blocks, MFCC_THREADS, MfccSmem<int16_t, 64>::TOTAL, st>>>(a);
+    else
+        mfcc_kernel<float, 32><<<(unsigned)total_blocks, MFCC_THREADS, MfccSmem<float, 32>::TOTAL, st>>>(a);
+    CK(cudaGetLastError());
+    return WW_OK;
+}
+
+extern "C" int ww_mfcc_batch(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_signals, int n_samples,
+                             long long sig_stride, int feat_mode, int layout, float* out, ww_stream_t stream) {
+    if (!ctx) return WW_ERR_INVALID;
+    const int T = ww_num_frames(feat_mode, n_samples);
+    long long oss = (long long)T * WW_N_MFCC, ocs, ofs;
+    if (layout == WW_LAYOUT_COEF_MAJOR) { ocs = T; ofs = 1; }
+    else if (layout == WW_LAYOUT_FRAME_MAJOR) { ocs = 1; ofs = WW_N_MFCC; }
+    else return fail(ctx, WW_ERR_INVALID, "mfcc: bad layout");
+    return launch_mfcc(ctx, pcm, pcm_type, n_signals, n_samples, sig_stride, feat_mode, out, oss, ocs, ofs,
+                       (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CMVN / CNN
+// ------------------------------------------------------------------------------------------------
+static int launch_cnn_fp32(ww_ctx* ctx, const float* feats, long long ws, long long cs, long long fs, long long n,
+                           const long long* index, const int* index_count, int cmvn_mode, int decide_mode,
+                           float threshold, float* logits, unsigned char* decisions, float* norm_out, cudaStream_t st) {
+    CnnArgs a;
+    a.feats = feats;
+    a.win_stride = ws;
+    a.coef_stride = cs;
+    a.frame_stride = fs;
+    a.n_windows = n;
+    a.index = index;
+    a.index_count = index_count;
+    a.cmvn_mode = cmvn_mode;
+    a.decide_mode = decide_mode;
+    a.threshold = threshold;
+    a.logits = logits;
+    a.decisions = decisions;
+    a.norm_out = norm_out;
+    a.w = ctx->w;
+    if (n == 0) return WW_OK;
+    long long grid = (long long)ctx->sm_count * 8;
+    if (grid > n) grid = n;
+    cnn_fp32_kernel<<<(unsigned)grid, CNN_THREADS, 0, st>>>(a);
+    CK(cudaGetLastError());
+    return WW_OK;
+}
+
+extern "C" int ww_cmvn(ww_ctx* ctx, const float* feats, long long n_windows, int cmvn_mode, float* out,
+                       ww_stream_t stream) {
+    if (!ctx) return WW_ERR_INVALID;
+    if (!feats || !out || n_windows < 0) return fail(ctx, WW_ERR_INVALID, "cmvn: bad arguments");
+    if (cmvn_mode < WW_CMVN_NONE || cmvn_mode > WW_CMVN_DEVICE) return fail(ctx, WW_ERR_INVALID, "cmvn: bad mode");
+    return launch_cnn_fp32(ctx, feats, WW_N_MFCC * WW_WINDOW_FRAMES, WW_WINDOW_FRAMES, 1, n_windows, nullptr, nullptr,
+                           cmvn_mode, WW_DECIDE_NONE, 0.f, nullptr, nullptr, out, (cudaStream_t)stream);
+}
+
+static int check_cnn_args(ww_ctx* ctx, int cmvn_mode, int decide_mode, int cnn_impl) {
+    if (!ctx->have_weights) return fail(ctx, WW_ERR_NO_WEIGHTS, "weights not loaded (ww_load_weights)");
+    if (cmvn_mode < WW_CMVN_NONE || cmvn_mode > WW_CMVN_DEVICE) return fail(ctx, WW_ERR_INVALID, "bad cmvn_mode");
+    if (decide_mode < WW_DECIDE_NONE || decide_mode > WW_DECIDE_DEVICE) return fail(ctx, WW_ERR_INVALID, "bad decide_mode");
+    if (cnn_impl != WW_CNN_FP32 && cnn_impl != WW_CNN_TENSOR) return fail(ctx, WW_ERR_INVALID, "bad cnn_impl");
+#ifndef WW_WITH_TC
+    if (cnn_impl == WW_CNN_TENSOR) return fail(ctx, WW_ERR_UNSUPPORTED, "tensor-core CNN not built into this library");
+#endif
+    return WW_OK;
+}
+
+static int run_cnn(ww_ctx* ctx, const float* feats, long long ws, long long cs, long long fs, long long n,
+                   int cmvn_mode, int decide_mode, float threshold, int cnn_impl, float* logits,
+                   unsigned char* decisions, cudaStream_t st) {
+#ifdef WW_WITH_TC
+    if (cnn_impl == WW_CNN_TENSOR) {
+        int rc = tc_forward(ctx, feats, ws, cs, fs, n, cmvn_mode, decide_mode, threshold, logits, decisions, st);
+        return rc;
+    }
+#endif
+    return launch_cnn_fp32(ctx, feats, ws, cs, fs, n, nullptr, nullptr, cmvn_mode, decide_mode, threshold, logits,
+                           decisions, nullptr, st);
+}
+
+extern "C" int ww_cnn_forward(ww_ctx* ctx, const float* feats, long long win_stride, long long coef_stride,
+                              long long frame_stride, long long n_windows, int cmvn_mode, int decide_mode,
+                              float threshold, int cnn_impl, float* logits, uint8_t* decisions, ww_stream_t stream) {
+    if (!ctx) return WW_ERR_INVALID;
+    if (!feats || !logits || n_windows < 0) return fail(ctx, WW_ERR_INVALID, "cnn_forward: bad arguments");
+    int rc = check_cnn_args(ctx, cmvn_mode, decide_mode, cnn_impl);
+    if (rc) return rc;
+    return run_cnn(ctx, feats, win_stride, coef_stride, frame_stride, n_windows, cmvn_mode, decide_mode, threshold,
+                   cnn_impl, logits, decisions, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused clip scoring
+// ------------------------------------------------------------------------------------------------
+static int ensure_scratch(ww_ctx* ctx) {
+    if (ctx->scratch) return WW_OK;
+    CK(cudaMalloc(&ctx->scratch, (size_t)kScratchClips * WW_N_MFCC * WW_WINDOW_FRAMES * sizeof(float)));
+    ctx->scratch_clips = kScratchClips;
+    return WW_OK;
+}
+
+static int score_clips_dev(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_clips, int cmvn_mode,
+                           int decide_mode, float threshold, int cnn_impl, float* logits, unsigned char* decisions,
+                           cudaStream_t st) {
+    int rc = ensure_scratch(ctx);
+    if (rc) return rc;
+    const size_t esz = pcm_type == WW_PCM_S16 ? 2 : 4;
+    const int C = ctx->w.num_classes;
+    for (long long c0 = 0; c0 < n_clips; c0 += ctx->scratch_clips) {
+        const long long nc = (n_clips - c0) < ctx->scratch_clips ? (n_clips - c0) : ctx->scratch_clips;
+        const char* p = (const char*)pcm + (size_t)c0 * WW_CLIP_SAMPLES * esz;
+        rc = launch_mfcc(ctx, p, pcm_type, nc, WW_CLIP_SAMPLES, WW_CLIP_SAMPLES, WW_FEAT_PY, ctx->scratch,
+                         WW_N_MFCC * WW_WINDOW_FRAMES, WW_WINDOW_FRAMES, 1, st);
+        if (rc) return rc;
+        rc = run_cnn(ctx, ctx->scratch, WW_N_MFCC * WW_WINDOW_FRAMES, WW_WINDOW_FRAMES, 1, nc, cmvn_mode, decide_mode,
+                     threshold, cnn_impl, logits + c0 * C, decisions ? decisions + c0 : nullptr, st);
+        if (rc) return rc;
+    }
+    return WW_OK;
+}
+
+extern "C" int ww_score_clips(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_clips, int cmvn_mode,
+                              int decide_mode, float threshold, int cnn_impl, float* logits, uint8_t* decisions,
+                              ww_stream_t stream) {
+    if (!ctx) return WW_ERR_INVALID;
+    if (!pcm || !logits || n_clips < 0) return fail(ctx, WW_ERR_INVALID, "score_clips: bad arguments");
+    if (pcm_type != WW_PCM_S16 && pcm_type != WW_PCM_F32) return fail(ctx, WW_ERR_INVALID, "score_clips: bad pcm_type");
+    int rc = check_cnn_args(ctx, cmvn_mode, decide_mode, cnn_impl);
+    if (rc) return rc;
+    return score_clips_dev(ctx, pcm, pcm_type, n_clips, cmvn_mode, decide_mode, threshold, cnn_impl, logits, decisions,
+                           (cudaStream_t)stream);
+}
+
+static int ensure_host_path(ww_ctx* ctx, size_t esz) {
+    const long long chunk = kScratchClips;
+    const size_t bytes = (size_t)chunk * WW_CLIP_SAMPLES * esz;
+    if (ctx->host_chunk == chunk && ctx->host_chunk_bytes >= bytes) return WW_OK;
+    for (int i = 0; i < 2; ++i) {
+        if (!ctx->hs[i]) CK(cudaStreamCreateWithFlags(&ctx->hs[i], cudaStreamNonBlocking));
+        if (!ctx->hev[i]) CK(cudaEventCreateWithFlags(&ctx->hev[i], cudaEventDisableTiming));
+        if (ctx->h_pin[i]) { cudaFreeHost(ctx->h_pin[i]); ctx->h_pin[i] = nullptr; }
+        cudaFree(ctx->d_pcm[i]); ctx->d_pcm[i] = nullptr;
+        CK(cudaMallocHost(&ctx->h_pin[i], bytes));
+        CK(cudaMalloc(&ctx->d_pcm[i], bytes));
+        if (!ctx->d_logits[i]) {
+            const size_t lb = (size_t)chunk * sizeof(float) * (size_t)ctx->w.num_classes;
+            CK(cudaMalloc(&ctx->d_logits[i], lb));
+            CK(cudaMalloc(&ctx->d_dec[i], (size_t)chunk));
+            CK(cudaMallocHost((void**)&ctx->h_logits[i], lb));
+            CK(cudaMallocHost((void**)&ctx->h_dec[i], (size_t)chunk));
+        }
+    }
+    ctx->host_chunk = chunk;
+    ctx->host_chunk_bytes = bytes;
+    return WW_OK;
+}
+
+extern "C" int ww_score_clips_host(ww_ctx* ctx, const void* pcm_host, int pcm_type, long long n_clips, int cmvn_mode,
+                                   int decide_mode, float threshold, int cnn_impl, float* logits_host,
+                                   uint8_t* decisions_host) {
+    if (!ctx) return WW_ERR_INVALID;
+    if (!pcm_host || !logits_host || n_clips < 0) return fail(ctx, WW_ERR_INVALID, "score_clips_host: bad arguments");
+    if (pcm_type != WW_PCM_S16 && pcm_type != WW_PCM_F32) return fail(ctx, WW_ERR_INVALID, "score_clips_host: bad pcm_type");
+    int rc = check_cnn_args(ctx, cmvn_mode, decide_mode, cnn_impl);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const size_t esz = pcm_type == WW_PCM_S16 ? 2 : 4;
+    rc = ensure_host_path(ctx, esz);
+    if (rc) return rc;
+    rc = ensure_scratch(ctx);
+    if (rc) return rc;
+    // is the caller's buffer page-locked?  then DMA straight from it
+    cudaPointerAttributes pa;
+    bool pinned = (cudaPointerGetAttributes(&pa, pcm_host) == cudaSuccess) && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const int C = ctx->w.num_classes;
+    const long long chunk = ctx->host_chunk;
+    const long long n_chunks = (n_clips + chunk - 1) / chunk;
+    // the two chunks in flight share one feature scratch, so compute is serialised on hs[0] while copies
+    // run on their own stream per buffer
+    for (long long k = 0; k < n_chunks + 2; ++k) {
+        // retire chunk k-2 (its buffers are reused by chunk k)
+        if (k >= 2) {
+            const long long kk = k - 2;
+            const int b = (int)(kk & 1);
+            const long long c0 = kk * chunk, nc = (n_clips - c0) < chunk ? (n_clips - c0) : chunk;
+            CK(cudaStreamSynchronize(ctx->hs[b]));
+            memcpy(logits_host + c0 * C, ctx->h_logits[b], (size_t)nc * C * sizeof(float));
+            if (decisions_host) memcpy(decisions_host + c0, ctx->h_dec[b], (size_t)nc);
+        }
+        if (k < n_chunks) {
+            const int b = (int)(k & 1);
+            const long long c0 = k * chunk, nc = (n_clips - c0) < chunk ? (n_clips - c0) : chunk;
+            const size_t bytes = (size_t)nc * WW_CLIP_SAMPLES * esz;
+            const char* src = (const char*)pcm_host + (size_t)c0 * WW_CLIP_SAMPLES * esz;
+            if (pinned) {
+                CK(cudaMemcpyAsync(ctx->d_pcm[b], src, bytes, cudaMemcpyHostToDevice, ctx->hs[b]));
+            } else {
+                memcpy(ctx->h_pin[b], src, bytes);
+                CK(cudaMemcpyAsync(ctx->d_pcm[b], ctx->h_pin[b], bytes, cudaMemcpyHostToDevice, ctx->hs[b]));
+            }
+            // compute of chunk k must wait for compute of chunk k-1 (shared scratch)
+            if (k >= 1) CK(cudaStreamWaitEvent(ctx->hs[b], ctx->hev[(k - 1) & 1], 0));
+            rc = score_clips_dev(ctx, ctx->d_pcm[b], pcm_type, nc, cmvn_mode, decide_mode, threshold, cnn_impl,
+                                 ctx->d_logits[b], ctx->d_dec[b], ctx->hs[b]);
+            if (rc) return rc;
+            CK(cudaEventRecord(ctx->hev[b], ctx->hs[b]));
+            CK(cudaMemcpyAsync(ctx->h_logits[b], ctx->d_logits[b], (size_t)nc * C * sizeof(float), cudaMemcpyDeviceToHost,
+                               ctx->hs[b]));
+            CK(cudaMemcpyAsync(ctx->h_dec[b], ctx->d_dec[b], (size_t)nc, cudaMemcpyDeviceToHost, ctx->hs[b]));
+        }
+    }
+    return WW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// streaming
+// ------------------------------------------------------------------------------------------------
+extern "C" int ww_stream_score(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_samples, int cmvn_mode,
+                               int cnn_impl, float* feats_work, float* logits, ww_stream_t stream) {
+    if (!ctx) return WW_ERR_INVALID;
+    if (!pcm || !feats_work || !logits) return fail(ctx, WW_ERR_INVALID, "stream_score: null buffer");
+    if (n_samples <= 0 || n_samples > 0x7fffff00LL) return fail(ctx, WW_ERR_INVALID, "stream_score: bad n_samples");
+    int rc = check_cnn_args(ctx, cmvn_mode, WW_DECIDE_NONE, cnn_impl);
+    if (rc) return rc;
+    const int T = ww_num_frames(WW_FEAT_PY, (int)n_samples);
+    if (T < WW_WINDOW_FRAMES) return fail(ctx, WW_ERR_INVALID, "stream_score: stream shorter than one window");
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = launch_mfcc(ctx, pcm, pcm_type, 1, (int)n_samples, n_samples, WW_FEAT_PY, feats_work, (long long)T * WW_N_MFCC,
+                     T, 1, st);
+    if (rc) return rc;
+    const long long W = T - WW_WINDOW_FRAMES + 1;
+    return run_cnn(ctx, feats_work, /*win_stride=*/1, /*coef_stride=*/T, /*frame_stride=*/1, W, cmvn_mode,
+                   WW_DECIDE_NONE, 0.f, cnn_impl, logits, nullptr, st);
+}
+
+extern "C" long long ww_stream_events(const float* logits_host, long long n_windows, int num_classes,
+                                      float threshold_logit, int warmup, int refractory, long long* hits,
+                                      long long max_hits) {
+    if (!logits_host || n_windows < 0 || num_classes < 1 || warmup < WW_WINDOW_FRAMES || refractory < 0) return WW_ERR_INVALID;
+    long long n_hits = 0;
+    const long long n_frames = n_windows + WW_WINDOW_FRAMES - 1;
+    long long reset_f = 0;
+    long long f = 0;
+    while (f < n_frames) {
+        const long long count = f - reset_f + 1;
+        if (count >= warmup) {
+            const long long w = f - (WW_WINDOW_FRAMES - 1);
+            if (logits_host[w * num_classes] >= threshold_logit) {
+                if (hits && n_hits < max_hits) hits[n_hits] = w;
+                ++n_hits;
+                reset_f = f + refractory + 1;
+                f = reset_f;
+                continue;
+            }
+        }
+        ++f;
+    }
+    return n_hits;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTC
+// ------------------------------------------------------------------------------------------------
+extern "C" int ww_ctc_greedy(ww_ctx* ctx, const float* log_probs, long long t_stride, long long b_stride, int T, int B,
+                             int C, const int32_t* lengths, int decode_mode, int32_t* labels, int32_t* out_len,
+                             const int32_t* keyword, int keyword_len, uint8_t* hits, ww_stream_t stream) {
+    if (!ctx) return WW_ERR_INVALID;
+    if (!log_probs || !labels || !out_len || T < 0 || B < 0 || C < 1) return fail(ctx, WW_ERR_INVALID, "ctc_greedy: bad arguments");
+    if (decode_mode != WW_DECODE_KEEP_REPEATS && decode_mode != WW_DECODE_COLLAPSE)
+        return fail(ctx, WW_ERR_INVALID, "ctc_greedy: bad decode_mode");
+    if (hits && keyword_len > 0 && !keyword) return fail(ctx, WW_ERR_INVALID, "ctc_greedy: hits without keyword");
+    if (B == 0) return WW_OK;
+    GreedyArgs a;
+    a.lp = log_probs;
+    a.t_stride = t_stride;
+    a.b_stride = b_stride;
+    a.T = T;
+    a.B = B;
+    a.C = C;
+    a.lengths = lengths;
+    a.mode = decode_mode;
+    a.labels = labels;
+    a.out_len = out_len;
+    a.keyword = keyword;
+    a.K = keyword_len;
+    a.hits = hits;
+    ctc_greedy_kernel<<<(B + CTC_WARPS - 1) / CTC_WARPS, CTC_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    CK(cudaGetLastError());
+    return WW_OK;
+}
+
+extern "C" size_t ww_ctc_loss_workspace_bytes(int T, int B, int S) {
+    if (T < 0 || B < 0 || S < 0) return 0;
+    return (size_t)B * (size_t)T * (size_t)(2 * S + 1) * sizeof(float) + 16;
+}
+
+static int ctc_common(ww_ctx* ctx, CtcLossArgs& a, const float* log_probs, long long t_stride, long long b_stride, int T,
+                      int B, int C, const int32_t* targets, int S, const int32_t* il, const int32_t* tl, int blank,
+                      int zero_infinity) {
+    if (!log_probs || !il || !tl || T < 1 || B < 0 || C < 1 || S < 0 || blank < 0 || blank >= C)
+        return fail(ctx, WW_ERR_INVALID, "ctc_loss: bad arguments");
+    if (S > 0 && !targets) return fail(ctx, WW_ERR_INVALID, "ctc_loss: null targets");
+    if (S > 2048) return fail(ctx, WW_ERR_UNSUPPORTED, "ctc_loss: target length > 2048");
+    a.lp = log_probs;
+    a.t_stride = t_stride;
+    a.b_stride = b_stride;
+    a.T = T;
+    a.B = B;
+    a.C = C;
+    a.S = S;
+    a.targets = targets;
+    a.in_len = il;
+    a.tgt_len = tl;
+    a.blank = blank;
+    a.zero_infinity = zero_infinity;
+    return WW_OK;
+}
+
+extern "C" int ww_ctc_loss_fwd(ww_ctx* ctx, const float* log_probs, long long t_stride, long long b_stride, int T, int B,
+                               int C, const int32_t* targets, int S, const int32_t* input_lengths,
+                               const int32_t* target_lengths, int blank, int zero_infinity, float* nll, void* workspace,
+                               ww_stream_t stream) {
+    if (!ctx) return WW_ERR_INVALID;
+    CtcLossArgs a{};
+    int rc = ctc_common(ctx, a, log_probs, t_stride, b_stride, T, B, C, targets, S, input_lengths, target_lengths, blank,
+                        zero_infinity);
+    if (rc) return rc;
+    if (!nll || !workspace) return fail(ctx, WW_ERR_INVALID, "ctc_loss_fwd: null output");
+    if (B == 0) return WW_OK;
+    a.nll = nll;
+    a.alpha = (float*)workspace;
+    const size_t smem = (size_t)CTC_WARPS * 2 * ctc_lp(S) * sizeof(float);
+    if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(ctc_loss_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctc_loss_fwd_kernel<<<(B + CTC_WARPS - 1) / CTC_WARPS, CTC_WARPS * 32, smem, (cudaStream_t)stream>>>(a);
+    CK(cudaGetLastError());
+    return WW_OK;
+}
+
+extern "C" int ww_ctc_loss_bwd(ww_ctx* ctx, const float* log_probs, long long t_stride, long long b_stride, int T, int B,
+                               int C, const int32_t* targets, int S, const int32_t* input_lengths,
+                               const int32_t* target_lengths, int blank, int zero_infinity, const float* grad_out,
+                               const void* workspace, float* grad, long long gt_stride, long long gb_stride,
+                               ww_stream_t stream) {
+    if (!ctx) return WW_ERR_INVALID;
+    CtcLossArgs a{};
+    int rc = ctc_common(ctx, a, log_probs, t_stride, b_stride, T, B, C, targets, S, input_lengths, target_lengths, blank,
+                        zero_infinity);
+    if (rc) return rc;
+    if (!grad || !workspace) return fail(ctx, WW_ERR_INVALID, "ctc_loss_bwd: null buffer");
+    if (B == 0) return WW_OK;
+    a.alpha = (float*)workspace;
+    a.grad_out = grad_out;
+    a.grad = grad;
+    a.gt_stride = gt_stride;
+    a.gb_stride = gb_stride;
+    const size_t smem = (size_t)CTC_WARPS * (2 * ctc_lp(S) + 3 * S) * sizeof(float);
+    if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(ctc_loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctc_loss_bwd_kernel<<<(B + CTC_WARPS - 1) / CTC_WARPS, CTC_WARPS * 32, smem, (cudaStream_t)stream>>>(a);
+    CK(cudaGetLastError());
+    return WW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mfcc.h drop-in
+// ------------------------------------------------------------------------------------------------
+static std::mutex g_shim_mu;
+static ww_ctx* g_shim_ctx = nullptr;
+
+extern "C" float* ww_extract_mfcc(const float* signal, int signal_len, int sampling_rate, int frame_size, int hop_size,
+                                  int n_fft, int n_filters, int n_mfcc) {
+    if (!signal || signal_len < frame_size) {  // mfcc.c:434-437
+        fprintf(stderr, "E MFCC: Invalid signal parameters\n");
+        return nullptr;
+    }
+    if (sampling_rate != 16000 || frame_size != WW_WIN || hop_size != WW_HOP || n_fft != WW_N_FFT ||
+        n_filters != WW_N_MELS || n_mfcc != WW_N_MFCC) {
+        fprintf(stderr, "E MFCC: only (16000, 320, 256, 512, 40, 13) is supported by ww_b200\n");
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lk(g_shim_mu);
+    if (!g_shim_ctx && ww_create(&g_shim_ctx, 0) != WW_OK) return nullptr;
+    ww_ctx* ctx = g_shim_ctx;
+    const int T = ww_num_frames(WW_FEAT_ESP, signal_len);
+    float* out = (float*)malloc(sizeof(float) * (size_t)T * n_mfcc);
+    if (!out) return nullptr;
+    float *d_in = nullptr, *d_out = nullptr;
+    const size_t padded = ((size_t)signal_len + 3) / 4 * 4;
+    bool ok = cudaMalloc(&d_in, padded * sizeof(float)) == cudaSuccess &&
+              cudaMalloc(&d_out, sizeof(float) * (size_t)T * n_mfcc) == cudaSuccess &&
+              cudaMemcpy(d_in, signal, sizeof(float) * (size_t)signal_len, cudaMemcpyHostToDevice) == cudaSuccess &&
+              ww_mfcc_batch(ctx, d_in, WW_PCM_F32, 1, signal_len, signal_len, WW_FEAT_ESP, WW_LAYOUT_FRAME_MAJOR, d_out,
+                            nullptr) == WW_OK &&
+              cudaMemcpy(out, d_out, sizeof(float) * (size_t)T * n_mfcc, cudaMemcpyDeviceToHost) == cudaSuccess;
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (!ok) {
+        free(out);
+        return nullptr;
+    }
+    return out;
+}
+
+extern "C" void ww_free_mfcc(float* mfcc) { free(mfcc); }

@@ -1,0 +1,324 @@
+// CTC best-path decoding, keyword match and CTC loss forward/backward (sm_100a), warp per utterance.
+//
+// Replaces  CTCKeywordDetector.ctc_greedy_decode     ml_models/test.py:201-217   (MODE_KEEP_REPEATS)
+//           THCHS30Trainer.decode_predictions        ml_models/ctc.py:453-471    (MODE_COLLAPSE)
+//           `keyword in decoded_text`                ml_models/test.py:189-194
+//           nn.CTCLoss(...)(log_probs, targets, input_lengths, target_lengths)
+//                                                    ml_models/test.py:89,111-112; ml_models/ctc.py:369,396
+// All of these are streaming reductions over [T, C] rows: HBM-bound, no tensor-core work.
+#pragma once
+#include <math_constants.h>
+#include "ww_common.cuh"
+
+namespace ww {
+
+enum { DECODE_KEEP_REPEATS = 0, DECODE_COLLAPSE = 1 };
+
+struct GreedyArgs {
+    const float* lp;       // lp[t*t_stride + b*b_stride + c]
+    long long t_stride, b_stride;
+    int T, B, C;
+    const int* lengths;    // optional [B] valid frames per utterance
+    int mode;
+    int* labels;           // [B][T]
+    int* out_len;          // [B]
+    const int* keyword;    // optional [K] label ids
+    int K;
+    unsigned char* hits;   // optional [B]
+};
+
+constexpr int CTC_WARPS = 4;
+
+__global__ void __launch_bounds__(CTC_WARPS * 32) ctc_greedy_kernel(const GreedyArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long b = (long long)blockIdx.x * CTC_WARPS + warp;
+    if (b >= a.B) return;
+    const int Tb = a.lengths ? min(max(a.lengths[b], 0), a.T) : a.T;
+    const float* base = a.lp + b * a.b_stride;
+    int* lab = a.labels + b * (long long)a.T;
+    int pos = 0;
+    int carry = 0;  // argmax of the previous frame (blank before the first frame)
+    for (int tb = 0; tb < Tb; tb += 32) {
+        const int t = tb + lane;
+        int idx = 0;
+        if (a.C <= 32) {
+            // lane per frame
+            if (t < Tb) {
+                const float* row = base + (long long)t * a.t_stride;
+                float best = row[0];
+                for (int c = 1; c < a.C; ++c) {
+                    const float v = row[c];
+                    if (v > best) { best = v; idx = c; }
+                }
+            }
+        } else {
+            // warp per frame, lanes stride the classes (coalesced); first index wins ties
+            const int nt = min(32, Tb - tb);
+            for (int tt = 0; tt < nt; ++tt) {
+                const float* row = base + (long long)(tb + tt) * a.t_stride;
+                float best = -CUDART_INF_F;
+                int bi = 0x7fffffff;
+                for (int c = lane; c < a.C; c += 32) {
+                    const float v = row[c];
+                    if (v > best || bi == 0x7fffffff) { best = v; bi = c; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+                }
+                if (lane == tt) idx = bi;
+            }
+        }
+        int prev = __shfl_up_sync(0xffffffffu, idx, 1);
+        if (lane == 0) prev = carry;
+        bool keep = (t < Tb) && (idx != 0);
+        if (a.mode == DECODE_COLLAPSE) keep = keep && (idx != prev);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) lab[pos + __popc(m & ((1u << lane) - 1u))] = idx;
+        pos += __popc(m);
+        carry = __shfl_sync(0xffffffffu, idx, 31);
+    }
+    // pad the tail so the label matrix is deterministic
+    for (int i = pos + lane; i < a.T; i += 32) lab[i] = 0;
+    if (lane == 0) a.out_len[b] = pos;
+    if (a.hits) {
+        __syncwarp();
+        bool hit = (a.K == 0);
+        for (int s = lane; s + a.K <= pos && a.K > 0; s += 32) {
+            bool eq = true;
+            for (int k = 0; k < a.K; ++k) eq = eq && (lab[s + k] == a.keyword[k]);
+            hit = hit || eq;
+        }
+        hit = __any_sync(0xffffffffu, hit);
+        if (lane == 0) a.hits[b] = hit ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTC loss
+// ------------------------------------------------------------------------------------------------
+struct CtcLossArgs {
+    const float* lp;        // lp[t*t_stride + b*b_stride + c]   (log-softmax rows)
+    long long t_stride, b_stride;
+    int T, B, C, S;         // S = padded target length (row stride of `targets`)
+    const int* targets;     // [B][S]
+    const int* in_len;      // [B]
+    const int* tgt_len;     // [B]
+    int blank;
+    int zero_infinity;
+    float* nll;             // [B] per-sample negative log likelihood (before any reduction)
+    float* alpha;           // workspace [B][T][2S+1]
+    const float* grad_out;  // [B] upstream gradient of nll_b (backward only)
+    float* grad;            // grad[t*gt_stride + b*gb_stride + c] (backward only)
+    long long gt_stride, gb_stride;
+};
+
+__device__ __forceinline__ float lse3(float a, float b, float c) {
+    float m = fmaxf(a, fmaxf(b, c));
+    if (m == -CUDART_INF_F) m = 0.f;
+    return logf(expf(a - m) + expf(b - m) + expf(c - m)) + m;
+}
+__device__ __forceinline__ float lse2(float a, float b) {
+    float m = fmaxf(a, b);
+    if (m == -CUDART_INF_F) return -CUDART_INF_F;
+    return logf(expf(a - m) + expf(b - m)) + m;
+}
+
+// dynamic smem per warp: 2*Lp floats (double-buffered alpha/beta row), Lp = 2S+1 rounded up to 32,
+// plus (backward) S floats label accumulators and 2*S ints (first-occurrence map, duplicate list)
+__host__ __device__ inline int ctc_lp(int S) { return ((2 * S + 1 + 31) / 32) * 32; }
+
+__global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_fwd_kernel(const CtcLossArgs a) {
+    extern __shared__ float ctc_sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long b = (long long)blockIdx.x * CTC_WARPS + warp;
+    if (b >= a.B) return;
+    const int Lp = ctc_lp(a.S);
+    float* buf = ctc_sm + warp * 2 * Lp;
+    const int Tb = min(max(a.in_len[b], 0), a.T);
+    const int Sb = min(max(a.tgt_len[b], 0), a.S);
+    const int L = 2 * Sb + 1;
+    const int Lw = 2 * a.S + 1;
+    const int* tgt = a.targets + b * (long long)a.S;
+    const float* base = a.lp + b * a.b_stride;
+    float* al = a.alpha + b * (long long)a.T * Lw;
+    const float NEG = -CUDART_INF_F;
+
+    if (Tb == 0) {
+        if (lane == 0) {
+            float v = Sb == 0 ? 0.f : CUDART_INF_F;
+            if (a.zero_infinity && v == CUDART_INF_F) v = 0.f;
+            a.nll[b] = v;
+        }
+        return;
+    }
+    // t = 0
+    for (int s = lane; s < Lp; s += 32) {
+        float v = NEG;
+        if (s == 0) v = base[a.blank];
+        else if (s == 1 && L > 1) v = base[tgt[0]];
+        buf[s] = v;
+        if (s < L) al[s] = v;
+    }
+    __syncwarp();
+    int cur = 0;
+    for (int t = 1; t < Tb; ++t) {
+        const float* row = base + (long long)t * a.t_stride;
+        const float* prev = buf + cur * Lp;
+        float* next = buf + (cur ^ 1) * Lp;
+        for (int s = lane; s < Lp; s += 32) {
+            float v = NEG;
+            if (s < L) {
+                const int lab = (s & 1) ? tgt[s >> 1] : a.blank;
+                const float a0 = prev[s];
+                const float a1 = s >= 1 ? prev[s - 1] : NEG;
+                const bool skip = (s & 1) && s >= 3 && tgt[s >> 1] != tgt[(s >> 1) - 1];
+                const float a2 = skip ? prev[s - 2] : NEG;
+                v = lse3(a0, a1, a2) + row[lab];
+                al[(long long)t * Lw + s] = v;
+            }
+            next[s] = v;
+        }
+        cur ^= 1;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        const float* fin = buf + cur * Lp;
+        float ll = fin[L - 1];
+        if (L > 1) ll = lse2(ll, fin[L - 2]);
+        float v = -ll;
+        if (a.zero_infinity && v == CUDART_INF_F) v = 0.f;
+        a.nll[b] = v;
+    }
+}
+
+__global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_bwd_kernel(const CtcLossArgs a) {
+    extern __shared__ float ctc_sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long b = (long long)blockIdx.x * CTC_WARPS + warp;
+    if (b >= a.B) return;
+    const int Lp = ctc_lp(a.S);
+    const int per_warp = 2 * Lp + 3 * a.S;
+    float* buf = ctc_sm + warp * per_warp;       // beta double buffer
+    float* acc = buf + 2 * Lp;                   // [S] per-label log-sum of alpha*beta
+    int* first = reinterpret_cast<int*>(acc + a.S);  // [S] first occurrence of the same label
+    int* dups = first + a.S;                         // [S] positions whose label occurred before
+    const int Tb = min(max(a.in_len[b], 0), a.T);
+    const int Sb = min(max(a.tgt_len[b], 0), a.S);
+    const int L = 2 * Sb + 1;
+    const int Lw = 2 * a.S + 1;
+    const int* tgt = a.targets + b * (long long)a.S;
+    const float* base = a.lp + b * a.b_stride;
+    const float* al = a.alpha + b * (long long)a.T * Lw;
+    float* gbase = a.grad + b * a.gb_stride;
+    const float NEG = -CUDART_INF_F;
+
+    // recompute nll from alpha (unclamped by zero_infinity)
+    float nll;
+    {
+        float ll = NEG;
+        if (Tb > 0) {
+            ll = al[(long long)(Tb - 1) * Lw + L - 1];
+            if (L > 1) ll = lse2(ll, al[(long long)(Tb - 1) * Lw + L - 2]);
+        } else if (Sb == 0) {
+            ll = 0.f;
+        }
+        nll = -ll;
+    }
+    const float go = a.grad_out ? a.grad_out[b] : 1.f;
+    const bool dead = (a.zero_infinity && nll == CUDART_INF_F);
+
+    // rows past the input length (and everything for an infinite loss under zero_infinity) are zero
+    const int t_live = dead ? 0 : Tb;
+    for (int t = t_live; t < a.T; ++t) {
+        float* grow = gbase + (long long)t * a.gt_stride;
+        for (int c = lane; c < a.C; c += 32) grow[c] = 0.f;
+    }
+    if (t_live == 0) return;
+
+    // first-occurrence map of the target labels
+    int ndup = 0;
+    for (int i0 = 0; i0 < Sb; i0 += 32) {
+        const int i = i0 + lane;
+        int f = i;
+        if (i < Sb) {
+            const int li = tgt[i];
+            for (int j = 0; j < i; ++j)
+                if (tgt[j] == li) { f = j; break; }
+            first[i] = f;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, i < Sb && f != i);
+        if (i < Sb && f != i) dups[ndup + __popc(m & ((1u << lane) - 1u))] = i;
+        ndup += __popc(m);
+    }
+    __syncwarp();
+
+    int cur = 0;
+    for (int t = Tb - 1; t >= 0; --t) {
+        const float* row = base + (long long)t * a.t_stride;
+        float* grow = gbase + (long long)t * a.gt_stride;
+        const float* nxt = buf + cur * Lp;
+        float* now = buf + (cur ^ 1) * Lp;
+        float blank_m = NEG;
+        // beta_t and alpha_t + beta_t
+        for (int s = lane; s < Lp; s += 32) {
+            float v = NEG;
+            if (s < L) {
+                const int lab = (s & 1) ? tgt[s >> 1] : a.blank;
+                if (t == Tb - 1) {
+                    v = (s == L - 1 || s == L - 2) ? row[lab] : NEG;
+                } else {
+                    const float b0 = nxt[s];
+                    const float b1 = s + 1 < L ? nxt[s + 1] : NEG;
+                    const bool skip = (s & 1) && s + 2 < L && tgt[s >> 1] != tgt[(s >> 1) + 1];
+                    const float b2 = skip ? nxt[s + 2] : NEG;
+                    v = lse3(b0, b1, b2) + row[lab];
+                }
+                const float ab = al[(long long)t * Lw + s] + v;
+                if (s & 1) acc[s >> 1] = ab;
+                else blank_m = lse2(blank_m, ab);
+            }
+            now[s] = v;
+        }
+        cur ^= 1;
+        // blank total: log-sum-exp across lanes
+        {
+            float m = blank_m;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            float e = (m == NEG) ? 0.f : expf(blank_m - m);
+            e = warp_sum(e);
+            blank_m = (m == NEG) ? NEG : logf(e) + m;
+        }
+        // default gradient for every class: exp(lp)
+        for (int c = lane; c < a.C; c += 32) grow[c] = expf(row[c]) * go;
+        __syncwarp();
+        // fold repeated labels into their first occurrence (rare, sequential)
+        if (lane == 0)
+            for (int d = 0; d < ndup; ++d) acc[first[dups[d]]] = lse2(acc[first[dups[d]]], acc[dups[d]]);
+        __syncwarp();
+        for (int i = lane; i < Sb; i += 32) {
+            if (first[i] == i) {
+                const int c = tgt[i];
+                if (c != a.blank) {
+                    const float lpv = row[c];
+                    grow[c] = (expf(lpv) - expf(acc[i] + nll - lpv)) * go;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            // a target label equal to the blank index is folded into the blank class as PyTorch does
+            float tot = blank_m;
+            for (int i = 0; i < Sb; ++i)
+                if (first[i] == i && tgt[i] == a.blank) tot = lse2(tot, acc[i]);
+            const float lpv = row[a.blank];
+            grow[a.blank] = (expf(lpv) - expf(tot + nll - lpv)) * go;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace ww

@@ -1,0 +1,342 @@
+// MFCC frontend kernel (sm_100a): PCM -> [13 x T] cepstra with no intermediate in HBM.
+//
+// Replaces, per clip / stream block, the reference chain
+//   torchaudio.functional.preemphasis(x, 0.97)            ml_models/src/extract_mfcc.py:171
+//   T.MFCC(16 kHz, 13, log_mels, n_fft 512, win 320, hop 256, 40 mels, hamming)   :137-148,172
+// and, with the ESP table set, main/esp_mfcc/mfcc.c:431-527 (extract_mfcc).
+//
+// One CTA = one block of FRAMES consecutive frames of one signal (a 1 s clip is one block of 64, 63 valid).
+//   * the PCM span of the block is staged once into shared memory with a 1-D TMA bulk copy
+//     (cp.async.bulk + mbarrier); int16 PCM is kept as int16 in smem (32 KB per clip)
+//   * a warp transforms TWO frames at a time, one per half-warp: the 512-point real FFT is a 256-point
+//     complex FFT of the packed frame (z[m] = x[2m] + i x[2m+1]) done as radix-16 (registers) x
+//     radix-16 (registers) with one transposition through a per-warp smem tile, followed by the
+//     real-FFT split that yields two power bins per butterfly
+//   * pre-emphasis and the window are folded into the load (w*x[i] - 0.97w*x[i-1]); only the 160
+//     complex points under the 320-tap window are loaded
+//   * mel (CSR filterbank), log and the 40x13 DCT are done from shared memory; the DCT matrix sits in
+//     the kernel-parameter constant bank so every FFMA takes its weight as an immediate constant operand
+//   * output is written once, coalesced along time
+#pragma once
+#include "ww_common.cuh"
+
+namespace ww {
+
+// ---- table blob (one per feature mode, device memory, copied to smem by every CTA) ----------------
+constexpr int TB_WIN_OFF = 0;                       // float4[160]  {w[2m], .97w[2m], w[2m+1], .97w[2m+1]}
+constexpr int TB_TW1_OFF = TB_WIN_OFF + 160 * 16;   // float4[8][16] {W256^(l*2j), W256^(l*(2j+1))}
+constexpr int TB_TW2_OFF = TB_TW1_OFF + 128 * 16;   // float2[132]  W512^k, k = 0..128
+constexpr int TB_MELW_OFF = TB_TW2_OFF + 132 * 8;   // float[640]   filterbank weights, filter-major
+constexpr int TB_MELM_OFF = TB_MELW_OFF + 640 * 4;  // int4[40]     {start, len, off, bias bits}
+constexpr int TB_BYTES = TB_MELM_OFF + 40 * 16;     // 8864
+static_assert(TB_BYTES % 16 == 0, "table blob must be a multiple of 16 bytes");
+constexpr int MEL_W_CAP = 640;
+
+constexpr int MFCC_THREADS = 256;
+constexpr int MFCC_WARPS = MFCC_THREADS / 32;
+constexpr int EXCH_ROW_BYTES = 144;                    // 16 complex + 16 B pad: conflict-free LDS.128
+constexpr int EXCH_FRAME_BYTES = 16 * EXCH_ROW_BYTES;  // 2304 (>= 257 complex for the natural-order pass)
+constexpr int PS_STRIDE = 260;                         // floats per frame of power spectrum
+constexpr int LM_STRIDE = 41;                          // floats per frame of log-mel
+
+struct MfccArgs {
+    const void* pcm;          // [n_signals][sig_stride] samples
+    long long sig_stride;     // samples between signals
+    int n_samples;            // valid samples per signal
+    int n_frames;             // frames per signal
+    int blocks_per_sig;       // ceil(n_frames / FRAMES)
+    float* out;               // out[sig*out_sig_stride + coef*out_coef_stride + frame*out_frame_stride]
+    long long out_sig_stride;
+    long long out_coef_stride;
+    long long out_frame_stride;
+    const uint4* tables;      // TB_BYTES blob
+    int origin_off;           // sample index of FFT-frame point n=0 relative to 256*t: -256 (PY), -96 (ESP)
+    int reflect;              // 1: reflect-pad at the signal ends (torch.stft center=True)
+    int use_bulk;             // 1: TMA bulk copy is legal for this launch (alignment checked on host)
+    float pscale;             // power scale folded after the mel sum (0.25 * input scale^2 * mode scale)
+    float log_floor;          // lm = log(max(mel + bias, floor) + offset)
+    float log_offset;
+    float preemph;            // 0.97
+    float dct[WW_N_MELS * WW_N_MFCC];  // row-major [40][13]; lives in the parameter constant bank
+};
+
+template <typename TIN>
+__device__ __forceinline__ float pcm_to_float(TIN v);
+template <>
+__device__ __forceinline__ float pcm_to_float<int16_t>(int16_t v) { return static_cast<float>(v); }
+template <>
+__device__ __forceinline__ float pcm_to_float<float>(float v) { return v; }
+
+// ---- 16-point complex FFT in registers (forward, natural order in and out) -----------------------
+__device__ __forceinline__ void dft4(float2& p0, float2& p1, float2& p2, float2& p3) {
+    const float2 t0 = cadd(p0, p2), t1 = csub(p0, p2), t2 = cadd(p1, p3), t3 = cmul_mi(csub(p1, p3));
+    p0 = cadd(t0, t2);
+    p1 = cadd(t1, t3);
+    p2 = csub(t0, t2);
+    p3 = csub(t1, t3);
+}
+
+__device__ __forceinline__ void fft16(float2 (&v)[16]) {
+    constexpr float C1 = 0.92387953251128674f;  // cos(pi/8)
+    constexpr float S1 = 0.38268343236508977f;  // sin(pi/8)
+    constexpr float R2 = 0.70710678118654752f;  // sqrt(1/2)
+    // n = 4a + b, k = c + 4d.  Step 1: DFT4 over a for each b  -> v[4c + b] = Y[b][c]
+#pragma unroll
+    for (int b = 0; b < 4; ++b) dft4(v[b], v[4 + b], v[8 + b], v[12 + b]);
+    // Step 2: twiddle W16^(b*c)
+    v[4 * 1 + 1] = cmul(v[4 * 1 + 1], make_float2(C1, -S1));   // W^1
+    v[4 * 1 + 2] = cmul(v[4 * 1 + 2], make_float2(R2, -R2));   // W^2
+    v[4 * 1 + 3] = cmul(v[4 * 1 + 3], make_float2(S1, -C1));   // W^3
+    v[4 * 2 + 1] = cmul(v[4 * 2 + 1], make_float2(R2, -R2));   // W^2
+    v[4 * 2 + 2] = cmul_mi(v[4 * 2 + 2]);                      // W^4 = -i
+    v[4 * 2 + 3] = cmul(v[4 * 2 + 3], make_float2(-R2, -R2));  // W^6
+    v[4 * 3 + 1] = cmul(v[4 * 3 + 1], make_float2(S1, -C1));   // W^3
+    v[4 * 3 + 2] = cmul(v[4 * 3 + 2], make_float2(-R2, -R2));  // W^6
+    v[4 * 3 + 3] = cmul(v[4 * 3 + 3], make_float2(-C1, S1));   // W^9
+    // Step 3: DFT4 over b for each c -> v[4c + d] = X[c + 4d]
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dft4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    // natural order: X[k] = v[4*(k&3) + (k>>2)]  (register renaming only)
+    float2 r[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) r[k] = v[4 * (k & 3) + (k >> 2)];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = r[k];
+}
+
+// ---- generic (edge-frame) sample fetch: reflect + pre-emphasis, sample index s relative to the signal
+template <typename TIN>
+__device__ __forceinline__ float emph_sample(const TIN* spcm, int lo, int s, int L, int reflect, float pre) {
+    if (reflect) {
+        if (s < 0) s = -s;
+        if (s >= L) s = 2 * (L - 1) - s;
+    }
+    if (s < 0 || s >= L) return 0.f;
+    float x = pcm_to_float<TIN>(spcm[s - lo]);
+    if (s > 0) x = __fsub_rn(x, __fmul_rn(pre, pcm_to_float<TIN>(spcm[s - 1 - lo])));
+    return x;
+}
+
+template <typename TIN, int FRAMES>
+struct MfccSmem {
+    static constexpr int PCM_SAMPLES = FRAMES * WW_HOP + 72;  // (FRAMES-1)*256 + 320 + 8 lead, rounded
+    static constexpr int PCM_BYTES = ((PCM_SAMPLES * (int)sizeof(TIN) + 15) / 16) * 16;
+    static constexpr int OFF_BAR = 0;
+    static constexpr int OFF_TAB = 16;
+    static constexpr int OFF_PCM = OFF_TAB + TB_BYTES;
+    static constexpr int OFF_EXCH = OFF_PCM + PCM_BYTES;
+    static constexpr int OFF_PS = OFF_EXCH + MFCC_WARPS * 2 * EXCH_FRAME_BYTES;
+    static constexpr int OFF_LM = OFF_PS + MFCC_WARPS * 2 * PS_STRIDE * 4;
+    static constexpr int TOTAL = OFF_LM + FRAMES * LM_STRIDE * 4;
+    static_assert(OFF_PCM % 16 == 0 && OFF_EXCH % 16 == 0 && OFF_PS % 16 == 0, "smem alignment");
+};
+
+// DCT of one frame for the coefficient subset {G0, G0+G, ...}: weights are immediate constant operands.
+template <int G, int G0>
+__device__ __forceinline__ void dct_store(const MfccArgs& a, const float* lm_row, float* outp) {
+    constexpr int NQ = (WW_N_MFCC - G0 + G - 1) / G;
+    float acc[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < WW_N_MELS; ++j) {
+        const float l = lm_row[j];
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) acc[i] = fmaf(l, a.dct[j * WW_N_MFCC + G0 + G * i], acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) outp[(long long)(G0 + G * i) * a.out_coef_stride] = acc[i];
+}
+
+template <int G, int G0>
+struct DctDispatch {
+    static __device__ __forceinline__ void run(int g, const MfccArgs& a, const float* lm_row, float* outp) {
+        if (g == G0) dct_store<G, G0>(a, lm_row, outp);
+        else DctDispatch<G, G0 + 1>::run(g, a, lm_row, outp);
+    }
+};
+template <int G>
+struct DctDispatch<G, G> {
+    static __device__ __forceinline__ void run(int, const MfccArgs&, const float*, float*) {}
+};
+
+template <typename TIN, int FRAMES>
+__global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_constant__ MfccArgs a) {
+    using SM = MfccSmem<TIN, FRAMES>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
+    const unsigned char* tab = smem + SM::OFF_TAB;
+    const TIN* spcm = reinterpret_cast<const TIN*>(smem + SM::OFF_PCM);
+    float* lm = reinterpret_cast<float*>(smem + SM::OFF_LM);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int half = lane >> 4, l16 = lane & 15;
+
+    const long long sig = blockIdx.x / a.blocks_per_sig;
+    const int blk = blockIdx.x - (int)(sig * a.blocks_per_sig);
+    const int t0 = blk * FRAMES;
+    const int L = a.n_samples;
+
+    // staged sample range [lo, hi) of this signal
+    int lo = WW_HOP * t0 + a.origin_off + 88;   // 8 samples ahead of the first window tap (multiple of 8)
+    int hi = WW_HOP * (t0 + FRAMES - 1) + a.origin_off + 416;
+    lo = lo < 0 ? 0 : lo;
+    hi = hi > L ? L : hi;
+    const TIN* gsrc = reinterpret_cast<const TIN*>(a.pcm) + sig * a.sig_stride + lo;
+    const int n_stage = hi - lo;
+
+    if (a.use_bulk) {
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // bytes is a multiple of 16 by construction when use_bulk is set (host-checked)
+            const uint32_t bytes = (uint32_t)(n_stage * (int)sizeof(TIN));
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(smem + SM::OFF_PCM, gsrc, bytes, bar);
+        }
+    } else {
+        TIN* dst = reinterpret_cast<TIN*>(smem + SM::OFF_PCM);
+        for (int i = tid; i < n_stage; i += MFCC_THREADS) dst[i] = gsrc[i];
+    }
+    // tables -> smem
+    {
+        uint4* dst = reinterpret_cast<uint4*>(smem + SM::OFF_TAB);
+        for (int i = tid; i < TB_BYTES / 16; i += MFCC_THREADS) dst[i] = __ldg(a.tables + i);
+    }
+    __syncthreads();
+    if (a.use_bulk) mbar_wait(bar, 0);
+
+    const float4* s_win = reinterpret_cast<const float4*>(tab + TB_WIN_OFF);
+    const float4* s_tw1 = reinterpret_cast<const float4*>(tab + TB_TW1_OFF);
+    const float2* s_tw2 = reinterpret_cast<const float2*>(tab + TB_TW2_OFF);
+    const float* s_melw = reinterpret_cast<const float*>(tab + TB_MELW_OFF);
+    const int4* s_melm = reinterpret_cast<const int4*>(tab + TB_MELM_OFF);
+
+    unsigned char* exch = smem + SM::OFF_EXCH + (warp * 2 + half) * EXCH_FRAME_BYTES;
+    float* ps = reinterpret_cast<float*>(smem + SM::OFF_PS) + (warp * 2 + half) * PS_STRIDE;
+
+    constexpr int ITERS = FRAMES / (2 * MFCC_WARPS);
+    static_assert(ITERS * 2 * MFCC_WARPS == FRAMES, "FRAMES must be a multiple of 16");
+
+#pragma unroll 1
+    for (int it = 0; it < ITERS; ++it) {
+        const int fl = (it * MFCC_WARPS + warp) * 2 + half;  // frame index inside the block
+        const int t = t0 + fl;
+        const bool valid = t < a.n_frames;
+        const int fo = WW_HOP * t + a.origin_off;  // signal sample index of frame point n = 0
+        const bool interior = valid && (fo + 95 >= 0) && (fo + 415 < L);
+
+        float2 v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = make_float2(0.f, 0.f);
+
+        if (interior) {
+            // complex point m = 16*n1 + l16 (n1 = 3..12) <-> samples fo + 2m, fo + 2m + 1
+            const int base = fo - lo + 2 * l16;  // smem sample index of m = l16
+#pragma unroll
+            for (int n1 = 3; n1 <= 12; ++n1) {
+                const float4 w = s_win[16 * (n1 - 3) + l16];
+                float x0, x1, xm1;
+                if constexpr (sizeof(TIN) == 2) {
+                    const uint32_t* p32 = reinterpret_cast<const uint32_t*>(spcm) + ((base + 32 * n1) >> 1);
+                    const uint32_t cur = p32[0], prv = p32[-1];
+                    x0 = static_cast<float>(static_cast<int16_t>(cur & 0xffffu));
+                    x1 = static_cast<float>(static_cast<int16_t>(cur >> 16));
+                    xm1 = static_cast<float>(static_cast<int16_t>(prv >> 16));
+                } else {
+                    const float* pf = reinterpret_cast<const float*>(spcm) + (base + 32 * n1);
+                    const float2 c2 = *reinterpret_cast<const float2*>(pf);
+                    x0 = c2.x;
+                    x1 = c2.y;
+                    xm1 = pf[-1];
+                }
+                v[n1].x = fmaf(w.x, x0, -w.y * xm1);
+                v[n1].y = fmaf(w.z, x1, -w.w * x0);
+            }
+        } else if (valid) {
+#pragma unroll
+            for (int n1 = 3; n1 <= 12; ++n1) {
+                const float4 w = s_win[16 * (n1 - 3) + l16];
+                const int s = fo + 2 * (16 * n1 + l16);
+                v[n1].x = w.x * emph_sample<TIN>(spcm, lo, s, L, a.reflect, a.preemph);
+                v[n1].y = w.z * emph_sample<TIN>(spcm, lo, s + 1, L, a.reflect, a.preemph);
+            }
+        }
+
+        // pass 1: DFT16 over n1, twiddle W256^(l16*k1), transpose through smem
+        fft16(v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 tw = s_tw1[16 * j + l16];
+            if (j > 0) v[2 * j] = cmul(v[2 * j], make_float2(tw.x, tw.y));
+            v[2 * j + 1] = cmul(v[2 * j + 1], make_float2(tw.z, tw.w));
+        }
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1)
+            *reinterpret_cast<float2*>(exch + k1 * EXCH_ROW_BYTES + l16 * 8) = v[k1];
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 q = *reinterpret_cast<const float4*>(exch + l16 * EXCH_ROW_BYTES + j * 16);
+            v[2 * j] = make_float2(q.x, q.y);
+            v[2 * j + 1] = make_float2(q.z, q.w);
+        }
+        __syncwarp();
+        // pass 2: DFT16 over n2 -> Z[l16 + 16*k2] = v[k2]; park Z in natural order
+        fft16(v);
+        float2* zs = reinterpret_cast<float2*>(exch);
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) zs[l16 + 16 * k2] = v[k2];
+        if (l16 == 0) zs[256] = v[0];
+        __syncwarp();
+        // real-FFT split: pair (k, 256-k) -> 4*|X[k]|^2 and 4*|X[256-k]|^2
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int k = l16 + 16 * i;
+            const float2 za = zs[k], zb = zs[256 - k], w = s_tw2[k];
+            const float er = za.x + zb.x, ei = za.y - zb.y;
+            const float orr = za.y + zb.y, oi = zb.x - za.x;
+            const float tr = fmaf(w.x, orr, -w.y * oi), ti = fmaf(w.x, oi, w.y * orr);
+            const float x1r = er + tr, x1i = ei + ti, x2r = er - tr, x2i = ei - ti;
+            ps[k] = fmaf(x1r, x1r, x1i * x1i);
+            ps[256 - k] = fmaf(x2r, x2r, x2i * x2i);
+        }
+        if (l16 == 0) {
+            const float2 z = zs[128];
+            ps[128] = 4.f * fmaf(z.x, z.x, z.y * z.y);
+        }
+        __syncwarp();
+        // mel + log: lane handles filters l16, l16+16, l16+32
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int j = l16 + 16 * r;
+            if (j < WW_N_MELS) {
+                const int4 m = s_melm[j];
+                const float* pp = ps + m.x;
+                const float* ww_ = s_melw + m.z;
+                float acc = 0.f;
+                for (int i = 0; i < m.y; ++i) acc = fmaf(pp[i], ww_[i], acc);
+                const float e = fmaf(acc, a.pscale, __int_as_float(m.w));
+                lm[fl * LM_STRIDE + j] = __logf(fmaxf(e, a.log_floor) + a.log_offset);
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // DCT: thread <-> (frame, coefficient group); store coalesced along time
+    {
+        constexpr int G = MFCC_THREADS / FRAMES;
+        const int fl = tid % FRAMES, g = tid / FRAMES;
+        const int t = t0 + fl;
+        if (t < a.n_frames) {
+            float* outp = a.out + sig * a.out_sig_stride + (long long)t * a.out_frame_stride;
+            DctDispatch<G, 0>::run(g, a, lm + fl * LM_STRIDE, outp);
+        }
+    }
+}
+
+}  // namespace ww

@@ -1,0 +1,13 @@
+"""ww_b200 -- B200-native batch engine for the wake-word hot path of Socrates666/esp32-wake-word.
+
+Mirrors the reference's `ml_models` entry points (feature, model-forward and CTC calls) on top of
+libwwb200.so (hand-written sm_100a CUDA behind a C ABI, include/ww_b200.h).  No CPU fallback.
+"""
+from ._lib import WWError, get_context, load_library  # noqa: F401
+from .features import (add_random_noise, augment_audio_waveform, cmvn_batch, extract_features,  # noqa: F401
+                       load_wav, mfcc_batch, normalize_mfcc, pad_audio)
+from .model import LightweightKWS, WakeWordScorer  # noqa: F401
+from .ctc import (CTCKeywordDetector, CTCLoss, ctc_greedy_decode, ctc_loss, decode_predictions,  # noqa: F401
+                  greedy_batch)
+from .stream import StreamScorer, events, refractory_frames  # noqa: F401
+from .onnx_reader import load_kws_state_dict, read_initializers  # noqa: F401

@@ -1,0 +1,143 @@
+"""ctypes binding of libwwb200.so (include/ww_b200.h).
+
+PyTorch is used for device memory and streams only: every call hands raw device
+pointers and the current CUDA stream to the C ABI.  There is no CPU fallback:
+if the library is missing, or no B200 is present, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libwwb200.so")
+
+WW_OK = 0
+FEAT_PY, FEAT_ESP = 0, 1
+PCM_S16, PCM_F32 = 0, 1
+LAYOUT_COEF_MAJOR, LAYOUT_FRAME_MAJOR = 0, 1
+CMVN_NONE, CMVN_PY, CMVN_DEVICE = 0, 1, 2
+DECIDE_NONE, DECIDE_LOGIT, DECIDE_DEVICE = 0, 1, 2
+DECODE_KEEP_REPEATS, DECODE_COLLAPSE = 0, 1
+CNN_FP32, CNN_TENSOR = 0, 1
+
+EXPORTS = [
+    "ww_version", "ww_create", "ww_destroy", "ww_last_error", "ww_load_weights", "ww_num_frames",
+    "ww_mfcc_batch", "ww_cmvn", "ww_cnn_forward", "ww_score_clips", "ww_score_clips_host",
+    "ww_stream_score", "ww_stream_events", "ww_ctc_greedy", "ww_ctc_loss_workspace_bytes",
+    "ww_ctc_loss_fwd", "ww_ctc_loss_bwd", "ww_extract_mfcc", "ww_free_mfcc",
+]
+
+
+class WWError(RuntimeError):
+    pass
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load_library():
+    """dlopen libwwb200.so and declare the prototypes.  Raises if it is not built."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise WWError(
+                f"{LIB_PATH} is not built; run `python __graft_entry__.py build` "
+                "(nvcc, sm_100a).  ww_b200 has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+        lib.ww_version.restype = i32
+        lib.ww_create.argtypes = [C.POINTER(vp), i32]
+        lib.ww_destroy.argtypes = [vp]
+        lib.ww_destroy.restype = None
+        lib.ww_last_error.argtypes = [vp]
+        lib.ww_last_error.restype = C.c_char_p
+        lib.ww_load_weights.argtypes = [vp, vp, vp, vp, vp, vp, i32]
+        lib.ww_num_frames.argtypes = [i32, i32]
+        lib.ww_mfcc_batch.argtypes = [vp, vp, i32, i64, i32, i64, i32, i32, vp, vp]
+        lib.ww_cmvn.argtypes = [vp, vp, i64, i32, vp, vp]
+        lib.ww_cnn_forward.argtypes = [vp, vp, i64, i64, i64, i64, i32, i32, f32, i32, vp, vp, vp]
+        lib.ww_score_clips.argtypes = [vp, vp, i32, i64, i32, i32, f32, i32, vp, vp, vp]
+        lib.ww_score_clips_host.argtypes = [vp, vp, i32, i64, i32, i32, f32, i32, vp, vp]
+        lib.ww_stream_score.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, vp]
+        lib.ww_stream_events.argtypes = [vp, i64, i32, f32, i32, i32, vp, i64]
+        lib.ww_stream_events.restype = i64
+        lib.ww_ctc_greedy.argtypes = [vp, vp, i64, i64, i32, i32, i32, vp, i32, vp, vp, vp, i32, vp, vp]
+        lib.ww_ctc_loss_workspace_bytes.argtypes = [i32, i32, i32]
+        lib.ww_ctc_loss_workspace_bytes.restype = C.c_size_t
+        lib.ww_ctc_loss_fwd.argtypes = [vp, vp, i64, i64, i32, i32, i32, vp, i32, vp, vp, i32, i32, vp, vp, vp]
+        lib.ww_ctc_loss_bwd.argtypes = [vp, vp, i64, i64, i32, i32, i32, vp, i32, vp, vp, i32, i32, vp, vp, vp,
+                                        i64, i64, vp]
+        lib.ww_extract_mfcc.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32]
+        lib.ww_extract_mfcc.restype = C.POINTER(C.c_float)
+        lib.ww_free_mfcc.argtypes = [C.POINTER(C.c_float)]
+        lib.ww_free_mfcc.restype = None
+        _lib = lib
+        return lib
+
+
+class Context:
+    """One engine context per GPU (opaque ww_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.ww_create(C.byref(h), int(device))
+        if rc != WW_OK or not h:
+            raise WWError(f"ww_create(device={device}) failed with {rc}: no usable B200 "
+                          "(ww_b200 has no CPU fallback)")
+        self.h = h
+        self.device = int(device)
+        self.num_classes = 0
+
+    def check(self, rc: int, what: str):
+        if rc != WW_OK:
+            msg = self.lib.ww_last_error(self.h)
+            raise WWError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ww_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_contexts = {}
+
+
+def get_context(device=None) -> Context:
+    """Process-wide context for a CUDA device index (default: torch's current device)."""
+    import torch
+
+    if device is None:
+        if not torch.cuda.is_available():
+            raise WWError("CUDA is not available; ww_b200 has no CPU fallback")
+        device = torch.cuda.current_device()
+    device = int(device)
+    with _lock:
+        ctx = _contexts.get(device)
+    if ctx is None:
+        ctx = Context(device)
+        with _lock:
+            _contexts[device] = ctx
+    return ctx
+
+
+def ptr(t):
+    """Device/host pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def cur_stream(device):
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

@@ -1,0 +1,180 @@
+"""Drop-in for the reference's feature module `ml_models/src/extract_mfcc.py`.
+
+Same names and argument meaning as the reference (pad_audio :7, add_random_noise :25,
+normalize_mfcc :47, augment_audio_waveform :90, extract_features :123), with the
+hot arithmetic -- pre-emphasis + T.MFCC (:171-172) and CMVN (:175) -- executed by
+libwwb200.so on the GPU.  File walking, padding and augmentation stay host PyTorch,
+as in the reference.  Batched forms (`mfcc_batch`, `cmvn_batch`) are what large jobs
+call directly.
+"""
+from __future__ import annotations
+
+import os
+import wave
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+CLIP_SAMPLES = 16000
+N_MFCC = 13
+WINDOW_FRAMES = 63
+
+
+# ---------------------------------------------------------------------------------------------
+# host-side glue (same behaviour as the reference helpers)
+# ---------------------------------------------------------------------------------------------
+def pad_audio(audio, target_length, add_noise_to_pad=True, noise_level=0.005):
+    """Pad (noise or zeros) / truncate `audio` [C, N] to `target_length` samples."""
+    n = audio.shape[1]
+    if n < target_length:
+        extra = target_length - n
+        if add_noise_to_pad:
+            tail = torch.randn(audio.shape[0], extra, dtype=audio.dtype) * noise_level
+            return torch.cat([audio, tail.to(audio.device)], dim=1)
+        return torch.nn.functional.pad(audio, (0, extra))
+    if n > target_length:
+        return audio[:, :target_length]
+    return audio
+
+
+def add_random_noise(waveform, noise_level=0.01, snr_range=(5, 20)):
+    """White noise at a random SNR (amplitude ratio 10**(snr_db/20)), clamped to [-1, 1]."""
+    noise = torch.randn_like(waveform) * noise_level
+    lo, hi = snr_range
+    snr = 10 ** ((torch.rand(1) * (hi - lo) + lo) / 20)
+    p_sig, p_noise = torch.mean(waveform ** 2), torch.mean(noise ** 2)
+    if p_noise > 0:
+        noise = noise * torch.sqrt(p_sig / (p_noise * snr)).to(noise.device)
+    return torch.clamp(waveform + noise, -1.0, 1.0)
+
+
+def augment_audio_waveform(audio, augment_factor=3):
+    """Original + speed 0.8/1.2 (linear interpolation, re-padded to 1 s) + volume 0.7/1.3."""
+    out = [audio]
+    for speed in (0.8, 1.2):
+        size = int(audio.shape[1] * speed)
+        y = torch.nn.functional.interpolate(audio.unsqueeze(0), size=size, mode="linear",
+                                            align_corners=False).squeeze(0)
+        out.append(pad_audio(y, CLIP_SAMPLES))
+    for vol in (0.7, 1.3):
+        out.append(torch.clamp(audio * vol, -1.0, 1.0))
+    return out
+
+
+def load_wav(path):
+    """16-bit PCM WAV -> (float32 [channels, N] in [-1, 1), sample_rate); torchaudio.load semantics."""
+    with wave.open(path, "rb") as w:
+        if w.getsampwidth() != 2:
+            raise ValueError(f"{path}: only 16-bit PCM is supported")
+        n, ch, sr = w.getnframes(), w.getnchannels(), w.getframerate()
+        pcm = np.frombuffer(w.readframes(n), dtype="<i2").reshape(-1, ch).T
+    return torch.from_numpy(pcm.astype(np.float32) / 32768.0), sr
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU calls
+# ---------------------------------------------------------------------------------------------
+def _as_cuda_2d(x):
+    if not isinstance(x, torch.Tensor):
+        x = torch.as_tensor(x)
+    if x.dim() == 1:
+        x = x[None]
+    if x.dim() != 2:
+        raise ValueError("expected [B, N] samples")
+    if not x.is_cuda:
+        if not torch.cuda.is_available():
+            raise L.WWError("CUDA is not available; ww_b200 has no CPU fallback")
+        x = x.cuda(non_blocking=True)
+    if x.dtype == torch.int16:
+        return x.contiguous(), L.PCM_S16
+    return x.to(torch.float32).contiguous(), L.PCM_F32
+
+
+def mfcc_batch(x, mode="py", layout="coef_major"):
+    """Pre-emphasis (0.97) + MFCC of a batch of signals.
+
+    x: [B, N] int16 PCM or float waveform in [-1, 1] (CPU tensors are copied to the current GPU).
+    Returns float32 [B, 13, T] (T = 1 + N//256, the reference's T.MFCC output) for mode 'py';
+    mode 'esp' follows main/esp_mfcc/mfcc.c (T = (N-320)//256 + 1).  layout 'frame_major' -> [B, T, 13].
+    """
+    x, pcm_type = _as_cuda_2d(x)
+    ctx = L.get_context(x.device.index)
+    feat = L.FEAT_PY if mode == "py" else L.FEAT_ESP
+    B, N = x.shape
+    T = ctx.lib.ww_num_frames(feat, N)
+    if T <= 0:
+        raise ValueError(f"signal of {N} samples is shorter than one frame")
+    lay = L.LAYOUT_COEF_MAJOR if layout == "coef_major" else L.LAYOUT_FRAME_MAJOR
+    shape = (B, N_MFCC, T) if lay == L.LAYOUT_COEF_MAJOR else (B, T, N_MFCC)
+    out = torch.empty(shape, dtype=torch.float32, device=x.device)
+    ctx.check(ctx.lib.ww_mfcc_batch(ctx.h, L.ptr(x), pcm_type, B, N, x.stride(0), feat, lay, L.ptr(out),
+                                    L.cur_stream(x.device)), "ww_mfcc_batch")
+    return out
+
+
+def cmvn_batch(feats, device_style=False):
+    """CMVN of [B, 13, 63] windows on the GPU (python-style unbiased std, or the firmware's)."""
+    if feats.dim() != 3 or feats.shape[1] != N_MFCC or feats.shape[2] != WINDOW_FRAMES:
+        raise ValueError("cmvn_batch expects [B, 13, 63]")
+    x = feats.to(torch.float32).contiguous()
+    ctx = L.get_context(x.device.index)
+    out = torch.empty_like(x)
+    mode = L.CMVN_DEVICE if device_style else L.CMVN_PY
+    ctx.check(ctx.lib.ww_cmvn(ctx.h, L.ptr(x), x.shape[0], mode, L.ptr(out), L.cur_stream(x.device)), "ww_cmvn")
+    return out
+
+
+def normalize_mfcc(mfcc, method="standardization"):
+    """Reference signature: mfcc [13, T] (or [B, 13, T]) -> normalised tensor of the same shape.
+
+    'cmvn' and 'standardization' (identical arithmetic in the reference) on 63-frame CUDA
+    features run in the CMVN kernel; other shapes/methods are evaluated with device tensor ops
+    of the same formula.
+    """
+    if method in ("cmvn", "standardization") and mfcc.is_cuda and mfcc.shape[-1] == WINDOW_FRAMES \
+            and mfcc.shape[-2] == N_MFCC:
+        squeeze = mfcc.dim() == 2
+        out = cmvn_batch(mfcc[None] if squeeze else mfcc)
+        return out[0] if squeeze else out
+    if method in ("cmvn", "standardization"):
+        mean = mfcc.mean(dim=-1, keepdim=True)
+        std = mfcc.std(dim=-1, keepdim=True)
+        std = torch.where(std == 0, torch.ones_like(std), std)
+        return (mfcc - mean) / (std + 1e-8)
+    if method == "minmax":
+        lo = mfcc.min(dim=-1, keepdim=True)[0]
+        hi = mfcc.max(dim=-1, keepdim=True)[0]
+        return (mfcc - lo) / (hi - lo + 1e-8)
+    return mfcc
+
+
+def extract_features(audio_path="./audio_data/train_data/xiaoa", label=0, is_noise=False,
+                     add_noise_to_pad=True, augment_audio=True, normalize_method="cmvn"):
+    """Reference signature (extract_mfcc.py:123): walk `audio_path`, return
+    (list of [13, 63] feature tensors, list of label tensors).
+
+    All variants of all files are stacked and sent through ONE frontend launch.
+    """
+    clips = []
+    n_files = 0
+    for name in os.listdir(audio_path):
+        if not name.endswith(".wav"):
+            continue
+        n_files += 1
+        audio, _ = load_wav(os.path.join(audio_path, name))
+        audio = pad_audio(audio, CLIP_SAMPLES, add_noise_to_pad=add_noise_to_pad, noise_level=0.005)
+        variants = augment_audio_waveform(audio, augment_factor=3) if augment_audio else [audio]
+        for v in variants:
+            if is_noise:
+                v = add_random_noise(v, noise_level=0.01)
+            clips.append(v[0])
+    if not clips:
+        return [], []
+    feats = mfcc_batch(torch.stack(clips))
+    feats = normalize_mfcc(feats, method=normalize_method)
+    features = [f for f in feats]
+    labels = [torch.tensor(label) for _ in features]
+    print(f"extracted {len(features)} MFCC features from {n_files} files (normalisation: {normalize_method})")
+    return features, labels

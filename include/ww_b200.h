@@ -1,0 +1,152 @@
+/*
+ * ww_b200.h -- C ABI of libwwb200.so, the B200 (sm_100a) batch engine for the wake-word hot path
+ *              MFCC -> CMVN -> LightweightKWS CNN -> decision / CTC scoring.
+ *
+ * Every entry point names the reference interface it stands in for (paths relative to the
+ * Socrates666/esp32-wake-word tree).  Conventions:
+ *   - opaque context, no hidden statics (the reference's mfcc.c:37-38,362-363 caches are not thread-safe)
+ *   - device-buffer calls take caller-owned CUDA device pointers and an explicit cudaStream_t (as void*);
+ *     they enqueue work and return without synchronising
+ *   - host-buffer calls (`*_host`) take plain host pointers, do their own H2D/D2H and return when done
+ *   - int status: WW_OK (0) or a negative WW_ERR_* (mirrors ESP_OK / ESP_FAIL,
+ *     main/esp_wake_word_detector/include/esp_wake_word_detector.hpp:35); no exceptions cross the ABI
+ *   - there is no CPU fallback: without a CUDA device ww_create() fails
+ */
+#ifndef WW_B200_H_
+#define WW_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ww_ctx ww_ctx;
+typedef void* ww_stream_t; /* cudaStream_t */
+
+enum {
+    WW_OK = 0,
+    WW_ERR_INVALID = -1,     /* bad argument (the reference returns NULL / ESP_FAIL, mfcc.c:434-437) */
+    WW_ERR_CUDA = -2,        /* CUDA runtime error, see ww_last_error() */
+    WW_ERR_NO_WEIGHTS = -3,  /* ww_load_weights() has not been called */
+    WW_ERR_UNSUPPORTED = -4,
+    WW_ERR_NOMEM = -5
+};
+
+/* feature definition */
+enum {
+    WW_FEAT_PY = 0,  /* torchaudio T.MFCC as configured at ml_models/src/extract_mfcc.py:137-148,171 */
+    WW_FEAT_ESP = 1  /* main/esp_mfcc/mfcc.c:431-527 (extract_mfcc), intended math */
+};
+enum { WW_PCM_S16 = 0, WW_PCM_F32 = 1 };
+/* feature output layout */
+enum { WW_LAYOUT_COEF_MAJOR = 0 /* [n][13][T], PY */, WW_LAYOUT_FRAME_MAJOR = 1 /* [n][T][13], mfcc.c */ };
+enum {
+    WW_CMVN_NONE = 0,
+    WW_CMVN_PY = 1,     /* normalize_mfcc(...,'cmvn'|'standardization'), extract_mfcc.py:47-88 */
+    WW_CMVN_DEVICE = 2  /* detect_task, esp_wake_word_detector.cpp:128-131,179-211 */
+};
+enum {
+    WW_DECIDE_NONE = 0,
+    WW_DECIDE_LOGIT = 1,  /* logit > threshold; threshold 0 == sigmoid(out) > 0.5, ml_models/main.py:53 */
+    WW_DECIDE_DEVICE = 2  /* 1/(1+expf(-x))*100 >= threshold (80), esp_wake_word_detector.cpp:226-228,245 */
+};
+enum {
+    WW_DECODE_KEEP_REPEATS = 0, /* CTCKeywordDetector.ctc_greedy_decode, ml_models/test.py:201-217 */
+    WW_DECODE_COLLAPSE = 1      /* THCHS30Trainer.decode_predictions, ml_models/ctc.py:453-471 */
+};
+enum { WW_CNN_FP32 = 0, WW_CNN_TENSOR = 1 };
+
+#define WW_CLIP_SAMPLES 16000
+#define WW_N_MFCC 13
+#define WW_WINDOW_FRAMES 63
+
+/* ---- context ----------------------------------------------------------------------------------- */
+int ww_version(void);
+/* Create a context on CUDA device `device`.  Fails with WW_ERR_CUDA when no usable GPU is present. */
+int ww_create(ww_ctx** out, int device);
+void ww_destroy(ww_ctx* ctx);
+const char* ww_last_error(const ww_ctx* ctx);
+
+/* Load LightweightKWS weights from HOST arrays in torch state_dict layout
+ * (ml_models/src/wakeModel.py:8-27): conv_layers.{0,3,6}.weight [32,13,3] [64,32,3] [128,64,3],
+ * classifier.0.weight [64,128], classifier.2.weight [num_classes,64].  All layers are bias-free. */
+int ww_load_weights(ww_ctx* ctx, const float* conv1, const float* conv2, const float* conv3,
+                    const float* fc1, const float* fc2, int num_classes);
+
+/* frames produced for n_samples: PY 1 + n/256 (torch.stft center=True); ESP (n-320)/256+1 (mfcc.c:448) */
+int ww_num_frames(int feat_mode, int n_samples);
+
+/* ---- features: extract_features' inner T.MFCC call / mfcc.c extract_mfcc ---------------------- */
+/* pcm: device [n_signals][sig_stride] int16 or fp32 samples, n_samples valid per signal.
+ * out: device fp32, [n][13][T] or [n][T][13].  No intermediate is written to device memory. */
+int ww_mfcc_batch(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_signals, int n_samples,
+                  long long sig_stride, int feat_mode, int layout, float* out, ww_stream_t stream);
+
+/* normalize_mfcc / device CMVN over 63-frame windows [n][13][63] -> [n][13][63] */
+int ww_cmvn(ww_ctx* ctx, const float* feats, long long n_windows, int cmvn_mode, float* out,
+            ww_stream_t stream);
+
+/* ---- model forward: LightweightKWS.forward (ml_models/src/wakeModel.py:29-34) ------------------ */
+/* feats[win*win_stride + coef*coef_stride + frame*frame_stride], 63 frames per window.
+ * logits: [n_windows][num_classes]; decisions (class 0) may be NULL. */
+int ww_cnn_forward(ww_ctx* ctx, const float* feats, long long win_stride, long long coef_stride,
+                   long long frame_stride, long long n_windows, int cmvn_mode, int decide_mode,
+                   float threshold, int cnn_impl, float* logits, uint8_t* decisions, ww_stream_t stream);
+
+/* ---- fused clip scoring: PCM -> MFCC -> CMVN -> CNN -> decision -------------------------------- */
+/* pcm: device [n_clips][16000].  The feature intermediate stays in an L2-sized context scratch. */
+int ww_score_clips(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_clips, int cmvn_mode,
+                   int decide_mode, float threshold, int cnn_impl, float* logits, uint8_t* decisions,
+                   ww_stream_t stream);
+/* same, HOST buffers in and out (chunked, double-buffered H2D / compute / D2H); synchronous */
+int ww_score_clips_host(ww_ctx* ctx, const void* pcm_host, int pcm_type, long long n_clips, int cmvn_mode,
+                        int decide_mode, float threshold, int cnn_impl, float* logits_host,
+                        uint8_t* decisions_host);
+
+/* ---- streaming: sliding 63-frame window at hop 1 frame (esp_wake_word_detector.cpp:10-48,154-263) */
+/* pcm: device [n_samples] of ONE stream.  feats_work: device fp32 [13][T], T = ww_num_frames(PY, n).
+ * logits: device [T-62][num_classes].  Window w = frames w..w+62, CMVN recomputed per window. */
+int ww_stream_score(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_samples, int cmvn_mode,
+                    int cnn_impl, float* feats_work, float* logits, ww_stream_t stream);
+/* Host-side hit logic over per-window logits (class 0 column of [n_windows][num_classes]): first score
+ * after `warmup` (64) frames, threshold on the logit, `refractory` frames of lock-out then ring reset
+ * (esp_wake_word_detector.cpp:38-44,245-258).  Returns the number of hits (<= max_hits written). */
+long long ww_stream_events(const float* logits_host, long long n_windows, int num_classes, float threshold_logit,
+                           int warmup, int refractory, long long* hits, long long max_hits);
+
+/* ---- CTC best path / keyword (ml_models/test.py:168-217, ml_models/ctc.py:453-471) ------------- */
+/* log_probs[t*t_stride + b*b_stride + c]; labels: [B][T] int32 (zero padded), out_len: [B].
+ * lengths (valid frames per utterance) and keyword/hits may be NULL. */
+int ww_ctc_greedy(ww_ctx* ctx, const float* log_probs, long long t_stride, long long b_stride, int T, int B,
+                  int C, const int32_t* lengths, int decode_mode, int32_t* labels, int32_t* out_len,
+                  const int32_t* keyword, int keyword_len, uint8_t* hits, ww_stream_t stream);
+
+/* ---- CTC loss (nn.CTCLoss call shape: ml_models/test.py:89,111-112, ml_models/ctc.py:369,396) -- */
+size_t ww_ctc_loss_workspace_bytes(int T, int B, int S);
+/* nll: [B] per-sample loss before reduction; zero_infinity as in torch. */
+int ww_ctc_loss_fwd(ww_ctx* ctx, const float* log_probs, long long t_stride, long long b_stride, int T, int B,
+                    int C, const int32_t* targets, int S, const int32_t* input_lengths,
+                    const int32_t* target_lengths, int blank, int zero_infinity, float* nll, void* workspace,
+                    ww_stream_t stream);
+/* grad[t*gt_stride + b*gb_stride + c] = d(sum_b grad_out[b]*nll[b]) / d(activations), PyTorch convention */
+int ww_ctc_loss_bwd(ww_ctx* ctx, const float* log_probs, long long t_stride, long long b_stride, int T, int B,
+                    int C, const int32_t* targets, int S, const int32_t* input_lengths,
+                    const int32_t* target_lengths, int blank, int zero_infinity, const float* grad_out,
+                    const void* workspace, float* grad, long long gt_stride, long long gb_stride,
+                    ww_stream_t stream);
+
+/* ---- drop-in for main/esp_mfcc/mfcc.h:10-17 ---------------------------------------------------- */
+/* Same signature and ownership as the reference's extract_mfcc(): returns a malloc'd
+ * float[num_frames * n_mfcc] (frame-major) that the caller releases with ww_free_mfcc(); NULL on bad
+ * arguments (mfcc.c:434-437) or when no GPU is available.  Only the reference's fixed parameter set
+ * (16000, 320, 256, 512, 40, 13; hello_world_main.cpp:227) is accepted.  Uses a process-wide context. */
+float* ww_extract_mfcc(const float* signal, int signal_len, int sampling_rate, int frame_size, int hop_size,
+                       int n_fft, int n_filters, int n_mfcc);
+void ww_free_mfcc(float* mfcc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WW_B200_H_ */

@@ -1,0 +1,94 @@
+"""CPU: the C-ABI library loads, exports every symbol include/ww_b200.h declares, and its host-only
+entry points behave (no compute calls are made without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import stream as ostream
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+
+    ge.build()
+    import ww_b200
+
+    return ww_b200.load_library()
+
+
+def test_header_symbols_are_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "ww_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(ww_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 19
+    from ww_b200._lib import EXPORTS
+
+    assert names == set(EXPORTS)
+    for n in names:
+        assert getattr(lib, n) is not None
+
+
+def test_num_frames(lib):
+    assert lib.ww_num_frames(0, 16000) == 63       # torch.stft center=True
+    assert lib.ww_num_frames(1, 16000) == 62       # mfcc.c:448
+    assert lib.ww_num_frames(0, 57600000) == 225001
+    assert lib.ww_num_frames(0, 256) == 0 and lib.ww_num_frames(1, 319) == 0
+    assert lib.ww_num_frames(1, 320) == 1
+
+
+def test_create_fails_loudly_without_gpu(lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = C.c_void_p()
+    assert lib.ww_create(C.byref(h), 0) == -2 and not h
+    import ww_b200
+
+    with pytest.raises(ww_b200.WWError):
+        ww_b200.mfcc_batch(torch.zeros(1, 16000))
+    with pytest.raises(ww_b200.WWError):
+        ww_b200.LightweightKWS(1)(torch.zeros(1, 13, 63))
+
+
+def test_workspace_bytes(lib):
+    assert lib.ww_ctc_loss_workspace_bytes(63, 8, 2) == 8 * 63 * 5 * 4 + 16
+
+
+def test_extract_mfcc_shim_rejects_bad_args(lib):
+    x = np.zeros(100, np.float32)
+    assert not lib.ww_extract_mfcc(x.ctypes.data, 100, 16000, 320, 256, 512, 40, 13)   # signal_len < frame
+    assert not lib.ww_extract_mfcc(None, 16000, 16000, 320, 256, 512, 40, 13)         # NULL signal
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_stream_events_match_oracle(lib, seed):
+    import ww_b200
+
+    rng = np.random.default_rng(seed)
+    n = 5000
+    lg = rng.normal(-2.0, 1.5, size=(n, 1)).astype(np.float32)
+    lg[rng.integers(0, n, 12)] += 6.0
+    for refr in (0, 17, 313):
+        want = ostream.events(lg, refractory=refr)
+        got = ww_b200.events(lg, refractory=refr)
+        assert got == want
+    assert ww_b200.events(lg[:0]) == []
+    # the very first window (frames 0..62) is never scored: esp_wake_word_detector.cpp:38-44
+    lg2 = np.full((100, 1), -5.0, np.float32)
+    lg2[0] = 9.0
+    assert ww_b200.events(lg2) == []
+    lg2[1] = 9.0
+    assert ww_b200.events(lg2) == [1]
+
+
+def test_refractory_frames():
+    import ww_b200
+
+    assert ww_b200.refractory_frames() == ostream.refractory_frames() == 313

@@ -1,0 +1,141 @@
+"""GPU parity: CTC greedy decode (both reference semantics), keyword match, CTC loss forward/backward."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ctc as octc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("i", [0, 1, 2])
+def test_decoders_against_reference_goldens(cuda_device, golden_dir, i):
+    import ww_b200
+
+    g = np.load(os.path.join(golden_dir, "ctc_decode.npz"))
+    lp = torch.from_numpy(g[f"lp{i}"]).to(cuda_device)
+    Cn = lp.shape[-1]
+    chars = {k: chr(ord("a") + k - 1) if k else "_" for k in range(Cn)}
+    keep = [ww_b200.ctc_greedy_decode(lp[b], chars) for b in range(lp.shape[0])]
+    assert keep == list(g[f"keep{i}"])
+    assert ww_b200.ctc_greedy_decode(lp[:1], chars) == g[f"keep{i}"][0]  # [1, T, C] form
+    assert ww_b200.decode_predictions(lp, chars) == list(g[f"collapse{i}"])
+
+
+@pytest.mark.parametrize("B,T,C", [(1, 1, 2), (37, 63, 3), (5, 100, 40), (3, 33, 4096), (2, 64, 33)])
+@pytest.mark.parametrize("mode", ["collapse", "keep_repeats"])
+def test_greedy_batch_vs_oracle(cuda_device, B, T, C, mode):
+    import ww_b200
+
+    rng = np.random.default_rng(B * 1000 + T)
+    x = rng.normal(size=(B, T, C)).astype(np.float32)
+    x[..., 0] += 1.0
+    x = np.ascontiguousarray(np.repeat(x[:, ::2], 2, axis=1)[:, :T])  # runs of equal argmax
+    lengths = rng.integers(0, T + 1, size=B).astype(np.int32)
+    lengths[0] = T
+    kw = [1, 2] if C > 2 else [1]
+    labels, n, hits = ww_b200.greedy_batch(torch.from_numpy(x).to(cuda_device), mode=mode,
+                                           lengths=torch.from_numpy(lengths), keyword=kw)
+    torch.cuda.synchronize()
+    labels, n, hits = labels.cpu().numpy(), n.cpu().numpy(), hits.cpu().numpy()
+    m = octc.MODE_COLLAPSE if mode == "collapse" else octc.MODE_KEEP_REPEATS
+    for b in range(B):
+        want = octc.greedy_labels(x[b], m, length=int(lengths[b]))
+        assert n[b] == len(want)
+        assert labels[b, : n[b]].tolist() == want
+        assert (labels[b, n[b]:] == 0).all()
+        assert bool(hits[b]) == octc.keyword_hit(want, kw)
+    # time-major view gives the same answer
+    l2, n2, _ = ww_b200.greedy_batch(torch.from_numpy(x).to(cuda_device).transpose(0, 1).contiguous(), mode=mode,
+                                     lengths=torch.from_numpy(lengths), batch_first=False)
+    assert np.array_equal(l2.cpu().numpy(), labels) and np.array_equal(n2.cpu().numpy(), n)
+
+
+def test_argmax_ties_take_first_index(cuda_device):
+    import ww_b200
+
+    lp = torch.zeros(2, 8, 40, device=cuda_device)
+    lp[0, :, 5] = 1.0
+    lp[0, :, 9] = 1.0
+    labels, n, _ = ww_b200.greedy_batch(lp, mode="keep_repeats")
+    assert labels[0, :8].tolist() == [5] * 8 and int(n[1]) == 0
+    lp3 = torch.zeros(1, 4, 3, device=cuda_device)
+    lp3[0, :, 1:] = 2.0
+    labels, n, _ = ww_b200.greedy_batch(lp3, mode="collapse")
+    assert labels[0, : int(n[0])].tolist() == [1]
+    want = torch.max(lp3.cpu()[0], dim=1)[1].tolist()
+    assert want == [1, 1, 1, 1]
+
+
+def test_keyword_detector(cuda_device):
+    import ww_b200
+
+    c2i = {"_": 0, "x": 1, "a": 2}
+    det = ww_b200.CTCKeywordDetector(c2i, ["xa", "ax"], threshold=0.8)
+    seq = [0, 1, 1, 0, 2, 0, 0]
+    lp = torch.full((2, 7, 3), -5.0, device=cuda_device)
+    for t, s in enumerate(seq):
+        lp[0, t, s] = 0.0
+    lp[1, :, 0] = 0.0
+    assert det.ctc_greedy_decode(lp[0]) == "xxa"
+    res = det.detect_batch(lp)
+    assert res[0] == [("xa", 0.9)] and res[1] == []
+    assert det.calculate_confidence("xxa", "xa") == 0.9 and det.calculate_confidence("xx", "xa") == 0.0
+
+
+def _rand_problem(T, B, C, S, seed, full_len=False):
+    rng = np.random.default_rng(seed)
+    x = rng.normal(size=(T, B, C)).astype(np.float32)
+    lp = x - np.log(np.exp(x).sum(-1, keepdims=True))
+    tg = rng.integers(1, C, size=(B, max(S, 1))).astype(np.int64)
+    if S >= 2:
+        tg[0, 1] = tg[0, 0]
+    il = np.full(B, T) if full_len else rng.integers(min(2 * S + 1, T), T + 1, size=B)
+    tl = np.full(B, S) if full_len else rng.integers(0, S + 1, size=B)
+    return lp.astype(np.float32), tg, il, tl
+
+
+@pytest.mark.parametrize("T,B,C,S", [(63, 64, 3, 1), (63, 200, 3, 2), (50, 9, 20, 7), (120, 5, 50, 40), (801, 2, 300, 32)])
+@pytest.mark.parametrize("reduction", ["mean", "none"])
+def test_ctc_loss_fwd_bwd_vs_torch(cuda_device, T, B, C, S, reduction):
+    """loss rtol 1e-5, grad atol 1e-5 against torch.nn.functional.ctc_loss on CPU."""
+    import ww_b200
+
+    lp, tg, il, tl = _rand_problem(T, B, C, S, seed=T + B)
+    want_loss, want_grad = octc.ctc_loss_torch(lp, tg, il, tl, reduction=reduction)
+    x = torch.from_numpy(lp).to(cuda_device).requires_grad_(True)
+    crit = ww_b200.CTCLoss(blank=0, reduction=reduction)
+    loss = crit(x, torch.from_numpy(tg), torch.from_numpy(il), torch.from_numpy(tl))
+    (loss.sum() if reduction == "none" else loss).backward()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(loss.detach().cpu().numpy(), want_loss, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), want_grad, atol=1e-5)
+
+
+def test_ctc_loss_zero_infinity_and_blank_index(cuda_device):
+    import ww_b200
+
+    # impossible alignment: T=2 frames cannot emit "112"
+    lp = torch.log(torch.full((2, 2, 3), 1 / 3, device=cuda_device)).requires_grad_(True)
+    tg = torch.tensor([[1, 1, 2], [1, 0, 0]])
+    il, tl = torch.tensor([2, 2]), torch.tensor([3, 1])
+    inf = ww_b200.ctc_loss(lp, tg, il, tl, reduction="none", zero_infinity=False)
+    assert torch.isinf(inf[0]) and torch.isfinite(inf[1])
+    z = ww_b200.ctc_loss(lp, tg, il, tl, reduction="none", zero_infinity=True)
+    z.sum().backward()
+    want, wg = octc.ctc_loss_torch(lp.detach().cpu().numpy(), tg.numpy(), il.numpy(), tl.numpy(), reduction="none",
+                                   zero_infinity=True)
+    np.testing.assert_allclose(z.detach().cpu().numpy(), want, atol=1e-6)
+    np.testing.assert_allclose(lp.grad.cpu().numpy(), wg, atol=1e-6)
+    # test.py uses a non-zero blank index (char_to_idx['_'])
+    lp2, tg2, il2, tl2 = _rand_problem(30, 6, 4, 3, seed=1)
+    tg2 = np.where(tg2 == 2, 3, tg2)  # blank = 2 must not appear in targets
+    want, wg = octc.ctc_loss_torch(lp2, tg2, il2, tl2, blank=2, reduction="mean")
+    x = torch.from_numpy(lp2).to(cuda_device).requires_grad_(True)
+    loss = ww_b200.CTCLoss(blank=2, zero_infinity=True)(x, torch.from_numpy(tg2), torch.from_numpy(il2),
+                                                       torch.from_numpy(tl2))
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), want, rtol=1e-5)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), wg, atol=1e-5)

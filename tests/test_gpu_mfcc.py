@@ -1,0 +1,140 @@
+"""GPU parity: the MFCC frontend kernel against the PY-MFCC oracle and the reference-generated goldens.
+
+Tolerance (BASELINE.json north_star / SURVEY.md section 8d): 1e-3 absolute on the cepstra; the
+expected error is ~1e-4 (the oracle's own fp32-vs-fp64 noise floor is 3e-5)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import esp_mfcc as oesp
+from oracle import mfcc as om
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def _gpu_mfcc(x, **kw):
+    import ww_b200
+
+    out = ww_b200.mfcc_batch(x, **kw)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def test_golden_reference_features(cuda_device, golden_dir):
+    r = np.load(os.path.join(golden_dir, "ref_features.npz"))
+    got = _gpu_mfcc(torch.from_numpy(r["pcm"]).to(cuda_device))
+    assert got.shape == (14, 13, 63)
+    err = np.abs(got - r["mfcc"]).max()
+    print("max abs err vs reference extract_features goldens:", err)
+    assert err < TOL
+    # and against the fp64 oracle (who is closer to the truth?)
+    f64 = om.mfcc_numpy64(om.pcm16_to_float(r["pcm"]), tables="torchaudio")
+    assert np.abs(got - f64).max() < TOL
+
+
+@pytest.mark.parametrize("dtype", ["int16", "float32"])
+def test_synthetic_clips_vs_oracle(cuda_device, dtype):
+    pcm = om.synth_clips_int16(256, seed=1234)
+    xf = om.pcm16_to_float(pcm)
+    want = om.mfcc_torchaudio(xf).numpy()
+    x = torch.from_numpy(pcm if dtype == "int16" else xf).to(cuda_device)
+    got = _gpu_mfcc(x)
+    err = np.abs(got - want)
+    print(dtype, "max", err.max(), "mean", err.mean())
+    assert err.max() < TOL
+    assert err.mean() < 2e-5
+
+
+def test_float_input_full_scale_and_silence(cuda_device):
+    rng = np.random.default_rng(7)
+    x = np.zeros((6, 16000), np.float32)
+    x[0] = rng.uniform(-1, 1, 16000)
+    x[1, 5000:5100] = 1.0
+    x[2] = 1e-4 * rng.normal(size=16000)
+    x[3] = np.sin(2 * np.pi * 1000 * np.arange(16000) / 16000) * 0.9 + 1e-3 * rng.normal(size=16000)
+    x[5, 0] = 1.0  # impulse in the reflect-padded region
+    want = om.mfcc_torchaudio(x).numpy()
+    got = _gpu_mfcc(torch.from_numpy(x).to(cuda_device))
+    assert np.abs(got - want).max() < TOL
+    c0 = np.sqrt(40.0) * np.log(1e-6)
+    np.testing.assert_allclose(got[4, 0], c0, atol=1e-4)  # digital silence: c0 = -87.377, others 0
+    np.testing.assert_allclose(got[4, 1:], 0, atol=1e-4)
+
+
+@pytest.mark.parametrize("n", [257, 320, 4000, 8000, 15999, 16001, 17280, 40000, 100003])
+def test_ragged_lengths_and_multi_block_streams(cuda_device, n):
+    # lengths that are not multiples of 8 take the non-TMA staging path; > 16128 samples span several blocks
+    rng = np.random.default_rng(n)
+    x = (rng.normal(0, 0.1, size=(3, n))).astype(np.float32)
+    want = om.mfcc_torchaudio(x).numpy()
+    got = _gpu_mfcc(torch.from_numpy(x).to(cuda_device))
+    assert got.shape == want.shape == (3, 13, 1 + n // 256)
+    assert np.abs(got - want).max() < TOL
+    p = np.clip(np.round(x * 32767), -32768, 32767).astype(np.int16)
+    want16 = om.mfcc_torchaudio(om.pcm16_to_float(p)).numpy()
+    got16 = _gpu_mfcc(torch.from_numpy(p).to(cuda_device))
+    assert np.abs(got16 - want16).max() < TOL
+
+
+def test_too_short_raises(cuda_device):
+    import ww_b200
+
+    with pytest.raises(ValueError):
+        ww_b200.mfcc_batch(torch.zeros(1, 256, device=cuda_device))
+
+
+def test_frame_major_layout_and_strided_batch(cuda_device):
+    pcm = om.synth_clips_int16(8, seed=3)
+    big = torch.zeros(8, 16384, dtype=torch.int16, device=cuda_device)
+    big[:, :16000] = torch.from_numpy(pcm).to(cuda_device)
+    import ww_b200
+
+    a = ww_b200.mfcc_batch(big[:, :16000].contiguous())
+    x = big[:, :16000]  # non-contiguous rows are made contiguous by the wrapper
+    b = ww_b200.mfcc_batch(x, layout="frame_major")
+    torch.cuda.synchronize()
+    assert b.shape == (8, 63, 13)
+    assert torch.equal(a, b.transpose(1, 2))
+
+
+def test_deterministic(cuda_device):
+    pcm = torch.from_numpy(om.synth_clips_int16(64, seed=9)).to(cuda_device)
+    import ww_b200
+
+    a = ww_b200.mfcc_batch(pcm)
+    b = ww_b200.mfcc_batch(pcm)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+
+
+def test_esp_mode_vs_c_port(cuda_device):
+    """C-MFCC secondary mode (main/esp_mfcc/mfcc.c semantics) against the plain-C restatement."""
+    pcm = om.synth_clips_int16(8, seed=11)
+    xf = om.pcm16_to_float(pcm)
+    got = _gpu_mfcc(torch.from_numpy(xf).to(cuda_device), mode="esp", layout="frame_major")
+    assert got.shape == (8, 62, 13)
+    for i in range(8):
+        want = oesp.esp_mfcc_port(xf[i])
+        # clip 3 ends in digital silence: log(1e-12 * sum(w)) ~ -25 per mel bin -> still well defined
+        assert np.abs(got[i] - want).max() < 2e-3, i
+    if oesp.have_ref():
+        assert np.abs(got[0] - oesp.esp_mfcc_ref(xf[0])).max() < 2e-3
+
+
+def test_extract_mfcc_c_shim(cuda_device):
+    """ww_extract_mfcc keeps main/esp_mfcc/mfcc.h:10-15's signature, ownership and frame-major layout."""
+    import ctypes as C
+
+    import ww_b200
+
+    lib = ww_b200.load_library()
+    x = om.pcm16_to_float(om.synth_clips_int16(1, seed=5))[0]
+    p = lib.ww_extract_mfcc(x.ctypes.data, 16000, 16000, 320, 256, 512, 40, 13)
+    assert p
+    got = np.ctypeslib.as_array(p, shape=(62 * 13,)).copy().reshape(62, 13)
+    lib.ww_free_mfcc(p)
+    assert np.abs(got - oesp.esp_mfcc_port(x)).max() < 2e-3
+    assert not lib.ww_extract_mfcc(x.ctypes.data, 16000, 8000, 320, 256, 512, 40, 13)  # unsupported params
