@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- clips/s (1 s, 16 kHz) through MFCC + CMVN + CNN + decision + CTC best path.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W [--impl reference]`
+prints ONE JSON line on rank 0.
+
+Workload (BASELINE.json configs[2] at its single-GPU size; configs[1] is the `roofline` kernel):
+  * synthetic int16 PCM, `--clips` 1 s clips per GPU resident in HBM (four value
+    distributions by clip index mod 4, seed 1234 + rank), larger than L2 so no flush is needed
+  * step = ww_score_clips over all clips (frontend + CMVN + xiaoa CNN + sigmoid>0.5 decision) followed by
+    the CTC best-path / keyword kernel over the binary posteriors grouped 63 windows per utterance,
+    then (N > 1) a gather of the decisions to rank 0 -- the only collective
+  * `value` = clips of all ranks / max-over-ranks device time (CUDA events on the launching stream)
+  * `e2e`   = the same call with HOST buffers (pinned), H2D and D2H inside the timed region
+  * `roofline` = the frontend kernel alone (ww_mfcc_batch over the same clips): algorithmic bytes
+    35 276 B/clip over its CUDA-event time, against MEASURED_PEAKS.json's HBM copy bandwidth
+  * `cpu_baseline` / `--impl reference`: the oracle port of the reference's CPU path (torchaudio T.MFCC +
+    normalize_mfcc + LightweightKWS + sigmoid>0.5 + greedy decode) on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "esp32-wake-word_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "clips/sec (1 s 16 kHz) MFCC+CNN+CTC"
+UNIT = "clips/s"
+FRONTEND_BYTES_PER_CLIP = 16000 * 2 + 13 * 63 * 4  # 35 276
+FUSED_BYTES_PER_CLIP = 16000 * 2 + 5
+UTT = 63  # windows per CTC utterance
+
+
+def load_weights():
+    d = np.load(os.path.join(ROOT, "tests", "golden", "xiaoa_weights.npz"))
+    return {k: d[k] for k in d.files}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic PCM (same four distributions on either device; RNG streams differ between CPU and CUDA)
+# ------------------------------------------------------------------------------------------------
+def synth_pcm(n_clips, device, seed, chunk=32768, pin=False):
+    import torch
+
+    out = torch.empty((n_clips, 16000), dtype=torch.int16, device=device,
+                      pin_memory=(pin and device == "cpu"))
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    t = torch.arange(16000, device=device, dtype=torch.float32) / 16000.0
+    for c0 in range(0, n_clips, chunk):
+        n = min(chunk, n_clips - c0)
+        x = torch.randn((n, 16000), generator=g, device=device) * 0.1               # (0) white
+        idx = torch.arange(c0, c0 + n, device=device) % 4
+        u = torch.rand((n, 16000), generator=g, device=device) - 0.5                   # (1) uniform
+        ph = torch.rand((n, 2), generator=g, device=device) * (2 * np.pi)
+        tone = 0.3 * torch.sin(2 * np.pi * 440.0 * t[None] + ph[:, :1]) + \
+            0.3 * torch.sin(2 * np.pi * 3000.0 * t[None] + ph[:, 1:]) + x * 0.1       # (2) tones + N(0,.01^2)
+        sp = x.clone()
+        sp[:, 9000:] = 0.0                                                             # (3) burst then silence
+        y = torch.where((idx == 0)[:, None], x, torch.where((idx == 1)[:, None], u,
+                        torch.where((idx == 2)[:, None], tone, sp)))
+        y = torch.clamp(y, -1.0, 32767.0 / 32768.0)
+        out[c0:c0 + n] = torch.round(y * 32767.0).to(torch.int16)
+        del x, u, tone, sp, y
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.15:
+                continue
+            f = [v.strip() for v in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                for nm, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference path (oracle port) -- the checker used as the timed baseline, never as the product
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step(pcm_i16, sd):
+    """One pass of the reference's CPU path over a batch of clips; returns (#positives, #keyword hits)."""
+    import torch
+
+    from oracle import cnn as ocnn
+    from oracle import ctc as octc
+    from oracle import mfcc as omfcc
+
+    x = pcm_i16.to(torch.float32) / 32768.0                     # torchaudio.load normalisation
+    feats = omfcc.mfcc_torchaudio(x)                            # preemphasis + T.MFCC
+    z = omfcc.normalize_mfcc(feats, "cmvn")
+    logits = ocnn.forward_torch(z.numpy(), sd)[:, 0]
+    dec = ocnn.decide_python(logits)
+    n_utt = len(logits) // UTT
+    hits = 0
+    if n_utt:
+        lg = torch.from_numpy(logits[: n_utt * UTT].reshape(n_utt, UTT))
+        lp = torch.stack([torch.nn.functional.logsigmoid(-lg), torch.nn.functional.logsigmoid(lg)], dim=-1).numpy()
+        for b in range(n_utt):
+            hits += octc.keyword_hit(octc.greedy_labels(lp[b], octc.MODE_COLLAPSE), [1])
+    return int(dec.sum()), int(hits)
+
+
+def time_cpu(clips, steps, warmup, seed=1234):
+    import torch
+
+    sd = load_weights()
+    pcm = synth_pcm(clips, "cpu", seed, chunk=4096)
+    for _ in range(warmup):
+        cpu_reference_step(pcm, sd)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_step(pcm, sd)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return clips / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    clips = args.cpu_clips
+    v, dt, cores = time_cpu(clips, args.steps, args.warmup)
+    sample = f"{clips} synthetic clips per step (bounded sample of the {args.clips}-clip/GPU workload), " \
+             f"torch {cores} threads of {os.cpu_count()} cpus"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n):
+    return {"workload": "configs[2]: fused MFCC(esp_mfcc/ml_models params: 320/256/512, 40 mel, 13 cep) + CMVN + "
+                        "xiaoa.onnx LightweightKWS CNN + sigmoid>0.5 decision + CTC best-path/keyword over 63-window "
+                        "utterances, clip-sharded",
+            "clips_per_gpu": args.clips, "global_clips": args.clips * n, "clip_samples": 16000, "pcm": "int16",
+            "cnn_impl": args.cnn, "parallelism": f"dp{n} (clip shards, no hot-path collective)",
+            "l2_policy": "inputs (32 KB/clip x clips) exceed L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import ww_b200
+    from ww_b200 import _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (ww_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sd = load_weights()
+    cnn_impl = args.cnn
+    scorer = ww_b200.WakeWordScorer(sd, device=local, cmvn="python", decision="python", cnn_impl=cnn_impl)
+    ctx = scorer.ctx
+    B = args.clips
+    pcm = synth_pcm(B, dev, 1234 + rank)
+    logits = torch.empty((B, 1), dtype=torch.float32, device=dev)
+    dec = torch.empty((B,), dtype=torch.uint8, device=dev)
+    n_utt = B // UTT
+    labels = torch.empty((max(n_utt, 1), UTT), dtype=torch.int32, device=dev)
+    lab_len = torch.empty((max(n_utt, 1),), dtype=torch.int32, device=dev)
+    hits = torch.empty((max(n_utt, 1),), dtype=torch.uint8, device=dev)
+    kw = torch.tensor([1], dtype=torch.int32, device=dev)
+    gathered = torch.empty((world * B,), dtype=torch.uint8, device=dev) if world > 1 else None
+    stream = torch.cuda.current_stream(dev)
+    sp = L.cur_stream(dev)
+    impl_id = L.CNN_TENSOR if cnn_impl == "tensor" else L.CNN_FP32
+
+    def step():
+        ctx.check(ctx.lib.ww_score_clips(ctx.h, L.ptr(pcm), L.PCM_S16, B, L.CMVN_PY, L.DECIDE_LOGIT, 0.0, impl_id,
+                                         L.ptr(logits), L.ptr(dec), sp), "ww_score_clips")
+        if n_utt:
+            ctx.check(ctx.lib.ww_ctc_greedy(ctx.h, L.ptr(logits), 1, UTT, UTT, n_utt, 1, None, L.DECODE_COLLAPSE,
+                                            L.ptr(labels), L.ptr(lab_len), L.ptr(kw), 1, L.ptr(hits), sp),
+                      "ww_ctc_greedy")
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, dec)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    t_wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_max = float(tt.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    ms_per_step = ms_max / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---- roofline: the frontend kernel alone over the same clips (configs[1]) ----------------------
+    roof = None
+    if rank == 0:
+        rb = min(B, args.roofline_clips)
+        feats = torch.empty((rb, 13, 63), dtype=torch.float32, device=dev)
+
+        def front():
+            ctx.check(ctx.lib.ww_mfcc_batch(ctx.h, L.ptr(pcm), L.PCM_S16, rb, 16000, 16000, L.FEAT_PY,
+                                            L.LAYOUT_COEF_MAJOR, L.ptr(feats), sp), "ww_mfcc_batch")
+
+        for _ in range(3):
+            front()
+        torch.cuda.synchronize()
+        reps = max(3, args.steps)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(reps):
+            front()
+        f1.record(stream)
+        torch.cuda.synchronize()
+        fms = f0.elapsed_time(f1) / reps
+        peak, how = measured_peaks()
+        ach = rb * FRONTEND_BYTES_PER_CLIP / (fms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "mfcc_kernel<int16,64> (frontend alone, 1 launch over %d clips)" % rb,
+                "achieved": ach, "peak": peak, "peak_source": how, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "ms_per_launch": fms, "clips_per_s": rb / (fms * 1e-3),
+                "algorithmic_bytes_per_clip": FRONTEND_BYTES_PER_CLIP}
+        del feats
+
+    # ---- e2e: host buffers through the public call ---------------------------------------------------
+    eb = min(args.e2e_clips, B)
+    host = synth_pcm(eb, "cpu", 99 + rank, chunk=8192, pin=True)
+    lh = np.empty((eb, 1), np.float32)
+    dh = np.empty((eb,), np.uint8)
+    scorer.score_host(host, lh, dh)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        scorer.score_host(host, lh, dh)
+    torch.cuda.synchronize()
+    e2e_dt = (time.perf_counter() - t0) / args.steps
+    te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * eb / float(te.item())
+
+    if rank == 0:
+        chunks = (B + 16383) // 16384
+        launches = args.steps * (chunks * 2 + (1 if n_utt else 0))
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            v, dt, cores = time_cpu(args.cpu_clips, 2, 1)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{args.cpu_clips} synthetic clips x 2 passes through the oracle port of the reference CPU "
+                             f"path (torchaudio MFCC + CMVN + LightweightKWS + decision + greedy), {dt:.2f} s/pass"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": eb * 32000, "d2h_bytes_per_step": eb * 5,
+                    "clips_per_step_per_gpu": eb, "api": "WakeWordScorer.score_host -> ww_score_clips_host (pinned host "
+                    "PCM in, host logits+decisions out)"},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "positives": int(dec.sum().item()), "keyword_hits": int(hits[:n_utt].sum().item()) if n_utt else 0,
+            "fused_hbm_frac": (value / world) * FUSED_BYTES_PER_CLIP / 1e9 / measured_peaks()[0],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=1 << 20, help="clips per GPU resident in HBM")
+    ap.add_argument("--e2e-clips", type=int, default=1 << 17, help="clips per e2e step (pinned host buffer)")
+    ap.add_argument("--roofline-clips", type=int, default=1 << 20)
+    ap.add_argument("--cpu-clips", type=int, default=8192, help="bounded CPU-baseline sample")
+    ap.add_argument("--cnn", default="fp32", choices=["fp32", "tensor"])
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -256,12 +256,14 @@ extern "C" int ww_create(ww_ctx** out, int device) {
     ctx->feat[1].log_offset = 0.f;
 
     // opt in to the dynamic shared memory the frontend needs
-    if ((e = cudaFuncSetAttribute(mfcc_kernel<int16_t, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  MfccSmem<int16_t, 64>::TOTAL)) != cudaSuccess)
-        return bail(e, "cudaFuncSetAttribute(mfcc s16)");
-    if ((e = cudaFuncSetAttribute(mfcc_kernel<float, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  MfccSmem<float, 32>::TOTAL)) != cudaSuccess)
-        return bail(e, "cudaFuncSetAttribute(mfcc f32)");
+#define WW_SET_SMEM(K, S)                                                                                  \
+    if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, S)) != cudaSuccess)       \
+        return bail(e, "cudaFuncSetAttribute(" #K ")");
+    WW_SET_SMEM((mfcc_kernel<int16_t, true>), (MfccSmem<int16_t, true>::TOTAL))
+    WW_SET_SMEM((mfcc_kernel<int16_t, false>), (MfccSmem<int16_t, false>::TOTAL))
+    WW_SET_SMEM((mfcc_kernel<float, true>), (MfccSmem<float, true>::TOTAL))
+    WW_SET_SMEM((mfcc_kernel<float, false>), (MfccSmem<float, false>::TOTAL))
+#undef WW_SET_SMEM
 #ifdef WW_WITH_TC
     if ((e = tc_init()) != cudaSuccess) return bail(e, "tc_init");
 #endif
@@ -353,7 +355,7 @@ static int launch_mfcc(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_s
     const int T = ww_num_frames(feat_mode, n_samples);
     if (T <= 0) return fail(ctx, WW_ERR_INVALID, "mfcc: signal shorter than one frame");  // mfcc.c:434-437
     if (n_signals == 0) return WW_OK;
-    const int frames = pcm_type == WW_PCM_S16 ? 64 : 32;
+    const int frames = MFCC_FRAMES;
     const size_t esz = pcm_type == WW_PCM_S16 ? 2 : 4;
     MfccArgs a;
     a.pcm = pcm;
@@ -377,10 +379,15 @@ static int launch_mfcc(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_s
     memcpy(a.dct, fm.dct, sizeof(a.dct));
     const long long total_blocks = n_signals * a.blocks_per_sig;
     if (total_blocks > 0x7fffffffLL) return fail(ctx, WW_ERR_INVALID, "mfcc: too many blocks for one launch");
-    if (pcm_type == WW_PCM_S16)
-        mfcc_kernel<int16_t, 64><<<(unsigned)total_blocks, MFCC_THREADS, MfccSmem<int16_t, 64>::TOTAL, st>>>(a);
-    else
-        mfcc_kernel<float, 32><<<(unsigned)total_blocks, MFCC_THREADS, MfccSmem<float, 32>::TOTAL, st>>>(a);
+    const unsigned grid = (unsigned)total_blocks;
+    const bool py = feat_mode == WW_FEAT_PY;  // PY filterbank is compiled in (ww_mel_py.inc); others are table-driven
+    if (pcm_type == WW_PCM_S16) {
+        if (py) mfcc_kernel<int16_t, true><<<grid, MFCC_THREADS, MfccSmem<int16_t, true>::TOTAL, st>>>(a);
+        else mfcc_kernel<int16_t, false><<<grid, MFCC_THREADS, MfccSmem<int16_t, false>::TOTAL, st>>>(a);
+    } else {
+        if (py) mfcc_kernel<float, true><<<grid, MFCC_THREADS, MfccSmem<float, true>::TOTAL, st>>>(a);
+        else mfcc_kernel<float, false><<<grid, MFCC_THREADS, MfccSmem<float, false>::TOTAL, st>>>(a);
+    }
     CK(cudaGetLastError());
     return WW_OK;
 }
@@ -429,6 +436,7 @@ static int launch_cnn_fp32(ww_ctx* ctx, const float* feats, long long ws, long l
 extern "C" int ww_cmvn(ww_ctx* ctx, const float* feats, long long n_windows, int cmvn_mode, float* out,
                        ww_stream_t stream) {
     if (!ctx) return WW_ERR_INVALID;
+    if (n_windows == 0) return WW_OK;
     if (!feats || !out || n_windows < 0) return fail(ctx, WW_ERR_INVALID, "cmvn: bad arguments");
     if (cmvn_mode < WW_CMVN_NONE || cmvn_mode > WW_CMVN_DEVICE) return fail(ctx, WW_ERR_INVALID, "cmvn: bad mode");
     return launch_cnn_fp32(ctx, feats, WW_N_MFCC * WW_WINDOW_FRAMES, WW_WINDOW_FRAMES, 1, n_windows, nullptr, nullptr,
@@ -463,6 +471,7 @@ extern "C" int ww_cnn_forward(ww_ctx* ctx, const float* feats, long long win_str
                               long long frame_stride, long long n_windows, int cmvn_mode, int decide_mode,
                               float threshold, int cnn_impl, float* logits, uint8_t* decisions, ww_stream_t stream) {
     if (!ctx) return WW_ERR_INVALID;
+    if (n_windows == 0) return WW_OK;
     if (!feats || !logits || n_windows < 0) return fail(ctx, WW_ERR_INVALID, "cnn_forward: bad arguments");
     int rc = check_cnn_args(ctx, cmvn_mode, decide_mode, cnn_impl);
     if (rc) return rc;
@@ -504,6 +513,7 @@ extern "C" int ww_score_clips(ww_ctx* ctx, const void* pcm, int pcm_type, long l
                               int decide_mode, float threshold, int cnn_impl, float* logits, uint8_t* decisions,
                               ww_stream_t stream) {
     if (!ctx) return WW_ERR_INVALID;
+    if (n_clips == 0) return WW_OK;
     if (!pcm || !logits || n_clips < 0) return fail(ctx, WW_ERR_INVALID, "score_clips: bad arguments");
     if (pcm_type != WW_PCM_S16 && pcm_type != WW_PCM_F32) return fail(ctx, WW_ERR_INVALID, "score_clips: bad pcm_type");
     int rc = check_cnn_args(ctx, cmvn_mode, decide_mode, cnn_impl);
@@ -540,6 +550,7 @@ extern "C" int ww_score_clips_host(ww_ctx* ctx, const void* pcm_host, int pcm_ty
                                    int decide_mode, float threshold, int cnn_impl, float* logits_host,
                                    uint8_t* decisions_host) {
     if (!ctx) return WW_ERR_INVALID;
+    if (n_clips == 0) return WW_OK;
     if (!pcm_host || !logits_host || n_clips < 0) return fail(ctx, WW_ERR_INVALID, "score_clips_host: bad arguments");
     if (pcm_type != WW_PCM_S16 && pcm_type != WW_PCM_F32) return fail(ctx, WW_ERR_INVALID, "score_clips_host: bad pcm_type");
     int rc = check_cnn_args(ctx, cmvn_mode, decide_mode, cnn_impl);

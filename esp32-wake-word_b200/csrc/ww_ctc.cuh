@@ -41,7 +41,10 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_greedy_kernel(const Greedy
     for (int tb = 0; tb < Tb; tb += 32) {
         const int t = tb + lane;
         int idx = 0;
-        if (a.C <= 32) {
+        if (a.C == 1) {
+            // binary posterior in logit form: class 1 (keyword) iff logit > 0, else blank
+            if (t < Tb) idx = base[(long long)t * a.t_stride] > 0.f ? 1 : 0;
+        } else if (a.C <= 32) {
             // lane per frame
             if (t < Tb) {
                 const float* row = base + (long long)t * a.t_stride;

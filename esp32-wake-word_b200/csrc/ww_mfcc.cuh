@@ -5,17 +5,19 @@
 //   T.MFCC(16 kHz, 13, log_mels, n_fft 512, win 320, hop 256, 40 mels, hamming)   :137-148,172
 // and, with the ESP table set, main/esp_mfcc/mfcc.c:431-527 (extract_mfcc).
 //
-// One CTA = one block of FRAMES consecutive frames of one signal (a 1 s clip is one block of 64, 63 valid).
+// One CTA = one block of 32 consecutive frames of one signal (a 1 s clip is two blocks, 63 frames valid).
 //   * the PCM span of the block is staged once into shared memory with a 1-D TMA bulk copy
-//     (cp.async.bulk + mbarrier); int16 PCM is kept as int16 in smem (32 KB per clip)
+//     (cp.async.bulk + mbarrier); int16 PCM is kept as int16 in smem (16.5 KB per block)
 //   * a warp transforms TWO frames at a time, one per half-warp: the 512-point real FFT is a 256-point
 //     complex FFT of the packed frame (z[m] = x[2m] + i x[2m+1]) done as radix-16 (registers) x
 //     radix-16 (registers) with one transposition through a per-warp smem tile, followed by the
 //     real-FFT split that yields two power bins per butterfly
 //   * pre-emphasis and the window are folded into the load (w*x[i] - 0.97w*x[i-1]); only the 160
 //     complex points under the 320-tap window are loaded
-//   * mel (CSR filterbank), log and the 40x13 DCT are done from shared memory; the DCT matrix sits in
-//     the kernel-parameter constant bank so every FFMA takes its weight as an immediate constant operand
+//   * the 32 power spectra of the block are parked in shared memory (33 KB); after a CTA barrier the mel
+//     filterbank runs with lane <-> frame and warp <-> filter range as generated straight-line code
+//     (ww_mel_py.inc) whose weights are FFMA immediates; log-mel rows go back to smem and the 40x13 DCT
+//     runs the same way with its matrix in the kernel-parameter constant bank
 //   * output is written once, coalesced along time
 #pragma once
 #include "ww_common.cuh"
@@ -36,7 +38,6 @@ constexpr int MFCC_THREADS = 256;
 constexpr int MFCC_WARPS = MFCC_THREADS / 32;
 constexpr int EXCH_ROW_BYTES = 144;                    // 16 complex + 16 B pad: conflict-free LDS.128
 constexpr int EXCH_FRAME_BYTES = 16 * EXCH_ROW_BYTES;  // 2304 (>= 257 complex for the natural-order pass)
-constexpr int PS_STRIDE = 260;                         // floats per frame of power spectrum
 constexpr int LM_STRIDE = 41;                          // floats per frame of log-mel
 
 struct MfccArgs {
@@ -76,13 +77,39 @@ __device__ __forceinline__ void dft4(float2& p0, float2& p1, float2& p2, float2&
     p3 = csub(t1, t3);
 }
 
+// DFT4 with compile-time knowledge of zero inputs (Z0..Z3): skips the additions with 0
+template <bool Z0, bool Z1, bool Z2, bool Z3>
+__device__ __forceinline__ void dft4z(float2& p0, float2& p1, float2& p2, float2& p3) {
+    const float2 zero = make_float2(0.f, 0.f);
+    const float2 n2 = make_float2(-p2.x, -p2.y);
+    const float2 t0 = Z0 ? (Z2 ? zero : p2) : (Z2 ? p0 : cadd(p0, p2));
+    const float2 t1 = Z0 ? (Z2 ? zero : n2) : (Z2 ? p0 : csub(p0, p2));
+    const float2 t2 = Z1 ? (Z3 ? zero : p3) : (Z3 ? p1 : cadd(p1, p3));
+    const float2 d13 = Z1 ? (Z3 ? zero : make_float2(-p3.x, -p3.y)) : (Z3 ? p1 : csub(p1, p3));
+    const float2 t3 = cmul_mi(d13);
+    p0 = cadd(t0, t2);
+    p1 = cadd(t1, t3);
+    p2 = csub(t0, t2);
+    p3 = csub(t1, t3);
+}
+
+// WINDOWED: inputs v[0..2] and v[13..15] are known to be zero (only 160 of the 256 packed points lie
+// under the 320-tap window), which prunes a third of the first butterfly stage.
+template <bool WINDOWED>
 __device__ __forceinline__ void fft16(float2 (&v)[16]) {
     constexpr float C1 = 0.92387953251128674f;  // cos(pi/8)
     constexpr float S1 = 0.38268343236508977f;  // sin(pi/8)
     constexpr float R2 = 0.70710678118654752f;  // sqrt(1/2)
     // n = 4a + b, k = c + 4d.  Step 1: DFT4 over a for each b  -> v[4c + b] = Y[b][c]
+    if constexpr (WINDOWED) {
+        dft4z<true, false, false, false>(v[0], v[4], v[8], v[12]);
+        dft4z<true, false, false, true>(v[1], v[5], v[9], v[13]);
+        dft4z<true, false, false, true>(v[2], v[6], v[10], v[14]);
+        dft4z<false, false, false, true>(v[3], v[7], v[11], v[15]);
+    } else {
 #pragma unroll
-    for (int b = 0; b < 4; ++b) dft4(v[b], v[4 + b], v[8 + b], v[12 + b]);
+        for (int b = 0; b < 4; ++b) dft4(v[b], v[4 + b], v[8 + b], v[12 + b]);
+    }
     // Step 2: twiddle W16^(b*c)
     v[4 * 1 + 1] = cmul(v[4 * 1 + 1], make_float2(C1, -S1));   // W^1
     v[4 * 1 + 2] = cmul(v[4 * 1 + 2], make_float2(R2, -R2));   // W^2
@@ -117,19 +144,30 @@ __device__ __forceinline__ float emph_sample(const TIN* spcm, int lo, int s, int
     return x;
 }
 
-template <typename TIN, int FRAMES>
+constexpr int MFCC_FRAMES = 32;   // frames per CTA (lane <-> frame in the mel / DCT phases)
+constexpr int P_STRIDE = 257;     // floats per frame of power spectrum (odd: conflict-free lane <-> frame reads)
+constexpr int TB_BYTES_PY = TB_MELW_OFF;  // the PY path needs no mel tables in smem
+
+template <typename TIN, bool PYMEL>
 struct MfccSmem {
+    static constexpr int FRAMES = MFCC_FRAMES;
     static constexpr int PCM_SAMPLES = FRAMES * WW_HOP + 72;  // (FRAMES-1)*256 + 320 + 8 lead, rounded
     static constexpr int PCM_BYTES = ((PCM_SAMPLES * (int)sizeof(TIN) + 15) / 16) * 16;
+    static constexpr int TAB_BYTES = PYMEL ? TB_BYTES_PY : TB_BYTES;
     static constexpr int OFF_BAR = 0;
     static constexpr int OFF_TAB = 16;
-    static constexpr int OFF_PCM = OFF_TAB + TB_BYTES;
+    static constexpr int OFF_PCM = OFF_TAB + TAB_BYTES;
     static constexpr int OFF_EXCH = OFF_PCM + PCM_BYTES;
-    static constexpr int OFF_PS = OFF_EXCH + MFCC_WARPS * 2 * EXCH_FRAME_BYTES;
-    static constexpr int OFF_LM = OFF_PS + MFCC_WARPS * 2 * PS_STRIDE * 4;
+    static constexpr int OFF_P = OFF_EXCH + MFCC_WARPS * 2 * EXCH_FRAME_BYTES;
+    static constexpr int OFF_LM = OFF_P + FRAMES * P_STRIDE * 4;
     static constexpr int TOTAL = OFF_LM + FRAMES * LM_STRIDE * 4;
-    static_assert(OFF_PCM % 16 == 0 && OFF_EXCH % 16 == 0 && OFF_PS % 16 == 0, "smem alignment");
+    static_assert(OFF_PCM % 16 == 0 && OFF_EXCH % 16 == 0 && OFF_P % 16 == 0, "smem alignment");
+    // two CTAs per SM need TOTAL <= 115712 B; only the (float PCM, table-driven mel) variant exceeds it
+    static_assert(TOTAL <= 115712 || (!PYMEL && sizeof(TIN) == 4), "two CTAs per SM must fit");
 };
+
+#include "ww_mel_py.inc"
+static_assert(WW_MEL_PY_GROUPS == MFCC_WARPS, "one generated mel group per warp");
 
 // DCT of one frame for the coefficient subset {G0, G0+G, ...}: weights are immediate constant operands.
 template <int G, int G0>
@@ -160,13 +198,15 @@ struct DctDispatch<G, G> {
     static __device__ __forceinline__ void run(int, const MfccArgs&, const float*, float*) {}
 };
 
-template <typename TIN, int FRAMES>
+template <typename TIN, bool PYMEL>
 __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_constant__ MfccArgs a) {
-    using SM = MfccSmem<TIN, FRAMES>;
+    using SM = MfccSmem<TIN, PYMEL>;
+    constexpr int FRAMES = MFCC_FRAMES;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
     const unsigned char* tab = smem + SM::OFF_TAB;
     const TIN* spcm = reinterpret_cast<const TIN*>(smem + SM::OFF_PCM);
+    float* pw = reinterpret_cast<float*>(smem + SM::OFF_P);
     float* lm = reinterpret_cast<float*>(smem + SM::OFF_LM);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -176,10 +216,12 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
     const int blk = blockIdx.x - (int)(sig * a.blocks_per_sig);
     const int t0 = blk * FRAMES;
     const int L = a.n_samples;
+    const int n_frames = a.n_frames;
+    const int origin_off = a.origin_off;
 
     // staged sample range [lo, hi) of this signal
-    int lo = WW_HOP * t0 + a.origin_off + 88;   // 8 samples ahead of the first window tap (multiple of 8)
-    int hi = WW_HOP * (t0 + FRAMES - 1) + a.origin_off + 416;
+    int lo = WW_HOP * t0 + origin_off + 88;   // 8 samples ahead of the first window tap (multiple of 8)
+    int hi = WW_HOP * (t0 + FRAMES - 1) + origin_off + 416;
     lo = lo < 0 ? 0 : lo;
     hi = hi > L ? L : hi;
     const TIN* gsrc = reinterpret_cast<const TIN*>(a.pcm) + sig * a.sig_stride + lo;
@@ -204,7 +246,7 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
     // tables -> smem
     {
         uint4* dst = reinterpret_cast<uint4*>(smem + SM::OFF_TAB);
-        for (int i = tid; i < TB_BYTES / 16; i += MFCC_THREADS) dst[i] = __ldg(a.tables + i);
+        for (int i = tid; i < SM::TAB_BYTES / 16; i += MFCC_THREADS) dst[i] = __ldg(a.tables + i);
     }
     __syncthreads();
     if (a.use_bulk) mbar_wait(bar, 0);
@@ -212,22 +254,21 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
     const float4* s_win = reinterpret_cast<const float4*>(tab + TB_WIN_OFF);
     const float4* s_tw1 = reinterpret_cast<const float4*>(tab + TB_TW1_OFF);
     const float2* s_tw2 = reinterpret_cast<const float2*>(tab + TB_TW2_OFF);
-    const float* s_melw = reinterpret_cast<const float*>(tab + TB_MELW_OFF);
-    const int4* s_melm = reinterpret_cast<const int4*>(tab + TB_MELM_OFF);
 
     unsigned char* exch = smem + SM::OFF_EXCH + (warp * 2 + half) * EXCH_FRAME_BYTES;
-    float* ps = reinterpret_cast<float*>(smem + SM::OFF_PS) + (warp * 2 + half) * PS_STRIDE;
 
     constexpr int ITERS = FRAMES / (2 * MFCC_WARPS);
     static_assert(ITERS * 2 * MFCC_WARPS == FRAMES, "FRAMES must be a multiple of 16");
 
 #pragma unroll 1
     for (int it = 0; it < ITERS; ++it) {
-        const int fl = (it * MFCC_WARPS + warp) * 2 + half;  // frame index inside the block
+        // the two half-warps take frames 16 apart: their power-spectrum rows are 16 banks apart
+        const int fl = 16 * half + MFCC_WARPS * it + warp;  // frame index inside the block
         const int t = t0 + fl;
-        const bool valid = t < a.n_frames;
-        const int fo = WW_HOP * t + a.origin_off;  // signal sample index of frame point n = 0
+        const bool valid = t < n_frames;
+        const int fo = WW_HOP * t + origin_off;  // signal sample index of frame point n = 0
         const bool interior = valid && (fo + 95 >= 0) && (fo + 415 < L);
+        float* ps = pw + fl * P_STRIDE;
 
         float2 v[16];
 #pragma unroll
@@ -257,17 +298,19 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
                 v[n1].y = fmaf(w.z, x1, -w.w * x0);
             }
         } else if (valid) {
+            const int reflect = a.reflect;
+            const float pre = a.preemph;
 #pragma unroll
             for (int n1 = 3; n1 <= 12; ++n1) {
                 const float4 w = s_win[16 * (n1 - 3) + l16];
                 const int s = fo + 2 * (16 * n1 + l16);
-                v[n1].x = w.x * emph_sample<TIN>(spcm, lo, s, L, a.reflect, a.preemph);
-                v[n1].y = w.z * emph_sample<TIN>(spcm, lo, s + 1, L, a.reflect, a.preemph);
+                v[n1].x = w.x * emph_sample<TIN>(spcm, lo, s, L, reflect, pre);
+                v[n1].y = w.z * emph_sample<TIN>(spcm, lo, s + 1, L, reflect, pre);
             }
         }
 
         // pass 1: DFT16 over n1, twiddle W256^(l16*k1), transpose through smem
-        fft16(v);
+        fft16<true>(v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float4 tw = s_tw1[16 * j + l16];
@@ -286,7 +329,7 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
         }
         __syncwarp();
         // pass 2: DFT16 over n2 -> Z[l16 + 16*k2] = v[k2]; park Z in natural order
-        fft16(v);
+        fft16<false>(v);
         float2* zs = reinterpret_cast<float2*>(exch);
 #pragma unroll
         for (int k2 = 0; k2 < 16; ++k2) zs[l16 + 16 * k2] = v[k2];
@@ -309,32 +352,64 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
             ps[128] = 4.f * fmaf(z.x, z.x, z.y * z.y);
         }
         __syncwarp();
-        // mel + log: lane handles filters l16, l16+16, l16+32
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const int j = l16 + 16 * r;
-            if (j < WW_N_MELS) {
-                const int4 m = s_melm[j];
-                const float* pp = ps + m.x;
-                const float* ww_ = s_melw + m.z;
-                float acc = 0.f;
-                for (int i = 0; i < m.y; ++i) acc = fmaf(pp[i], ww_[i], acc);
-                const float e = fmaf(acc, a.pscale, __int_as_float(m.w));
-                lm[fl * LM_STRIDE + j] = __logf(fmaxf(e, a.log_floor) + a.log_offset);
-            }
-        }
-        __syncwarp();
     }
     __syncthreads();
 
-    // DCT: thread <-> (frame, coefficient group); store coalesced along time
+    // mel + log: lane <-> frame, warp <-> filter range
     {
-        constexpr int G = MFCC_THREADS / FRAMES;
-        const int fl = tid % FRAMES, g = tid / FRAMES;
-        const int t = t0 + fl;
-        if (t < a.n_frames) {
+        const float pscale = a.pscale, log_offset = a.log_offset;
+        const float* prow = pw + lane * P_STRIDE;
+        float* lrow = lm + lane * LM_STRIDE;
+        if constexpr (PYMEL) {
+            switch (warp) {
+                case 0: mel_py_group<0>(prow, lrow, pscale, log_offset); break;
+                case 1: mel_py_group<1>(prow, lrow, pscale, log_offset); break;
+                case 2: mel_py_group<2>(prow, lrow, pscale, log_offset); break;
+                case 3: mel_py_group<3>(prow, lrow, pscale, log_offset); break;
+                case 4: mel_py_group<4>(prow, lrow, pscale, log_offset); break;
+                case 5: mel_py_group<5>(prow, lrow, pscale, log_offset); break;
+                case 6: mel_py_group<6>(prow, lrow, pscale, log_offset); break;
+                default: mel_py_group<7>(prow, lrow, pscale, log_offset); break;
+            }
+        } else {
+            // table-driven filterbank (weights broadcast from smem): any contiguous-support filter set
+            const float* s_melw = reinterpret_cast<const float*>(tab + TB_MELW_OFF);
+            const int4* s_melm = reinterpret_cast<const int4*>(tab + TB_MELM_OFF);
+            const float log_floor = a.log_floor;
+            for (int j = warp; j < WW_N_MELS; j += MFCC_WARPS) {
+                const int4 m = s_melm[j];
+                const float* pp = prow + m.x;
+                const float* ww_ = s_melw + m.z;
+                float acc = 0.f;
+                for (int i = 0; i < m.y; ++i) acc = fmaf(pp[i], ww_[i], acc);
+                const float e = fmaf(acc, pscale, __int_as_float(m.w));
+                lrow[j] = __logf(fmaxf(e, log_floor) + log_offset);
+            }
+        }
+    }
+    __syncthreads();
+
+    // DCT: lane <-> frame, warp <-> coefficient pair {warp, warp + 8}; stores coalesced along time
+    {
+        const int t = t0 + lane;
+        if (t < n_frames) {
             float* outp = a.out + sig * a.out_sig_stride + (long long)t * a.out_frame_stride;
-            DctDispatch<G, 0>::run(g, a, lm + fl * LM_STRIDE, outp);
+            const float* lrow = lm + lane * LM_STRIDE;
+            if constexpr (PYMEL) {
+                const long long cs = a.out_coef_stride;
+                switch (warp) {
+                    case 0: dct_py_group<0>(lrow, outp, cs); break;
+                    case 1: dct_py_group<1>(lrow, outp, cs); break;
+                    case 2: dct_py_group<2>(lrow, outp, cs); break;
+                    case 3: dct_py_group<3>(lrow, outp, cs); break;
+                    case 4: dct_py_group<4>(lrow, outp, cs); break;
+                    case 5: dct_py_group<5>(lrow, outp, cs); break;
+                    case 6: dct_py_group<6>(lrow, outp, cs); break;
+                    default: dct_py_group<7>(lrow, outp, cs); break;
+                }
+            } else {
+                DctDispatch<MFCC_WARPS, 0>::run(warp, a, lrow, outp);
+            }
         }
     }
 }

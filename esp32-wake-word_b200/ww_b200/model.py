@@ -7,6 +7,7 @@ runs in libwwb200.so (inference only -- the reference's training loop is out of 
 from __future__ import annotations
 
 import ctypes as C
+import itertools
 import math
 
 import numpy as np
@@ -17,6 +18,7 @@ from . import _lib as L
 from .onnx_reader import load_kws_state_dict
 
 LN4 = math.log(4.0)
+_tokens = itertools.count(1)  # unique per weight owner: id() values are recycled after garbage collection
 
 
 def _push_weights(ctx, sd, owner_key):
@@ -54,6 +56,7 @@ class LightweightKWS(nn.Module):
         self.classifier = nn.Sequential(
             nn.Linear(128, 64, bias=False), nn.ReLU(), nn.Linear(64, num_classes, bias=False))
         self.cnn_impl = "fp32"
+        self._ww_token = next(_tokens)
 
     @classmethod
     def from_onnx(cls, path):
@@ -63,7 +66,7 @@ class LightweightKWS(nn.Module):
         return m
 
     def _weights_key(self):
-        return (id(self), tuple(p._version for p in self.parameters()),
+        return ("module", self._ww_token, tuple(p._version for p in self.parameters()),
                 tuple(p.data_ptr() for p in self.parameters()))
 
     def forward(self, x):
@@ -104,7 +107,7 @@ class WakeWordScorer:
         else:
             raise ValueError(decision)
         self.cnn_impl = L.CNN_TENSOR if cnn_impl == "tensor" else L.CNN_FP32
-        self._key = ("scorer", id(self))
+        self._key = ("scorer", next(_tokens))
         _push_weights(self.ctx, self.sd, self._key)
 
     @classmethod

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .model import _push_weights
+from .model import _push_weights, _tokens
 
 WINDOW = 63
 LN4 = math.log(4.0)  # sigmoid(x)*100 >= 80  <=>  x >= ln 4
@@ -31,7 +31,7 @@ class StreamScorer:
         self.sd = state_dict
         self.cmvn = {"none": L.CMVN_NONE, "python": L.CMVN_PY, "device": L.CMVN_DEVICE}[cmvn]
         self.cnn_impl = L.CNN_TENSOR if cnn_impl == "tensor" else L.CNN_FP32
-        self._key = ("stream", id(self))
+        self._key = ("stream", next(_tokens))
 
     def score(self, pcm):
         """pcm: CUDA [N] int16 / float32 -> (features [13, T], logits [T-62, C])."""

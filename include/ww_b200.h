@@ -118,7 +118,8 @@ long long ww_stream_events(const float* logits_host, long long n_windows, int nu
 
 /* ---- CTC best path / keyword (ml_models/test.py:168-217, ml_models/ctc.py:453-471) ------------- */
 /* log_probs[t*t_stride + b*b_stride + c]; labels: [B][T] int32 (zero padded), out_len: [B].
- * lengths (valid frames per utterance) and keyword/hits may be NULL. */
+ * lengths (valid frames per utterance) and keyword/hits may be NULL.
+ * C == 1: the rows are binary logits (keyword posterior of a num_classes=1 model); label 1 iff logit > 0. */
 int ww_ctc_greedy(ww_ctx* ctx, const float* log_probs, long long t_stride, long long b_stride, int T, int B,
                   int C, const int32_t* lengths, int decode_mode, int32_t* labels, int32_t* out_len,
                   const int32_t* keyword, int keyword_len, uint8_t* hits, ww_stream_t stream);

@@ -88,7 +88,7 @@ def detect_confidence(labels, keyword_labels):
 # CTC loss
 # ----------------------------------------------------------------------------
 def ctc_loss_torch(log_probs, targets, input_lengths, target_lengths, blank=0,
-                   reduction="mean", zero_infinity=False, want_grad=True):
+                   reduction="mean", zero_infinity=False, want_grad=True, dtype="float32"):
     """torch.nn.functional.ctc_loss on CPU.  log_probs [T,B,C] float32.
 
     Returns (loss, grad wrt log_probs or None).
@@ -96,7 +96,8 @@ def ctc_loss_torch(log_probs, targets, input_lengths, target_lengths, blank=0,
     import torch
     import torch.nn.functional as F
 
-    lp = torch.tensor(np.asarray(log_probs), dtype=torch.float32, requires_grad=want_grad)
+    lp = torch.tensor(np.asarray(log_probs), dtype=torch.float64 if dtype == "float64" else torch.float32,
+                      requires_grad=want_grad)
     loss = F.ctc_loss(lp, torch.as_tensor(np.asarray(targets)).long(),
                       torch.as_tensor(np.asarray(input_lengths)).long(),
                       torch.as_tensor(np.asarray(target_lengths)).long(),
