@@ -39,7 +39,12 @@ struct ww_ctx {
     CnnWeights w{};
     bool have_weights = false;
 #ifdef WW_WITH_TC
-    TcWeights tcw{};
+    uint4* tc_blob = nullptr;       // fp16 weights in UMMA layout (ww_cnn_tc.cuh)
+    long long* rs_list = nullptr;   // windows to re-score in fp32
+    int* rs_count = nullptr;
+    long long rs_cap = 0;
+    float tc_band = 0.03f;          // |logit - threshold| below which the fp32 kernel decides
+    float* tc_dbg = nullptr;
 #endif
     // fused-path scratch
     float* scratch = nullptr;          // [chunk][13][63]
@@ -265,7 +270,9 @@ extern "C" int ww_create(ww_ctx** out, int device) {
     WW_SET_SMEM((mfcc_kernel<float, false>), (MfccSmem<float, false>::TOTAL))
 #undef WW_SET_SMEM
 #ifdef WW_WITH_TC
-    if ((e = tc_init()) != cudaSuccess) return bail(e, "tc_init");
+    if ((e = cudaFuncSetAttribute(cnn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)) != cudaSuccess)
+        return bail(e, "cudaFuncSetAttribute(cnn_tc_kernel)");
+    if (const char* b = getenv("WW_TC_BAND")) ctx->tc_band = (float)atof(b);
 #endif
     *out = ctx;
     return WW_OK;
@@ -288,7 +295,9 @@ extern "C" void ww_destroy(ww_ctx* ctx) {
         if (ctx->h_dec[i]) cudaFreeHost(ctx->h_dec[i]);
     }
 #ifdef WW_WITH_TC
-    tc_free_weights(ctx->tcw);
+    cudaFree(ctx->tc_blob);
+    cudaFree(ctx->rs_list);
+    cudaFree(ctx->rs_count);
 #endif
     delete ctx;
 }
@@ -326,8 +335,10 @@ extern "C" int ww_load_weights(ww_ctx* ctx, const float* conv1, const float* con
     ctx->w.num_classes = num_classes;
 #ifdef WW_WITH_TC
     {
-        cudaError_t e = tc_load_weights(ctx->tcw, conv1, conv2, conv3, fc1, fc2, num_classes);
-        if (e != cudaSuccess) return cuda_fail(ctx, e, "tc_load_weights");
+        std::vector<unsigned char> blob;
+        tc_build_blob(blob, conv1, conv2, conv3, fc1);
+        if (!ctx->tc_blob) CK(cudaMalloc(&ctx->tc_blob, TC_W_BYTES));
+        CK(cudaMemcpy(ctx->tc_blob, blob.data(), TC_W_BYTES, cudaMemcpyHostToDevice));
     }
 #endif
     ctx->have_weights = true;
@@ -453,6 +464,72 @@ static int check_cnn_args(ww_ctx* ctx, int cmvn_mode, int decide_mode, int cnn_i
 #endif
     return WW_OK;
 }
+
+#ifdef WW_WITH_TC
+// tensor-core forward + exact fp32 re-score of the windows that land within tc_band of the threshold
+static int tc_forward(ww_ctx* ctx, const float* feats, long long ws, long long cs, long long fs, long long n,
+                      int cmvn_mode, int decide_mode, float threshold, float* logits, unsigned char* decisions,
+                      cudaStream_t st) {
+    if (ctx->w.num_classes > TC_MAX_CLASSES)
+        return fail(ctx, WW_ERR_UNSUPPORTED, "tensor-core CNN supports at most 8 classes");
+    if (n == 0) return WW_OK;
+    const bool rescoring = decisions && decide_mode != WW_DECIDE_NONE;
+    if (rescoring && ctx->rs_cap < n) {
+        cudaFree(ctx->rs_list);
+        ctx->rs_list = nullptr;
+        ctx->rs_cap = 0;
+        if (!ctx->rs_count) CK(cudaMalloc(&ctx->rs_count, sizeof(int)));
+        CK(cudaMalloc(&ctx->rs_list, sizeof(long long) * (size_t)n));
+        ctx->rs_cap = n;
+    }
+    TcArgs a;
+    a.feats = feats;
+    a.win_stride = ws;
+    a.coef_stride = cs;
+    a.frame_stride = fs;
+    a.n_windows = n;
+    a.cmvn_mode = cmvn_mode;
+    a.decide_mode = decide_mode;
+    a.threshold = threshold;
+    a.thr_logit = decide_mode == WW_DECIDE_DEVICE ? logf(threshold / (100.f - threshold)) : threshold;
+    a.band = ctx->tc_band;
+    a.logits = logits;
+    a.decisions = decisions;
+    a.rescore_list = rescoring ? ctx->rs_list : nullptr;
+    a.rescore_count = ctx->rs_count;
+    a.wblob = ctx->tc_blob;
+    a.fc2 = ctx->w.fc2;
+    a.num_classes = ctx->w.num_classes;
+    a.dbg = ctx->tc_dbg;
+    if (rescoring) CK(cudaMemsetAsync(ctx->rs_count, 0, sizeof(int), st));
+    const long long n_oct = (n + TC_CLIPS - 1) / TC_CLIPS;
+    const unsigned grid = (unsigned)(n_oct < ctx->sm_count ? n_oct : ctx->sm_count);
+    cnn_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(a);
+    CK(cudaGetLastError());
+    if (rescoring) {
+        CnnArgs r;
+        r.feats = feats;
+        r.win_stride = ws;
+        r.coef_stride = cs;
+        r.frame_stride = fs;
+        r.n_windows = n;  // capacity; the device-side count bounds the loop
+        r.index = ctx->rs_list;
+        r.index_count = ctx->rs_count;
+        r.cmvn_mode = cmvn_mode;
+        r.decide_mode = decide_mode;
+        r.threshold = threshold;
+        r.logits = logits;
+        r.decisions = decisions;
+        r.norm_out = nullptr;
+        r.w = ctx->w;
+        long long g = (long long)ctx->sm_count * 2;
+        if (g > n) g = n;
+        cnn_fp32_kernel<<<(unsigned)g, CNN_THREADS, 0, st>>>(r);
+        CK(cudaGetLastError());
+    }
+    return WW_OK;
+}
+#endif
 
 static int run_cnn(ww_ctx* ctx, const float* feats, long long ws, long long cs, long long fs, long long n,
                    int cmvn_mode, int decide_mode, float threshold, int cnn_impl, float* logits,
@@ -753,6 +830,24 @@ extern "C" int ww_ctc_loss_bwd(ww_ctx* ctx, const float* log_probs, long long t_
     ctc_loss_bwd_kernel<<<(B + CTC_WARPS - 1) / CTC_WARPS, CTC_WARPS * 32, smem, (cudaStream_t)stream>>>(a);
     CK(cudaGetLastError());
     return WW_OK;
+}
+
+// test hook: device buffer that receives the per-layer activations of the first 8 windows of every
+// tensor-core launch (null disables); also returns how many windows the last launch re-scored in fp32
+extern "C" int ww_debug_tc(ww_ctx* ctx, float* dbg_dev, int* last_rescored) {
+    if (!ctx) return WW_ERR_INVALID;
+#ifdef WW_WITH_TC
+    ctx->tc_dbg = dbg_dev;
+    if (last_rescored) {
+        *last_rescored = 0;
+        if (ctx->rs_count) CK(cudaMemcpy(last_rescored, ctx->rs_count, sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    return WW_OK;
+#else
+    (void)dbg_dev;
+    (void)last_rescored;
+    return fail(ctx, WW_ERR_UNSUPPORTED, "tensor-core CNN not built into this library");
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------

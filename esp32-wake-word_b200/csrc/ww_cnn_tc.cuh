@@ -1,0 +1,482 @@
+// CMVN + LightweightKWS forward on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a.
+//
+// Same contract as cnn_fp32_kernel (ww_cnn.cuh): replaces normalize_mfcc (extract_mfcc.py:47-88) /
+// device CMVN (esp_wake_word_detector.cpp:179-211), LightweightKWS.forward (wakeModel.py:29-34) and the
+// decision (ml_models/main.py:53, esp_wake_word_detector.cpp:226-245) for 63-frame windows.
+//
+// One persistent CTA per SM scores EIGHT windows per iteration.  Every layer is an implicit GEMM issued by a
+// single thread with tcgen05.mma (kind::f16: fp16 operands, fp32 accumulation in TMEM):
+//   conv1  D[512 pos x 32]  = sum_tap A1[pos+tap][16] . W1_tap[32][16]^T     4 tiles of M=128, K=16 per tap
+//   conv2  D[256 pos x 64]  = sum_tap A2[pos+tap][32] . W2_tap[64][32]^T     2 tiles of M=128
+//   conv3  D[128 ch x 128 pos] = sum_tap W3_tap[128][64] . X3[pos+tap][64]^T   (roles swapped: channel = TMEM lane,
+//                                                            so MaxPool and the global average are per-thread)
+//   fc1    D[128(64) x 16(8 windows)] = WF1[128][128] . G[16][128]^T
+// Operands live in shared memory in the canonical K-major, no-swizzle UMMA layout with an 8-row group stride of
+// 128 B, i.e. row r of a 16-byte K-chunk sits at chunk_base + 16*r.  That makes the k=3 convolution im2col-free:
+// tap r is the same tile with its start address advanced by r rows (16*r bytes); a zero row between consecutive
+// windows provides the padding.  ReLU + MaxPool(2) are fused into the TMEM->register epilogue, which writes the
+// next layer's operand directly in that layout (fp16).  fc2 (64 -> C) is a warp reduction on the fc1 epilogue.
+// Windows whose logit lands within `band` of the decision threshold are appended to a re-score list that the
+// fp32 kernel then recomputes exactly: decisions are those of the fp32 path.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "ww_cnn.cuh"
+#include "ww_common.cuh"
+
+namespace ww {
+
+constexpr int TC_THREADS = 256;
+constexpr int TC_CLIPS = 8;
+constexpr int TC_MAX_CLASSES = 8;
+
+constexpr int A1_ROWS = 64 * TC_CLIPS + 2;   // 514: row 0 and every 64th row are zero (conv padding)
+constexpr int A2_ROWS = 32 * TC_CLIPS + 2;   // 258
+constexpr int X3_ROWS = 16 * TC_CLIPS + 2;   // 130
+constexpr int G_ROWS = 16;                   // fc1 B operand: 8 windows + 8 zero rows (N must be a multiple of 16)
+constexpr int A1_LBO = A1_ROWS * 16, A2_LBO = A2_ROWS * 16, X3_LBO = X3_ROWS * 16, G_LBO = G_ROWS * 16;
+constexpr int W1_LBO = 32 * 16, W2_LBO = 64 * 16, W3_LBO = 128 * 16, WF1_LBO = 128 * 16;
+constexpr int W1_TAP = 2 * W1_LBO, W2_TAP = 4 * W2_LBO, W3_TAP = 8 * W3_LBO;
+
+// shared memory map (bytes)
+constexpr int TC_OFF_BAR = 0;                                  // mbarrier (8) + tmem base (4)
+constexpr int TC_OFF_PART = 64;                                // fc2 partial sums [2][8][8] floats
+constexpr int TC_OFF_FC2 = TC_OFF_PART + 2 * 8 * 8 * 4;        // fc2 weights [8][64] floats
+constexpr int TC_OFF_W = TC_OFF_FC2 + TC_MAX_CLASSES * 64 * 4;  // weight blob (same layout as the device blob)
+constexpr int TC_W1 = 0;
+constexpr int TC_W2 = TC_W1 + 3 * W1_TAP;
+constexpr int TC_W3 = TC_W2 + 3 * W2_TAP;
+constexpr int TC_WF1 = TC_W3 + 3 * W3_TAP;
+constexpr int TC_W_BYTES = TC_WF1 + 16 * WF1_LBO;              // 97 280
+constexpr int TC_OFF_A1 = TC_OFF_W + TC_W_BYTES;
+constexpr int TC_OFF_A2 = TC_OFF_A1 + 2 * A1_LBO;
+constexpr int TC_OFF_X3 = TC_OFF_A2 + 4 * A2_LBO;
+constexpr int TC_OFF_G = TC_OFF_X3 + 8 * X3_LBO;
+constexpr int TC_SMEM = TC_OFF_G + 16 * G_LBO;
+static_assert(TC_OFF_W % 16 == 0 && TC_OFF_A1 % 16 == 0 && TC_OFF_A2 % 16 == 0 && TC_OFF_X3 % 16 == 0 &&
+                  TC_OFF_G % 16 == 0,
+              "UMMA operands need 16-byte alignment");
+static_assert(TC_SMEM <= 232448, "shared memory budget");
+constexpr int TC_TMEM_COLS = 256;  // conv accumulators use columns [0,128), fc1 uses [128,144)
+
+struct TcArgs {
+    const float* feats;  // feats[win*win_stride + coef*coef_stride + frame*frame_stride]
+    long long win_stride, coef_stride, frame_stride;
+    long long n_windows;
+    int cmvn_mode, decide_mode;
+    float threshold;        // as in CnnArgs
+    float thr_logit;        // the threshold expressed as a logit
+    float band;             // |logit - thr_logit| < band -> re-score in fp32
+    float* logits;          // [n][C]
+    unsigned char* decisions;
+    long long* rescore_list;  // may be null
+    int* rescore_count;
+    const uint4* wblob;     // TC_W_BYTES
+    const float* fc2;       // [C][64]
+    int num_classes;
+    float* dbg;             // optional stage dump of the first octet (tests)
+};
+
+// ---- tcgen05 primitives -----------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t lbo_bytes) {
+    // K-major, SWIZZLE_NONE: 8-row core matrices of 8 x 16 B; SBO = 128 B (rows 16 B apart), LBO = K-chunk stride
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((128u >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+    return d;
+}
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+    // c_format F32 (bits 4-5 = 1), a/b format F16 (0), both K-major, N>>3 at bit 17, M>>4 at bit 24
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint4 pack_h8(const float* v) {
+    return make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_constant__ TcArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TC_OFF_BAR + 8);
+    float* part = reinterpret_cast<float*>(smem + TC_OFF_PART);
+    float* sfc2 = reinterpret_cast<float*>(smem + TC_OFF_FC2);
+    unsigned char* sW = smem + TC_OFF_W;
+    unsigned char* sA1 = smem + TC_OFF_A1;
+    unsigned char* sA2 = smem + TC_OFF_A2;
+    unsigned char* sX3 = smem + TC_OFF_X3;
+    unsigned char* sG = smem + TC_OFF_G;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int C = a.num_classes;
+
+    // ---- one-time setup: zero the activation tiles, stage the weights, allocate TMEM ----
+    for (int i = tid; i < (TC_SMEM - TC_OFF_A1) / 16; i += TC_THREADS)
+        reinterpret_cast<uint4*>(smem + TC_OFF_A1)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < TC_W_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sW)[i] = __ldg(a.wblob + i);
+    for (int i = tid; i < C * 64; i += TC_THREADS) sfc2[i] = __ldg(a.fc2 + i);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)TC_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t sA1a = smem_u32(sA1), sA2a = smem_u32(sA2), sX3a = smem_u32(sX3), sGa = smem_u32(sG);
+    const uint32_t sWa = smem_u32(sW);
+    uint32_t phase = 0;
+
+    const int q4 = warp & 3;        // TMEM lane quadrant this warp may read
+    const int hi = warp >> 2;       // which half of the tiles / columns this warp takes
+    const uint32_t tlane = (uint32_t)(32 * q4) << 16;
+
+    const long long n_oct = (a.n_windows + TC_CLIPS - 1) / TC_CLIPS;
+    for (long long oct = blockIdx.x; oct < n_oct; oct += gridDim.x) {
+        // ================= S0: load + CMVN one window per warp, write A1 (fp16) =================
+        {
+            const long long win = oct * TC_CLIPS + warp;
+            const bool live = win < a.n_windows;
+            float x0[WW_N_MFCC], x1[WW_N_MFCC];
+            const bool has1 = lane + 32 < WW_WINDOW_FRAMES;
+#pragma unroll
+            for (int q = 0; q < WW_N_MFCC; ++q) {
+                x0[q] = 0.f;
+                x1[q] = 0.f;
+                if (live) {
+                    const float* row = a.feats + win * a.win_stride + q * a.coef_stride;
+                    x0[q] = row[lane * a.frame_stride];
+                    if (has1) x1[q] = row[(lane + 32) * a.frame_stride];
+                }
+            }
+            if (a.cmvn_mode != CMVN_NONE) {
+#pragma unroll
+                for (int q = 0; q < WW_N_MFCC; ++q) {
+                    float v0 = x0[q], v1 = x1[q];
+                    if (a.cmvn_mode == CMVN_DEVICE) {
+                        v0 = lround_clamp_i8(v0);
+                        v1 = has1 ? lround_clamp_i8(v1) : 0.f;
+                    }
+                    const float mean = warp_sum(v0 + v1) / (float)WW_WINDOW_FRAMES;
+                    const float d0 = v0 - mean, d1 = has1 ? v1 - mean : 0.f;
+                    const float ss = warp_sum(d0 * d0 + d1 * d1);
+                    if (a.cmvn_mode == CMVN_PY) {
+                        float sd = sqrtf(ss / (float)(WW_WINDOW_FRAMES - 1));
+                        if (sd == 0.f) sd = 1.f;
+                        const float den = sd + 1e-8f;
+                        x0[q] = d0 / den;
+                        x1[q] = d1 / den;
+                    } else {
+                        const float den = sqrtf(ss / (float)WW_WINDOW_FRAMES) + 1e-8f;
+                        x0[q] = fminf(fmaxf(lround_clamp_i8(d0 / den) * 16.f, -128.f), 127.f) * 0.0625f;
+                        x1[q] = fminf(fmaxf(lround_clamp_i8(d1 / den) * 16.f, -128.f), 127.f) * 0.0625f;
+                    }
+                }
+            }
+            // row R = 64*warp + t + 1; channels 0-7 -> chunk 0, channels 8-12 (+3 zeros) -> chunk 1
+            {
+                const float lo8[8] = {x0[0], x0[1], x0[2], x0[3], x0[4], x0[5], x0[6], x0[7]};
+                const float hi8[8] = {x0[8], x0[9], x0[10], x0[11], x0[12], 0.f, 0.f, 0.f};
+                const int R = 64 * warp + lane + 1;
+                *reinterpret_cast<uint4*>(sA1 + R * 16) = pack_h8(lo8);
+                *reinterpret_cast<uint4*>(sA1 + A1_LBO + R * 16) = pack_h8(hi8);
+            }
+            if (has1) {
+                const float lo8[8] = {x1[0], x1[1], x1[2], x1[3], x1[4], x1[5], x1[6], x1[7]};
+                const float hi8[8] = {x1[8], x1[9], x1[10], x1[11], x1[12], 0.f, 0.f, 0.f};
+                const int R = 64 * warp + lane + 33;
+                *reinterpret_cast<uint4*>(sA1 + R * 16) = pack_h8(lo8);
+                *reinterpret_cast<uint4*>(sA1 + A1_LBO + R * 16) = pack_h8(hi8);
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+
+        // ================= conv1: 4 tiles x 3 taps (K = 16) =================
+        if (tid == 0) {
+            tc_fence_after();
+            constexpr uint32_t idesc = umma_idesc_f16(128, 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                    umma_f16(tmem + 32 * i, umma_desc_kmajor(sA1a + (128 * i + r) * 16, A1_LBO),
+                             umma_desc_kmajor(sWa + TC_W1 + r * W1_TAP, W1_LBO), idesc, r > 0);
+            umma_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        // ---- epilogue 1: ReLU + MaxPool(2) over adjacent rows, write A2 rows m/2 + 1 (32 channels) ----
+#pragma unroll 1
+        for (int ii = 0; ii < 2; ++ii) {
+            const int i = 2 * hi + ii;
+            float v[32];
+            tmem_ld32(tmem + tlane + 32 * i, v);
+            const int m = 128 * i + 32 * q4 + lane;
+            const bool odd = lane & 1;
+            float mine[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const float send = odd ? v[c] : v[16 + c];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                const float own = odd ? v[16 + c] : v[c];
+                mine[c] = fmaxf(fmaxf(own, recv), 0.f);
+            }
+            const bool valid = ((m & 63) >> 1) < 31;
+            if (!valid) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) mine[c] = 0.f;
+            }
+            const int R2 = (m >> 1) + 1;
+            unsigned char* dst = sA2 + (odd ? 2 : 0) * A2_LBO + R2 * 16;
+            *reinterpret_cast<uint4*>(dst) = pack_h8(mine);
+            *reinterpret_cast<uint4*>(dst + A2_LBO) = pack_h8(mine + 8);
+            if (a.dbg && oct == 0 && valid) {
+                // dbg[0 .. 8*31*32): pooled conv1 activations [clip][t][ch]
+                const int clip = m >> 6, t = (m & 63) >> 1;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) a.dbg[(clip * 31 + t) * 32 + (odd ? 16 : 0) + c] = mine[c];
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+
+        // ================= conv2: 2 tiles x 3 taps x 2 K-steps =================
+        if (tid == 0) {
+            tc_fence_after();
+            constexpr uint32_t idesc = umma_idesc_f16(128, 64);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+                        umma_f16(tmem + 64 * i,
+                                 umma_desc_kmajor(sA2a + (128 * i + r) * 16 + ks * 2 * A2_LBO, A2_LBO),
+                                 umma_desc_kmajor(sWa + TC_W2 + r * W2_TAP + ks * 2 * W2_LBO, W2_LBO), idesc,
+                                 (r | ks) > 0);
+            umma_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        // ---- epilogue 2: rows m2 = 128*hi + 32*q4 + lane, 64 channels, write X3 rows m2/2 + 1 ----
+        {
+            const int m2 = 128 * hi + 32 * q4 + lane;
+            const bool odd = lane & 1;
+            const bool valid = ((m2 & 31) >> 1) < 15;
+            const int R3 = (m2 >> 1) + 1;
+            float va[32], vb[32];
+            tmem_ld32(tmem + tlane + 64 * hi, va);
+            tmem_ld32(tmem + tlane + 64 * hi + 32, vb);
+            float mine[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const float send = odd ? va[c] : vb[c];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                const float own = odd ? vb[c] : va[c];
+                mine[c] = valid ? fmaxf(fmaxf(own, recv), 0.f) : 0.f;
+            }
+            unsigned char* dst = sX3 + (odd ? 4 : 0) * X3_LBO + R3 * 16;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(dst + g * X3_LBO) = pack_h8(mine + 8 * g);
+            if (a.dbg && oct == 0 && valid) {
+                // dbg[8*31*32 ..): pooled conv2 activations [clip][t][ch]
+                float* d2 = a.dbg + 8 * 31 * 32;
+                const int clip = m2 >> 5, t = (m2 & 31) >> 1;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) d2[(clip * 15 + t) * 64 + (odd ? 32 : 0) + c] = mine[c];
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+
+        // ================= conv3 (channels on M): 3 taps x 4 K-steps, N = 128 positions =================
+        if (tid == 0) {
+            tc_fence_after();
+            constexpr uint32_t idesc = umma_idesc_f16(128, 128);
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    umma_f16(tmem, umma_desc_kmajor(sWa + TC_W3 + r * W3_TAP + ks * 2 * W3_LBO, W3_LBO),
+                             umma_desc_kmajor(sX3a + r * 16 + ks * 2 * X3_LBO, X3_LBO), idesc, (r | ks) > 0);
+            umma_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        // ---- epilogue 3: thread = channel o; per window ReLU + MaxPool + mean over the 7 pooled steps -> G ----
+        {
+            const int o = 32 * q4 + lane;
+            float va[32], vb[32];
+            tmem_ld32(tmem + tlane + 64 * hi, va);
+            tmem_ld32(tmem + tlane + 64 * hi + 32, vb);
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const float* v = cc < 2 ? va + 16 * cc : vb + 16 * (cc - 2);
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < 7; ++j) s += fmaxf(fmaxf(v[2 * j], v[2 * j + 1]), 0.f);
+                const float g = s / 7.f;
+                const int clip = 4 * hi + cc;
+                *reinterpret_cast<__half*>(sG + (o >> 3) * G_LBO + clip * 16 + (o & 7) * 2) = __float2half_rn(g);
+                if (a.dbg && oct == 0) a.dbg[8 * 31 * 32 + 8 * 15 * 64 + clip * 128 + o] = g;
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+
+        // ================= fc1: [128(64) x 128] . [16 x 128]^T, 8 K-steps =================
+        if (tid == 0) {
+            tc_fence_after();
+            constexpr uint32_t idesc = umma_idesc_f16(128, 16);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+                umma_f16(tmem + 128, umma_desc_kmajor(sWa + TC_WF1 + ks * 2 * WF1_LBO, WF1_LBO),
+                         umma_desc_kmajor(sGa + ks * 2 * G_LBO, G_LBO), idesc, ks > 0);
+            umma_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        // ---- epilogue 4: ReLU, fc2 as a warp reduction (rows 0-63 = warps with quadrant 0/1, first half) ----
+        if (warp < 2) {
+            float h[16];
+            tmem_ld16(tmem + tlane + 128, h);
+            const int o = 32 * warp + lane;
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) h[c8] = fmaxf(h[c8], 0.f);
+            if (a.dbg && oct == 0) {
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) a.dbg[8 * 31 * 32 + 8 * 15 * 64 + 8 * 128 + c8 * 64 + o] = h[c8];
+            }
+            for (int c = 0; c < C; ++c) {
+                const float w = sfc2[c * 64 + o];
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    const float s = warp_sum(h[c8] * w);
+                    if (lane == 0) part[(warp * 8 + c) * 8 + c8] = s;
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        if (tid < 8 * C) {
+            const int c8 = tid & 7, c = tid >> 3;
+            const long long win = oct * TC_CLIPS + c8;
+            if (win < a.n_windows) {
+                const float s = part[(0 * 8 + c) * 8 + c8] + part[(1 * 8 + c) * 8 + c8];
+                a.logits[win * C + c] = s;
+                if (c == 0 && a.decisions) {
+                    unsigned char d = 0;
+                    if (a.decide_mode == DECIDE_LOGIT) d = s > a.threshold;
+                    else if (a.decide_mode == DECIDE_DEVICE) d = (1.f / (1.f + expf(-s)) * 100.f) >= a.threshold;
+                    a.decisions[win] = d;
+                    if (a.rescore_list && fabsf(s - a.thr_logit) < a.band) {
+                        const int slot = atomicAdd(a.rescore_count, 1);
+                        a.rescore_list[slot] = win;
+                    }
+                }
+            }
+        }
+        // `part` is rewritten only after the next octet's four barriers
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TC_TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// ---- host: fp16 weight blob in UMMA K-major layout ---------------------------------------------------
+// element (row n, k) of a [rows x K] operand: byte (k/8)*rows*16 + n*16 + (k%8)*2
+inline void tc_pack_operand(__half* dst, int rows, int K_padded, const float* src, int src_rows, int src_K,
+                            long long row_stride, long long k_stride) {
+    for (int kc = 0; kc < K_padded / 8; ++kc)
+        for (int n = 0; n < rows; ++n)
+            for (int i = 0; i < 8; ++i) {
+                const int k = kc * 8 + i;
+                const float v = (n < src_rows && k < src_K) ? src[n * row_stride + k * k_stride] : 0.f;
+                dst[((size_t)kc * rows + n) * 8 + i] = __float2half_rn(v);
+            }
+}
+
+inline void tc_build_blob(std::vector<unsigned char>& blob, const float* conv1, const float* conv2, const float* conv3,
+                          const float* fc1) {
+    blob.assign(TC_W_BYTES, 0);
+    for (int r = 0; r < 3; ++r) {
+        // torch conv weight [O][I][3]: element (o, i, r) at o*I*3 + i*3 + r
+        tc_pack_operand(reinterpret_cast<__half*>(blob.data() + TC_W1 + r * W1_TAP), 32, 16, conv1 + r, 32, 13, 13 * 3, 3);
+        tc_pack_operand(reinterpret_cast<__half*>(blob.data() + TC_W2 + r * W2_TAP), 64, 32, conv2 + r, 64, 32, 32 * 3, 3);
+        tc_pack_operand(reinterpret_cast<__half*>(blob.data() + TC_W3 + r * W3_TAP), 128, 64, conv3 + r, 128, 64, 64 * 3, 3);
+    }
+    tc_pack_operand(reinterpret_cast<__half*>(blob.data() + TC_WF1), 128, 128, fc1, 64, 128, 128, 1);
+}
+
+}  // namespace ww

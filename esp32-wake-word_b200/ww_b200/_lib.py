@@ -26,7 +26,7 @@ EXPORTS = [
     "ww_version", "ww_create", "ww_destroy", "ww_last_error", "ww_load_weights", "ww_num_frames",
     "ww_mfcc_batch", "ww_cmvn", "ww_cnn_forward", "ww_score_clips", "ww_score_clips_host",
     "ww_stream_score", "ww_stream_events", "ww_ctc_greedy", "ww_ctc_loss_workspace_bytes",
-    "ww_ctc_loss_fwd", "ww_ctc_loss_bwd", "ww_extract_mfcc", "ww_free_mfcc",
+    "ww_ctc_loss_fwd", "ww_ctc_loss_bwd", "ww_debug_tc", "ww_extract_mfcc", "ww_free_mfcc",
 ]
 
 
@@ -72,6 +72,7 @@ def load_library():
         lib.ww_ctc_loss_fwd.argtypes = [vp, vp, i64, i64, i32, i32, i32, vp, i32, vp, vp, i32, i32, vp, vp, vp]
         lib.ww_ctc_loss_bwd.argtypes = [vp, vp, i64, i64, i32, i32, i32, vp, i32, vp, vp, i32, i32, vp, vp, vp,
                                         i64, i64, vp]
+        lib.ww_debug_tc.argtypes = [vp, vp, vp]
         lib.ww_extract_mfcc.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32]
         lib.ww_extract_mfcc.restype = C.POINTER(C.c_float)
         lib.ww_free_mfcc.argtypes = [C.POINTER(C.c_float)]

@@ -138,6 +138,12 @@ int ww_ctc_loss_bwd(ww_ctx* ctx, const float* log_probs, long long t_stride, lon
                     const void* workspace, float* grad, long long gt_stride, long long gb_stride,
                     ww_stream_t stream);
 
+/* ---- diagnostics ------------------------------------------------------------------------------ */
+/* Test hook for the tensor-core CNN: `dbg_dev` (device, >= 8*31*32 + 8*15*64 + 8*128 + 8*64 floats, or NULL)
+ * receives the per-layer activations of the first 8 windows of each launch; *last_rescored receives the
+ * number of windows the previous launch handed to the exact fp32 kernel. */
+int ww_debug_tc(ww_ctx* ctx, float* dbg_dev, int* last_rescored);
+
 /* ---- drop-in for main/esp_mfcc/mfcc.h:10-17 ---------------------------------------------------- */
 /* Same signature and ownership as the reference's extract_mfcc(): returns a malloc'd
  * float[num_frames * n_mfcc] (frame-major) that the caller releases with ww_free_mfcc(); NULL on bad
