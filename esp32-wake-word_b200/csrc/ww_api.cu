@@ -522,7 +522,7 @@ static int tc_forward(ww_ctx* ctx, const float* feats, long long ws, long long c
         r.decisions = decisions;
         r.norm_out = nullptr;
         r.w = ctx->w;
-        long long g = (long long)ctx->sm_count * 2;
+        long long g = 64;  // the list is short (windows within tc_band of the threshold)
         if (g > n) g = n;
         cnn_fp32_kernel<<<(unsigned)g, CNN_THREADS, 0, st>>>(r);
         CK(cudaGetLastError());

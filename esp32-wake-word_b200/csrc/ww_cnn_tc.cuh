@@ -146,6 +146,41 @@ __device__ __forceinline__ uint4 pack_h8(const float* v) {
     return make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
 }
 
+// Sum each of 16 per-lane values over the 32 lanes with 16 shuffles (recursive halving): afterwards lane l holds
+// the warp total of value index (l >> 1) & 15.
+__device__ __forceinline__ float reduce16(const float (&v)[16], int lane) {
+    float a8[8], a4[4], a2[2];
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float send = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i];
+            a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float send = up ? a8[i] : a8[i + 4], keep = up ? a8[i + 4] : a8[i];
+            a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float send = up ? a4[i] : a4[i + 2], keep = up ? a4[i + 2] : a4[i];
+            a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    const bool up = lane & 2;
+    const float send = up ? a2[0] : a2[1], keep = up ? a2[1] : a2[0];
+    float a1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+    return a1;
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
@@ -207,28 +242,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
                     if (has1) x1[q] = row[(lane + 32) * a.frame_stride];
                 }
             }
-            if (a.cmvn_mode != CMVN_NONE) {
+            if (a.cmvn_mode == CMVN_PY) {
+                // python-style CMVN: two transposed warp reductions (16 shuffles each) instead of 26 butterflies
+                float v[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[q] = q < WW_N_MFCC ? x0[q] + x1[q] : 0.f;
+                const float tot = reduce16(v, lane);  // lane 2q holds sum_t x[q][t]
+                float mean[WW_N_MFCC];
+#pragma unroll
+                for (int q = 0; q < WW_N_MFCC; ++q)
+                    mean[q] = __shfl_sync(0xffffffffu, tot, 2 * q) / (float)WW_WINDOW_FRAMES;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    if (q < WW_N_MFCC) {
+                        x0[q] -= mean[q];
+                        x1[q] = has1 ? x1[q] - mean[q] : 0.f;
+                        v[q] = fmaf(x0[q], x0[q], x1[q] * x1[q]);
+                    } else {
+                        v[q] = 0.f;
+                    }
+                }
+                const float ss = reduce16(v, lane);
+                float sd = sqrtf(ss / (float)(WW_WINDOW_FRAMES - 1));
+                if (sd == 0.f) sd = 1.f;
+                const float inv = __frcp_rn(sd + 1e-8f);
 #pragma unroll
                 for (int q = 0; q < WW_N_MFCC; ++q) {
-                    float v0 = x0[q], v1 = x1[q];
-                    if (a.cmvn_mode == CMVN_DEVICE) {
-                        v0 = lround_clamp_i8(v0);
-                        v1 = has1 ? lround_clamp_i8(v1) : 0.f;
-                    }
+                    const float iq = __shfl_sync(0xffffffffu, inv, 2 * q);
+                    x0[q] *= iq;
+                    x1[q] *= iq;
+                }
+            } else if (a.cmvn_mode == CMVN_DEVICE) {
+                // device-style CMVN rounds to int8: keep EXACTLY the arithmetic of cnn_fp32_kernel so that both
+                // paths quantise identically
+#pragma unroll 1
+                for (int q = 0; q < WW_N_MFCC; ++q) {
+                    float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+                    for (int qq = 0; qq < WW_N_MFCC; ++qq)
+                        if (qq == q) { v0 = x0[qq]; v1 = x1[qq]; }
+                    v0 = lround_clamp_i8(v0);
+                    v1 = has1 ? lround_clamp_i8(v1) : 0.f;
                     const float mean = warp_sum(v0 + v1) / (float)WW_WINDOW_FRAMES;
                     const float d0 = v0 - mean, d1 = has1 ? v1 - mean : 0.f;
                     const float ss = warp_sum(d0 * d0 + d1 * d1);
-                    if (a.cmvn_mode == CMVN_PY) {
-                        float sd = sqrtf(ss / (float)(WW_WINDOW_FRAMES - 1));
-                        if (sd == 0.f) sd = 1.f;
-                        const float den = sd + 1e-8f;
-                        x0[q] = d0 / den;
-                        x1[q] = d1 / den;
-                    } else {
-                        const float den = sqrtf(ss / (float)WW_WINDOW_FRAMES) + 1e-8f;
-                        x0[q] = fminf(fmaxf(lround_clamp_i8(d0 / den) * 16.f, -128.f), 127.f) * 0.0625f;
-                        x1[q] = fminf(fmaxf(lround_clamp_i8(d1 / den) * 16.f, -128.f), 127.f) * 0.0625f;
-                    }
+                    const float den = sqrtf(ss / (float)WW_WINDOW_FRAMES) + 1e-8f;
+                    const float z0 = fminf(fmaxf(lround_clamp_i8(d0 / den) * 16.f, -128.f), 127.f) * 0.0625f;
+                    const float z1 = fminf(fmaxf(lround_clamp_i8(d1 / den) * 16.f, -128.f), 127.f) * 0.0625f;
+#pragma unroll
+                    for (int qq = 0; qq < WW_N_MFCC; ++qq)
+                        if (qq == q) { x0[qq] = z0; x1[qq] = z1; }
                 }
             }
             // row R = 64*warp + t + 1; channels 0-7 -> chunk 0, channels 8-12 (+3 zeros) -> chunk 1
