@@ -87,14 +87,9 @@ static void fill_common(HostTables& t, const float* window320, float preemph, co
                         const std::vector<int>& len, const std::vector<int>& off, const std::vector<float>& w,
                         const std::vector<float>& bias) {
     t.blob.assign(TB_BYTES, 0);
+    (void)preemph;
     float* win = reinterpret_cast<float*>(t.blob.data() + TB_WIN_OFF);
-    for (int i = 0; i < 160; ++i) {
-        const float w0 = window320[2 * i], w1 = window320[2 * i + 1];
-        win[4 * i + 0] = w0;
-        win[4 * i + 1] = preemph * w0;
-        win[4 * i + 2] = w1;
-        win[4 * i + 3] = preemph * w1;
-    }
+    for (int i = 0; i < 320; ++i) win[i] = window320[i];
     float* tw1 = reinterpret_cast<float*>(t.blob.data() + TB_TW1_OFF);
     for (int j = 0; j < 8; ++j)
         for (int l = 0; l < 16; ++l)

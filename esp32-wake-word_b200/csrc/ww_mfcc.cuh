@@ -12,8 +12,11 @@
 //     complex FFT of the packed frame (z[m] = x[2m] + i x[2m+1]) done as radix-16 (registers) x
 //     radix-16 (registers) with one transposition through a per-warp smem tile, followed by the
 //     real-FFT split that yields two power bins per butterfly
-//   * pre-emphasis and the window are folded into the load (w*x[i] - 0.97w*x[i-1]); only the 160
-//     complex points under the 320-tap window are loaded
+//   * pre-emphasis and the window are folded into the load (w*(x[i] - 0.97*x[i-1])); only the 160 complex
+//     points under the 320-tap window are loaded.  The block's PCM is staged as two halves whose smem
+//     bases differ by 64 B mod 128, so the two half-warps of a warp (frames t and t+16) hit disjoint banks
+//   * the real-FFT split takes its partner values Z[256-k] with 16 width-16 shuffles instead of parking Z in
+//     shared memory: the kernel is co-limited by issue slots and shared-memory wavefronts, not by HBM
 //   * the 32 power spectra of the block are parked in shared memory (33 KB); after a CTA barrier the mel
 //     filterbank runs with lane <-> frame and warp <-> filter range as generated straight-line code
 //     (ww_mel_py.inc) whose weights are FFMA immediates; log-mel rows go back to smem and the 40x13 DCT
@@ -25,8 +28,8 @@
 namespace ww {
 
 // ---- table blob (one per feature mode, device memory, copied to smem by every CTA) ----------------
-constexpr int TB_WIN_OFF = 0;                       // float4[160]  {w[2m], .97w[2m], w[2m+1], .97w[2m+1]}
-constexpr int TB_TW1_OFF = TB_WIN_OFF + 160 * 16;   // float4[8][16] {W256^(l*2j), W256^(l*(2j+1))}
+constexpr int TB_WIN_OFF = 0;                       // float2[160]  {w[2m], w[2m+1]} for packed point m = 48 + i
+constexpr int TB_TW1_OFF = TB_WIN_OFF + 160 * 8;    // float4[8][16] {W256^(l*2j), W256^(l*(2j+1))}
 constexpr int TB_TW2_OFF = TB_TW1_OFF + 128 * 16;   // float2[132]  W512^k, k = 0..128
 constexpr int TB_MELW_OFF = TB_TW2_OFF + 132 * 8;   // float[640]   filterbank weights, filter-major
 constexpr int TB_MELM_OFF = TB_MELW_OFF + 640 * 4;  // int4[40]     {start, len, off, bias bits}
@@ -151,8 +154,13 @@ constexpr int TB_BYTES_PY = TB_MELW_OFF;  // the PY path needs no mel tables in 
 template <typename TIN, bool PYMEL>
 struct MfccSmem {
     static constexpr int FRAMES = MFCC_FRAMES;
-    static constexpr int PCM_SAMPLES = FRAMES * WW_HOP + 72;  // (FRAMES-1)*256 + 320 + 8 lead, rounded
-    static constexpr int PCM_BYTES = ((PCM_SAMPLES * (int)sizeof(TIN) + 15) / 16) * 16;
+    // the block is staged as two halves of 16 frames: 15*256 + 320 taps + 8 lead samples each
+    static constexpr int HALF_SAMPLES = 15 * WW_HOP + 328;
+    static constexpr int HALF_RAW = HALF_SAMPLES * (int)sizeof(TIN);
+    // second half starts 64 B (mod 128) after the first: frames t and t+16 then read disjoint banks
+    static constexpr int HALF_STRIDE = HALF_RAW + ((64 - HALF_RAW % 128) + 128) % 128;
+    static constexpr int PCM_BYTES = HALF_STRIDE + ((HALF_RAW + 15) / 16) * 16;
+    static_assert(HALF_STRIDE % 16 == 0 && HALF_STRIDE % 128 == 64, "half-warp bank stagger");
     static constexpr int TAB_BYTES = PYMEL ? TB_BYTES_PY : TB_BYTES;
     static constexpr int OFF_BAR = 0;
     static constexpr int OFF_TAB = 16;
@@ -160,7 +168,8 @@ struct MfccSmem {
     static constexpr int OFF_EXCH = OFF_PCM + PCM_BYTES;
     static constexpr int OFF_P = OFF_EXCH + MFCC_WARPS * 2 * EXCH_FRAME_BYTES;
     static constexpr int OFF_LM = OFF_P + FRAMES * P_STRIDE * 4;
-    static constexpr int TOTAL = OFF_LM + FRAMES * LM_STRIDE * 4;
+    static constexpr int OFF_EDGE = OFF_LM + FRAMES * LM_STRIDE * 4;   // 2 x 320 pre-emphasised edge-frame samples
+    static constexpr int TOTAL = OFF_EDGE + 2 * WW_WIN * 4;
     static_assert(OFF_PCM % 16 == 0 && OFF_EXCH % 16 == 0 && OFF_P % 16 == 0, "smem alignment");
     // two CTAs per SM need TOTAL <= 115712 B; only the (float PCM, table-driven mel) variant exceeds it
     static_assert(TOTAL <= 115712 || (!PYMEL && sizeof(TIN) == 4), "two CTAs per SM must fit");
@@ -205,7 +214,6 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
     const unsigned char* tab = smem + SM::OFF_TAB;
-    const TIN* spcm = reinterpret_cast<const TIN*>(smem + SM::OFF_PCM);
     float* pw = reinterpret_cast<float*>(smem + SM::OFF_P);
     float* lm = reinterpret_cast<float*>(smem + SM::OFF_LM);
 
@@ -219,14 +227,17 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
     const int n_frames = a.n_frames;
     const int origin_off = a.origin_off;
 
-    // staged sample range [lo, hi) of this signal
-    int lo = WW_HOP * t0 + origin_off + 88;   // 8 samples ahead of the first window tap (multiple of 8)
-    int hi = WW_HOP * (t0 + FRAMES - 1) + origin_off + 416;
-    lo = lo < 0 ? 0 : lo;
-    hi = hi > L ? L : hi;
-    const TIN* gsrc = reinterpret_cast<const TIN*>(a.pcm) + sig * a.sig_stride + lo;
-    const int n_stage = hi - lo;
-
+    // staged sample ranges: half h holds frames 16h..16h+15, smem sample index = s - org[h]
+    const int org0 = WW_HOP * t0 + origin_off + 88;  // 8 samples ahead of the first window tap (multiple of 8)
+    const int org1 = org0 + 16 * WW_HOP;
+    const TIN* gsig = reinterpret_cast<const TIN*>(a.pcm) + sig * a.sig_stride;
+    auto half_range = [&](int h, int& lo, int& n) {
+        const int org = h ? org1 : org0;
+        lo = org < 0 ? 0 : org;
+        int hi = org + SM::HALF_SAMPLES;
+        hi = hi > L ? L : hi;
+        n = hi > lo ? hi - lo : 0;
+    };
     if (a.use_bulk) {
         if (tid == 0) {
             mbar_init(bar, 1);
@@ -234,14 +245,22 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
         }
         __syncthreads();
         if (tid == 0) {
-            // bytes is a multiple of 16 by construction when use_bulk is set (host-checked)
-            const uint32_t bytes = (uint32_t)(n_stage * (int)sizeof(TIN));
-            mbar_expect_tx(bar, bytes);
-            bulk_g2s(smem + SM::OFF_PCM, gsrc, bytes, bar);
+            int lo0, n0, lo1, n1;
+            half_range(0, lo0, n0);
+            half_range(1, lo1, n1);
+            // byte counts are multiples of 16 by construction when use_bulk is set (host-checked)
+            mbar_expect_tx(bar, (uint32_t)((n0 + n1) * (int)sizeof(TIN)));
+            if (n0) bulk_g2s(smem + SM::OFF_PCM + (lo0 - org0) * (int)sizeof(TIN), gsig + lo0, (uint32_t)(n0 * (int)sizeof(TIN)), bar);
+            if (n1) bulk_g2s(smem + SM::OFF_PCM + SM::HALF_STRIDE + (lo1 - org1) * (int)sizeof(TIN), gsig + lo1,
+                             (uint32_t)(n1 * (int)sizeof(TIN)), bar);
         }
     } else {
-        TIN* dst = reinterpret_cast<TIN*>(smem + SM::OFF_PCM);
-        for (int i = tid; i < n_stage; i += MFCC_THREADS) dst[i] = gsrc[i];
+        for (int h = 0; h < 2; ++h) {
+            int lo_h, n_h;
+            half_range(h, lo_h, n_h);
+            TIN* dst = reinterpret_cast<TIN*>(smem + SM::OFF_PCM + h * SM::HALF_STRIDE) + (lo_h - (h ? org1 : org0));
+            for (int i = tid; i < n_h; i += MFCC_THREADS) dst[i] = gsig[lo_h + i];
+        }
     }
     // tables -> smem
     {
@@ -251,7 +270,32 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
     __syncthreads();
     if (a.use_bulk) mbar_wait(bar, 0);
 
-    const float4* s_win = reinterpret_cast<const float4*>(tab + TB_WIN_OFF);
+    // Edge frames (t = 0: reflected / no previous sample; the last frame: reflected tail) cannot use the packed
+    // fast path.  Their 320 pre-emphasised taps are materialised once, cooperatively, so that no warp of the
+    // block is slower than the others (a slow warp stalls the whole CTA at the phase barrier).
+    float* edge = reinterpret_cast<float*>(smem + SM::OFF_EDGE);
+    const int t_tail = (L - origin_off - 416) / WW_HOP + 1;  // first frame whose taps run past the signal end
+    {
+        const bool has0 = (t0 == 0) && (origin_off + 95 < 0);
+        const bool has1 = (t_tail >= t0) && (t_tail < t0 + FRAMES) && (t_tail < n_frames) && (t_tail > 0 || !has0);
+        if (has0 || has1) {
+            const int reflect = a.reflect;
+            const float pre = a.preemph;
+            for (int i = tid; i < 2 * WW_WIN; i += MFCC_THREADS) {
+                const int slot = i >= WW_WIN, j = i - slot * WW_WIN;
+                if (slot ? has1 : has0) {
+                    const int te = slot ? t_tail : 0;
+                    const int hh = (te - t0) >> 4;
+                    const TIN* sp = reinterpret_cast<const TIN*>(smem + SM::OFF_PCM + hh * SM::HALF_STRIDE);
+                    const int s = WW_HOP * te + origin_off + 96 + j;
+                    edge[i] = emph_sample<TIN>(sp, hh ? org1 : org0, s, L, reflect, pre);
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    const float2* s_win = reinterpret_cast<const float2*>(tab + TB_WIN_OFF);
     const float4* s_tw1 = reinterpret_cast<const float4*>(tab + TB_TW1_OFF);
     const float2* s_tw2 = reinterpret_cast<const float2*>(tab + TB_TW2_OFF);
 
@@ -274,12 +318,16 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = make_float2(0.f, 0.f);
 
+        // this half-warp's staging half: frames 16*half.. live in half `half` (fl = 16*half + ...)
+        const TIN* spcm = reinterpret_cast<const TIN*>(smem + SM::OFF_PCM + half * SM::HALF_STRIDE);
+        const int org = half ? org1 : org0;
+        const float pre = a.preemph;
         if (interior) {
             // complex point m = 16*n1 + l16 (n1 = 3..12) <-> samples fo + 2m, fo + 2m + 1
-            const int base = fo - lo + 2 * l16;  // smem sample index of m = l16
+            const int base = fo - org + 2 * l16;  // smem sample index of m = l16
 #pragma unroll
             for (int n1 = 3; n1 <= 12; ++n1) {
-                const float4 w = s_win[16 * (n1 - 3) + l16];
+                const float2 w = s_win[16 * (n1 - 3) + l16];
                 float x0, x1, xm1;
                 if constexpr (sizeof(TIN) == 2) {
                     const uint32_t* p32 = reinterpret_cast<const uint32_t*>(spcm) + ((base + 32 * n1) >> 1);
@@ -294,18 +342,17 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
                     x1 = c2.y;
                     xm1 = pf[-1];
                 }
-                v[n1].x = fmaf(w.x, x0, -w.y * xm1);
-                v[n1].y = fmaf(w.z, x1, -w.w * x0);
+                v[n1].x = w.x * fmaf(-pre, xm1, x0);
+                v[n1].y = w.y * fmaf(-pre, x0, x1);
             }
         } else if (valid) {
-            const int reflect = a.reflect;
-            const float pre = a.preemph;
+            // edge frame: taps were pre-emphasised into `edge` (slot 0: frame 0, slot 1: the tail frame)
+            const float* ep = edge + (t == 0 ? 0 : WW_WIN) + 2 * l16;
 #pragma unroll
             for (int n1 = 3; n1 <= 12; ++n1) {
-                const float4 w = s_win[16 * (n1 - 3) + l16];
-                const int s = fo + 2 * (16 * n1 + l16);
-                v[n1].x = w.x * emph_sample<TIN>(spcm, lo, s, L, reflect, pre);
-                v[n1].y = w.z * emph_sample<TIN>(spcm, lo, s + 1, L, reflect, pre);
+                const float2 w = s_win[16 * (n1 - 3) + l16];
+                const float2 y = *reinterpret_cast<const float2*>(ep + 32 * (n1 - 3));
+                v[n1] = make_float2(w.x * y.x, w.y * y.y);
             }
         }
 
@@ -328,18 +375,20 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
             v[2 * j + 1] = make_float2(q.z, q.w);
         }
         __syncwarp();
-        // pass 2: DFT16 over n2 -> Z[l16 + 16*k2] = v[k2]; park Z in natural order
+        // pass 2: DFT16 over n2 -> Z[l16 + 16*k2] = v[k2]
         fft16<false>(v);
-        float2* zs = reinterpret_cast<float2*>(exch);
-#pragma unroll
-        for (int k2 = 0; k2 < 16; ++k2) zs[l16 + 16 * k2] = v[k2];
-        if (l16 == 0) zs[256] = v[0];
-        __syncwarp();
-        // real-FFT split: pair (k, 256-k) -> 4*|X[k]|^2 and 4*|X[256-k]|^2
+        // real-FFT split: pair (k, 256-k), k = l16 + 16*i -> 4*|X[k]|^2 and 4*|X[256-k]|^2.  Z[256-k] lives in lane
+        // 16-l16, register 15-i (lane 0 pairs with itself: register 16-i, and Z[256] = Z[0])
+        const int partner = (16 - l16) & 15;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int k = l16 + 16 * i;
-            const float2 za = zs[k], zb = zs[256 - k], w = s_tw2[k];
+            const float2 za = v[i];
+            float2 zb;
+            zb.x = __shfl_sync(0xffffffffu, v[15 - i].x, partner, 16);
+            zb.y = __shfl_sync(0xffffffffu, v[15 - i].y, partner, 16);
+            if (l16 == 0) zb = (i == 0) ? v[0] : v[(16 - i) & 15];
+            const float2 w = s_tw2[k];
             const float er = za.x + zb.x, ei = za.y - zb.y;
             const float orr = za.y + zb.y, oi = zb.x - za.x;
             const float tr = fmaf(w.x, orr, -w.y * oi), ti = fmaf(w.x, oi, w.y * orr);
@@ -347,10 +396,7 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
             ps[k] = fmaf(x1r, x1r, x1i * x1i);
             ps[256 - k] = fmaf(x2r, x2r, x2i * x2i);
         }
-        if (l16 == 0) {
-            const float2 z = zs[128];
-            ps[128] = 4.f * fmaf(z.x, z.x, z.y * z.y);
-        }
+        if (l16 == 0) ps[128] = 4.f * fmaf(v[8].x, v[8].x, v[8].y * v[8].y);
         __syncwarp();
     }
     __syncthreads();
