@@ -204,7 +204,7 @@ extern "C" int ww_version(void) { return WW_VERSION_NUM; }
 
 extern "C" const char* ww_last_error(const ww_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
-static const long long kScratchClips = 16384;  // 16384 * 3276 B = 54 MB: stays in the 126 MB L2
+static long long kScratchClips = 16384;  // 16384 * 3276 B = 54 MB: stays in the 126 MB L2 (WW_CHUNK_CLIPS overrides)
 
 extern "C" int ww_create(ww_ctx** out, int device) {
     if (!out) return WW_ERR_INVALID;
@@ -268,6 +268,10 @@ extern "C" int ww_create(ww_ctx** out, int device) {
     if ((e = cudaFuncSetAttribute(cnn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)) != cudaSuccess)
         return bail(e, "cudaFuncSetAttribute(cnn_tc_kernel)");
     if (const char* b = getenv("WW_TC_BAND")) ctx->tc_band = (float)atof(b);
+    if (const char* c = getenv("WW_CHUNK_CLIPS")) {
+        const long long v = atoll(c);
+        if (v >= 256 && v <= (1LL << 22)) kScratchClips = v;
+    }
 #endif
     *out = ctx;
     return WW_OK;
@@ -384,8 +388,9 @@ static int launch_mfcc(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_s
     a.preemph = 0.97f;
     memcpy(a.dct, fm.dct, sizeof(a.dct));
     const long long total_blocks = n_signals * a.blocks_per_sig;
-    if (total_blocks > 0x7fffffffLL) return fail(ctx, WW_ERR_INVALID, "mfcc: too many blocks for one launch");
-    const unsigned grid = (unsigned)total_blocks;
+    a.n_blocks = total_blocks;
+    const long long resident = 2LL * ctx->sm_count;  // persistent: two CTAs per SM walk over the blocks
+    const unsigned grid = (unsigned)(total_blocks < resident ? total_blocks : resident);
     const bool py = feat_mode == WW_FEAT_PY;  // PY filterbank is compiled in (ww_mel_py.inc); others are table-driven
     if (pcm_type == WW_PCM_S16) {
         if (py) mfcc_kernel<int16_t, true><<<grid, MFCC_THREADS, MfccSmem<int16_t, true>::TOTAL, st>>>(a);

@@ -5,7 +5,9 @@
 //   T.MFCC(16 kHz, 13, log_mels, n_fft 512, win 320, hop 256, 40 mels, hamming)   :137-148,172
 // and, with the ESP table set, main/esp_mfcc/mfcc.c:431-527 (extract_mfcc).
 //
-// One CTA = one block of 32 consecutive frames of one signal (a 1 s clip is two blocks, 63 frames valid).
+// Work unit = one block of 32 consecutive frames of one signal (a 1 s clip is two blocks, 63 frames valid).
+// The grid is persistent (two 8-warp CTAs per SM); each CTA walks over blocks and prefetches the PCM of its next
+// block with TMA while it transforms the current one.
 //   * the PCM span of the block is staged once into shared memory with a 1-D TMA bulk copy
 //     (cp.async.bulk + mbarrier); int16 PCM is kept as int16 in smem (16.5 KB per block)
 //   * a warp transforms TWO frames at a time, one per half-warp: the 512-point real FFT is a 256-point
@@ -49,6 +51,7 @@ struct MfccArgs {
     int n_samples;            // valid samples per signal
     int n_frames;             // frames per signal
     int blocks_per_sig;       // ceil(n_frames / FRAMES)
+    long long n_blocks;       // n_signals * blocks_per_sig
     float* out;               // out[sig*out_sig_stride + coef*out_coef_stride + frame*out_frame_stride]
     long long out_sig_stride;
     long long out_coef_stride;
@@ -161,11 +164,14 @@ struct MfccSmem {
     static constexpr int HALF_STRIDE = HALF_RAW + ((64 - HALF_RAW % 128) + 128) % 128;
     static constexpr int PCM_BYTES = HALF_STRIDE + ((HALF_RAW + 15) / 16) * 16;
     static_assert(HALF_STRIDE % 16 == 0 && HALF_STRIDE % 128 == 64, "half-warp bank stagger");
+    // int16 PCM on the PY path is double-buffered (the next block is prefetched by TMA while this one is
+    // transformed); the other variants are single-buffered to keep two CTAs per SM
+    static constexpr int PCM_BUFS = (sizeof(TIN) == 2 && PYMEL) ? 2 : 1;
     static constexpr int TAB_BYTES = PYMEL ? TB_BYTES_PY : TB_BYTES;
     static constexpr int OFF_BAR = 0;
     static constexpr int OFF_TAB = 16;
     static constexpr int OFF_PCM = OFF_TAB + TAB_BYTES;
-    static constexpr int OFF_EXCH = OFF_PCM + PCM_BYTES;
+    static constexpr int OFF_EXCH = OFF_PCM + PCM_BUFS * PCM_BYTES;
     static constexpr int OFF_P = OFF_EXCH + MFCC_WARPS * 2 * EXCH_FRAME_BYTES;
     static constexpr int OFF_LM = OFF_P + FRAMES * P_STRIDE * 4;
     static constexpr int OFF_EDGE = OFF_LM + FRAMES * LM_STRIDE * 4;   // 2 x 320 pre-emphasised edge-frame samples
@@ -220,80 +226,52 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int half = lane >> 4, l16 = lane & 15;
 
-    const long long sig = blockIdx.x / a.blocks_per_sig;
-    const int blk = blockIdx.x - (int)(sig * a.blocks_per_sig);
-    const int t0 = blk * FRAMES;
     const int L = a.n_samples;
     const int n_frames = a.n_frames;
     const int origin_off = a.origin_off;
+    const bool use_bulk = a.use_bulk != 0;
+    constexpr int NBUF = SM::PCM_BUFS;
+    uint64_t* bars = bar;  // one mbarrier per PCM buffer
 
-    // staged sample ranges: half h holds frames 16h..16h+15, smem sample index = s - org[h]
-    const int org0 = WW_HOP * t0 + origin_off + 88;  // 8 samples ahead of the first window tap (multiple of 8)
-    const int org1 = org0 + 16 * WW_HOP;
-    const TIN* gsig = reinterpret_cast<const TIN*>(a.pcm) + sig * a.sig_stride;
-    auto half_range = [&](int h, int& lo, int& n) {
-        const int org = h ? org1 : org0;
-        lo = org < 0 ? 0 : org;
-        int hi = org + SM::HALF_SAMPLES;
-        hi = hi > L ? L : hi;
-        n = hi > lo ? hi - lo : 0;
-    };
-    if (a.use_bulk) {
-        if (tid == 0) {
-            mbar_init(bar, 1);
-            mbar_fence_init();
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int lo0, n0, lo1, n1;
-            half_range(0, lo0, n0);
-            half_range(1, lo1, n1);
-            // byte counts are multiples of 16 by construction when use_bulk is set (host-checked)
-            mbar_expect_tx(bar, (uint32_t)((n0 + n1) * (int)sizeof(TIN)));
-            if (n0) bulk_g2s(smem + SM::OFF_PCM + (lo0 - org0) * (int)sizeof(TIN), gsig + lo0, (uint32_t)(n0 * (int)sizeof(TIN)), bar);
-            if (n1) bulk_g2s(smem + SM::OFF_PCM + SM::HALF_STRIDE + (lo1 - org1) * (int)sizeof(TIN), gsig + lo1,
-                             (uint32_t)(n1 * (int)sizeof(TIN)), bar);
-        }
-    } else {
+    // half h of a block holds frames 16h..16h+15; smem sample index = s - org[h]
+    auto stage_block = [&](long long b, int buf) {  // one thread: TMA both halves of block b into buffer `buf`
+        const long long sg = b / a.blocks_per_sig;
+        const int bt0 = (int)(b - sg * a.blocks_per_sig) * FRAMES;
+        const TIN* gs = reinterpret_cast<const TIN*>(a.pcm) + sg * a.sig_stride;
+        int lo[2], n[2];
         for (int h = 0; h < 2; ++h) {
-            int lo_h, n_h;
-            half_range(h, lo_h, n_h);
-            TIN* dst = reinterpret_cast<TIN*>(smem + SM::OFF_PCM + h * SM::HALF_STRIDE) + (lo_h - (h ? org1 : org0));
-            for (int i = tid; i < n_h; i += MFCC_THREADS) dst[i] = gsig[lo_h + i];
+            const int org = WW_HOP * (bt0 + 16 * h) + origin_off + 88;
+            lo[h] = org < 0 ? 0 : org;
+            int hi = org + SM::HALF_SAMPLES;
+            hi = hi > L ? L : hi;
+            n[h] = hi > lo[h] ? hi - lo[h] : 0;
         }
+        // byte counts are multiples of 16 by construction when use_bulk is set (host-checked)
+        mbar_expect_tx(&bars[buf], (uint32_t)((n[0] + n[1]) * (int)sizeof(TIN)));
+        for (int h = 0; h < 2; ++h) {
+            const int org = WW_HOP * (bt0 + 16 * h) + origin_off + 88;
+            if (n[h])
+                bulk_g2s(smem + SM::OFF_PCM + buf * SM::PCM_BYTES + h * SM::HALF_STRIDE + (lo[h] - org) * (int)sizeof(TIN),
+                         gs + lo[h], (uint32_t)(n[h] * (int)sizeof(TIN)), &bars[buf]);
+        }
+    };
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
     }
-    // tables -> smem
+    // tables -> smem (once per persistent CTA)
     {
         uint4* dst = reinterpret_cast<uint4*>(smem + SM::OFF_TAB);
         for (int i = tid; i < SM::TAB_BYTES / 16; i += MFCC_THREADS) dst[i] = __ldg(a.tables + i);
     }
     __syncthreads();
-    if (a.use_bulk) mbar_wait(bar, 0);
+    const long long first = blockIdx.x, stride = gridDim.x;
+    if (use_bulk && tid == 0 && first < a.n_blocks) stage_block(first, 0);
 
-    // Edge frames (t = 0: reflected / no previous sample; the last frame: reflected tail) cannot use the packed
-    // fast path.  Their 320 pre-emphasised taps are materialised once, cooperatively, so that no warp of the
-    // block is slower than the others (a slow warp stalls the whole CTA at the phase barrier).
     float* edge = reinterpret_cast<float*>(smem + SM::OFF_EDGE);
     const int t_tail = (L - origin_off - 416) / WW_HOP + 1;  // first frame whose taps run past the signal end
-    {
-        const bool has0 = (t0 == 0) && (origin_off + 95 < 0);
-        const bool has1 = (t_tail >= t0) && (t_tail < t0 + FRAMES) && (t_tail < n_frames) && (t_tail > 0 || !has0);
-        if (has0 || has1) {
-            const int reflect = a.reflect;
-            const float pre = a.preemph;
-            for (int i = tid; i < 2 * WW_WIN; i += MFCC_THREADS) {
-                const int slot = i >= WW_WIN, j = i - slot * WW_WIN;
-                if (slot ? has1 : has0) {
-                    const int te = slot ? t_tail : 0;
-                    const int hh = (te - t0) >> 4;
-                    const TIN* sp = reinterpret_cast<const TIN*>(smem + SM::OFF_PCM + hh * SM::HALF_STRIDE);
-                    const int s = WW_HOP * te + origin_off + 96 + j;
-                    edge[i] = emph_sample<TIN>(sp, hh ? org1 : org0, s, L, reflect, pre);
-                }
-            }
-            __syncthreads();
-        }
-    }
 
     const float2* s_win = reinterpret_cast<const float2*>(tab + TB_WIN_OFF);
     const float4* s_tw1 = reinterpret_cast<const float4*>(tab + TB_TW1_OFF);
@@ -301,160 +279,220 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
 
     unsigned char* exch = smem + SM::OFF_EXCH + (warp * 2 + half) * EXCH_FRAME_BYTES;
 
-    constexpr int ITERS = FRAMES / (2 * MFCC_WARPS);
-    static_assert(ITERS * 2 * MFCC_WARPS == FRAMES, "FRAMES must be a multiple of 16");
-
+    long long iter = 0;
 #pragma unroll 1
-    for (int it = 0; it < ITERS; ++it) {
-        // the two half-warps take frames 16 apart: their power-spectrum rows are 16 banks apart
-        const int fl = 16 * half + MFCC_WARPS * it + warp;  // frame index inside the block
-        const int t = t0 + fl;
-        const bool valid = t < n_frames;
-        const int fo = WW_HOP * t + origin_off;  // signal sample index of frame point n = 0
-        const bool interior = valid && (fo + 95 >= 0) && (fo + 415 < L);
-        float* ps = pw + fl * P_STRIDE;
-
-        float2 v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = make_float2(0.f, 0.f);
-
-        // this half-warp's staging half: frames 16*half.. live in half `half` (fl = 16*half + ...)
-        const TIN* spcm = reinterpret_cast<const TIN*>(smem + SM::OFF_PCM + half * SM::HALF_STRIDE);
-        const int org = half ? org1 : org0;
-        const float pre = a.preemph;
-        if (interior) {
-            // complex point m = 16*n1 + l16 (n1 = 3..12) <-> samples fo + 2m, fo + 2m + 1
-            const int base = fo - org + 2 * l16;  // smem sample index of m = l16
-#pragma unroll
-            for (int n1 = 3; n1 <= 12; ++n1) {
-                const float2 w = s_win[16 * (n1 - 3) + l16];
-                float x0, x1, xm1;
-                if constexpr (sizeof(TIN) == 2) {
-                    const uint32_t* p32 = reinterpret_cast<const uint32_t*>(spcm) + ((base + 32 * n1) >> 1);
-                    const uint32_t cur = p32[0], prv = p32[-1];
-                    x0 = static_cast<float>(static_cast<int16_t>(cur & 0xffffu));
-                    x1 = static_cast<float>(static_cast<int16_t>(cur >> 16));
-                    xm1 = static_cast<float>(static_cast<int16_t>(prv >> 16));
-                } else {
-                    const float* pf = reinterpret_cast<const float*>(spcm) + (base + 32 * n1);
-                    const float2 c2 = *reinterpret_cast<const float2*>(pf);
-                    x0 = c2.x;
-                    x1 = c2.y;
-                    xm1 = pf[-1];
+    for (long long blk_id = first; blk_id < a.n_blocks; blk_id += stride, ++iter) {
+        const long long sig = blk_id / a.blocks_per_sig;
+        const int t0 = (int)(blk_id - sig * a.blocks_per_sig) * FRAMES;
+        const int org0 = WW_HOP * t0 + origin_off + 88;  // 8 samples ahead of the first window tap (multiple of 8)
+        const int org1 = org0 + 16 * WW_HOP;
+        const int buf = NBUF == 2 ? (int)(iter & 1) : 0;
+        unsigned char* pcm_buf = smem + SM::OFF_PCM + buf * SM::PCM_BYTES;
+        if (use_bulk) {
+            if (NBUF == 2) {
+                // the other buffer was last read in the FFT phase of the previous block (two barriers ago)
+                if (tid == 0 && blk_id + stride < a.n_blocks) stage_block(blk_id + stride, buf ^ 1);
+                mbar_wait(&bars[buf], (uint32_t)((iter >> 1) & 1));
+            } else {
+                if (iter > 0) {
+                    __syncthreads();  // single buffer: everyone is done with the previous block's samples
+                    if (tid == 0) stage_block(blk_id, 0);
                 }
-                v[n1].x = w.x * fmaf(-pre, xm1, x0);
-                v[n1].y = w.y * fmaf(-pre, x0, x1);
-            }
-        } else if (valid) {
-            // edge frame: taps were pre-emphasised into `edge` (slot 0: frame 0, slot 1: the tail frame)
-            const float* ep = edge + (t == 0 ? 0 : WW_WIN) + 2 * l16;
-#pragma unroll
-            for (int n1 = 3; n1 <= 12; ++n1) {
-                const float2 w = s_win[16 * (n1 - 3) + l16];
-                const float2 y = *reinterpret_cast<const float2*>(ep + 32 * (n1 - 3));
-                v[n1] = make_float2(w.x * y.x, w.y * y.y);
-            }
-        }
-
-        // pass 1: DFT16 over n1, twiddle W256^(l16*k1), transpose through smem
-        fft16<true>(v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float4 tw = s_tw1[16 * j + l16];
-            if (j > 0) v[2 * j] = cmul(v[2 * j], make_float2(tw.x, tw.y));
-            v[2 * j + 1] = cmul(v[2 * j + 1], make_float2(tw.z, tw.w));
-        }
-#pragma unroll
-        for (int k1 = 0; k1 < 16; ++k1)
-            *reinterpret_cast<float2*>(exch + k1 * EXCH_ROW_BYTES + l16 * 8) = v[k1];
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float4 q = *reinterpret_cast<const float4*>(exch + l16 * EXCH_ROW_BYTES + j * 16);
-            v[2 * j] = make_float2(q.x, q.y);
-            v[2 * j + 1] = make_float2(q.z, q.w);
-        }
-        __syncwarp();
-        // pass 2: DFT16 over n2 -> Z[l16 + 16*k2] = v[k2]
-        fft16<false>(v);
-        // real-FFT split: pair (k, 256-k), k = l16 + 16*i -> 4*|X[k]|^2 and 4*|X[256-k]|^2.  Z[256-k] lives in lane
-        // 16-l16, register 15-i (lane 0 pairs with itself: register 16-i, and Z[256] = Z[0])
-        const int partner = (16 - l16) & 15;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int k = l16 + 16 * i;
-            const float2 za = v[i];
-            float2 zb;
-            zb.x = __shfl_sync(0xffffffffu, v[15 - i].x, partner, 16);
-            zb.y = __shfl_sync(0xffffffffu, v[15 - i].y, partner, 16);
-            if (l16 == 0) zb = (i == 0) ? v[0] : v[(16 - i) & 15];
-            const float2 w = s_tw2[k];
-            const float er = za.x + zb.x, ei = za.y - zb.y;
-            const float orr = za.y + zb.y, oi = zb.x - za.x;
-            const float tr = fmaf(w.x, orr, -w.y * oi), ti = fmaf(w.x, oi, w.y * orr);
-            const float x1r = er + tr, x1i = ei + ti, x2r = er - tr, x2i = ei - ti;
-            ps[k] = fmaf(x1r, x1r, x1i * x1i);
-            ps[256 - k] = fmaf(x2r, x2r, x2i * x2i);
-        }
-        if (l16 == 0) ps[128] = 4.f * fmaf(v[8].x, v[8].x, v[8].y * v[8].y);
-        __syncwarp();
-    }
-    __syncthreads();
-
-    // mel + log: lane <-> frame, warp <-> filter range
-    {
-        const float pscale = a.pscale, log_offset = a.log_offset;
-        const float* prow = pw + lane * P_STRIDE;
-        float* lrow = lm + lane * LM_STRIDE;
-        if constexpr (PYMEL) {
-            switch (warp) {
-                case 0: mel_py_group<0>(prow, lrow, pscale, log_offset); break;
-                case 1: mel_py_group<1>(prow, lrow, pscale, log_offset); break;
-                case 2: mel_py_group<2>(prow, lrow, pscale, log_offset); break;
-                case 3: mel_py_group<3>(prow, lrow, pscale, log_offset); break;
-                case 4: mel_py_group<4>(prow, lrow, pscale, log_offset); break;
-                case 5: mel_py_group<5>(prow, lrow, pscale, log_offset); break;
-                case 6: mel_py_group<6>(prow, lrow, pscale, log_offset); break;
-                default: mel_py_group<7>(prow, lrow, pscale, log_offset); break;
+                mbar_wait(&bars[0], (uint32_t)(iter & 1));
             }
         } else {
-            // table-driven filterbank (weights broadcast from smem): any contiguous-support filter set
-            const float* s_melw = reinterpret_cast<const float*>(tab + TB_MELW_OFF);
-            const int4* s_melm = reinterpret_cast<const int4*>(tab + TB_MELM_OFF);
-            const float log_floor = a.log_floor;
-            for (int j = warp; j < WW_N_MELS; j += MFCC_WARPS) {
-                const int4 m = s_melm[j];
-                const float* pp = prow + m.x;
-                const float* ww_ = s_melw + m.z;
-                float acc = 0.f;
-                for (int i = 0; i < m.y; ++i) acc = fmaf(pp[i], ww_[i], acc);
-                const float e = fmaf(acc, pscale, __int_as_float(m.w));
-                lrow[j] = __logf(fmaxf(e, log_floor) + log_offset);
+            // unaligned / odd-length signals: cooperative copy instead of TMA
+            if (iter > 0) __syncthreads();
+            const TIN* gsig = reinterpret_cast<const TIN*>(a.pcm) + sig * a.sig_stride;
+            for (int h = 0; h < 2; ++h) {
+                const int org = h ? org1 : org0;
+                const int lo_h = org < 0 ? 0 : org;
+                int hi_h = org + SM::HALF_SAMPLES;
+                hi_h = hi_h > L ? L : hi_h;
+                TIN* dst = reinterpret_cast<TIN*>(pcm_buf + h * SM::HALF_STRIDE) + (lo_h - org);
+                for (int i = tid; i < hi_h - lo_h; i += MFCC_THREADS) dst[i] = gsig[lo_h + i];
+            }
+            __syncthreads();
+        }
+
+        // Edge frames (t = 0: reflected / no previous sample; the last frame: reflected tail) cannot use the
+        // packed fast path.  Their 320 pre-emphasised taps are materialised once, cooperatively, so that no warp
+        // of the block is slower than the others (a slow warp stalls the whole CTA at the phase barrier).
+        {
+            const bool has0 = (t0 == 0) && (origin_off + 95 < 0);
+            const bool has1 = (t_tail >= t0) && (t_tail < t0 + FRAMES) && (t_tail < n_frames) && (t_tail > 0 || !has0);
+            if (has0 || has1) {
+                const int reflect = a.reflect;
+                const float pre = a.preemph;
+                for (int i = tid; i < 2 * WW_WIN; i += MFCC_THREADS) {
+                    const int slot = i >= WW_WIN, j = i - slot * WW_WIN;
+                    if (slot ? has1 : has0) {
+                        const int te = slot ? t_tail : 0;
+                        const int hh = (te - t0) >> 4;
+                        const TIN* sp = reinterpret_cast<const TIN*>(pcm_buf + hh * SM::HALF_STRIDE);
+                        const int s = WW_HOP * te + origin_off + 96 + j;
+                        edge[i] = emph_sample<TIN>(sp, hh ? org1 : org0, s, L, reflect, pre);
+                    }
+                }
+                __syncthreads();
             }
         }
-    }
-    __syncthreads();
 
-    // DCT: lane <-> frame, warp <-> coefficient pair {warp, warp + 8}; stores coalesced along time
-    {
-        const int t = t0 + lane;
-        if (t < n_frames) {
-            float* outp = a.out + sig * a.out_sig_stride + (long long)t * a.out_frame_stride;
-            const float* lrow = lm + lane * LM_STRIDE;
+        constexpr int ITERS = FRAMES / (2 * MFCC_WARPS);
+        static_assert(ITERS * 2 * MFCC_WARPS == FRAMES, "FRAMES must be a multiple of 16");
+
+    #pragma unroll 1
+        for (int it = 0; it < ITERS; ++it) {
+            // the two half-warps take frames 16 apart: their power-spectrum rows are 16 banks apart
+            const int fl = 16 * half + MFCC_WARPS * it + warp;  // frame index inside the block
+            const int t = t0 + fl;
+            const bool valid = t < n_frames;
+            const int fo = WW_HOP * t + origin_off;  // signal sample index of frame point n = 0
+            const bool interior = valid && (fo + 95 >= 0) && (fo + 415 < L);
+            float* ps = pw + fl * P_STRIDE;
+
+            float2 v[16];
+    #pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = make_float2(0.f, 0.f);
+
+            // this half-warp's staging half: frames 16*half.. live in half `half` (fl = 16*half + ...)
+            const TIN* spcm = reinterpret_cast<const TIN*>(pcm_buf + half * SM::HALF_STRIDE);
+            const int org = half ? org1 : org0;
+            const float pre = a.preemph;
+            if (interior) {
+                // complex point m = 16*n1 + l16 (n1 = 3..12) <-> samples fo + 2m, fo + 2m + 1
+                const int base = fo - org + 2 * l16;  // smem sample index of m = l16
+    #pragma unroll
+                for (int n1 = 3; n1 <= 12; ++n1) {
+                    const float2 w = s_win[16 * (n1 - 3) + l16];
+                    float x0, x1, xm1;
+                    if constexpr (sizeof(TIN) == 2) {
+                        const uint32_t* p32 = reinterpret_cast<const uint32_t*>(spcm) + ((base + 32 * n1) >> 1);
+                        const uint32_t cur = p32[0], prv = p32[-1];
+                        x0 = static_cast<float>(static_cast<int16_t>(cur & 0xffffu));
+                        x1 = static_cast<float>(static_cast<int16_t>(cur >> 16));
+                        xm1 = static_cast<float>(static_cast<int16_t>(prv >> 16));
+                    } else {
+                        const float* pf = reinterpret_cast<const float*>(spcm) + (base + 32 * n1);
+                        const float2 c2 = *reinterpret_cast<const float2*>(pf);
+                        x0 = c2.x;
+                        x1 = c2.y;
+                        xm1 = pf[-1];
+                    }
+                    v[n1].x = w.x * fmaf(-pre, xm1, x0);
+                    v[n1].y = w.y * fmaf(-pre, x0, x1);
+                }
+            } else if (valid) {
+                // edge frame: taps were pre-emphasised into `edge` (slot 0: frame 0, slot 1: the tail frame)
+                const float* ep = edge + (t == 0 ? 0 : WW_WIN) + 2 * l16;
+    #pragma unroll
+                for (int n1 = 3; n1 <= 12; ++n1) {
+                    const float2 w = s_win[16 * (n1 - 3) + l16];
+                    const float2 y = *reinterpret_cast<const float2*>(ep + 32 * (n1 - 3));
+                    v[n1] = make_float2(w.x * y.x, w.y * y.y);
+                }
+            }
+
+            // pass 1: DFT16 over n1, twiddle W256^(l16*k1), transpose through smem
+            fft16<true>(v);
+    #pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 tw = s_tw1[16 * j + l16];
+                if (j > 0) v[2 * j] = cmul(v[2 * j], make_float2(tw.x, tw.y));
+                v[2 * j + 1] = cmul(v[2 * j + 1], make_float2(tw.z, tw.w));
+            }
+    #pragma unroll
+            for (int k1 = 0; k1 < 16; ++k1)
+                *reinterpret_cast<float2*>(exch + k1 * EXCH_ROW_BYTES + l16 * 8) = v[k1];
+            __syncwarp();
+    #pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 q = *reinterpret_cast<const float4*>(exch + l16 * EXCH_ROW_BYTES + j * 16);
+                v[2 * j] = make_float2(q.x, q.y);
+                v[2 * j + 1] = make_float2(q.z, q.w);
+            }
+            __syncwarp();
+            // pass 2: DFT16 over n2 -> Z[l16 + 16*k2] = v[k2]
+            fft16<false>(v);
+            // real-FFT split: pair (k, 256-k), k = l16 + 16*i -> 4*|X[k]|^2 and 4*|X[256-k]|^2.  Z[256-k] lives in lane
+            // 16-l16, register 15-i (lane 0 pairs with itself: register 16-i, and Z[256] = Z[0])
+            const int partner = (16 - l16) & 15;
+    #pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = l16 + 16 * i;
+                const float2 za = v[i];
+                float2 zb;
+                zb.x = __shfl_sync(0xffffffffu, v[15 - i].x, partner, 16);
+                zb.y = __shfl_sync(0xffffffffu, v[15 - i].y, partner, 16);
+                if (l16 == 0) zb = (i == 0) ? v[0] : v[(16 - i) & 15];
+                const float2 w = s_tw2[k];
+                const float er = za.x + zb.x, ei = za.y - zb.y;
+                const float orr = za.y + zb.y, oi = zb.x - za.x;
+                const float tr = fmaf(w.x, orr, -w.y * oi), ti = fmaf(w.x, oi, w.y * orr);
+                const float x1r = er + tr, x1i = ei + ti, x2r = er - tr, x2i = ei - ti;
+                ps[k] = fmaf(x1r, x1r, x1i * x1i);
+                ps[256 - k] = fmaf(x2r, x2r, x2i * x2i);
+            }
+            if (l16 == 0) ps[128] = 4.f * fmaf(v[8].x, v[8].x, v[8].y * v[8].y);
+            __syncwarp();
+        }
+        __syncthreads();
+
+        // mel + log: lane <-> frame, warp <-> filter range
+        {
+            const float pscale = a.pscale, log_offset = a.log_offset;
+            const float* prow = pw + lane * P_STRIDE;
+            float* lrow = lm + lane * LM_STRIDE;
             if constexpr (PYMEL) {
-                const long long cs = a.out_coef_stride;
                 switch (warp) {
-                    case 0: dct_py_group<0>(lrow, outp, cs); break;
-                    case 1: dct_py_group<1>(lrow, outp, cs); break;
-                    case 2: dct_py_group<2>(lrow, outp, cs); break;
-                    case 3: dct_py_group<3>(lrow, outp, cs); break;
-                    case 4: dct_py_group<4>(lrow, outp, cs); break;
-                    case 5: dct_py_group<5>(lrow, outp, cs); break;
-                    case 6: dct_py_group<6>(lrow, outp, cs); break;
-                    default: dct_py_group<7>(lrow, outp, cs); break;
+                    case 0: mel_py_group<0>(prow, lrow, pscale, log_offset); break;
+                    case 1: mel_py_group<1>(prow, lrow, pscale, log_offset); break;
+                    case 2: mel_py_group<2>(prow, lrow, pscale, log_offset); break;
+                    case 3: mel_py_group<3>(prow, lrow, pscale, log_offset); break;
+                    case 4: mel_py_group<4>(prow, lrow, pscale, log_offset); break;
+                    case 5: mel_py_group<5>(prow, lrow, pscale, log_offset); break;
+                    case 6: mel_py_group<6>(prow, lrow, pscale, log_offset); break;
+                    default: mel_py_group<7>(prow, lrow, pscale, log_offset); break;
                 }
             } else {
-                DctDispatch<MFCC_WARPS, 0>::run(warp, a, lrow, outp);
+                // table-driven filterbank (weights broadcast from smem): any contiguous-support filter set
+                const float* s_melw = reinterpret_cast<const float*>(tab + TB_MELW_OFF);
+                const int4* s_melm = reinterpret_cast<const int4*>(tab + TB_MELM_OFF);
+                const float log_floor = a.log_floor;
+                for (int j = warp; j < WW_N_MELS; j += MFCC_WARPS) {
+                    const int4 m = s_melm[j];
+                    const float* pp = prow + m.x;
+                    const float* ww_ = s_melw + m.z;
+                    float acc = 0.f;
+                    for (int i = 0; i < m.y; ++i) acc = fmaf(pp[i], ww_[i], acc);
+                    const float e = fmaf(acc, pscale, __int_as_float(m.w));
+                    lrow[j] = __logf(fmaxf(e, log_floor) + log_offset);
+                }
+            }
+        }
+        __syncthreads();
+
+        // DCT: lane <-> frame, warp <-> coefficient pair {warp, warp + 8}; stores coalesced along time
+        {
+            const int t = t0 + lane;
+            if (t < n_frames) {
+                float* outp = a.out + sig * a.out_sig_stride + (long long)t * a.out_frame_stride;
+                const float* lrow = lm + lane * LM_STRIDE;
+                if constexpr (PYMEL) {
+                    const long long cs = a.out_coef_stride;
+                    switch (warp) {
+                        case 0: dct_py_group<0>(lrow, outp, cs); break;
+                        case 1: dct_py_group<1>(lrow, outp, cs); break;
+                        case 2: dct_py_group<2>(lrow, outp, cs); break;
+                        case 3: dct_py_group<3>(lrow, outp, cs); break;
+                        case 4: dct_py_group<4>(lrow, outp, cs); break;
+                        case 5: dct_py_group<5>(lrow, outp, cs); break;
+                        case 6: dct_py_group<6>(lrow, outp, cs); break;
+                        default: dct_py_group<7>(lrow, outp, cs); break;
+                    }
+                } else {
+                    DctDispatch<MFCC_WARPS, 0>::run(warp, a, lrow, outp);
+                }
             }
         }
     }
