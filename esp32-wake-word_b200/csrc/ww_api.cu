@@ -204,7 +204,11 @@ extern "C" int ww_version(void) { return WW_VERSION_NUM; }
 
 extern "C" const char* ww_last_error(const ww_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
-static long long kScratchClips = 16384;  // 16384 * 3276 B = 54 MB: stays in the 126 MB L2 (WW_CHUNK_CLIPS overrides)
+// Feature scratch of the fused path: frontend and CNN run chunk by chunk so the [13,63] features never leave
+// the device as a full [B,13,63] tensor.  Measured on B200 (tools/sweep_chunks.sh): 8192 -> 17.0, 16384 -> 17.9,
+// 32768 -> 18.3, 65536 -> 18.5 M clips/s; the host-buffer pipeline keeps 16384-clip chunks for copy overlap.
+static long long kScratchClips = 65536;  // WW_CHUNK_CLIPS overrides
+static const long long kHostChunkClips = 16384;
 
 extern "C" int ww_create(ww_ctx** out, int device) {
     if (!out) return WW_ERR_INVALID;
@@ -600,7 +604,7 @@ extern "C" int ww_score_clips(ww_ctx* ctx, const void* pcm, int pcm_type, long l
 }
 
 static int ensure_host_path(ww_ctx* ctx, size_t esz) {
-    const long long chunk = kScratchClips;
+    const long long chunk = kHostChunkClips;
     const size_t bytes = (size_t)chunk * WW_CLIP_SAMPLES * esz;
     if (ctx->host_chunk == chunk && ctx->host_chunk_bytes >= bytes) return WW_OK;
     for (int i = 0; i < 2; ++i) {

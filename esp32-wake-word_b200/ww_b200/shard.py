@@ -1,0 +1,59 @@
+"""Clip / stream sharding across the GPUs of one box.
+
+Clips are independent (CMVN is per clip, the 161 KB of weights are replicated), so a job is split into
+contiguous clip ranges, one process per GPU, with NO collective on the hot path; the only exchange is the
+final gather of the per-clip scores (5 B per clip).  Streams are split into time segments that carry a halo of
+62 frames (+ the centre-pad / pre-emphasis context), so segments need no exchange either.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+HOP = 256
+WINDOW = 63
+
+
+def shard_range(n_items: int, rank: int, world: int):
+    """Contiguous [start, stop) of rank `rank`: sizes differ by at most one, earlier ranks take the remainder."""
+    base, rem = divmod(n_items, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def gather_scores(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """All-gather variable-length per-rank score vectors into the global order (every rank gets the result)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local
+    rank = dist.get_rank(group)
+    sizes = [shard_range(n_total, r, world) for r in range(world)]
+    width = max(b - a for a, b in sizes)
+    pad = torch.zeros((width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty((world * width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad, group=group) if local.is_cuda else \
+        dist.all_gather(list(out.view((world, width) + tuple(local.shape[1:])).unbind(0)), pad, group=group)
+    parts = [out[r * width: r * width + (b - a)] for r, (a, b) in enumerate(sizes)]
+    del rank
+    return torch.cat(parts, dim=0)
+
+
+def stream_segments(n_samples: int, world: int):
+    """Split a stream's WINDOWS into `world` contiguous ranges and give each the sample span it needs.
+
+    Returns a list of (sample_start, sample_stop, first_window, n_windows).  Window w covers frames w..w+62 and
+    frame t needs samples 256 t - 256 .. 256 t + 255 (reflect padding only at the true stream ends), plus one
+    earlier sample for the pre-emphasis; so a segment of windows [w0, w1) needs samples
+    [256 w0 - 257, 256 (w1 + 61) + 256) clipped to the stream.  The halo is 62 frames + 513 samples and no
+    segment ever needs data from another rank.
+    """
+    n_frames = 1 + n_samples // HOP
+    n_windows = n_frames - WINDOW + 1
+    out = []
+    for r in range(world):
+        w0, w1 = shard_range(max(n_windows, 0), r, world)
+        s0 = max(0, HOP * w0 - 257)
+        s1 = min(n_samples, HOP * (w1 + WINDOW - 2) + 256) if w1 > w0 else s0
+        out.append((s0, s1, w0, w1 - w0))
+    return out

@@ -1,0 +1,68 @@
+"""CPU, world_size 2, gloo: the N > 1 host logic (clip sharding + final score gather) without any GPU."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ww_b200 import shard
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_total, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        a, b = shard.shard_range(n_total, rank, world)
+        # stand-in for the per-GPU scorer: a deterministic function of the global clip index
+        idx = torch.arange(a, b)
+        logits = (idx.float() * 0.25 - 3.0)[:, None]
+        dec = (logits[:, 0] > 0).to(torch.uint8)
+        g_dec = shard.gather_scores(dec, n_total)
+        g_log = shard.gather_scores(logits, n_total)
+        want = torch.arange(n_total).float() * 0.25 - 3.0
+        ok = torch.equal(g_log[:, 0], want) and torch.equal(g_dec, (want > 0).to(torch.uint8))
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [10, 11, 1])
+def test_two_rank_shard_and_gather(n_total):
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), n_total, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 8, 1000003):
+        for world in (1, 2, 4, 8):
+            spans = [shard.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_stream_segments_cover_windows_with_halo():
+    n = 3600 * 16000
+    segs = shard.stream_segments(n, 8)
+    n_frames = 1 + n // 256
+    assert sum(s[3] for s in segs) == n_frames - 62 == 224939
+    for s0, s1, w0, nw in segs:
+        # every frame of every window of the segment has its 512-sample support (or the true stream edge)
+        first, last = 256 * w0 - 256, 256 * (w0 + nw - 1 + 62) + 255
+        assert s0 <= max(first - 1, 0) and s1 >= min(last + 1, n)
+    # halo: consecutive segments overlap by 62 frames plus context
+    assert segs[0][1] - segs[1][0] == 62 * 256 + 513 - 256 or segs[0][1] > segs[1][0]

@@ -1,0 +1,102 @@
+#!/usr/bin/env python
+"""Secondary measurements for BASELINE.json configs[3] (streaming) and configs[4] (CTC loss fwd+bwd).
+
+Run on the GPU box; prints one JSON object per measurement (kept under profiles/).  Timing: CUDA events on
+the launching stream, 3 warm-ups, inputs larger than L2 or freshly produced per iteration.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "esp32-wake-word_b200"))
+import bench  # noqa: E402
+import ww_b200  # noqa: E402
+
+
+def timed(fn, reps=5, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e-3
+
+
+def stream_bench(dev, sd, seconds=3600, impl="tensor"):
+    """One 1-hour synthetic stream (seed 4321): white-noise bed + a 1 s burst every 10 s."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(4321)
+    n = seconds * 16000
+    x = torch.randn(n, generator=g, device=dev) * 0.02
+    burst = torch.randn(n, generator=g, device=dev) * 0.2
+    t = torch.arange(n, device=dev)
+    x = x + burst * (((t // 16000) % 10) == 3)
+    pcm = torch.round(torch.clamp(x, -1, 32767 / 32768) * 32767).to(torch.int16)
+    del x, burst, t
+    out = []
+    for cmvn in ("device", "python"):
+        sc = ww_b200.StreamScorer(sd, device=0, cmvn=cmvn, cnn_impl=impl)
+        dt = timed(lambda: sc.score(pcm))
+        feats, logits = sc.score(pcm)
+        hits = ww_b200.events(logits)
+        out.append({"config": "configs[3] streaming, 1 x 3600 s stream, hop 1 frame", "cmvn": cmvn, "cnn_impl": impl,
+                    "frames": int(feats.shape[1]), "windows": int(logits.shape[0]), "seconds_per_pass": dt,
+                    "audio_seconds_per_s": seconds / dt, "windows_per_s": logits.shape[0] / dt, "hits": len(hits)})
+    return out
+
+
+def ctc_bench(dev, T, B, C, S, seed=777):
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    lp = torch.log_softmax(torch.randn((T, B, C), generator=g, device=dev), dim=-1)
+    tg = torch.randint(1, C, (B, S), generator=g, device=dev)
+    il = torch.full((B,), T, dtype=torch.int32, device=dev)
+    tl = torch.full((B,), S, dtype=torch.int32, device=dev)
+    crit = ww_b200.CTCLoss(blank=0, zero_infinity=True)
+    ref = torch.nn.CTCLoss(blank=0, zero_infinity=True)
+
+    def ours():
+        x = lp.detach().requires_grad_(True)
+        crit(x, tg, il, tl).backward()
+
+    def torch_gpu():
+        x = lp.detach().requires_grad_(True)
+        ref(x, tg, il.long(), tl.long()).backward()
+
+    d_ours, d_torch = timed(ours), timed(torch_gpu)
+    nb = min(B, 4096)
+    lpc, tgc = lp[:, :nb].cpu(), tg[:nb].cpu()
+    t0 = time.perf_counter()
+    x = lpc.detach().requires_grad_(True)
+    ref(x, tgc, il[:nb].cpu().long(), tl[:nb].cpu().long()).backward()
+    d_cpu = (time.perf_counter() - t0) * B / nb
+    bytes_alg = 2 * T * C * 4 * B
+    return {"config": f"configs[4] CTC loss fwd+bwd T={T} B={B} C={C} S={S}", "seq_per_s": B / d_ours,
+            "torch_cuda_seq_per_s": B / d_torch, "torch_cpu_seq_per_s": B / d_cpu,
+            "algorithmic_GBps": bytes_alg / d_ours / 1e9}
+
+
+def main():
+    dev = torch.device("cuda", 0)
+    sd = bench.load_weights()
+    res = []
+    res += stream_bench(dev, sd)
+    res.append(ctc_bench(dev, 63, 1 << 18, 3, 2))
+    res.append(ctc_bench(dev, 63, 1 << 18, 3, 1))
+    res.append(ctc_bench(dev, 801, 256, 4096, 32))
+    for r in res:
+        print(json.dumps(r), flush=True)
+
+
+if __name__ == "__main__":
+    main()
