@@ -803,6 +803,11 @@ extern "C" int ww_ctc_loss_fwd(ww_ctx* ctx, const float* log_probs, long long t_
     if (B == 0) return WW_OK;
     a.nll = nll;
     a.alpha = (float*)workspace;
+    if (S <= 3) {  // short targets: 8 lanes per utterance, 4 utterances per warp
+        ctc_small_fwd_kernel<<<(B + CTC_WARPS * 4 - 1) / (CTC_WARPS * 4), CTC_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+        CK(cudaGetLastError());
+        return WW_OK;
+    }
     const size_t smem = (size_t)CTC_WARPS * 2 * ctc_lp(S) * sizeof(float);
     if (smem > 48 * 1024)
         CK(cudaFuncSetAttribute(ctc_loss_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -828,6 +833,22 @@ extern "C" int ww_ctc_loss_bwd(ww_ctx* ctx, const float* log_probs, long long t_
     a.grad = grad;
     a.gt_stride = gt_stride;
     a.gb_stride = gb_stride;
+    if (S <= 3 && C <= 64) {
+        a.skip_fill = 0;
+        ctc_small_bwd_kernel<<<(B + CTC_WARPS * 4 - 1) / (CTC_WARPS * 4), CTC_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+        CK(cudaGetLastError());
+        return WW_OK;
+    }
+    a.skip_fill = C >= 64 ? 1 : 0;
+    if (a.skip_fill) {
+        // wide vocabulary: the exp(lp) fill is a bandwidth-bound pass over all T*B rows, not warp-per-utterance work
+        long long rows = (long long)T * B;
+        long long blocks = (rows + 7) / 8;
+        const long long cap = (long long)ctx->sm_count * 8;
+        if (blocks > cap) blocks = cap;
+        ctc_grad_fill_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+        CK(cudaGetLastError());
+    }
     const size_t smem = (size_t)CTC_WARPS * (2 * ctc_lp(S) + 3 * S) * sizeof(float);
     if (smem > 48 * 1024)
         CK(cudaFuncSetAttribute(ctc_loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -116,6 +116,7 @@ struct CtcLossArgs {
     const float* grad_out;  // [B] upstream gradient of nll_b (backward only)
     float* grad;            // grad[t*gt_stride + b*gb_stride + c] (backward only)
     long long gt_stride, gb_stride;
+    int skip_fill;          // backward: grad rows were pre-filled with exp(lp)*go by ctc_grad_fill_kernel
 };
 
 __device__ __forceinline__ float lse3(float a, float b, float c) {
@@ -235,9 +236,11 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_bwd_kernel(const CtcL
 
     // rows past the input length (and everything for an infinite loss under zero_infinity) are zero
     const int t_live = dead ? 0 : Tb;
-    for (int t = t_live; t < a.T; ++t) {
-        float* grow = gbase + (long long)t * a.gt_stride;
-        for (int c = lane; c < a.C; c += 32) grow[c] = 0.f;
+    if (!a.skip_fill) {
+        for (int t = t_live; t < a.T; ++t) {
+            float* grow = gbase + (long long)t * a.gt_stride;
+            for (int c = lane; c < a.C; c += 32) grow[c] = 0.f;
+        }
     }
     if (t_live == 0) return;
 
@@ -296,7 +299,8 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_bwd_kernel(const CtcL
             blank_m = (m == NEG) ? NEG : logf(e) + m;
         }
         // default gradient for every class: exp(lp)
-        for (int c = lane; c < a.C; c += 32) grow[c] = expf(row[c]) * go;
+        if (!a.skip_fill)
+            for (int c = lane; c < a.C; c += 32) grow[c] = expf(row[c]) * go;
         __syncwarp();
         // fold repeated labels into their first occurrence (rare, sequential)
         if (lane == 0)
@@ -321,6 +325,180 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_bwd_kernel(const CtcL
             grow[a.blank] = (expf(lpv) - expf(tot + nll - lpv)) * go;
         }
         __syncwarp();
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Short-target specialisation (S <= 3, i.e. at most 7 extended states -- the reference's keyword shapes
+// T ~ 63, C = 3, S = 1..2 of ml_models/test.py): 8 lanes per utterance, 4 utterances per warp, one state per
+// lane, neighbours through width-8 shuffles, no shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int CTC_SMALL_G = 8;
+
+__device__ __forceinline__ int group_max(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__global__ void __launch_bounds__(CTC_WARPS * 32) ctc_small_fwd_kernel(const CtcLossArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = lane & 7;
+    long long b = ((long long)blockIdx.x * CTC_WARPS + warp) * 4 + (lane >> 3);
+    const bool live = b < a.B;
+    if (!live) b = a.B - 1;
+    const int Tb = live ? min(max(a.in_len[b], 0), a.T) : 0;
+    const int Sb = min(max(a.tgt_len[b], 0), a.S);
+    const int L = 2 * Sb + 1;
+    const int Lw = 2 * a.S + 1;
+    const int* tgt = a.targets + b * (long long)a.S;
+    const float* base = a.lp + b * a.b_stride;
+    float* al = a.alpha + b * (long long)a.T * Lw;
+    const float NEG = -CUDART_INF_F;
+    const bool vs = s < L;
+    const int lab = (vs && (s & 1)) ? tgt[s >> 1] : a.blank;
+    const bool skip = vs && (s & 1) && s >= 3 && tgt[s >> 1] != tgt[(s >> 1) - 1];
+    const int Tw = group_max(Tb);
+
+    float alpha = NEG;
+    if (Tb > 0) {
+        if (s == 0) alpha = base[a.blank];
+        else if (s == 1 && L > 1) alpha = base[lab];
+        if (vs) al[s] = alpha;
+    }
+    for (int t = 1; t < Tw; ++t) {
+        float a1 = __shfl_up_sync(0xffffffffu, alpha, 1, CTC_SMALL_G);
+        float a2 = __shfl_up_sync(0xffffffffu, alpha, 2, CTC_SMALL_G);
+        if (s < 1) a1 = NEG;
+        if (!skip) a2 = NEG;
+        if (t < Tb && vs) {
+            alpha = lse3(alpha, a1, a2) + base[(long long)t * a.t_stride + lab];
+            al[(long long)t * Lw + s] = alpha;
+        }
+    }
+    const float e1 = __shfl_sync(0xffffffffu, alpha, L - 1, CTC_SMALL_G);
+    const float e2 = __shfl_sync(0xffffffffu, alpha, L > 1 ? L - 2 : 0, CTC_SMALL_G);
+    if (live && s == 0) {
+        float v;
+        if (Tb == 0) v = Sb == 0 ? 0.f : CUDART_INF_F;
+        else v = -(L > 1 ? lse2(e1, e2) : e1);
+        if (a.zero_infinity && v == CUDART_INF_F) v = 0.f;
+        a.nll[b] = v;
+    }
+}
+
+__global__ void __launch_bounds__(CTC_WARPS * 32) ctc_small_bwd_kernel(const CtcLossArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = lane & 7;
+    long long b = ((long long)blockIdx.x * CTC_WARPS + warp) * 4 + (lane >> 3);
+    const bool live = b < a.B;
+    if (!live) b = a.B - 1;
+    const int Tb = live ? min(max(a.in_len[b], 0), a.T) : 0;
+    const int Sb = min(max(a.tgt_len[b], 0), a.S);
+    const int L = 2 * Sb + 1;
+    const int Lw = 2 * a.S + 1;
+    const int* tgt = a.targets + b * (long long)a.S;
+    const float* base = a.lp + b * a.b_stride;
+    const float* al = a.alpha + b * (long long)a.T * Lw;
+    float* gbase = a.grad + b * a.gb_stride;
+    const float NEG = -CUDART_INF_F;
+    const bool vs = s < L;
+    const int lab = (vs && (s & 1)) ? tgt[s >> 1] : a.blank;
+    const bool skip = vs && (s & 1) && s + 2 < L && tgt[s >> 1] != tgt[(s >> 1) + 1];
+
+    float nll;
+    {
+        float ll = NEG;
+        if (Tb > 0) {
+            ll = al[(long long)(Tb - 1) * Lw + L - 1];
+            if (L > 1) ll = lse2(ll, al[(long long)(Tb - 1) * Lw + L - 2]);
+        } else if (Sb == 0) {
+            ll = 0.f;
+        }
+        nll = -ll;
+    }
+    const float go = a.grad_out ? a.grad_out[b] : 1.f;
+    const bool dead = a.zero_infinity && nll == CUDART_INF_F;
+    const int Tl = dead ? 0 : Tb;        // rows that carry a gradient
+    const int Tw = group_max(Tl);
+
+    // rows without gradient
+    if (live)
+        for (int t = Tl; t < a.T; ++t)
+            for (int c = s; c < a.C; c += CTC_SMALL_G) gbase[(long long)t * a.gt_stride + c] = 0.f;
+
+    float beta = NEG;
+    for (int t = Tw - 1; t >= 0; --t) {
+        float b1 = __shfl_down_sync(0xffffffffu, beta, 1, CTC_SMALL_G);
+        float b2 = __shfl_down_sync(0xffffffffu, beta, 2, CTC_SMALL_G);
+        if (s + 1 >= L) b1 = NEG;
+        if (!skip) b2 = NEG;
+        const bool on = t < Tl;
+        const float* row = base + (long long)t * a.t_stride;
+        float ab = NEG;
+        if (on && vs) {
+            if (t == Tb - 1) beta = (s == L - 1 || s == L - 2) ? row[lab] : NEG;
+            else beta = lse3(beta, b1, b2) + row[lab];
+            ab = al[(long long)t * Lw + s] + beta;
+        }
+        // per class: log-sum-exp of alpha*beta over the states carrying that class (<= 7 states)
+        for (int c0 = 0; c0 < a.C; c0 += CTC_SMALL_G) {
+            const int c = c0 + s;
+            float m = NEG;
+#pragma unroll
+            for (int q = 0; q < CTC_SMALL_G; ++q) {
+                const float v = __shfl_sync(0xffffffffu, ab, q, CTC_SMALL_G);
+                const int l = __shfl_sync(0xffffffffu, lab, q, CTC_SMALL_G);
+                if (l == c && q < L) m = fmaxf(m, v);
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int q = 0; q < CTC_SMALL_G; ++q) {
+                const float v = __shfl_sync(0xffffffffu, ab, q, CTC_SMALL_G);
+                const int l = __shfl_sync(0xffffffffu, lab, q, CTC_SMALL_G);
+                if (l == c && q < L && m != NEG) sum += expf(v - m);
+            }
+            if (live && on && c < a.C) {
+                const float lpv = row[c];
+                const float tot = (m == NEG) ? NEG : logf(sum) + m;
+                gbase[(long long)t * a.gt_stride + c] = (expf(lpv) - expf(tot + nll - lpv)) * go;
+            }
+        }
+    }
+}
+
+// Wide-vocabulary backward, step 1: every (t, b) row gets exp(lp) * grad_out (or 0 past the input length / for
+// an infinite loss under zero_infinity) from a fully parallel, bandwidth-bound pass -- one warp per row, grid
+// stride.  ctc_loss_bwd_kernel (skip_fill = 1) then only patches the <= S+1 target classes of each row.
+__global__ void __launch_bounds__(256) ctc_grad_fill_kernel(const CtcLossArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long rows = (long long)a.T * a.B;
+    const int Lw = 2 * a.S + 1;
+    for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
+        const int t = (int)(r / a.B);
+        const long long b = r - (long long)t * a.B;
+        const int Tb = min(max(a.in_len[b], 0), a.T);
+        float scale = 0.f;
+        if (t < Tb) {
+            scale = a.grad_out ? a.grad_out[b] : 1.f;
+            if (a.zero_infinity) {
+                const int Sb = min(max(a.tgt_len[b], 0), a.S);
+                const int L = 2 * Sb + 1;
+                const float* al = a.alpha + (b * (long long)a.T + (Tb - 1)) * Lw;
+                float ll = al[L - 1];
+                if (L > 1) ll = lse2(ll, al[L - 2]);
+                if (ll == -CUDART_INF_F) scale = 0.f;
+            }
+        }
+        const float* row = a.lp + b * a.b_stride + (long long)t * a.t_stride;
+        float* grow = a.grad + b * a.gb_stride + (long long)t * a.gt_stride;
+        if (scale == 0.f) {
+            for (int c = lane; c < a.C; c += 32) grow[c] = 0.f;
+        } else {
+            for (int c = lane; c < a.C; c += 32) grow[c] = expf(row[c]) * scale;
+        }
     }
 }
 
