@@ -160,6 +160,12 @@ def cpu_reference_step(pcm_i16, sd):
 def time_cpu(clips, steps, warmup, seed=1234):
     import torch
 
+    # all the host threads the box offers (torchrun exports OMP_NUM_THREADS=1, which would cripple the baseline)
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
     sd = load_weights()
     pcm = synth_pcm(clips, "cpu", seed, chunk=4096)
     for _ in range(warmup):
@@ -219,7 +225,20 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # keep stdout to the single JSON line: NCCL's version banner goes to stderr
+        os.environ["NCCL_DEBUG"] = os.environ.get("WW_NCCL_DEBUG", "WARN")
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)  # creates the communicator (and prints whatever NCCL wants to print)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     sd = load_weights()
     cnn_impl = args.cnn
     scorer = ww_b200.WakeWordScorer(sd, device=local, cmvn="python", decision="python", cnn_impl=cnn_impl)
