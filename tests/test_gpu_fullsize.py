@@ -1,0 +1,101 @@
+"""GPU parity at BASELINE.json's FULL sizes through size-independent properties.
+
+The oracle cannot score 2^20 clips or a one-hour stream in seconds, so the full-size inputs are built
+periodically: the oracle pins one period, and batch-/position-invariance pins the rest (every clip of a batch
+and every window of a stream must score exactly as the same audio does at any other index)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cnn as ocnn
+from oracle import mfcc as om
+from oracle import stream as ostream
+
+pytestmark = pytest.mark.gpu
+
+
+def test_one_million_clips_periodic_batch(cuda_device, xiaoa_sd):
+    """configs[1]/[2] size: 2^20 one-second clips (33.5 GB int16 resident).  Period = 2048 distinct clips."""
+    import ww_b200
+
+    free, _ = torch.cuda.mem_get_info()
+    n = 1 << 20
+    if free < 60e9:
+        n = 1 << 17
+    period = 2048
+    base = om.synth_clips_int16(period, seed=1234)
+    pcm = torch.from_numpy(base).to(cuda_device).repeat(n // period, 1)
+    assert pcm.shape == (n, 16000)
+
+    # oracle on one period
+    feats_o = om.mfcc_torchaudio(om.pcm16_to_float(base)).numpy()
+    logit_o = ocnn.forward_torch(om.normalize_mfcc(feats_o, "cmvn").numpy(), xiaoa_sd)[:, 0]
+
+    # frontend alone over the full batch, chunked to bound the output (3.3 KB per clip)
+    step = 1 << 18
+    for c0 in range(0, n, step):
+        f = ww_b200.mfcc_batch(pcm[c0:c0 + step])
+        torch.cuda.synchronize()
+        assert torch.equal(f[:period], f[-period:])                       # position invariance
+        assert torch.equal(f.view(-1, period, 13, 63)[0], f.view(-1, period, 13, 63)[step // period // 2])
+        if c0 == 0:
+            assert np.abs(f[:period].cpu().numpy() - feats_o).max() < 1e-3   # the stated feature tolerance
+        del f
+
+    for impl in ("fp32", "tensor"):
+        sc = ww_b200.WakeWordScorer(xiaoa_sd, device=0, cnn_impl=impl)
+        logits, dec = sc.score(pcm)
+        torch.cuda.synchronize()
+        lg = logits[:, 0].view(-1, period)
+        dc = dec.view(-1, period)
+        # decisions identical for every repetition; logits identical within an implementation
+        assert bool((dc == dc[0:1]).all())
+        if impl == "fp32":
+            assert bool((lg == lg[0:1]).all())
+            assert np.abs(lg[0].cpu().numpy() - logit_o).max() < 2e-3
+            dec32 = dc[0].clone()
+        else:
+            assert (lg - lg[0:1]).abs().max().item() < 1e-2   # re-scored (fp32) vs tensor logits near the threshold
+            assert torch.equal(dc[0], dec32)                  # tensor path decisions == fp32 path decisions
+        clear = np.abs(logit_o) > 1e-3
+        assert (dc[0].cpu().numpy().astype(bool)[clear] == (logit_o > 0)[clear]).all()
+        del logits, dec
+
+
+def test_one_hour_stream_periodic(cuda_device, xiaoa_sd):
+    """configs[3] size: 3600 s stream (57.6 M samples, 225 001 frames, 224 939 windows).
+    The stream repeats a 10 s segment (= 625 hops exactly), so away from the two ends features and window
+    logits must repeat every 625 frames; the oracle pins the first 20 s."""
+    import ww_b200
+
+    seg = om.synth_clips_int16(10, seed=4321).reshape(-1)            # 160 000 samples
+    assert seg.size % 256 == 0
+    reps = 360
+    pcm = torch.from_numpy(np.tile(seg, reps)).to(cuda_device)
+    P = seg.size // 256
+    for cmvn in ("python", "device"):
+        sc = ww_b200.StreamScorer(xiaoa_sd, device=0, cmvn=cmvn, cnn_impl="tensor" if cmvn == "python" else "fp32")
+        feats, logits = sc.score(pcm)
+        torch.cuda.synchronize()
+        T = feats.shape[1]
+        assert T == 225001 and logits.shape[0] == 224939
+        # interior periodicity (frame 0 and the last frame see reflect padding; frame 1.. sees a different
+        # previous sample only at the very first sample of the stream)
+        a = feats[:, 2:2 + 300 * P]
+        b = feats[:, 2 + P:2 + 301 * P]
+        assert torch.equal(a, b)
+        la, lb = logits[2:2 + 300 * P], logits[2 + P:2 + 301 * P]
+        if cmvn == "device":
+            assert torch.equal(la, lb)
+        else:
+            assert (la - lb).abs().max().item() < 1e-2
+        # oracle on the first 20 s
+        n20 = 2 * seg.size
+        f_o, l_o = ostream.window_logits(om.pcm16_to_float(np.tile(seg, 3)[: n20 + 4096]), xiaoa_sd, cmvn=cmvn)
+        k = n20 // 256 - 70
+        assert np.abs(feats[:, :k].cpu().numpy() - f_o[:, :k]).max() < 1e-3
+        d = np.abs(logits[: k - 62].cpu().numpy() - l_o[: k - 62])
+        if cmvn == "python":
+            assert d.max() < 1e-2
+        else:
+            assert np.mean(d > 2e-3) < 0.03
