@@ -38,6 +38,9 @@ METRIC = "clips/sec (1 s 16 kHz) MFCC+CNN+CTC"
 UNIT = "clips/s"
 FRONTEND_BYTES_PER_CLIP = 16000 * 2 + 13 * 63 * 4  # 35 276
 FUSED_BYTES_PER_CLIP = 16000 * 2 + 5
+# dram__bytes_read.sum + dram__bytes_write.sum of mfcc_kernel<int16, PY> per clip, from the `ncu --set full` capture
+# profiles/r1_ncu_mfcc_kernel.txt (2.0978 GB + 212.2 MB over a 65 536-clip launch): traffic == algorithmic bytes
+FRONTEND_DRAM_BYTES_PER_CLIP_NCU = (2.097769e9 + 212.167168e6) / 65536
 UTT = 63  # windows per CTC utterance
 
 
@@ -322,7 +325,9 @@ def run_ours(args):
         ach = rb * FRONTEND_BYTES_PER_CLIP / (fms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "mfcc_kernel<int16, PY> (frontend alone, 1 persistent launch over %d clips)" % rb,
                 "achieved": ach, "peak": peak, "peak_source": how, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "ms_per_launch": fms, "clips_per_s": rb / (fms * 1e-3),
+                "traffic": FRONTEND_DRAM_BYTES_PER_CLIP_NCU * rb, "traffic_source": "profiles/r1_ncu_mfcc_kernel.txt "
+                "(ncu --set full, per-clip DRAM bytes x clips of this launch)", "algorithmic_bytes": rb * FRONTEND_BYTES_PER_CLIP,
+                "ms_per_launch": fms, "clips_per_s": rb / (fms * 1e-3),
                 "algorithmic_bytes_per_clip": FRONTEND_BYTES_PER_CLIP}
         del feats
 
