@@ -9,6 +9,7 @@
 
 #include "../../include/ww_b200.h"
 #include "ww_cnn.cuh"
+#include "ww_cnn_i8.cuh"
 #include "ww_ctc.cuh"
 #include "ww_mfcc.cuh"
 #include "ww_tables.h"
@@ -46,6 +47,10 @@ struct ww_ctx {
     float tc_band = 0.03f;          // |logit - threshold| below which the fp32 kernel decides
     float* tc_dbg = nullptr;
 #endif
+    std::vector<float> host_w[5];      // fp32 weights as loaded (for the int8 twin's quantisation)
+    signed char* i8blob = nullptr;
+    I8Weights i8w{};
+    bool have_i8 = false;
     // fused-path scratch
     float* scratch = nullptr;          // [chunk][13][63]
     long long scratch_clips = 0;
@@ -286,6 +291,7 @@ extern "C" void ww_destroy(ww_ctx* ctx) {
     cudaSetDevice(ctx->device);
     for (int m = 0; m < 2; ++m) cudaFree(ctx->feat[m].tables);
     cudaFree(ctx->wblob);
+    cudaFree(ctx->i8blob);
     cudaFree(ctx->scratch);
     for (int i = 0; i < 2; ++i) {
         if (ctx->hs[i]) cudaStreamDestroy(ctx->hs[i]);
@@ -336,6 +342,12 @@ extern "C" int ww_load_weights(ww_ctx* ctx, const float* conv1, const float* con
     ctx->w.fc1 = ctx->wblob + n1 + n2 + n3;
     ctx->w.fc2 = ctx->wblob + n1 + n2 + n3 + n4;
     ctx->w.num_classes = num_classes;
+    ctx->host_w[0].assign(conv1, conv1 + n1);
+    ctx->host_w[1].assign(conv2, conv2 + n2);
+    ctx->host_w[2].assign(conv3, conv3 + n3);
+    ctx->host_w[3].assign(fc1, fc1 + n4);
+    ctx->host_w[4].assign(fc2, fc2 + n5);
+    ctx->have_i8 = false;
 #ifdef WW_WITH_TC
     {
         std::vector<unsigned char> blob;
@@ -558,6 +570,74 @@ extern "C" int ww_cnn_forward(ww_ctx* ctx, const float* feats, long long win_str
     if (rc) return rc;
     return run_cnn(ctx, feats, win_stride, coef_stride, frame_stride, n_windows, cmvn_mode, decide_mode, threshold,
                    cnn_impl, logits, decisions, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// int8 power-of-two twin
+// ------------------------------------------------------------------------------------------------
+extern "C" int ww_quantize_weights_i8(ww_ctx* ctx, const int* exps) {
+    if (!ctx) return WW_ERR_INVALID;
+    if (!ctx->have_weights) return fail(ctx, WW_ERR_NO_WEIGHTS, "weights not loaded (ww_load_weights)");
+    if (!exps) return fail(ctx, WW_ERR_INVALID, "quantize_weights_i8: null exponents");
+    // exps: input, w1, a1, w2, a2, w3, a3, gap, wf1, f1, wf2, out  (ml_models/xiaoa.info:3139-3150)
+    const int C = ctx->w.num_classes;
+    const int n1 = 13 * 3 * 32, n2 = 32 * 3 * 64, n3 = 64 * 3 * 128, n4 = 64 * 128, n5 = C * 64;
+    std::vector<signed char> h((size_t)n1 + n2 + n3 + n4 + n5);
+    auto q = [](float w, int e) {
+        const double v = nearbyint((double)w / ldexp(1.0, e));  // round half to even
+        return (signed char)(v > 127 ? 127 : (v < -128 ? -128 : v));
+    };
+    auto trq = [&](const std::vector<float>& src, signed char* dst, int O, int I, int e) {
+        for (int o = 0; o < O; ++o)
+            for (int i = 0; i < I; ++i)
+                for (int r = 0; r < 3; ++r) dst[(i * 3 + r) * O + o] = q(src[(o * I + i) * 3 + r], e);
+    };
+    signed char* p = h.data();
+    trq(ctx->host_w[0], p, 32, 13, exps[1]);
+    trq(ctx->host_w[1], p + n1, 64, 32, exps[3]);
+    trq(ctx->host_w[2], p + n1 + n2, 128, 64, exps[5]);
+    for (int i = 0; i < n4; ++i) p[n1 + n2 + n3 + i] = q(ctx->host_w[3][i], exps[8]);
+    for (int i = 0; i < n5; ++i) p[n1 + n2 + n3 + n4 + i] = q(ctx->host_w[4][i], exps[10]);
+    CK(cudaSetDevice(ctx->device));
+    cudaFree(ctx->i8blob);
+    ctx->i8blob = nullptr;
+    CK(cudaMalloc(&ctx->i8blob, h.size()));
+    CK(cudaMemcpy(ctx->i8blob, h.data(), h.size(), cudaMemcpyHostToDevice));
+    I8Weights& w = ctx->i8w;
+    w.w1t = ctx->i8blob;
+    w.w2t = ctx->i8blob + n1;
+    w.w3t = ctx->i8blob + n1 + n2;
+    w.fc1 = ctx->i8blob + n1 + n2 + n3;
+    w.fc2 = ctx->i8blob + n1 + n2 + n3 + n4;
+    w.num_classes = C;
+    w.sh1 = exps[2] - (exps[0] + exps[1]);
+    w.sh2 = exps[4] - (exps[2] + exps[3]);
+    w.sh3 = exps[6] - (exps[4] + exps[5]);
+    w.gap_num_shift = exps[6] - exps[7];
+    w.shf1 = exps[9] - (exps[7] + exps[8]);
+    w.shf2 = exps[11] - (exps[9] + exps[10]);
+    if (w.sh1 < 0 || w.sh2 < 0 || w.sh3 < 0 || w.shf1 < 0 || w.shf2 < 0 || w.sh1 > 30 || w.sh2 > 30 || w.sh3 > 30 ||
+        w.shf1 > 30 || w.shf2 > 30 || w.gap_num_shift < -8 || w.gap_num_shift > 8)
+        return fail(ctx, WW_ERR_UNSUPPORTED, "quantize_weights_i8: unsupported exponent combination");
+    ctx->have_i8 = true;
+    return WW_OK;
+}
+
+extern "C" int ww_cnn_forward_i8(ww_ctx* ctx, const int8_t* x, long long n_windows, int8_t* out, ww_stream_t stream) {
+    if (!ctx) return WW_ERR_INVALID;
+    if (!ctx->have_i8) return fail(ctx, WW_ERR_NO_WEIGHTS, "int8 weights not prepared (ww_quantize_weights_i8)");
+    if (n_windows == 0) return WW_OK;
+    if (!x || !out || n_windows < 0) return fail(ctx, WW_ERR_INVALID, "cnn_forward_i8: bad arguments");
+    I8Args a;
+    a.x = reinterpret_cast<const signed char*>(x);
+    a.n_windows = n_windows;
+    a.out = reinterpret_cast<signed char*>(out);
+    a.w = ctx->i8w;
+    long long grid = (long long)ctx->sm_count * 8;
+    if (grid > n_windows) grid = n_windows;
+    cnn_i8_kernel<<<(unsigned)grid, CNN_THREADS, 0, (cudaStream_t)stream>>>(a);
+    CK(cudaGetLastError());
+    return WW_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -24,7 +24,7 @@ CNN_FP32, CNN_TENSOR = 0, 1
 
 EXPORTS = [
     "ww_version", "ww_create", "ww_destroy", "ww_last_error", "ww_load_weights", "ww_num_frames",
-    "ww_mfcc_batch", "ww_cmvn", "ww_cnn_forward", "ww_score_clips", "ww_score_clips_host",
+    "ww_mfcc_batch", "ww_cmvn", "ww_cnn_forward", "ww_quantize_weights_i8", "ww_cnn_forward_i8", "ww_score_clips", "ww_score_clips_host",
     "ww_stream_score", "ww_stream_events", "ww_ctc_greedy", "ww_ctc_loss_workspace_bytes",
     "ww_ctc_loss_fwd", "ww_ctc_loss_bwd", "ww_debug_tc", "ww_extract_mfcc", "ww_free_mfcc",
 ]
@@ -61,6 +61,8 @@ def load_library():
         lib.ww_mfcc_batch.argtypes = [vp, vp, i32, i64, i32, i64, i32, i32, vp, vp]
         lib.ww_cmvn.argtypes = [vp, vp, i64, i32, vp, vp]
         lib.ww_cnn_forward.argtypes = [vp, vp, i64, i64, i64, i64, i32, i32, f32, i32, vp, vp, vp]
+        lib.ww_quantize_weights_i8.argtypes = [vp, vp]
+        lib.ww_cnn_forward_i8.argtypes = [vp, vp, i64, vp, vp]
         lib.ww_score_clips.argtypes = [vp, vp, i32, i64, i32, i32, f32, i32, vp, vp, vp]
         lib.ww_score_clips_host.argtypes = [vp, vp, i32, i64, i32, i32, f32, i32, vp, vp]
         lib.ww_stream_score.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, vp]

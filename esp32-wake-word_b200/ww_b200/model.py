@@ -88,6 +88,33 @@ class LightweightKWS(nn.Module):
         return out
 
 
+# per-tensor exponents of the shipped export: ml_models/xiaoa.info:3139-3150
+XIAOA_EXPONENTS = (-4, -8, -5, -9, -5, -9, -4, -5, -9, -4, -9, -3)
+
+
+def forward_int8(state_dict, x_q, exponents=XIAOA_EXPONENTS, device=None):
+    """int8 power-of-two twin of the model (what esp-dl runs on the device).
+
+    x_q: int8 [B, 13, 63] at the input exponent (-4) -> int8 [B, C] at the output exponent (-3); integer exact.
+    """
+    if not x_q.is_cuda:
+        if not torch.cuda.is_available():
+            raise L.WWError("CUDA is not available; ww_b200 has no CPU fallback")
+        x_q = x_q.cuda()
+    if x_q.dtype != torch.int8 or x_q.dim() != 3 or x_q.shape[1] != 13 or x_q.shape[2] != 63:
+        raise ValueError("forward_int8 expects int8 [B, 13, 63]")
+    x_q = x_q.contiguous()
+    ctx = L.get_context(x_q.device.index if device is None else device)
+    key = ("int8", next(_tokens))
+    _push_weights(ctx, state_dict, key)
+    exps = (C.c_int * 12)(*[int(e) for e in exponents])
+    ctx.check(ctx.lib.ww_quantize_weights_i8(ctx.h, exps), "ww_quantize_weights_i8")
+    out = torch.empty((x_q.shape[0], ctx.num_classes), dtype=torch.int8, device=x_q.device)
+    ctx.check(ctx.lib.ww_cnn_forward_i8(ctx.h, L.ptr(x_q), x_q.shape[0], L.ptr(out), L.cur_stream(x_q.device)),
+              "ww_cnn_forward_i8")
+    return out
+
+
 class WakeWordScorer:
     """PCM -> logits / decisions: the fused engine call (MFCC + CMVN + CNN + decision).
 

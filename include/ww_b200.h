@@ -95,6 +95,16 @@ int ww_cnn_forward(ww_ctx* ctx, const float* feats, long long win_stride, long l
                    long long frame_stride, long long n_windows, int cmvn_mode, int decide_mode,
                    float threshold, int cnn_impl, float* logits, uint8_t* decisions, ww_stream_t stream);
 
+/* ---- int8 power-of-two twin of the model (esp-dl export) ---------- */
+/* Quantise the loaded fp32 weights to symmetric per-tensor power-of-two int8 (ml_models/xiaoa.json:5-20).
+ * exps[12] = exponents of {input, w1, act1, w2, act2, w3, act3, gap, w_fc1, act_fc1, w_fc2, output}
+ * (ml_models/xiaoa.info:3139-3150: -4,-8,-5,-9,-5,-9,-4,-5,-9,-4,-9,-3). */
+int ww_quantize_weights_i8(ww_ctx* ctx, const int* exps);
+/* x: device int8 [n][13][63] at the input exponent (what detect_task hands to the model,
+ * esp_wake_word_detector.cpp:200-220); out: device int8 [n][num_classes] at the output exponent.
+ * Integer-exact: reproduces the shipped known-answer vector ml_models/xiaoa.info:3153-3224 (-40). */
+int ww_cnn_forward_i8(ww_ctx* ctx, const int8_t* x, long long n_windows, int8_t* out, ww_stream_t stream);
+
 /* ---- fused clip scoring: PCM -> MFCC -> CMVN -> CNN -> decision -------------------------------- */
 /* pcm: device [n_clips][16000].  The feature intermediate stays in an L2-sized context scratch. */
 int ww_score_clips(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_clips, int cmvn_mode,

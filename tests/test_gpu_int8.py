@@ -1,0 +1,45 @@
+"""GPU: the int8 power-of-two twin (esp-dl export) is integer-exact against the shipped known-answer vector."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cnn as ocnn
+from oracle import mfcc as om
+
+pytestmark = pytest.mark.gpu
+
+
+def test_shipped_known_answer_vector(cuda_device, golden_dir, xiaoa_sd):
+    """ml_models/xiaoa.info:3153-3224: int8 input [1,63,13] at exponent -4 -> -40 at exponent -3 (= -5.0)."""
+    import ww_b200
+
+    k = np.load(os.path.join(golden_dir, "kat_xiaoa_info.npz"))
+    x = torch.from_numpy(np.ascontiguousarray(k["input_q"].T[None])).to(cuda_device)   # [1, 13, 63]
+    out = ww_b200.forward_int8(xiaoa_sd, x)
+    assert out.cpu().numpy().tolist() == [[-40]]
+    assert int(k["output_q"][0]) == -40
+
+
+def test_random_inputs_match_oracle_twin_exactly(cuda_device, xiaoa_sd):
+    import ww_b200
+
+    rng = np.random.default_rng(0)
+    x = rng.integers(-128, 128, size=(512, 13, 63)).astype(np.int8)
+    x[:64] = np.clip(rng.normal(0, 16, size=(64, 13, 63)).round(), -128, 127).astype(np.int8)  # realistic CMVN range
+    want = ocnn.forward_int8(x, xiaoa_sd)
+    got = ww_b200.forward_int8(xiaoa_sd, torch.from_numpy(x).to(cuda_device)).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+
+
+def test_device_pipeline_on_firmware_dumps(cuda_device, golden_dir, xiaoa_sd):
+    """int8 MFCC dumps (hello_world_main.cpp:50-132) -> device CMVN -> exponent -4 -> int8 model."""
+    import ww_b200
+
+    d = np.load(os.path.join(golden_dir, "device_dumps.npz"))
+    z, q = om.cmvn_device(d["mfcc_i8"].astype(np.float32))
+    xq = np.clip(q.astype(np.int32) * 16, -128, 127).astype(np.int8)   # exponent 0 -> exponent -4 with saturation
+    want = ocnn.forward_int8(xq, xiaoa_sd)
+    got = ww_b200.forward_int8(xiaoa_sd, torch.from_numpy(xq).to(cuda_device)).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
