@@ -42,6 +42,7 @@ FUSED_BYTES_PER_CLIP = 16000 * 2 + 5
 # profiles/r1_ncu_mfcc_kernel.txt (2.0978 GB + 212.2 MB over a 65 536-clip launch): traffic == algorithmic bytes
 FRONTEND_DRAM_BYTES_PER_CLIP_NCU = (2.097769e9 + 212.167168e6) / 65536
 UTT = 63  # windows per CTC utterance
+CPU_BATCH = 200
 
 
 def load_weights():
@@ -145,10 +146,15 @@ def cpu_reference_step(pcm_i16, sd):
     from oracle import ctc as octc
     from oracle import mfcc as omfcc
 
-    x = pcm_i16.to(torch.float32) / 32768.0                     # torchaudio.load normalisation
-    feats = omfcc.mfcc_torchaudio(x)                            # preemphasis + T.MFCC
-    z = omfcc.normalize_mfcc(feats, "cmvn")
-    logits = ocnn.forward_torch(z.numpy(), sd)[:, 0]
+    # batches of 200 clips: the reference script's own batch size (ml_models/main.py:141) and the CPU's sweet spot
+    # (profiles/r1_cpu_baseline_stages.jsonl: 22 k clips/s at B=200 vs 17 k at B=16384 on 16 threads)
+    parts = []
+    for c0 in range(0, pcm_i16.shape[0], CPU_BATCH):
+        x = pcm_i16[c0:c0 + CPU_BATCH].to(torch.float32) / 32768.0  # torchaudio.load normalisation
+        feats = omfcc.mfcc_torchaudio(x)                            # preemphasis + T.MFCC
+        z = omfcc.normalize_mfcc(feats, "cmvn")
+        parts.append(ocnn.forward_torch(z.numpy(), sd)[:, 0])
+    logits = np.concatenate(parts)
     dec = ocnn.decide_python(logits)
     n_utt = len(logits) // UTT
     hits = 0

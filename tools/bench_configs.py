@@ -86,10 +86,76 @@ def ctc_bench(dev, T, B, C, S, seed=777):
             "algorithmic_GBps": bytes_alg / d_ours / 1e9}
 
 
+def batch_sweep(dev, sd):
+    """configs[2]: per-GPU batch-size sweep of the fused scorer (tensor CNN) and the frontend alone."""
+    out = []
+    big = bench.synth_pcm(1 << 20, dev, 1234)
+    sc = ww_b200.WakeWordScorer(sd, device=0, cnn_impl="tensor")
+    for lg in range(10, 21, 2):
+        B = 1 << lg
+        x = big[:B]
+        dt = timed(lambda: sc.score(x), reps=5 if lg >= 16 else 20)
+        df = timed(lambda: ww_b200.mfcc_batch(x) if lg <= 18 else None, reps=5 if lg >= 16 else 20) if lg <= 18 else None
+        out.append({"config": "configs[2] batch sweep, fused MFCC+CMVN+CNN(tcgen05)+decision", "clips": B,
+                    "ms": dt * 1e3, "clips_per_s": B / dt,
+                    "frontend_alone_clips_per_s": (B / df) if df else None})
+    # configs[1], fp32-input variant: 2^19 clips = 33.5 GB of float PCM
+    xf = big[: 1 << 19].to(torch.float32) / 32768.0
+    df = timed(lambda: ww_b200.mfcc_batch(xf), reps=3)
+    out.append({"config": "configs[1] frontend alone, fp32 PCM input", "clips": 1 << 19, "clips_per_s": (1 << 19) / df,
+                "algorithmic_GBps": (1 << 19) * 67276 / df / 1e9})
+    del xf, big
+    return out
+
+
+def cpu_stages(sd):
+    """configs[0]: the reference's CPU path per stage (oracle port), B in {1, 200, 4096, 16384}, all threads and 1."""
+    from oracle import cnn as ocnn
+    from oracle import mfcc as omfcc
+
+    out = []
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except Exception:
+        ncpu = os.cpu_count()
+    for threads in (ncpu, 1):
+        torch.set_num_threads(threads)
+        for B in (1, 200, 4096, 16384):
+            if threads == 1 and B > 4096:
+                continue
+            pcm = bench.synth_pcm(B, "cpu", 1234, chunk=4096)
+            x = pcm.to(torch.float32) / 32768.0
+
+            def best(fn, n=5):
+                fn(); fn()
+                ts = []
+                for _ in range(n):
+                    t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+                return min(ts), float(np.median(ts))
+
+            feats = omfcc.mfcc_torchaudio(x)
+            z = omfcc.normalize_mfcc(feats, "cmvn")
+            zn = z.numpy()
+            t_m = best(lambda: omfcc.mfcc_torchaudio(x))
+            t_c = best(lambda: ocnn.forward_torch(omfcc.normalize_mfcc(feats, "cmvn").numpy(), sd))
+            t_e = best(lambda: bench.cpu_reference_step(pcm, sd))
+            out.append({"config": "configs[0] reference CPU path (oracle port), per stage", "threads": threads,
+                        "cpus": ncpu, "clips": B, "mfcc_clips_per_s_best": B / t_m[0], "mfcc_clips_per_s_median": B / t_m[1],
+                        "cmvn_cnn_clips_per_s_best": B / t_c[0], "end_to_end_clips_per_s_best": B / t_e[0],
+                        "end_to_end_clips_per_s_median": B / t_e[1]})
+            del zn
+    return out
+
+
 def main():
     dev = torch.device("cuda", 0)
     sd = bench.load_weights()
     res = []
+    if "--cpu" in sys.argv:
+        for r in cpu_stages(sd):
+            print(json.dumps(r), flush=True)
+        return
+    res += batch_sweep(dev, sd)
     res += stream_bench(dev, sd)
     res.append(ctc_bench(dev, 63, 1 << 18, 3, 2))
     res.append(ctc_bench(dev, 63, 1 << 18, 3, 1))
