@@ -169,7 +169,7 @@ struct MfccSmem {
     static constexpr int PCM_BUFS = (sizeof(TIN) == 2 && PYMEL) ? 2 : 1;
     static constexpr int TAB_BYTES = PYMEL ? TB_BYTES_PY : TB_BYTES;
     static constexpr int OFF_BAR = 0;
-    static constexpr int OFF_TAB = 16;
+    static constexpr int OFF_TAB = 32;
     static constexpr int OFF_PCM = OFF_TAB + TAB_BYTES;
     static constexpr int OFF_EXCH = OFF_PCM + PCM_BUFS * PCM_BYTES;
     static constexpr int OFF_P = OFF_EXCH + MFCC_WARPS * 2 * EXCH_FRAME_BYTES;
@@ -259,6 +259,8 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
+        mbar_init(&bars[2], MFCC_WARPS);  // every warp has finished its mel stage (P free, LM complete)
+        mbar_init(&bars[3], MFCC_WARPS);  // every warp has written its share of the edge taps
         mbar_fence_init();
     }
     // tables -> smem (once per persistent CTA)
@@ -279,49 +281,106 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
 
     unsigned char* exch = smem + SM::OFF_EXCH + (warp * 2 + half) * EXCH_FRAME_BYTES;
 
+    // Per-CTA software pipeline over this CTA's blocks (one CTA-wide barrier per block):
+    //   iteration k:  mel(k-1) | stage PCM(k) + edge taps | FFT(k) first pass | DCT(k-1) | FFT(k) second pass | barrier
+    // mel(k-1) and DCT(k-1) run between the FFT passes without waiting: P(k-1) was completed by the barrier of
+    // iteration k-1, and the only cross-warp conditions -- "every warp is done reading P(k-1)" before P(k) is
+    // written, "every warp has written its log-mel rows" before the DCT, "edge taps are in place" -- are mbarriers
+    // that are normally already complete when they are tested.
+    //   bars[0..1] PCM buffers (TMA), bars[2] mel done (8 warps), bars[3] edge taps done (8 warps)
     long long iter = 0;
+    bool prev_valid = false;
+    long long prev_sig = 0;
+    int prev_t0 = 0;
+    uint32_t mel_uses = 0, edge_uses = 0;
 #pragma unroll 1
-    for (long long blk_id = first; blk_id < a.n_blocks; blk_id += stride, ++iter) {
-        const long long sig = blk_id / a.blocks_per_sig;
-        const int t0 = (int)(blk_id - sig * a.blocks_per_sig) * FRAMES;
-        const int org0 = WW_HOP * t0 + origin_off + 88;  // 8 samples ahead of the first window tap (multiple of 8)
-        const int org1 = org0 + 16 * WW_HOP;
-        const int buf = NBUF == 2 ? (int)(iter & 1) : 0;
-        unsigned char* pcm_buf = smem + SM::OFF_PCM + buf * SM::PCM_BYTES;
-        if (use_bulk) {
-            if (NBUF == 2) {
-                // the other buffer was last read in the FFT phase of the previous block (two barriers ago)
-                if (tid == 0 && blk_id + stride < a.n_blocks) stage_block(blk_id + stride, buf ^ 1);
-                mbar_wait(&bars[buf], (uint32_t)((iter >> 1) & 1));
-            } else {
-                if (iter > 0) {
-                    __syncthreads();  // single buffer: everyone is done with the previous block's samples
-                    if (tid == 0) stage_block(blk_id, 0);
+    for (long long blk_id = first;; blk_id += stride, ++iter) {
+        const bool have = blk_id < a.n_blocks;
+        if (!have && !prev_valid) break;
+        bool mel_pending = false;
+
+        // ---- mel + log of the previous block -> LM
+        if (prev_valid) {
+            // mel + log: lane <-> frame, warp <-> filter range
+            {
+                const float pscale = a.pscale, log_offset = a.log_offset;
+                const float* prow = pw + lane * P_STRIDE;
+                float* lrow = lm + lane * LM_STRIDE;
+                if constexpr (PYMEL) {
+                    switch (warp) {
+                        case 0: mel_py_group<0>(prow, lrow, pscale, log_offset); break;
+                        case 1: mel_py_group<1>(prow, lrow, pscale, log_offset); break;
+                        case 2: mel_py_group<2>(prow, lrow, pscale, log_offset); break;
+                        case 3: mel_py_group<3>(prow, lrow, pscale, log_offset); break;
+                        case 4: mel_py_group<4>(prow, lrow, pscale, log_offset); break;
+                        case 5: mel_py_group<5>(prow, lrow, pscale, log_offset); break;
+                        case 6: mel_py_group<6>(prow, lrow, pscale, log_offset); break;
+                        default: mel_py_group<7>(prow, lrow, pscale, log_offset); break;
+                    }
+                } else {
+                    // table-driven filterbank (weights broadcast from smem): any contiguous-support filter set
+                    const float* s_melw = reinterpret_cast<const float*>(tab + TB_MELW_OFF);
+                    const int4* s_melm = reinterpret_cast<const int4*>(tab + TB_MELM_OFF);
+                    const float log_floor = a.log_floor;
+                    for (int j = warp; j < WW_N_MELS; j += MFCC_WARPS) {
+                        const int4 m = s_melm[j];
+                        const float* pp = prow + m.x;
+                        const float* ww_ = s_melw + m.z;
+                        float acc = 0.f;
+                        for (int i = 0; i < m.y; ++i) acc = fmaf(pp[i], ww_[i], acc);
+                        const float e = fmaf(acc, pscale, __int_as_float(m.w));
+                        lrow[j] = __logf(fmaxf(e, log_floor) + log_offset);
+                    }
                 }
-                mbar_wait(&bars[0], (uint32_t)(iter & 1));
             }
-        } else {
-            // unaligned / odd-length signals: cooperative copy instead of TMA
-            if (iter > 0) __syncthreads();
-            const TIN* gsig = reinterpret_cast<const TIN*>(a.pcm) + sig * a.sig_stride;
-            for (int h = 0; h < 2; ++h) {
-                const int org = h ? org1 : org0;
-                const int lo_h = org < 0 ? 0 : org;
-                int hi_h = org + SM::HALF_SAMPLES;
-                hi_h = hi_h > L ? L : hi_h;
-                TIN* dst = reinterpret_cast<TIN*>(pcm_buf + h * SM::HALF_STRIDE) + (lo_h - org);
-                for (int i = tid; i < hi_h - lo_h; i += MFCC_THREADS) dst[i] = gsig[lo_h + i];
-            }
-            __syncthreads();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[2]);
+            mel_pending = true;
         }
 
-        // Edge frames (t = 0: reflected / no previous sample; the last frame: reflected tail) cannot use the
-        // packed fast path.  Their 320 pre-emphasised taps are materialised once, cooperatively, so that no warp
-        // of the block is slower than the others (a slow warp stalls the whole CTA at the phase barrier).
-        {
+        long long sig = 0;
+        int t0 = 0, org0 = 0, org1 = 0;
+        unsigned char* pcm_buf = smem + SM::OFF_PCM;
+        bool block_has_edge = false;
+        int it_first = 0;
+        if (have) {
+            sig = blk_id / a.blocks_per_sig;
+            t0 = (int)(blk_id - sig * a.blocks_per_sig) * FRAMES;
+            org0 = WW_HOP * t0 + origin_off + 88;  // 8 samples ahead of the first window tap (multiple of 8)
+            org1 = org0 + 16 * WW_HOP;
+            const int buf = NBUF == 2 ? (int)(iter & 1) : 0;
+            pcm_buf = smem + SM::OFF_PCM + buf * SM::PCM_BYTES;
+            if (use_bulk) {
+                if (NBUF == 2) {
+                    // the other buffer was last read in the FFT passes of the previous block (before its barrier)
+                    if (tid == 0 && blk_id + stride < a.n_blocks) stage_block(blk_id + stride, buf ^ 1);
+                    mbar_wait(&bars[buf], (uint32_t)((iter >> 1) & 1));
+                } else {
+                    if (iter > 0 && tid == 0) stage_block(blk_id, 0);
+                    mbar_wait(&bars[0], (uint32_t)(iter & 1));
+                }
+            } else {
+                // unaligned / odd-length signals: cooperative copy instead of TMA
+                const TIN* gsig = reinterpret_cast<const TIN*>(a.pcm) + sig * a.sig_stride;
+                for (int h = 0; h < 2; ++h) {
+                    const int org = h ? org1 : org0;
+                    const int lo_h = org < 0 ? 0 : org;
+                    int hi_h = org + SM::HALF_SAMPLES;
+                    hi_h = hi_h > L ? L : hi_h;
+                    TIN* dst = reinterpret_cast<TIN*>(pcm_buf + h * SM::HALF_STRIDE) + (lo_h - org);
+                    for (int i = tid; i < hi_h - lo_h; i += MFCC_THREADS) dst[i] = gsig[lo_h + i];
+                }
+                __syncthreads();
+            }
+
+            // Edge frames (t = 0: reflected / no previous sample; the last frame: reflected tail) cannot use the
+            // packed fast path.  Their 320 pre-emphasised taps are materialised once, cooperatively, so that no
+            // warp of the block is slower than the others; the frames that need them are scheduled in the second
+            // FFT pass, by when the fill (signalled through bars[3]) has long completed.
             const bool has0 = (t0 == 0) && (origin_off + 95 < 0);
             const bool has1 = (t_tail >= t0) && (t_tail < t0 + FRAMES) && (t_tail < n_frames) && (t_tail > 0 || !has0);
-            if (has0 || has1) {
+            block_has_edge = has0 || has1;
+            if (block_has_edge) {
                 const int reflect = a.reflect;
                 const float pre = a.preemph;
                 for (int i = tid; i < 2 * WW_WIN; i += MFCC_THREADS) {
@@ -334,15 +393,48 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
                         edge[i] = emph_sample<TIN>(sp, hh ? org1 : org0, s, L, reflect, pre);
                     }
                 }
-                __syncthreads();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[3]);
+                const int it_edge = has0 ? 0 : (((t_tail - t0) & 15) >> 3);
+                it_first = it_edge ^ 1;
             }
         }
 
         constexpr int ITERS = FRAMES / (2 * MFCC_WARPS);
-        static_assert(ITERS * 2 * MFCC_WARPS == FRAMES, "FRAMES must be a multiple of 16");
-
-    #pragma unroll 1
-        for (int it = 0; it < ITERS; ++it) {
+        static_assert(ITERS == 2, "the pipeline interleaves the DCT between exactly two FFT passes");
+#pragma unroll 1
+        for (int trip = 0; trip < ITERS; ++trip) {
+            if (trip == 1 && prev_valid) {
+                if (mel_pending) {  // no FFT pass waited for it (drain iteration)
+                    mbar_wait(&bars[2], mel_uses & 1);
+                    mel_pending = false;
+                }
+                // DCT: lane <-> frame, warp <-> coefficient pair {warp, warp + 8}; stores coalesced along time
+                {
+                    const int t = prev_t0 + lane;
+                    if (t < n_frames) {
+                        float* outp = a.out + prev_sig * a.out_sig_stride + (long long)t * a.out_frame_stride;
+                        const float* lrow = lm + lane * LM_STRIDE;
+                        if constexpr (PYMEL) {
+                            const long long cs = a.out_coef_stride;
+                            switch (warp) {
+                                case 0: dct_py_group<0>(lrow, outp, cs); break;
+                                case 1: dct_py_group<1>(lrow, outp, cs); break;
+                                case 2: dct_py_group<2>(lrow, outp, cs); break;
+                                case 3: dct_py_group<3>(lrow, outp, cs); break;
+                                case 4: dct_py_group<4>(lrow, outp, cs); break;
+                                case 5: dct_py_group<5>(lrow, outp, cs); break;
+                                case 6: dct_py_group<6>(lrow, outp, cs); break;
+                                default: dct_py_group<7>(lrow, outp, cs); break;
+                            }
+                        } else {
+                            DctDispatch<MFCC_WARPS, 0>::run(warp, a, lrow, outp);
+                        }
+                    }
+                }
+            }
+            if (!have) continue;
+            const int it = trip ^ it_first;
             // the two half-warps take frames 16 apart: their power-spectrum rows are 16 banks apart
             const int fl = 16 * half + MFCC_WARPS * it + warp;  // frame index inside the block
             const int t = t0 + fl;
@@ -354,6 +446,7 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
             float2 v[16];
     #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = make_float2(0.f, 0.f);
+            if (block_has_edge && __any_sync(0xffffffffu, valid && !interior)) mbar_wait(&bars[3], edge_uses & 1);
 
             // this half-warp's staging half: frames 16*half.. live in half `half` (fl = 16*half + ...)
             const TIN* spcm = reinterpret_cast<const TIN*>(pcm_buf + half * SM::HALF_STRIDE);
@@ -414,6 +507,11 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
             __syncwarp();
             // pass 2: DFT16 over n2 -> Z[l16 + 16*k2] = v[k2]
             fft16<false>(v);
+            // P still holds the previous block until every warp has finished its mel stage
+            if (mel_pending) {
+                mbar_wait(&bars[2], mel_uses & 1);
+                mel_pending = false;
+            }
             // real-FFT split: pair (k, 256-k), k = l16 + 16*i -> 4*|X[k]|^2 and 4*|X[256-k]|^2.  Z[256-k] lives in lane
             // 16-l16, register 15-i (lane 0 pairs with itself: register 16-i, and Z[256] = Z[0])
             const int partner = (16 - l16) & 15;
@@ -436,65 +534,13 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
             if (l16 == 0) ps[128] = 4.f * fmaf(v[8].x, v[8].x, v[8].y * v[8].y);
             __syncwarp();
         }
+        if (prev_valid) ++mel_uses;
+        if (block_has_edge) ++edge_uses;
+        // one CTA barrier per block: P(k) is complete; LM(k-1), the edge taps and PCM(k) are free again
         __syncthreads();
-
-        // mel + log: lane <-> frame, warp <-> filter range
-        {
-            const float pscale = a.pscale, log_offset = a.log_offset;
-            const float* prow = pw + lane * P_STRIDE;
-            float* lrow = lm + lane * LM_STRIDE;
-            if constexpr (PYMEL) {
-                switch (warp) {
-                    case 0: mel_py_group<0>(prow, lrow, pscale, log_offset); break;
-                    case 1: mel_py_group<1>(prow, lrow, pscale, log_offset); break;
-                    case 2: mel_py_group<2>(prow, lrow, pscale, log_offset); break;
-                    case 3: mel_py_group<3>(prow, lrow, pscale, log_offset); break;
-                    case 4: mel_py_group<4>(prow, lrow, pscale, log_offset); break;
-                    case 5: mel_py_group<5>(prow, lrow, pscale, log_offset); break;
-                    case 6: mel_py_group<6>(prow, lrow, pscale, log_offset); break;
-                    default: mel_py_group<7>(prow, lrow, pscale, log_offset); break;
-                }
-            } else {
-                // table-driven filterbank (weights broadcast from smem): any contiguous-support filter set
-                const float* s_melw = reinterpret_cast<const float*>(tab + TB_MELW_OFF);
-                const int4* s_melm = reinterpret_cast<const int4*>(tab + TB_MELM_OFF);
-                const float log_floor = a.log_floor;
-                for (int j = warp; j < WW_N_MELS; j += MFCC_WARPS) {
-                    const int4 m = s_melm[j];
-                    const float* pp = prow + m.x;
-                    const float* ww_ = s_melw + m.z;
-                    float acc = 0.f;
-                    for (int i = 0; i < m.y; ++i) acc = fmaf(pp[i], ww_[i], acc);
-                    const float e = fmaf(acc, pscale, __int_as_float(m.w));
-                    lrow[j] = __logf(fmaxf(e, log_floor) + log_offset);
-                }
-            }
-        }
-        __syncthreads();
-
-        // DCT: lane <-> frame, warp <-> coefficient pair {warp, warp + 8}; stores coalesced along time
-        {
-            const int t = t0 + lane;
-            if (t < n_frames) {
-                float* outp = a.out + sig * a.out_sig_stride + (long long)t * a.out_frame_stride;
-                const float* lrow = lm + lane * LM_STRIDE;
-                if constexpr (PYMEL) {
-                    const long long cs = a.out_coef_stride;
-                    switch (warp) {
-                        case 0: dct_py_group<0>(lrow, outp, cs); break;
-                        case 1: dct_py_group<1>(lrow, outp, cs); break;
-                        case 2: dct_py_group<2>(lrow, outp, cs); break;
-                        case 3: dct_py_group<3>(lrow, outp, cs); break;
-                        case 4: dct_py_group<4>(lrow, outp, cs); break;
-                        case 5: dct_py_group<5>(lrow, outp, cs); break;
-                        case 6: dct_py_group<6>(lrow, outp, cs); break;
-                        default: dct_py_group<7>(lrow, outp, cs); break;
-                    }
-                } else {
-                    DctDispatch<MFCC_WARPS, 0>::run(warp, a, lrow, outp);
-                }
-            }
-        }
+        prev_valid = have;
+        prev_sig = sig;
+        prev_t0 = t0;
     }
 }
 
