@@ -51,6 +51,7 @@ struct ww_ctx {
     signed char* i8blob = nullptr;
     I8Weights i8w{};
     bool have_i8 = false;
+    long long grp_windows = 0, grp_stride = 0;  // window grouping of the next CNN launch (streaming sessions)
     // fused-path scratch
     float* scratch = nullptr;          // [chunk][13][63]
     long long scratch_clips = 0;
@@ -369,34 +370,34 @@ extern "C" int ww_num_frames(int feat_mode, int n_samples) {
 // ------------------------------------------------------------------------------------------------
 // features
 // ------------------------------------------------------------------------------------------------
-static int launch_mfcc(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_signals, int n_samples,
-                       long long sig_stride, int feat_mode, float* out, long long oss, long long ocs, long long ofs,
-                       cudaStream_t st) {
-    if (!pcm || !out) return fail(ctx, WW_ERR_INVALID, "mfcc: null buffer");
-    if (feat_mode != WW_FEAT_PY && feat_mode != WW_FEAT_ESP) return fail(ctx, WW_ERR_INVALID, "mfcc: bad feat_mode");
-    if (pcm_type != WW_PCM_S16 && pcm_type != WW_PCM_F32) return fail(ctx, WW_ERR_INVALID, "mfcc: bad pcm_type");
-    if (n_signals < 0 || sig_stride < n_samples) return fail(ctx, WW_ERR_INVALID, "mfcc: bad sizes");
+// Lowest-level frontend launch.  `origin_off` is the sample index of FFT-frame point n = 0 of frame 0 (frame t starts
+// 256*t later), `reflect` enables torch.stft's reflect padding at the two signal ends, `n_frames` is how many
+// frames to produce.  Whole-signal calls use the mode's own origin (-256 PY, -96 ESP); streaming sessions continue
+// a stream by passing the retained tail + the new chunk with the origin that keeps frame phase.
+static int launch_mfcc_ex(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_signals, int n_samples,
+                          long long sig_stride, int feat_mode, int origin_off, int reflect, int n_frames, float* out,
+                          long long oss, long long ocs, long long ofs, cudaStream_t st) {
     const FeatMode& fm = ctx->feat[feat_mode];
-    if (!fm.tables) return fail(ctx, WW_ERR_UNSUPPORTED, "mfcc: feature mode unavailable");
-    const int T = ww_num_frames(feat_mode, n_samples);
-    if (T <= 0) return fail(ctx, WW_ERR_INVALID, "mfcc: signal shorter than one frame");  // mfcc.c:434-437
-    if (n_signals == 0) return WW_OK;
+    if (n_signals == 0 || n_frames <= 0) return WW_OK;
     const int frames = MFCC_FRAMES;
     const size_t esz = pcm_type == WW_PCM_S16 ? 2 : 4;
     MfccArgs a;
     a.pcm = pcm;
     a.sig_stride = sig_stride;
     a.n_samples = n_samples;
-    a.n_frames = T;
-    a.blocks_per_sig = (T + frames - 1) / frames;
+    a.n_frames = n_frames;
+    a.blocks_per_sig = (n_frames + frames - 1) / frames;
     a.out = out;
     a.out_sig_stride = oss;
     a.out_coef_stride = ocs;
     a.out_frame_stride = ofs;
     a.tables = fm.tables;
-    a.origin_off = fm.origin_off;
-    a.reflect = fm.reflect;
-    a.use_bulk = (((uintptr_t)pcm % 16) == 0 && (sig_stride * esz) % 16 == 0 && ((size_t)n_samples * esz) % 16 == 0) ? 1 : 0;
+    a.origin_off = origin_off;
+    a.reflect = reflect;
+    a.use_bulk = (((uintptr_t)pcm % 16) == 0 && (sig_stride * esz) % 16 == 0 && ((size_t)n_samples * esz) % 16 == 0 &&
+                  (origin_off % 8) == 0)
+                     ? 1
+                     : 0;
     const float in_scale = pcm_type == WW_PCM_S16 ? (1.0f / 32768.0f) : 1.0f;  // torchaudio.load normalisation
     a.pscale = 0.25f * in_scale * in_scale * fm.mode_pscale;
     a.log_floor = fm.log_floor;
@@ -417,6 +418,21 @@ static int launch_mfcc(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_s
     }
     CK(cudaGetLastError());
     return WW_OK;
+}
+
+static int launch_mfcc(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_signals, int n_samples,
+                       long long sig_stride, int feat_mode, float* out, long long oss, long long ocs, long long ofs,
+                       cudaStream_t st) {
+    if (!pcm || !out) return fail(ctx, WW_ERR_INVALID, "mfcc: null buffer");
+    if (feat_mode != WW_FEAT_PY && feat_mode != WW_FEAT_ESP) return fail(ctx, WW_ERR_INVALID, "mfcc: bad feat_mode");
+    if (pcm_type != WW_PCM_S16 && pcm_type != WW_PCM_F32) return fail(ctx, WW_ERR_INVALID, "mfcc: bad pcm_type");
+    if (n_signals < 0 || sig_stride < n_samples) return fail(ctx, WW_ERR_INVALID, "mfcc: bad sizes");
+    const FeatMode& fm = ctx->feat[feat_mode];
+    if (!fm.tables) return fail(ctx, WW_ERR_UNSUPPORTED, "mfcc: feature mode unavailable");
+    const int T = ww_num_frames(feat_mode, n_samples);
+    if (T <= 0) return fail(ctx, WW_ERR_INVALID, "mfcc: signal shorter than one frame");  // mfcc.c:434-437
+    return launch_mfcc_ex(ctx, pcm, pcm_type, n_signals, n_samples, sig_stride, feat_mode, fm.origin_off, fm.reflect, T,
+                          out, oss, ocs, ofs, st);
 }
 
 extern "C" int ww_mfcc_batch(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_signals, int n_samples,
@@ -443,6 +459,8 @@ static int launch_cnn_fp32(ww_ctx* ctx, const float* feats, long long ws, long l
     a.coef_stride = cs;
     a.frame_stride = fs;
     a.n_windows = n;
+    a.group_windows = ctx->grp_windows;
+    a.group_stride = ctx->grp_stride;
     a.index = index;
     a.index_count = index_count;
     a.cmvn_mode = cmvn_mode;
@@ -504,6 +522,8 @@ static int tc_forward(ww_ctx* ctx, const float* feats, long long ws, long long c
     a.coef_stride = cs;
     a.frame_stride = fs;
     a.n_windows = n;
+    a.group_windows = ctx->grp_windows;
+    a.group_stride = ctx->grp_stride;
     a.cmvn_mode = cmvn_mode;
     a.decide_mode = decide_mode;
     a.threshold = threshold;
@@ -529,6 +549,8 @@ static int tc_forward(ww_ctx* ctx, const float* feats, long long ws, long long c
         r.coef_stride = cs;
         r.frame_stride = fs;
         r.n_windows = n;  // capacity; the device-side count bounds the loop
+        r.group_windows = ctx->grp_windows;
+        r.group_stride = ctx->grp_stride;
         r.index = ctx->rs_list;
         r.index_count = ctx->rs_count;
         r.cmvn_mode = cmvn_mode;
@@ -810,6 +832,193 @@ extern "C" long long ww_stream_events(const float* logits_host, long long n_wind
         ++f;
     }
     return n_hits;
+}
+
+// ------------------------------------------------------------------------------------------------
+// streaming sessions: push PCM chunks for many concurrent streams, poll hits
+// ------------------------------------------------------------------------------------------------
+// Replaces the firmware's producer/consumer pair -- record_task writing one MFCC frame per 20 ms into the 63-frame
+// ring and detect_task scoring the ring (esp_wake_word_detector.cpp:10-48,52-150,154-263), and the intended
+// keep-last-N semantics of main/ring_buffer/ring_buffer.c:57-117 -- by a push/poll session: every write appends a
+// chunk to EVERY stream, the frames that became complete are computed once, every new 63-frame window is scored,
+// and the per-stream hit / refractory / ring-reset logic runs on the host.  Results are identical to
+// ww_stream_score over the concatenated stream (the stream end is never reflect-padded: a stream has no end).
+struct ww_session {
+    ww_ctx* ctx = nullptr;
+    int n_streams = 0, max_chunk = 0, cmvn_mode = 0, cnn_impl = 0;
+    float thr = 0.f;
+    int warmup = 64, refractory = 313;
+    long long n_samples = 0;   // samples received per stream
+    long long t_done = 0;      // frames computed per stream
+    // device: PCM tail + chunk (ping-pong), feature history 62 + new frames (ping-pong), logits
+    int16_t* d_pcm[2] = {nullptr, nullptr};
+    float* d_feat[2] = {nullptr, nullptr};
+    float* d_logits = nullptr;
+    int pcm_cur = 0, feat_cur = 0;
+    long long g0 = 0;          // global sample index of column 0 of d_pcm[cur]
+    int tail_len = 0;          // valid samples in d_pcm[cur] per stream
+    int pcm_cap = 0, feat_cap = 0, max_new = 0;
+    std::vector<float> h_logits;
+    std::vector<long long> reset_f;  // per stream: first frame index after the last ring reset
+    std::vector<ww_hit> hits;
+    cudaStream_t st = nullptr;
+};
+
+static const int kSessTail = 344;  // >= 328 samples may have to be retained between writes (multiple of 8)
+
+extern "C" int ww_session_open(ww_ctx* ctx, int n_streams, int max_chunk_samples, int cmvn_mode, int cnn_impl,
+                               float threshold_logit, int warmup_frames, int refractory_frames, ww_session** out) {
+    if (!ctx || !out) return WW_ERR_INVALID;
+    *out = nullptr;
+    if (n_streams < 1 || max_chunk_samples < 1 || max_chunk_samples > (1 << 24) || max_chunk_samples % 8 != 0)
+        return fail(ctx, WW_ERR_INVALID, "session_open: n_streams >= 1, chunk a positive multiple of 8 samples");
+    if (warmup_frames < WW_WINDOW_FRAMES || refractory_frames < 0) return fail(ctx, WW_ERR_INVALID, "session_open: bad warmup/refractory");
+    int rc = check_cnn_args(ctx, cmvn_mode, WW_DECIDE_NONE, cnn_impl);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    ww_session* s = new (std::nothrow) ww_session();
+    if (!s) return WW_ERR_NOMEM;
+    s->ctx = ctx;
+    s->n_streams = n_streams;
+    s->max_chunk = max_chunk_samples;
+    s->cmvn_mode = cmvn_mode;
+    s->cnn_impl = cnn_impl;
+    s->thr = threshold_logit;
+    s->warmup = warmup_frames;
+    s->refractory = refractory_frames;
+    s->pcm_cap = kSessTail + max_chunk_samples;
+    s->max_new = (kSessTail + max_chunk_samples) / WW_HOP + 2;
+    s->feat_cap = ((WW_WINDOW_FRAMES - 1) + s->max_new + 3) / 4 * 4;
+    s->reset_f.assign(n_streams, 0);
+    auto bail = [&](cudaError_t e, const char* what) {
+        cuda_fail(ctx, e, what);
+        ww_session_close(s);
+        return WW_ERR_CUDA;
+    };
+    cudaError_t e;
+    for (int i = 0; i < 2; ++i) {
+        if ((e = cudaMalloc(&s->d_pcm[i], sizeof(int16_t) * (size_t)n_streams * s->pcm_cap)) != cudaSuccess) return bail(e, "cudaMalloc session pcm");
+        if ((e = cudaMalloc(&s->d_feat[i], sizeof(float) * (size_t)n_streams * WW_N_MFCC * s->feat_cap)) != cudaSuccess) return bail(e, "cudaMalloc session feats");
+        if ((e = cudaMemset(s->d_feat[i], 0, sizeof(float) * (size_t)n_streams * WW_N_MFCC * s->feat_cap)) != cudaSuccess) return bail(e, "cudaMemset");
+    }
+    if ((e = cudaMalloc(&s->d_logits, sizeof(float) * (size_t)n_streams * s->max_new * ctx->w.num_classes)) != cudaSuccess) return bail(e, "cudaMalloc session logits");
+    if ((e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    *out = s;
+    return WW_OK;
+}
+
+extern "C" void ww_session_close(ww_session* s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(s->d_pcm[i]);
+        cudaFree(s->d_feat[i]);
+    }
+    cudaFree(s->d_logits);
+    if (s->st) cudaStreamDestroy(s->st);
+    delete s;
+}
+
+extern "C" long long ww_session_windows(const ww_session* s) {
+    if (!s) return WW_ERR_INVALID;
+    return s->t_done >= WW_WINDOW_FRAMES ? s->t_done - (WW_WINDOW_FRAMES - 1) : 0;
+}
+
+extern "C" int ww_session_write(ww_session* s, const int16_t* pcm_host, int chunk_samples) {
+    if (!s) return WW_ERR_INVALID;
+    ww_ctx* ctx = s->ctx;
+    if (!pcm_host || chunk_samples < 1 || chunk_samples > s->max_chunk || chunk_samples % 8 != 0)
+        return fail(ctx, WW_ERR_INVALID, "session_write: chunk must be a positive multiple of 8 samples <= max_chunk_samples");
+    CK(cudaSetDevice(ctx->device));
+    const int S = s->n_streams, C = ctx->w.num_classes;
+    int16_t* pcm = s->d_pcm[s->pcm_cur];
+    // append the chunk behind the retained tail of every stream
+    CK(cudaMemcpy2DAsync(pcm + s->tail_len, sizeof(int16_t) * s->pcm_cap, pcm_host, sizeof(int16_t) * chunk_samples,
+                         sizeof(int16_t) * chunk_samples, S, cudaMemcpyHostToDevice, s->st));
+    const int L = s->tail_len + chunk_samples;
+    s->n_samples += chunk_samples;
+    // frames whose 320 taps are complete: 256 t + 159 < n_samples
+    const long long t_count = s->n_samples >= 160 ? (s->n_samples - 160) / WW_HOP + 1 : 0;
+    const int n_new = (int)(t_count - s->t_done);
+    float* feat = s->d_feat[s->feat_cur];
+    const int H = WW_WINDOW_FRAMES - 1;  // 62 frames of history in front of the new ones
+    long long n_win_total = 0;
+    int j_lo = 0, n_win = 0;
+    if (n_new > 0) {
+        // frame j of this launch is global frame t_done + j; its FFT-frame origin in buffer coordinates
+        const int origin_off = (int)(WW_HOP * s->t_done - 256 - s->g0);
+        const int reflect = s->t_done == 0 ? 1 : 0;
+        int rc = launch_mfcc_ex(ctx, pcm, WW_PCM_S16, S, L, s->pcm_cap, WW_FEAT_PY, origin_off, reflect, n_new, feat + H,
+                                (long long)WW_N_MFCC * s->feat_cap, s->feat_cap, 1, s->st);
+        if (rc) return rc;
+        // windows that end in a new frame: local window j covers history columns j .. j+62
+        j_lo = (int)(s->t_done >= H ? 0 : H - s->t_done);
+        n_win = n_new - j_lo;
+        if (n_win > 0) {
+            ctx->grp_windows = n_win;
+            ctx->grp_stride = (long long)WW_N_MFCC * s->feat_cap;
+            rc = run_cnn(ctx, feat + j_lo, 1, s->feat_cap, 1, (long long)S * n_win, s->cmvn_mode, WW_DECIDE_NONE, 0.f,
+                         s->cnn_impl, s->d_logits, nullptr, s->st);
+            ctx->grp_windows = 0;
+            ctx->grp_stride = 0;
+            if (rc) return rc;
+            n_win_total = (long long)S * n_win;
+            s->h_logits.resize((size_t)n_win_total * C);
+            CK(cudaMemcpyAsync(s->h_logits.data(), s->d_logits, sizeof(float) * (size_t)n_win_total * C, cudaMemcpyDeviceToHost,
+                               s->st));
+        }
+    }
+    // retain what the next frames need: PCM from align8(256 t_count - 161), features: the last 62 frames
+    const long long g0_next = t_count == 0 ? 0 : ((WW_HOP * t_count - 161) / 8) * 8;
+    const int keep = (int)(s->g0 + L - g0_next);
+    CK(cudaMemcpy2DAsync(s->d_pcm[s->pcm_cur ^ 1], sizeof(int16_t) * s->pcm_cap, pcm + (g0_next - s->g0),
+                         sizeof(int16_t) * s->pcm_cap, sizeof(int16_t) * keep, S, cudaMemcpyDeviceToDevice, s->st));
+    if (n_new > 0)
+        CK(cudaMemcpy2DAsync(s->d_feat[s->feat_cur ^ 1], sizeof(float) * s->feat_cap, feat + n_new, sizeof(float) * s->feat_cap,
+                             sizeof(float) * H, (size_t)S * WW_N_MFCC, cudaMemcpyDeviceToDevice, s->st));
+    CK(cudaStreamSynchronize(s->st));
+    s->pcm_cur ^= 1;
+    if (n_new > 0) s->feat_cur ^= 1;
+    if (n_win <= 0) s->h_logits.clear();
+    s->g0 = g0_next;
+    s->tail_len = keep;
+    // host-side hit logic per stream (esp_wake_word_detector.cpp:38-44,245-258)
+    if (n_win > 0) {
+        for (int g = 0; g < S; ++g) {
+            long long& reset_f = s->reset_f[g];
+            for (int j = 0; j < n_win; ++j) {
+                const long long f = s->t_done + j_lo + j;  // global index of the window's last frame
+                if (f < reset_f) continue;
+                if (f - reset_f + 1 < s->warmup) continue;
+                const float lg = s->h_logits[((size_t)g * n_win + j) * C];
+                if (lg >= s->thr) {
+                    ww_hit h;
+                    h.stream = g;
+                    h.window = f - (WW_WINDOW_FRAMES - 1);
+                    h.logit = lg;
+                    s->hits.push_back(h);
+                    reset_f = f + s->refractory + 1;
+                }
+            }
+        }
+    }
+    s->t_done = t_count;
+    return WW_OK;
+}
+
+extern "C" long long ww_session_poll(ww_session* s, ww_hit* hits, long long max_hits) {
+    if (!s || max_hits < 0 || (max_hits > 0 && !hits)) return WW_ERR_INVALID;
+    const long long n = (long long)s->hits.size() < max_hits ? (long long)s->hits.size() : max_hits;
+    for (long long i = 0; i < n; ++i) hits[i] = s->hits[i];
+    s->hits.erase(s->hits.begin(), s->hits.begin() + n);
+    return n;
+}
+
+/* last scored logits of the most recent write: [n_streams][n_new_windows][C] (host); returns n_new_windows */
+extern "C" long long ww_session_last_logits(const ww_session* s, const float** logits) {
+    if (!s || !logits) return WW_ERR_INVALID;
+    *logits = s->h_logits.data();
+    return s->n_streams ? (long long)(s->h_logits.size() / ((size_t)s->n_streams * s->ctx->w.num_classes)) : 0;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -36,6 +36,8 @@ struct CnnArgs {
     long long coef_stride;
     long long frame_stride;
     long long n_windows;
+    long long group_windows;   // 0: flat addressing; else window id = group*group_windows + j and the window
+    long long group_stride;    //    lives at feats + group*group_stride + j*win_stride (concurrent streams)
     const long long* index;  // optional: window ids to score (re-score list); nullptr = 0..n_windows-1
     const int* index_count;  // optional device count for `index` (n_windows is then the capacity)
     int cmvn_mode;
@@ -105,7 +107,9 @@ __global__ void __launch_bounds__(CNN_THREADS) cnn_fp32_kernel(const __grid_cons
 
     for (long long it = blockIdx.x; it < n; it += gridDim.x) {
         const long long win = a.index ? a.index[it] : it;
-        const float* src = a.feats + win * a.win_stride;
+        const float* src = a.group_windows
+                               ? a.feats + (win / a.group_windows) * a.group_stride + (win % a.group_windows) * a.win_stride
+                               : a.feats + win * a.win_stride;
 
         // ---- CMVN: warp handles coefficients warp, warp+8 ----
         for (int q = warp; q < WW_N_MFCC; q += 8) {

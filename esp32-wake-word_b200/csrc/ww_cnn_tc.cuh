@@ -63,6 +63,7 @@ struct TcArgs {
     const float* feats;  // feats[win*win_stride + coef*coef_stride + frame*frame_stride]
     long long win_stride, coef_stride, frame_stride;
     long long n_windows;
+    long long group_windows, group_stride;  // as in CnnArgs
     int cmvn_mode, decide_mode;
     float threshold;        // as in CnnArgs
     float thr_logit;        // the threshold expressed as a logit
@@ -237,7 +238,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
                 x0[q] = 0.f;
                 x1[q] = 0.f;
                 if (live) {
-                    const float* row = a.feats + win * a.win_stride + q * a.coef_stride;
+                    const float* wbase = a.group_windows ? a.feats + (win / a.group_windows) * a.group_stride +
+                                                               (win % a.group_windows) * a.win_stride
+                                                         : a.feats + win * a.win_stride;
+                    const float* row = wbase + q * a.coef_stride;
                     x0[q] = row[lane * a.frame_stride];
                     if (has1) x1[q] = row[(lane + 32) * a.frame_stride];
                 }

@@ -9,5 +9,5 @@ from .features import (add_random_noise, augment_audio_waveform, cmvn_batch, ext
 from .model import LightweightKWS, WakeWordScorer, forward_int8, XIAOA_EXPONENTS  # noqa: F401
 from .ctc import (CTCKeywordDetector, CTCLoss, ctc_greedy_decode, ctc_loss, decode_predictions,  # noqa: F401
                   greedy_batch)
-from .stream import StreamScorer, events, refractory_frames  # noqa: F401
+from .stream import StreamScorer, StreamSession, events, refractory_frames  # noqa: F401
 from .onnx_reader import load_kws_state_dict, read_initializers  # noqa: F401

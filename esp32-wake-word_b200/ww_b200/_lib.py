@@ -25,7 +25,8 @@ CNN_FP32, CNN_TENSOR = 0, 1
 EXPORTS = [
     "ww_version", "ww_create", "ww_destroy", "ww_last_error", "ww_load_weights", "ww_num_frames",
     "ww_mfcc_batch", "ww_cmvn", "ww_cnn_forward", "ww_quantize_weights_i8", "ww_cnn_forward_i8", "ww_score_clips", "ww_score_clips_host",
-    "ww_stream_score", "ww_stream_events", "ww_ctc_greedy", "ww_ctc_loss_workspace_bytes",
+    "ww_stream_score", "ww_stream_events", "ww_session_open", "ww_session_write", "ww_session_poll",
+    "ww_session_windows", "ww_session_last_logits", "ww_session_close", "ww_ctc_greedy", "ww_ctc_loss_workspace_bytes",
     "ww_ctc_loss_fwd", "ww_ctc_loss_bwd", "ww_debug_tc", "ww_extract_mfcc", "ww_free_mfcc",
 ]
 
@@ -68,6 +69,16 @@ def load_library():
         lib.ww_stream_score.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, vp]
         lib.ww_stream_events.argtypes = [vp, i64, i32, f32, i32, i32, vp, i64]
         lib.ww_stream_events.restype = i64
+        lib.ww_session_open.argtypes = [vp, i32, i32, i32, i32, f32, i32, i32, C.POINTER(vp)]
+        lib.ww_session_write.argtypes = [vp, vp, i32]
+        lib.ww_session_poll.argtypes = [vp, vp, i64]
+        lib.ww_session_poll.restype = i64
+        lib.ww_session_windows.argtypes = [vp]
+        lib.ww_session_windows.restype = i64
+        lib.ww_session_last_logits.argtypes = [vp, C.POINTER(C.POINTER(C.c_float))]
+        lib.ww_session_last_logits.restype = i64
+        lib.ww_session_close.argtypes = [vp]
+        lib.ww_session_close.restype = None
         lib.ww_ctc_greedy.argtypes = [vp, vp, i64, i64, i32, i32, i32, vp, i32, vp, vp, vp, i32, vp, vp]
         lib.ww_ctc_loss_workspace_bytes.argtypes = [i32, i32, i32]
         lib.ww_ctc_loss_workspace_bytes.restype = C.c_size_t

@@ -70,3 +70,71 @@ def events(logits, threshold_logit=LN4, warmup=64, refractory=None, max_hits=1 <
     if n < 0:
         raise L.WWError(f"ww_stream_events failed ({n})")
     return hits[: min(n, max_hits)].tolist()
+
+
+class _Hit(C.Structure):
+    _fields_ = [("stream", C.c_int32), ("window", C.c_int64), ("logit", C.c_float)]
+
+
+class StreamSession:
+    """Push/poll scoring of many concurrent streams (the firmware's record/detect task pair as a batch service).
+
+    write(chunk[n_streams, n]) appends n samples (a multiple of 8) to every stream, computes the frames that became
+    complete, scores every new 63-frame window and applies the per-stream hit / refractory / ring-reset logic;
+    poll() returns the pending (stream, window, logit) events.  Scores equal StreamScorer.score over the
+    concatenated stream.
+    """
+
+    def __init__(self, state_dict, n_streams, max_chunk_samples=16000, device=None, cmvn="device", cnn_impl="fp32",
+                 threshold_logit=LN4, warmup=64, refractory=None):
+        self.ctx = L.get_context(device)
+        self._key = ("session", next(_tokens))
+        _push_weights(self.ctx, state_dict, self._key)
+        self.n_streams = int(n_streams)
+        cm = {"none": L.CMVN_NONE, "python": L.CMVN_PY, "device": L.CMVN_DEVICE}[cmvn]
+        impl = L.CNN_TENSOR if cnn_impl == "tensor" else L.CNN_FP32
+        if refractory is None:
+            refractory = refractory_frames()
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.ww_session_open(self.ctx.h, self.n_streams, int(max_chunk_samples), cm, impl,
+                                                    float(threshold_logit), int(warmup), int(refractory), C.byref(h)),
+                       "ww_session_open")
+        self.h = h
+
+    def write(self, chunk):
+        """chunk: int16 [n_streams, n] (numpy or CPU tensor). Returns the logits of the newly scored windows
+        as a numpy array [n_streams, n_new_windows, C]."""
+        if isinstance(chunk, torch.Tensor):
+            chunk = chunk.cpu().numpy()
+        chunk = np.ascontiguousarray(chunk, dtype=np.int16)
+        if chunk.ndim != 2 or chunk.shape[0] != self.n_streams:
+            raise ValueError("write() expects int16 [n_streams, n]")
+        if getattr(self.ctx, "weights_owner", None) != self._key:
+            raise L.WWError("another model's weights were loaded into this context while the session was open")
+        self.ctx.check(self.ctx.lib.ww_session_write(self.h, chunk.ctypes.data_as(C.c_void_p), chunk.shape[1]),
+                       "ww_session_write")
+        p = C.POINTER(C.c_float)()
+        n = self.ctx.lib.ww_session_last_logits(self.h, C.byref(p))
+        if n <= 0:
+            return np.zeros((self.n_streams, 0, self.ctx.num_classes), np.float32)
+        return np.ctypeslib.as_array(p, shape=(self.n_streams, n, self.ctx.num_classes)).copy()
+
+    def poll(self, max_hits=4096):
+        buf = (_Hit * max_hits)()
+        n = self.ctx.lib.ww_session_poll(self.h, buf, max_hits)
+        return [(int(buf[i].stream), int(buf[i].window), float(buf[i].logit)) for i in range(n)]
+
+    @property
+    def windows(self):
+        return int(self.ctx.lib.ww_session_windows(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.ww_session_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

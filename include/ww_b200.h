@@ -126,6 +126,31 @@ int ww_stream_score(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_samp
 long long ww_stream_events(const float* logits_host, long long n_windows, int num_classes, float threshold_logit,
                            int warmup, int refractory, long long* hits, long long max_hits);
 
+/* ---- streaming sessions: push chunks for many concurrent streams, poll hits ----------- */
+/* Push/poll form of the firmware's record_task / detect_task pair and its 63-frame MFCC ring
+ * (esp_wake_word_detector.cpp:10-48,52-150,154-263; read_mic_fn / wake_event_callback_t of
+ * esp_wake_word_detector.hpp:18-37; intended keep-last-N semantics of main/ring_buffer/ring_buffer.c:57-117).
+ * All streams of a session advance together; the scores equal ww_stream_score over the concatenated stream. */
+typedef struct ww_session ww_session;
+typedef struct {
+    int32_t stream;  /* stream index */
+    int64_t window;  /* window index (frames window .. window+62) */
+    float logit;     /* class-0 logit that crossed the threshold */
+} ww_hit;
+/* chunk sizes must be multiples of 8 samples; threshold is a logit (ln 4 == sigmoid*100 >= 80);
+ * warmup (64) and refractory (313 frames = 5 s) as in ww_stream_events */
+int ww_session_open(ww_ctx* ctx, int n_streams, int max_chunk_samples, int cmvn_mode, int cnn_impl,
+                    float threshold_logit, int warmup_frames, int refractory_frames, ww_session** out);
+/* pcm_host: [n_streams][chunk_samples] int16; computes the newly completed frames, scores the new windows */
+int ww_session_write(ww_session* s, const int16_t* pcm_host, int chunk_samples);
+/* drain up to max_hits pending WAKE_WORD_DETECTED events; returns how many were written */
+long long ww_session_poll(ww_session* s, ww_hit* hits, long long max_hits);
+/* windows scored so far per stream */
+long long ww_session_windows(const ww_session* s);
+/* logits of the windows scored by the last write: host [n_streams][n][num_classes]; returns n */
+long long ww_session_last_logits(const ww_session* s, const float** logits);
+void ww_session_close(ww_session* s);
+
 /* ---- CTC best path / keyword (ml_models/test.py:168-217, ml_models/ctc.py:453-471) ------------- */
 /* log_probs[t*t_stride + b*b_stride + c]; labels: [B][T] int32 (zero padded), out_len: [B].
  * lengths (valid frames per utterance) and keyword/hits may be NULL.
