@@ -21,6 +21,67 @@ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(
 // multiply by -i
 __device__ __forceinline__ float2 cmul_mi(float2 a) { return make_float2(a.y, -a.x); }
 
+// ---- packed complex arithmetic (sm_100 f32x2 family: SASS FADD2 / FMUL2 / FFMA2) -------------------------
+// A complex value lives in one aligned 64-bit register pair {re (lo), im (hi)}.  One packed instruction does
+// both halves and takes one issue slot (measured on B200, tools/ubench/f32x2_rate.cu: 2 packed warp-instructions
+// per clock per SM = the same 128 results/clk/SM as 4 scalar ones), and ptxas folds half swaps, per-half
+// negations and scalar broadcasts of the operands into the instruction's .LO_HI / .NP / .F32 modifiers, so a
+// complex add is 1 instruction, a complex multiply 2, and "t -+ i d" 1 -- half the scalar count.
+struct cpx {
+    unsigned long long v;
+};
+__device__ __forceinline__ cpx cpk(float re, float im) {
+    cpx r;
+    asm("mov.b64 %0,{%1,%2};" : "=l"(r.v) : "f"(re), "f"(im));
+    return r;
+}
+__device__ __forceinline__ float2 cunpk(cpx a) {
+    float2 r;
+    asm("mov.b64 {%0,%1},%2;" : "=f"(r.x), "=f"(r.y) : "l"(a.v));
+    return r;
+}
+__device__ __forceinline__ float cre(cpx a) { return cunpk(a).x; }
+__device__ __forceinline__ float cim(cpx a) { return cunpk(a).y; }
+__device__ __forceinline__ cpx cswap(cpx a) {
+    const float2 f = cunpk(a);
+    return cpk(f.y, f.x);
+}
+__device__ __forceinline__ cpx p_neg(cpx a) {
+    const float2 f = cunpk(a);
+    return cpk(-f.x, -f.y);
+}
+__device__ __forceinline__ cpx p_conj(cpx a) {
+    const float2 f = cunpk(a);
+    return cpk(f.x, -f.y);
+}
+__device__ __forceinline__ cpx p_add(cpx a, cpx b) {
+    cpx r;
+    asm("add.rn.f32x2 %0,%1,%2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ cpx p_sub(cpx a, cpx b) {
+    cpx r;
+    asm("sub.rn.f32x2 %0,%1,%2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ cpx p_mul(cpx a, cpx b) {
+    cpx r;
+    asm("mul.rn.f32x2 %0,%1,%2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ cpx p_fma(cpx a, cpx b, cpx c) {
+    cpx r;
+    asm("fma.rn.f32x2 %0,%1,%2,%3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+// t + (-i) d   and   t - (-i) d
+__device__ __forceinline__ cpx p_add_mi(cpx t, cpx d) { return p_fma(cswap(d), cpk(1.f, -1.f), t); }
+__device__ __forceinline__ cpx p_sub_mi(cpx t, cpx d) { return p_fma(cswap(d), cpk(-1.f, 1.f), t); }
+// a * (-i)
+__device__ __forceinline__ cpx p_mul_mi(cpx a) { return p_mul(cswap(a), cpk(1.f, -1.f)); }
+// a * (c + i s)
+__device__ __forceinline__ cpx p_cmul(cpx a, float c, float s) { return p_fma(cswap(a), cpk(-s, s), p_mul(a, cpk(c, c))); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
