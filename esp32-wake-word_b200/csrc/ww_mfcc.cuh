@@ -233,9 +233,9 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
     uint64_t* bars = bar;  // one mbarrier per PCM buffer
 
     // half h of a block holds frames 16h..16h+15; smem sample index = s - org[h]
-    auto stage_block = [&](long long b, int buf) {  // one thread: TMA both halves of block b into buffer `buf`
-        const long long sg = b / a.blocks_per_sig;
-        const int bt0 = (int)(b - sg * a.blocks_per_sig) * FRAMES;
+    // one thread: TMA both halves of block (signal sg, block-in-signal bi) into buffer `buf`
+    auto stage_block = [&](long long sg, int bi, int buf) {
+        const int bt0 = bi * FRAMES;
         const TIN* gs = reinterpret_cast<const TIN*>(a.pcm) + sg * a.sig_stride;
         int lo[2], n[2];
         for (int h = 0; h < 2; ++h) {
@@ -269,7 +269,12 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
     }
     __syncthreads();
     const long long first = blockIdx.x, stride = gridDim.x;
-    if (use_bulk && tid == 0 && first < a.n_blocks) stage_block(first, 0);
+    // (signal, block-in-signal) of the current block, advanced incrementally: no 64-bit division in the loop
+    const int bps = a.blocks_per_sig;
+    const int stride_q = (int)gridDim.x / bps, stride_r = (int)gridDim.x % bps;
+    long long sig_cur = first / bps;
+    int bi_cur = (int)(first - sig_cur * bps);
+    if (use_bulk && tid == 0 && first < a.n_blocks) stage_block(sig_cur, bi_cur, 0);
 
     float* edge = reinterpret_cast<float*>(smem + SM::OFF_EDGE);
     const int t_tail = (L - origin_off - 416) / WW_HOP + 1;  // first frame whose taps run past the signal end
@@ -342,9 +347,16 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
         unsigned char* pcm_buf = smem + SM::OFF_PCM;
         bool block_has_edge = false;
         int it_first = 0;
+        // the block after this one (same CTA)
+        long long sig_nxt = sig_cur + stride_q;
+        int bi_nxt = bi_cur + stride_r;
+        if (bi_nxt >= bps) {
+            bi_nxt -= bps;
+            ++sig_nxt;
+        }
         if (have) {
-            sig = blk_id / a.blocks_per_sig;
-            t0 = (int)(blk_id - sig * a.blocks_per_sig) * FRAMES;
+            sig = sig_cur;
+            t0 = bi_cur * FRAMES;
             org0 = WW_HOP * t0 + origin_off + 88;  // 8 samples ahead of the first window tap (multiple of 8)
             org1 = org0 + 16 * WW_HOP;
             const int buf = NBUF == 2 ? (int)(iter & 1) : 0;
@@ -352,10 +364,10 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
             if (use_bulk) {
                 if (NBUF == 2) {
                     // the other buffer was last read in the FFT passes of the previous block (before its barrier)
-                    if (tid == 0 && blk_id + stride < a.n_blocks) stage_block(blk_id + stride, buf ^ 1);
+                    if (tid == 0 && blk_id + stride < a.n_blocks) stage_block(sig_nxt, bi_nxt, buf ^ 1);
                     mbar_wait(&bars[buf], (uint32_t)((iter >> 1) & 1));
                 } else {
-                    if (iter > 0 && tid == 0) stage_block(blk_id, 0);
+                    if (iter > 0 && tid == 0) stage_block(sig_cur, bi_cur, 0);
                     mbar_wait(&bars[0], (uint32_t)(iter & 1));
                 }
             } else {
@@ -382,15 +394,14 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
             if (block_has_edge) {
                 const int reflect = a.reflect;
                 const float pre = a.preemph;
-                for (int i = tid; i < 2 * WW_WIN; i += MFCC_THREADS) {
-                    const int slot = i >= WW_WIN, j = i - slot * WW_WIN;
-                    if (slot ? has1 : has0) {
-                        const int te = slot ? t_tail : 0;
-                        const int hh = (te - t0) >> 4;
-                        const TIN* sp = reinterpret_cast<const TIN*>(pcm_buf + hh * SM::HALF_STRIDE);
-                        const int s = WW_HOP * te + origin_off + 96 + j;
-                        edge[i] = emph_sample<TIN>(sp, hh ? org1 : org0, s, L, reflect, pre);
-                    }
+    #pragma unroll 1
+                for (int slot = has0 ? 0 : 1; slot <= (has1 ? 1 : 0); ++slot) {
+                    const int te = slot ? t_tail : 0;
+                    const int hh = (te - t0) >> 4;
+                    const TIN* sp = reinterpret_cast<const TIN*>(pcm_buf + hh * SM::HALF_STRIDE);
+                    const int s0 = WW_HOP * te + origin_off + 96, lo_h = hh ? org1 : org0;
+                    for (int j = tid; j < WW_WIN; j += MFCC_THREADS)
+                        edge[slot * WW_WIN + j] = emph_sample<TIN>(sp, lo_h, s0 + j, L, reflect, pre);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars[3]);
@@ -454,15 +465,15 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
             const cpx* s_winp = reinterpret_cast<const cpx*>(s_win);
             if (interior) {
                 // complex point m = 16*n1 + l16 (n1 = 3..12) <-> samples fo + 2m, fo + 2m + 1
-                const int base = fo - org + 2 * l16;  // smem sample index of m = l16
+                const int base = fo - org + 2 * l16;  // smem sample index of m = l16 (even: fo - org is a multiple of 8)
                 const cpx mpre = cpk(-pre, -pre);
+                const uint32_t* p32b = reinterpret_cast<const uint32_t*>(spcm) + (base >> 1);
     #pragma unroll
                 for (int n1 = 3; n1 <= 12; ++n1) {
                     const cpx w = s_winp[16 * (n1 - 3) + l16];
                     float x0, x1, xm1;
                     if constexpr (sizeof(TIN) == 2) {
-                        const uint32_t* p32 = reinterpret_cast<const uint32_t*>(spcm) + ((base + 32 * n1) >> 1);
-                        const uint32_t cur = p32[0], prv = p32[-1];
+                        const uint32_t cur = p32b[16 * n1], prv = p32b[16 * n1 - 1];
                         x0 = static_cast<float>(static_cast<int16_t>(cur & 0xffffu));
                         x1 = static_cast<float>(static_cast<int16_t>(cur >> 16));
                         xm1 = static_cast<float>(static_cast<int16_t>(prv >> 16));
@@ -545,6 +556,8 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
         prev_valid = have;
         prev_sig = sig;
         prev_t0 = t0;
+        sig_cur = sig_nxt;
+        bi_cur = bi_nxt;
     }
 }
 
