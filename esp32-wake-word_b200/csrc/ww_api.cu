@@ -538,8 +538,8 @@ static int tc_forward(ww_ctx* ctx, const float* feats, long long ws, long long c
     a.num_classes = ctx->w.num_classes;
     a.dbg = ctx->tc_dbg;
     if (rescoring) CK(cudaMemsetAsync(ctx->rs_count, 0, sizeof(int), st));
-    const long long n_oct = (n + TC_CLIPS - 1) / TC_CLIPS;
-    const unsigned grid = (unsigned)(n_oct < ctx->sm_count ? n_oct : ctx->sm_count);
+    const long long n_cta = ((n + TC_CLIPS - 1) / TC_CLIPS + TC_GROUPS - 1) / TC_GROUPS;
+    const unsigned grid = (unsigned)(n_cta < ctx->sm_count ? n_cta : ctx->sm_count);
     cnn_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(a);
     CK(cudaGetLastError());
     if (rescoring) {

@@ -4,8 +4,9 @@
 // device CMVN (esp_wake_word_detector.cpp:179-211), LightweightKWS.forward (wakeModel.py:29-34) and the
 // decision (ml_models/main.py:53, esp_wake_word_detector.cpp:226-245) for 63-frame windows.
 //
-// One persistent CTA per SM scores EIGHT windows per iteration.  Every layer is an implicit GEMM issued by a
-// single thread with tcgen05.mma (kind::f16: fp16 operands, fp32 accumulation in TMEM):
+// One persistent CTA per SM runs two independent 4-warp groups; each group scores EIGHT windows per iteration, so
+// one group's TMEM epilogues (CUDA cores) overlap the other group's MMAs and waits.  Every layer is an implicit GEMM
+// issued by a single thread of the group with tcgen05.mma (kind::f16: fp16 operands, fp32 accumulation in TMEM):
 //   conv1  D[512 pos x 32]  = sum_tap A1[pos+tap][16] . W1_tap[32][16]^T     4 tiles of M=128, K=16 per tap
 //   conv2  D[256 pos x 64]  = sum_tap A2[pos+tap][32] . W2_tap[64][32]^T     2 tiles of M=128
 //   conv3  D[128 ch x 128 pos] = sum_tap W3_tap[128][64] . X3[pos+tap][64]^T   (roles swapped: channel = TMEM lane,
@@ -38,26 +39,32 @@ constexpr int A1_LBO = A1_ROWS * 16, A2_LBO = A2_ROWS * 16, X3_LBO = X3_ROWS * 1
 constexpr int W1_LBO = 32 * 16, W2_LBO = 64 * 16, W3_LBO = 128 * 16, WF1_LBO = 128 * 16;
 constexpr int W1_TAP = 2 * W1_LBO, W2_TAP = 4 * W2_LBO, W3_TAP = 8 * W3_LBO;
 
-// shared memory map (bytes)
-constexpr int TC_OFF_BAR = 0;                                  // mbarrier (8) + tmem base (4)
-constexpr int TC_OFF_PART = 64;                                // fc2 partial sums [2][8][8] floats
-constexpr int TC_OFF_FC2 = TC_OFF_PART + 2 * 8 * 8 * 4;        // fc2 weights [8][64] floats
+// shared memory map (bytes).  The CTA runs TWO independent 4-warp groups, each scoring its own octet of windows
+// with its own activation tiles, mbarrier and TMEM columns; the weights are shared.
+constexpr int TC_GROUPS = 2;
+constexpr int TC_GROUP_THREADS = TC_THREADS / TC_GROUPS;       // 128: one warp per TMEM lane quadrant
+constexpr int TC_OFF_BAR = 0;                                  // mbarrier[2] (16) + tmem base (4)
+constexpr int TC_OFF_PART = 64;                                // fc2 partial sums [group][2][8][8] floats
+constexpr int TC_OFF_FC2 = TC_OFF_PART + TC_GROUPS * 2 * 8 * 8 * 4;  // fc2 weights [8][64] floats
 constexpr int TC_OFF_W = TC_OFF_FC2 + TC_MAX_CLASSES * 64 * 4;  // weight blob (same layout as the device blob)
 constexpr int TC_W1 = 0;
 constexpr int TC_W2 = TC_W1 + 3 * W1_TAP;
 constexpr int TC_W3 = TC_W2 + 3 * W2_TAP;
 constexpr int TC_WF1 = TC_W3 + 3 * W3_TAP;
 constexpr int TC_W_BYTES = TC_WF1 + 16 * WF1_LBO;              // 97 280
-constexpr int TC_OFF_A1 = TC_OFF_W + TC_W_BYTES;
-constexpr int TC_OFF_A2 = TC_OFF_A1 + 2 * A1_LBO;
-constexpr int TC_OFF_X3 = TC_OFF_A2 + 4 * A2_LBO;
-constexpr int TC_OFF_G = TC_OFF_X3 + 8 * X3_LBO;
-constexpr int TC_SMEM = TC_OFF_G + 16 * G_LBO;
-static_assert(TC_OFF_W % 16 == 0 && TC_OFF_A1 % 16 == 0 && TC_OFF_A2 % 16 == 0 && TC_OFF_X3 % 16 == 0 &&
-                  TC_OFF_G % 16 == 0,
+constexpr int TC_OFF_ACT = TC_OFF_W + TC_W_BYTES;              // per-group activation tiles
+constexpr int TC_ACT_A1 = 0;
+constexpr int TC_ACT_A2 = TC_ACT_A1 + 2 * A1_LBO;
+constexpr int TC_ACT_X3 = TC_ACT_A2 + 4 * A2_LBO;
+constexpr int TC_ACT_G = TC_ACT_X3 + 8 * X3_LBO;
+constexpr int TC_ACT_BYTES = TC_ACT_G + 16 * G_LBO;            // 53 696
+constexpr int TC_SMEM = TC_OFF_ACT + TC_GROUPS * TC_ACT_BYTES;
+static_assert(TC_OFF_W % 16 == 0 && TC_OFF_ACT % 16 == 0 && TC_ACT_A2 % 16 == 0 && TC_ACT_X3 % 16 == 0 &&
+                  TC_ACT_G % 16 == 0 && TC_ACT_BYTES % 16 == 0,
               "UMMA operands need 16-byte alignment");
 static_assert(TC_SMEM <= 232448, "shared memory budget");
-constexpr int TC_TMEM_COLS = 256;  // conv accumulators use columns [0,128), fc1 uses [128,144)
+constexpr int TC_GROUP_COLS = 256;  // per group: conv accumulators use columns [0,128), fc1 uses [128,144)
+constexpr int TC_TMEM_COLS = TC_GROUPS * TC_GROUP_COLS;
 
 struct TcArgs {
     const float* feats;  // feats[win*win_stride + coef*coef_stride + frame*frame_stride]
@@ -182,28 +189,131 @@ __device__ __forceinline__ float reduce16(const float (&v)[16], int lane) {
     return a1;
 }
 
+__device__ __forceinline__ void group_sync(int group) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(TC_GROUP_THREADS) : "memory");
+}
+
+// raw features of one window held by a warp: lane <-> frame (t = lane and t = lane + 32)
+struct TcWin {
+    float x0[WW_N_MFCC], x1[WW_N_MFCC];
+};
+
+__device__ __forceinline__ void tc_load_window(const TcArgs& a, long long win, int lane, TcWin& w) {
+    const bool live = win < a.n_windows;
+    const bool has1 = lane + 32 < WW_WINDOW_FRAMES;
+    const float* wbase = a.feats;
+    if (live)
+        wbase = a.group_windows ? a.feats + (win / a.group_windows) * a.group_stride + (win % a.group_windows) * a.win_stride
+                                : a.feats + win * a.win_stride;
+#pragma unroll
+    for (int q = 0; q < WW_N_MFCC; ++q) {
+        const float* row = wbase + q * a.coef_stride;
+        w.x0[q] = live ? row[lane * a.frame_stride] : 0.f;
+        w.x1[q] = (live && has1) ? row[(lane + 32) * a.frame_stride] : 0.f;
+    }
+}
+
+// CMVN of one window (python or device style) and fp16 store into the conv1 operand rows 64*slot + t + 1
+__device__ __forceinline__ void tc_cmvn_store(const TcArgs& a, TcWin& w, int slot, int lane, unsigned char* sA1) {
+    float(&x0)[WW_N_MFCC] = w.x0;
+    float(&x1)[WW_N_MFCC] = w.x1;
+    const bool has1 = lane + 32 < WW_WINDOW_FRAMES;
+    if (a.cmvn_mode == CMVN_PY) {
+        // python-style CMVN: two transposed warp reductions (16 shuffles each) instead of 26 butterflies
+        float v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = q < WW_N_MFCC ? x0[q] + x1[q] : 0.f;
+        const float tot = reduce16(v, lane);  // lane 2q holds sum_t x[q][t]
+        float mean[WW_N_MFCC];
+#pragma unroll
+        for (int q = 0; q < WW_N_MFCC; ++q) mean[q] = __shfl_sync(0xffffffffu, tot, 2 * q) / (float)WW_WINDOW_FRAMES;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            if (q < WW_N_MFCC) {
+                x0[q] -= mean[q];
+                x1[q] = has1 ? x1[q] - mean[q] : 0.f;
+                v[q] = fmaf(x0[q], x0[q], x1[q] * x1[q]);
+            } else {
+                v[q] = 0.f;
+            }
+        }
+        const float ss = reduce16(v, lane);
+        float sd = sqrtf(ss / (float)(WW_WINDOW_FRAMES - 1));
+        if (sd == 0.f) sd = 1.f;
+        const float inv = __frcp_rn(sd + 1e-8f);
+#pragma unroll
+        for (int q = 0; q < WW_N_MFCC; ++q) {
+            const float iq = __shfl_sync(0xffffffffu, inv, 2 * q);
+            x0[q] *= iq;
+            x1[q] *= iq;
+        }
+    } else if (a.cmvn_mode == CMVN_DEVICE) {
+        // device-style CMVN rounds to int8: keep EXACTLY the arithmetic of cnn_fp32_kernel so that both
+        // paths quantise identically
+#pragma unroll 1
+        for (int q = 0; q < WW_N_MFCC; ++q) {
+            float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+            for (int qq = 0; qq < WW_N_MFCC; ++qq)
+                if (qq == q) { v0 = x0[qq]; v1 = x1[qq]; }
+            v0 = lround_clamp_i8(v0);
+            v1 = has1 ? lround_clamp_i8(v1) : 0.f;
+            const float mean = warp_sum(v0 + v1) / (float)WW_WINDOW_FRAMES;
+            const float d0 = v0 - mean, d1 = has1 ? v1 - mean : 0.f;
+            const float ss = warp_sum(d0 * d0 + d1 * d1);
+            const float den = sqrtf(ss / (float)WW_WINDOW_FRAMES) + 1e-8f;
+            const float z0 = fminf(fmaxf(lround_clamp_i8(d0 / den) * 16.f, -128.f), 127.f) * 0.0625f;
+            const float z1 = fminf(fmaxf(lround_clamp_i8(d1 / den) * 16.f, -128.f), 127.f) * 0.0625f;
+#pragma unroll
+            for (int qq = 0; qq < WW_N_MFCC; ++qq)
+                if (qq == q) { x0[qq] = z0; x1[qq] = z1; }
+        }
+    }
+    // row R = 64*slot + t + 1; channels 0-7 -> chunk 0, channels 8-12 (+3 zeros) -> chunk 1
+    {
+        const float lo8[8] = {x0[0], x0[1], x0[2], x0[3], x0[4], x0[5], x0[6], x0[7]};
+        const float hi8[8] = {x0[8], x0[9], x0[10], x0[11], x0[12], 0.f, 0.f, 0.f};
+        const int R = 64 * slot + lane + 1;
+        *reinterpret_cast<uint4*>(sA1 + R * 16) = pack_h8(lo8);
+        *reinterpret_cast<uint4*>(sA1 + A1_LBO + R * 16) = pack_h8(hi8);
+    }
+    if (has1) {
+        const float lo8[8] = {x1[0], x1[1], x1[2], x1[3], x1[4], x1[5], x1[6], x1[7]};
+        const float hi8[8] = {x1[8], x1[9], x1[10], x1[11], x1[12], 0.f, 0.f, 0.f};
+        const int R = 64 * slot + lane + 33;
+        *reinterpret_cast<uint4*>(sA1 + R * 16) = pack_h8(lo8);
+        *reinterpret_cast<uint4*>(sA1 + A1_LBO + R * 16) = pack_h8(hi8);
+    }
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TC_OFF_BAR + 8);
-    float* part = reinterpret_cast<float*>(smem + TC_OFF_PART);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TC_OFF_BAR + 16);
     float* sfc2 = reinterpret_cast<float*>(smem + TC_OFF_FC2);
     unsigned char* sW = smem + TC_OFF_W;
-    unsigned char* sA1 = smem + TC_OFF_A1;
-    unsigned char* sA2 = smem + TC_OFF_A2;
-    unsigned char* sX3 = smem + TC_OFF_X3;
-    unsigned char* sG = smem + TC_OFF_G;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int group = warp >> 2;     // independent 4-warp group (own octet stream, tiles, mbarrier, TMEM columns)
+    const int q4 = warp & 3;         // TMEM lane quadrant this warp may read (= warp % 4)
+    const int tig = tid & (TC_GROUP_THREADS - 1);
     const int C = a.num_classes;
 
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR) + group;
+    float* part = reinterpret_cast<float*>(smem + TC_OFF_PART) + group * (2 * 8 * 8);
+    unsigned char* act = smem + TC_OFF_ACT + group * TC_ACT_BYTES;
+    unsigned char* sA1 = act + TC_ACT_A1;
+    unsigned char* sA2 = act + TC_ACT_A2;
+    unsigned char* sX3 = act + TC_ACT_X3;
+    unsigned char* sG = act + TC_ACT_G;
+
     // ---- one-time setup: zero the activation tiles, stage the weights, allocate TMEM ----
-    for (int i = tid; i < (TC_SMEM - TC_OFF_A1) / 16; i += TC_THREADS)
-        reinterpret_cast<uint4*>(smem + TC_OFF_A1)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (TC_SMEM - TC_OFF_ACT) / 16; i += TC_THREADS)
+        reinterpret_cast<uint4*>(smem + TC_OFF_ACT)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < TC_W_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sW)[i] = __ldg(a.wblob + i);
     for (int i = tid; i < C * 64; i += TC_THREADS) sfc2[i] = __ldg(a.fc2 + i);
     if (tid == 0) {
-        mbar_init(bar, 1);
+        mbar_init(reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR), 1);
+        mbar_init(reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR) + 1, 1);
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -216,110 +326,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = *tmem_slot + (uint32_t)(group * TC_GROUP_COLS);
     const uint32_t sA1a = smem_u32(sA1), sA2a = smem_u32(sA2), sX3a = smem_u32(sX3), sGa = smem_u32(sG);
     const uint32_t sWa = smem_u32(sW);
     uint32_t phase = 0;
-
-    const int q4 = warp & 3;        // TMEM lane quadrant this warp may read
-    const int hi = warp >> 2;       // which half of the tiles / columns this warp takes
     const uint32_t tlane = (uint32_t)(32 * q4) << 16;
 
     const long long n_oct = (a.n_windows + TC_CLIPS - 1) / TC_CLIPS;
-    for (long long oct = blockIdx.x; oct < n_oct; oct += gridDim.x) {
-        // ================= S0: load + CMVN one window per warp, write A1 (fp16) =================
-        {
-            const long long win = oct * TC_CLIPS + warp;
-            const bool live = win < a.n_windows;
-            float x0[WW_N_MFCC], x1[WW_N_MFCC];
-            const bool has1 = lane + 32 < WW_WINDOW_FRAMES;
-#pragma unroll
-            for (int q = 0; q < WW_N_MFCC; ++q) {
-                x0[q] = 0.f;
-                x1[q] = 0.f;
-                if (live) {
-                    const float* wbase = a.group_windows ? a.feats + (win / a.group_windows) * a.group_stride +
-                                                               (win % a.group_windows) * a.win_stride
-                                                         : a.feats + win * a.win_stride;
-                    const float* row = wbase + q * a.coef_stride;
-                    x0[q] = row[lane * a.frame_stride];
-                    if (has1) x1[q] = row[(lane + 32) * a.frame_stride];
-                }
-            }
-            if (a.cmvn_mode == CMVN_PY) {
-                // python-style CMVN: two transposed warp reductions (16 shuffles each) instead of 26 butterflies
-                float v[16];
-#pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] = q < WW_N_MFCC ? x0[q] + x1[q] : 0.f;
-                const float tot = reduce16(v, lane);  // lane 2q holds sum_t x[q][t]
-                float mean[WW_N_MFCC];
-#pragma unroll
-                for (int q = 0; q < WW_N_MFCC; ++q)
-                    mean[q] = __shfl_sync(0xffffffffu, tot, 2 * q) / (float)WW_WINDOW_FRAMES;
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    if (q < WW_N_MFCC) {
-                        x0[q] -= mean[q];
-                        x1[q] = has1 ? x1[q] - mean[q] : 0.f;
-                        v[q] = fmaf(x0[q], x0[q], x1[q] * x1[q]);
-                    } else {
-                        v[q] = 0.f;
-                    }
-                }
-                const float ss = reduce16(v, lane);
-                float sd = sqrtf(ss / (float)(WW_WINDOW_FRAMES - 1));
-                if (sd == 0.f) sd = 1.f;
-                const float inv = __frcp_rn(sd + 1e-8f);
-#pragma unroll
-                for (int q = 0; q < WW_N_MFCC; ++q) {
-                    const float iq = __shfl_sync(0xffffffffu, inv, 2 * q);
-                    x0[q] *= iq;
-                    x1[q] *= iq;
-                }
-            } else if (a.cmvn_mode == CMVN_DEVICE) {
-                // device-style CMVN rounds to int8: keep EXACTLY the arithmetic of cnn_fp32_kernel so that both
-                // paths quantise identically
+    const long long oct_stride = (long long)gridDim.x * TC_GROUPS;
+    long long oct = (long long)blockIdx.x * TC_GROUPS + group;
+
+    // each warp owns two windows of the octet (slots 2*q4, 2*q4 + 1); the raw features of the NEXT octet are
+    // fetched right after this one's operand is written, so their latency hides behind the four GEMM stages
+    TcWin wa, wb;
+    if (oct < n_oct) {
+        tc_load_window(a, oct * TC_CLIPS + 2 * q4, lane, wa);
+        tc_load_window(a, oct * TC_CLIPS + 2 * q4 + 1, lane, wb);
+    }
 #pragma unroll 1
-                for (int q = 0; q < WW_N_MFCC; ++q) {
-                    float v0 = 0.f, v1 = 0.f;
-#pragma unroll
-                    for (int qq = 0; qq < WW_N_MFCC; ++qq)
-                        if (qq == q) { v0 = x0[qq]; v1 = x1[qq]; }
-                    v0 = lround_clamp_i8(v0);
-                    v1 = has1 ? lround_clamp_i8(v1) : 0.f;
-                    const float mean = warp_sum(v0 + v1) / (float)WW_WINDOW_FRAMES;
-                    const float d0 = v0 - mean, d1 = has1 ? v1 - mean : 0.f;
-                    const float ss = warp_sum(d0 * d0 + d1 * d1);
-                    const float den = sqrtf(ss / (float)WW_WINDOW_FRAMES) + 1e-8f;
-                    const float z0 = fminf(fmaxf(lround_clamp_i8(d0 / den) * 16.f, -128.f), 127.f) * 0.0625f;
-                    const float z1 = fminf(fmaxf(lround_clamp_i8(d1 / den) * 16.f, -128.f), 127.f) * 0.0625f;
-#pragma unroll
-                    for (int qq = 0; qq < WW_N_MFCC; ++qq)
-                        if (qq == q) { x0[qq] = z0; x1[qq] = z1; }
-                }
-            }
-            // row R = 64*warp + t + 1; channels 0-7 -> chunk 0, channels 8-12 (+3 zeros) -> chunk 1
-            {
-                const float lo8[8] = {x0[0], x0[1], x0[2], x0[3], x0[4], x0[5], x0[6], x0[7]};
-                const float hi8[8] = {x0[8], x0[9], x0[10], x0[11], x0[12], 0.f, 0.f, 0.f};
-                const int R = 64 * warp + lane + 1;
-                *reinterpret_cast<uint4*>(sA1 + R * 16) = pack_h8(lo8);
-                *reinterpret_cast<uint4*>(sA1 + A1_LBO + R * 16) = pack_h8(hi8);
-            }
-            if (has1) {
-                const float lo8[8] = {x1[0], x1[1], x1[2], x1[3], x1[4], x1[5], x1[6], x1[7]};
-                const float hi8[8] = {x1[8], x1[9], x1[10], x1[11], x1[12], 0.f, 0.f, 0.f};
-                const int R = 64 * warp + lane + 33;
-                *reinterpret_cast<uint4*>(sA1 + R * 16) = pack_h8(lo8);
-                *reinterpret_cast<uint4*>(sA1 + A1_LBO + R * 16) = pack_h8(hi8);
-            }
+    for (; oct < n_oct; oct += oct_stride) {
+        // ================= S0: CMVN two windows per warp, write A1 (fp16) =================
+        tc_cmvn_store(a, wa, 2 * q4, lane, sA1);
+        tc_cmvn_store(a, wb, 2 * q4 + 1, lane, sA1);
+        if (oct + oct_stride < n_oct) {
+            tc_load_window(a, (oct + oct_stride) * TC_CLIPS + 2 * q4, lane, wa);
+            tc_load_window(a, (oct + oct_stride) * TC_CLIPS + 2 * q4 + 1, lane, wb);
         }
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
+        group_sync(group);
 
         // ================= conv1: 4 tiles x 3 taps (K = 16) =================
-        if (tid == 0) {
+        if (tig == 0) {
             tc_fence_after();
             constexpr uint32_t idesc = umma_idesc_f16(128, 32);
 #pragma unroll
@@ -335,8 +373,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
         tc_fence_after();
         // ---- epilogue 1: ReLU + MaxPool(2) over adjacent rows, write A2 rows m/2 + 1 (32 channels) ----
 #pragma unroll 1
-        for (int ii = 0; ii < 2; ++ii) {
-            const int i = 2 * hi + ii;
+        for (int i = 0; i < 4; ++i) {
             float v[32];
             tmem_ld32(tmem + tlane + 32 * i, v);
             const int m = 128 * i + 32 * q4 + lane;
@@ -367,10 +404,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
         }
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
+        group_sync(group);
 
         // ================= conv2: 2 tiles x 3 taps x 2 K-steps =================
-        if (tid == 0) {
+        if (tig == 0) {
             tc_fence_after();
             constexpr uint32_t idesc = umma_idesc_f16(128, 64);
 #pragma unroll
@@ -388,15 +425,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
-        // ---- epilogue 2: rows m2 = 128*hi + 32*q4 + lane, 64 channels, write X3 rows m2/2 + 1 ----
-        {
-            const int m2 = 128 * hi + 32 * q4 + lane;
+        // ---- epilogue 2: rows m2 = 128*h + 32*q4 + lane, 64 channels, write X3 rows m2/2 + 1 ----
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const int m2 = 128 * h + 32 * q4 + lane;
             const bool odd = lane & 1;
             const bool valid = ((m2 & 31) >> 1) < 15;
             const int R3 = (m2 >> 1) + 1;
             float va[32], vb[32];
-            tmem_ld32(tmem + tlane + 64 * hi, va);
-            tmem_ld32(tmem + tlane + 64 * hi + 32, vb);
+            tmem_ld32(tmem + tlane + 64 * h, va);
+            tmem_ld32(tmem + tlane + 64 * h + 32, vb);
             float mine[32];
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
@@ -418,10 +456,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
         }
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
+        group_sync(group);
 
         // ================= conv3 (channels on M): 3 taps x 4 K-steps, N = 128 positions =================
-        if (tid == 0) {
+        if (tig == 0) {
             tc_fence_after();
             constexpr uint32_t idesc = umma_idesc_f16(128, 128);
 #pragma unroll
@@ -436,11 +474,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
         phase ^= 1;
         tc_fence_after();
         // ---- epilogue 3: thread = channel o; per window ReLU + MaxPool + mean over the 7 pooled steps -> G ----
-        {
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
             const int o = 32 * q4 + lane;
             float va[32], vb[32];
-            tmem_ld32(tmem + tlane + 64 * hi, va);
-            tmem_ld32(tmem + tlane + 64 * hi + 32, vb);
+            tmem_ld32(tmem + tlane + 64 * h, va);
+            tmem_ld32(tmem + tlane + 64 * h + 32, vb);
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
                 const float* v = cc < 2 ? va + 16 * cc : vb + 16 * (cc - 2);
@@ -448,17 +487,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
 #pragma unroll
                 for (int j = 0; j < 7; ++j) s += fmaxf(fmaxf(v[2 * j], v[2 * j + 1]), 0.f);
                 const float g = s / 7.f;
-                const int clip = 4 * hi + cc;
+                const int clip = 4 * h + cc;
                 *reinterpret_cast<__half*>(sG + (o >> 3) * G_LBO + clip * 16 + (o & 7) * 2) = __float2half_rn(g);
                 if (a.dbg && oct == 0) a.dbg[8 * 31 * 32 + 8 * 15 * 64 + clip * 128 + o] = g;
             }
         }
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
+        group_sync(group);
 
         // ================= fc1: [128(64) x 128] . [16 x 128]^T, 8 K-steps =================
-        if (tid == 0) {
+        if (tig == 0) {
             tc_fence_after();
             constexpr uint32_t idesc = umma_idesc_f16(128, 16);
 #pragma unroll
@@ -470,11 +509,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
-        // ---- epilogue 4: ReLU, fc2 as a warp reduction (rows 0-63 = warps with quadrant 0/1, first half) ----
-        if (warp < 2) {
+        // ---- epilogue 4: ReLU, fc2 as a warp reduction (rows 0-63 = the warps of lane quadrants 0 and 1) ----
+        if (q4 < 2) {
             float h[16];
             tmem_ld16(tmem + tlane + 128, h);
-            const int o = 32 * warp + lane;
+            const int o = 32 * q4 + lane;
 #pragma unroll
             for (int c8 = 0; c8 < 8; ++c8) h[c8] = fmaxf(h[c8], 0.f);
             if (a.dbg && oct == 0) {
@@ -486,14 +525,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
 #pragma unroll
                 for (int c8 = 0; c8 < 8; ++c8) {
                     const float s = warp_sum(h[c8] * w);
-                    if (lane == 0) part[(warp * 8 + c) * 8 + c8] = s;
+                    if (lane == 0) part[(q4 * 8 + c) * 8 + c8] = s;
                 }
             }
         }
         tc_fence_before();
-        __syncthreads();
-        if (tid < 8 * C) {
-            const int c8 = tid & 7, c = tid >> 3;
+        group_sync(group);
+        if (tig < 8 * C) {
+            const int c8 = tig & 7, c = tig >> 3;
             const long long win = oct * TC_CLIPS + c8;
             if (win < a.n_windows) {
                 const float s = part[(0 * 8 + c) * 8 + c8] + part[(1 * 8 + c) * 8 + c8];
@@ -510,13 +549,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
                 }
             }
         }
-        // `part` is rewritten only after the next octet's four barriers
+        // `part` is rewritten only after the next octet's four group barriers
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TC_TMEM_COLS)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"((uint32_t)TC_TMEM_COLS)
                      : "memory");
     }
 }
