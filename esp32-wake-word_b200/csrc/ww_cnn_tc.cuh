@@ -9,6 +9,7 @@
 // issued by a single thread of the group with tcgen05.mma (kind::f16: fp16 operands, fp32 accumulation in TMEM):
 //   conv1  D[512 pos x 32]  = sum_tap A1[pos+tap][16] . W1_tap[32][16]^T     4 tiles of M=128, K=16 per tap
 //   conv2  D[256 pos x 64]  = sum_tap A2[pos+tap][32] . W2_tap[64][32]^T     2 tiles of M=128
+//          (even and odd output positions are separate tiles, see A1P_ROWS below)
 //   conv3  D[128 ch x 128 pos] = sum_tap W3_tap[128][64] . X3[pos+tap][64]^T   (roles swapped: channel = TMEM lane,
 //                                                            so MaxPool and the global average are per-thread)
 //   fc1    D[128(64) x 16(8 windows)] = WF1[128][128] . G[16][128]^T
@@ -31,11 +32,17 @@ constexpr int TC_THREADS = 256;
 constexpr int TC_CLIPS = 8;
 constexpr int TC_MAX_CLASSES = 8;
 
-constexpr int A1_ROWS = 64 * TC_CLIPS + 2;   // 514: row 0 and every 64th row are zero (conv padding)
-constexpr int A2_ROWS = 32 * TC_CLIPS + 2;   // 258
-constexpr int X3_ROWS = 16 * TC_CLIPS + 2;   // 130
+// conv1 / conv2 operands are stored DE-INTERLEAVED: one tile holds the even positions of every window, a second
+// tile the odd ones (row 1 + 32*w + j <-> position 2j / 2j+1 of window w; row 0 and the last row of each odd
+// block stay zero = conv padding).  A k=3 tap is then still a row-shifted view of one of the two tiles, the conv
+// outputs at even and odd positions come out of separate MMAs into separate TMEM columns of the SAME lane, and
+// MaxPool(2) is a per-thread max -- no shuffles in the epilogues.
+constexpr int A1P_ROWS = 32 * TC_CLIPS + 2;  // 258 rows per parity tile (63 frames -> 32 even + 31 odd positions)
+constexpr int A2P_ROWS = 16 * TC_CLIPS + 2;  // 130 (31 positions -> 16 even + 15 odd)
+constexpr int X3_ROWS = 16 * TC_CLIPS + 2;   // 130: natural order (conv3 pools along TMEM columns)
 constexpr int G_ROWS = 16;                   // fc1 B operand: 8 windows + 8 zero rows (N must be a multiple of 16)
-constexpr int A1_LBO = A1_ROWS * 16, A2_LBO = A2_ROWS * 16, X3_LBO = X3_ROWS * 16, G_LBO = G_ROWS * 16;
+constexpr int A1_LBO = A1P_ROWS * 16, A2_LBO = A2P_ROWS * 16, X3_LBO = X3_ROWS * 16, G_LBO = G_ROWS * 16;
+constexpr int A1_PAR = 2 * A1_LBO, A2_PAR = 4 * A2_LBO;  // bytes per parity tile
 constexpr int W1_LBO = 32 * 16, W2_LBO = 64 * 16, W3_LBO = 128 * 16, WF1_LBO = 128 * 16;
 constexpr int W1_TAP = 2 * W1_LBO, W2_TAP = 4 * W2_LBO, W3_TAP = 8 * W3_LBO;
 
@@ -54,8 +61,8 @@ constexpr int TC_WF1 = TC_W3 + 3 * W3_TAP;
 constexpr int TC_W_BYTES = TC_WF1 + 16 * WF1_LBO;              // 97 280
 constexpr int TC_OFF_ACT = TC_OFF_W + TC_W_BYTES;              // per-group activation tiles
 constexpr int TC_ACT_A1 = 0;
-constexpr int TC_ACT_A2 = TC_ACT_A1 + 2 * A1_LBO;
-constexpr int TC_ACT_X3 = TC_ACT_A2 + 4 * A2_LBO;
+constexpr int TC_ACT_A2 = TC_ACT_A1 + 2 * A1_PAR;
+constexpr int TC_ACT_X3 = TC_ACT_A2 + 2 * A2_PAR;
 constexpr int TC_ACT_G = TC_ACT_X3 + 8 * X3_LBO;
 constexpr int TC_ACT_BYTES = TC_ACT_G + 16 * G_LBO;            // 53 696
 constexpr int TC_SMEM = TC_OFF_ACT + TC_GROUPS * TC_ACT_BYTES;
@@ -133,6 +140,34 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// two 32-column loads in flight, one wait
+__device__ __forceinline__ void tmem_ld32x2(uint32_t ta, uint32_t tb, float (&va)[32], float (&vb)[32]) {
+    uint32_t r[32], q[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(ta));
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+          "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15]), "=r"(q[16]),
+          "=r"(q[17]), "=r"(q[18]), "=r"(q[19]), "=r"(q[20]), "=r"(q[21]), "=r"(q[22]), "=r"(q[23]), "=r"(q[24]),
+          "=r"(q[25]), "=r"(q[26]), "=r"(q[27]), "=r"(q[28]), "=r"(q[29]), "=r"(q[30]), "=r"(q[31])
+        : "r"(tb));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        va[i] = __uint_as_float(r[i]);
+        vb[i] = __uint_as_float(q[i]);
+    }
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
     asm volatile(
@@ -205,11 +240,14 @@ __device__ __forceinline__ void tc_load_window(const TcArgs& a, long long win, i
     if (live)
         wbase = a.group_windows ? a.feats + (win / a.group_windows) * a.group_stride + (win % a.group_windows) * a.win_stride
                                 : a.feats + win * a.win_stride;
+    const float* p0 = wbase + lane * a.frame_stride;
+    const float* p1 = p0 + 32 * a.frame_stride;
 #pragma unroll
     for (int q = 0; q < WW_N_MFCC; ++q) {
-        const float* row = wbase + q * a.coef_stride;
-        w.x0[q] = live ? row[lane * a.frame_stride] : 0.f;
-        w.x1[q] = (live && has1) ? row[(lane + 32) * a.frame_stride] : 0.f;
+        w.x0[q] = live ? *p0 : 0.f;
+        w.x1[q] = (live && has1) ? *p1 : 0.f;
+        p0 += a.coef_stride;
+        p1 += a.coef_stride;
     }
 }
 
@@ -223,10 +261,12 @@ __device__ __forceinline__ void tc_cmvn_store(const TcArgs& a, TcWin& w, int slo
         float v[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) v[q] = q < WW_N_MFCC ? x0[q] + x1[q] : 0.f;
-        const float tot = reduce16(v, lane);  // lane 2q holds sum_t x[q][t]
+        // lane 2q holds sum_t x[q][t]; the mean is a multiply here (the operand is rounded to fp16 anyway; the exact
+        // division lives in cnn_fp32_kernel, which re-scores every window near the threshold)
+        const float tot = reduce16(v, lane) * (1.f / (float)WW_WINDOW_FRAMES);
         float mean[WW_N_MFCC];
 #pragma unroll
-        for (int q = 0; q < WW_N_MFCC; ++q) mean[q] = __shfl_sync(0xffffffffu, tot, 2 * q) / (float)WW_WINDOW_FRAMES;
+        for (int q = 0; q < WW_N_MFCC; ++q) mean[q] = __shfl_sync(0xffffffffu, tot, 2 * q);
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             if (q < WW_N_MFCC) {
@@ -238,7 +278,7 @@ __device__ __forceinline__ void tc_cmvn_store(const TcArgs& a, TcWin& w, int slo
             }
         }
         const float ss = reduce16(v, lane);
-        float sd = sqrtf(ss / (float)(WW_WINDOW_FRAMES - 1));
+        float sd = sqrtf(ss * (1.f / (float)(WW_WINDOW_FRAMES - 1)));
         if (sd == 0.f) sd = 1.f;
         const float inv = __frcp_rn(sd + 1e-8f);
 #pragma unroll
@@ -269,20 +309,20 @@ __device__ __forceinline__ void tc_cmvn_store(const TcArgs& a, TcWin& w, int slo
                 if (qq == q) { x0[qq] = z0; x1[qq] = z1; }
         }
     }
-    // row R = 64*slot + t + 1; channels 0-7 -> chunk 0, channels 8-12 (+3 zeros) -> chunk 1
+    // frame t -> parity tile t & 1, row 1 + 32*slot + (t >> 1); channels 0-7 -> chunk 0, 8-12 (+3 zeros) -> chunk 1
     {
         const float lo8[8] = {x0[0], x0[1], x0[2], x0[3], x0[4], x0[5], x0[6], x0[7]};
         const float hi8[8] = {x0[8], x0[9], x0[10], x0[11], x0[12], 0.f, 0.f, 0.f};
-        const int R = 64 * slot + lane + 1;
-        *reinterpret_cast<uint4*>(sA1 + R * 16) = pack_h8(lo8);
-        *reinterpret_cast<uint4*>(sA1 + A1_LBO + R * 16) = pack_h8(hi8);
+        unsigned char* dst = sA1 + (lane & 1) * A1_PAR + (1 + 32 * slot + (lane >> 1)) * 16;
+        *reinterpret_cast<uint4*>(dst) = pack_h8(lo8);
+        *reinterpret_cast<uint4*>(dst + A1_LBO) = pack_h8(hi8);
     }
     if (has1) {
         const float lo8[8] = {x1[0], x1[1], x1[2], x1[3], x1[4], x1[5], x1[6], x1[7]};
         const float hi8[8] = {x1[8], x1[9], x1[10], x1[11], x1[12], 0.f, 0.f, 0.f};
-        const int R = 64 * slot + lane + 33;
-        *reinterpret_cast<uint4*>(sA1 + R * 16) = pack_h8(lo8);
-        *reinterpret_cast<uint4*>(sA1 + A1_LBO + R * 16) = pack_h8(hi8);
+        unsigned char* dst = sA1 + (lane & 1) * A1_PAR + (1 + 32 * slot + 16 + (lane >> 1)) * 16;
+        *reinterpret_cast<uint4*>(dst) = pack_h8(lo8);
+        *reinterpret_cast<uint4*>(dst + A1_LBO) = pack_h8(hi8);
     }
 }
 
@@ -356,102 +396,98 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
         tc_fence_before();
         group_sync(group);
 
-        // ================= conv1: 4 tiles x 3 taps (K = 16) =================
+        // ================= conv1: 2 row tiles x {even, odd outputs} x 3 taps (K = 16) =================
+        // even output 2j = W0.x[2j-1] + W1.x[2j] + W2.x[2j+1] -> taps (odd, R-1), (even, R), (odd, R)
+        // odd  output 2j+1 = W0.x[2j] + W1.x[2j+1] + W2.x[2j+2] -> taps (even, R), (odd, R), (even, R+1)
         if (tig == 0) {
             tc_fence_after();
             constexpr uint32_t idesc = umma_idesc_f16(128, 32);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int r = 0; r < 3; ++r)
-                    umma_f16(tmem + 32 * i, umma_desc_kmajor(sA1a + (128 * i + r) * 16, A1_LBO),
-                             umma_desc_kmajor(sWa + TC_W1 + r * W1_TAP, W1_LBO), idesc, r > 0);
+                for (int par = 0; par < 2; ++par)
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const int src_par = par ? (r == 1) : (r != 1);             // tile holding this tap
+                        const int shift = par ? (r == 2) : -(r == 0);              // row shift inside that tile
+                        umma_f16(tmem + 64 * i + 32 * par,
+                                 umma_desc_kmajor(sA1a + src_par * A1_PAR + (1 + 128 * i + shift) * 16, A1_LBO),
+                                 umma_desc_kmajor(sWa + TC_W1 + r * W1_TAP, W1_LBO), idesc, r > 0);
+                    }
             umma_commit(bar);
         }
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
-        // ---- epilogue 1: ReLU + MaxPool(2) over adjacent rows, write A2 rows m/2 + 1 (32 channels) ----
+        // ---- epilogue 1: lane = pooled position (w, j): max(even, odd, 0) over 32 channels -> conv2 operand ----
 #pragma unroll 1
-        for (int i = 0; i < 4; ++i) {
-            float v[32];
-            tmem_ld32(tmem + tlane + 32 * i, v);
-            const int m = 128 * i + 32 * q4 + lane;
-            const bool odd = lane & 1;
-            float mine[16];
+        for (int i = 0; i < 2; ++i) {
+            float ve[32], vo[32];
+            tmem_ld32x2(tmem + tlane + 64 * i, tmem + tlane + 64 * i + 32, ve, vo);
+            const int g = 128 * i + 32 * q4 + lane;
+            const int w = g >> 5, j = g & 31;
+            float mine[32];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                const float send = odd ? v[c] : v[16 + c];
-                const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-                const float own = odd ? v[16 + c] : v[c];
-                mine[c] = fmaxf(fmaxf(own, recv), 0.f);
-            }
-            const bool valid = ((m & 63) >> 1) < 31;
-            if (!valid) {
+            for (int c = 0; c < 32; ++c) mine[c] = fmaxf(fmaxf(ve[c], vo[c]), 0.f);
+            if (j < 31) {
+                unsigned char* dst = sA2 + (j & 1) * A2_PAR + (1 + 16 * w + (j >> 1)) * 16;
 #pragma unroll
-                for (int c = 0; c < 16; ++c) mine[c] = 0.f;
-            }
-            const int R2 = (m >> 1) + 1;
-            unsigned char* dst = sA2 + (odd ? 2 : 0) * A2_LBO + R2 * 16;
-            *reinterpret_cast<uint4*>(dst) = pack_h8(mine);
-            *reinterpret_cast<uint4*>(dst + A2_LBO) = pack_h8(mine + 8);
-            if (a.dbg && oct == 0 && valid) {
-                // dbg[0 .. 8*31*32): pooled conv1 activations [clip][t][ch]
-                const int clip = m >> 6, t = (m & 63) >> 1;
+                for (int gch = 0; gch < 4; ++gch) *reinterpret_cast<uint4*>(dst + gch * A2_LBO) = pack_h8(mine + 8 * gch);
+                if (a.dbg && oct == 0) {
+                    // dbg[0 .. 8*31*32): pooled conv1 activations [clip][t][ch]
 #pragma unroll
-                for (int c = 0; c < 16; ++c) a.dbg[(clip * 31 + t) * 32 + (odd ? 16 : 0) + c] = mine[c];
+                    for (int c = 0; c < 32; ++c) a.dbg[(w * 31 + j) * 32 + c] = mine[c];
+                }
             }
         }
         fence_async_smem();
         tc_fence_before();
         group_sync(group);
 
-        // ================= conv2: 2 tiles x 3 taps x 2 K-steps =================
+        // ================= conv2: {even, odd outputs} x 3 taps x 2 K-steps (M = 128 pooled-pair rows) =================
         if (tig == 0) {
             tc_fence_after();
             constexpr uint32_t idesc = umma_idesc_f16(128, 64);
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
+            for (int par = 0; par < 2; ++par)
 #pragma unroll
                 for (int r = 0; r < 3; ++r)
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks)
-                        umma_f16(tmem + 64 * i,
-                                 umma_desc_kmajor(sA2a + (128 * i + r) * 16 + ks * 2 * A2_LBO, A2_LBO),
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const int src_par = par ? (r == 1) : (r != 1);
+                        const int shift = par ? (r == 2) : -(r == 0);
+                        umma_f16(tmem + 64 * par,
+                                 umma_desc_kmajor(sA2a + src_par * A2_PAR + (1 + shift) * 16 + ks * 2 * A2_LBO, A2_LBO),
                                  umma_desc_kmajor(sWa + TC_W2 + r * W2_TAP + ks * 2 * W2_LBO, W2_LBO), idesc,
                                  (r | ks) > 0);
+                    }
             umma_commit(bar);
         }
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
-        // ---- epilogue 2: rows m2 = 128*h + 32*q4 + lane, 64 channels, write X3 rows m2/2 + 1 ----
+        // ---- epilogue 2: lane = pooled position (w, m): 64 channels -> X3 row 1 + 16 w + m (natural order) ----
+        {
+            const int g = 32 * q4 + lane;
+            const int w = g >> 4, m = g & 15;
+            const bool valid = m < 15;
+            unsigned char* dst = sX3 + (1 + g) * 16;
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-            const int m2 = 128 * h + 32 * q4 + lane;
-            const bool odd = lane & 1;
-            const bool valid = ((m2 & 31) >> 1) < 15;
-            const int R3 = (m2 >> 1) + 1;
-            float va[32], vb[32];
-            tmem_ld32(tmem + tlane + 64 * h, va);
-            tmem_ld32(tmem + tlane + 64 * h + 32, vb);
-            float mine[32];
+            for (int hh = 0; hh < 2; ++hh) {
+                float ve[32], vo[32];
+                tmem_ld32x2(tmem + tlane + 32 * hh, tmem + tlane + 64 + 32 * hh, ve, vo);
+                float mine[32];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const float send = odd ? va[c] : vb[c];
-                const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-                const float own = odd ? vb[c] : va[c];
-                mine[c] = valid ? fmaxf(fmaxf(own, recv), 0.f) : 0.f;
-            }
-            unsigned char* dst = sX3 + (odd ? 4 : 0) * X3_LBO + R3 * 16;
+                for (int c = 0; c < 32; ++c) mine[c] = valid ? fmaxf(fmaxf(ve[c], vo[c]), 0.f) : 0.f;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(dst + g * X3_LBO) = pack_h8(mine + 8 * g);
-            if (a.dbg && oct == 0 && valid) {
-                // dbg[8*31*32 ..): pooled conv2 activations [clip][t][ch]
-                float* d2 = a.dbg + 8 * 31 * 32;
-                const int clip = m2 >> 5, t = (m2 & 31) >> 1;
+                for (int gch = 0; gch < 4; ++gch)
+                    *reinterpret_cast<uint4*>(dst + (4 * hh + gch) * X3_LBO) = pack_h8(mine + 8 * gch);
+                if (a.dbg && oct == 0 && valid) {
+                    // dbg[8*31*32 ..): pooled conv2 activations [clip][t][ch]
+                    float* d2 = a.dbg + 8 * 31 * 32;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) d2[(clip * 15 + t) * 64 + (odd ? 32 : 0) + c] = mine[c];
+                    for (int c = 0; c < 32; ++c) d2[(w * 15 + m) * 64 + 32 * hh + c] = mine[c];
+                }
             }
         }
         fence_async_smem();
@@ -486,7 +522,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
                 float s = 0.f;
 #pragma unroll
                 for (int j = 0; j < 7; ++j) s += fmaxf(fmaxf(v[2 * j], v[2 * j + 1]), 0.f);
-                const float g = s / 7.f;
+                const float g = s * (1.f / 7.f);
                 const int clip = 4 * h + cc;
                 *reinterpret_cast<__half*>(sG + (o >> 3) * G_LBO + clip * 16 + (o & 7) * 2) = __float2half_rn(g);
                 if (a.dbg && oct == 0) a.dbg[8 * 31 * 32 + 8 * 15 * 64 + clip * 128 + o] = g;
