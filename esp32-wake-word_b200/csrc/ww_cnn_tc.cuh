@@ -4,7 +4,7 @@
 // device CMVN (esp_wake_word_detector.cpp:179-211), LightweightKWS.forward (wakeModel.py:29-34) and the
 // decision (ml_models/main.py:53, esp_wake_word_detector.cpp:226-245) for 63-frame windows.
 //
-// One persistent CTA per SM runs two independent 4-warp groups; each group scores EIGHT windows per iteration, so
+// One persistent CTA per SM runs TC_GROUPS (3) independent 4-warp groups; each group scores EIGHT windows per iteration, so
 // one group's TMEM epilogues (CUDA cores) overlap the other group's MMAs and waits.  Every layer is an implicit GEMM
 // issued by a single thread of the group with tcgen05.mma (kind::f16: fp16 operands, fp32 accumulation in TMEM):
 //   conv1  D[512 pos x 32]  = sum_tap A1[pos+tap][16] . W1_tap[32][16]^T     4 tiles of M=128, K=16 per tap
@@ -28,7 +28,8 @@
 
 namespace ww {
 
-constexpr int TC_THREADS = 256;
+constexpr int TC_GROUPS = 3;      // independent 4-warp groups per CTA
+constexpr int TC_THREADS = 128 * TC_GROUPS;
 constexpr int TC_CLIPS = 8;
 constexpr int TC_MAX_CLASSES = 8;
 
@@ -48,9 +49,8 @@ constexpr int W1_TAP = 2 * W1_LBO, W2_TAP = 4 * W2_LBO, W3_TAP = 8 * W3_LBO;
 
 // shared memory map (bytes).  The CTA runs TWO independent 4-warp groups, each scoring its own octet of windows
 // with its own activation tiles, mbarrier and TMEM columns; the weights are shared.
-constexpr int TC_GROUPS = 2;
 constexpr int TC_GROUP_THREADS = TC_THREADS / TC_GROUPS;       // 128: one warp per TMEM lane quadrant
-constexpr int TC_OFF_BAR = 0;                                  // mbarrier[2] (16) + tmem base (4)
+constexpr int TC_OFF_BAR = 0;                                  // mbarrier[TC_GROUPS] + tmem base (4) at +32
 constexpr int TC_OFF_PART = 64;                                // fc2 partial sums [group][2][8][8] floats
 constexpr int TC_OFF_FC2 = TC_OFF_PART + TC_GROUPS * 2 * 8 * 8 * 4;  // fc2 weights [8][64] floats
 constexpr int TC_OFF_W = TC_OFF_FC2 + TC_MAX_CLASSES * 64 * 4;  // weight blob (same layout as the device blob)
@@ -60,18 +60,21 @@ constexpr int TC_W3 = TC_W2 + 3 * W2_TAP;
 constexpr int TC_WF1 = TC_W3 + 3 * W3_TAP;
 constexpr int TC_W_BYTES = TC_WF1 + 16 * WF1_LBO;              // 97 280
 constexpr int TC_OFF_ACT = TC_OFF_W + TC_W_BYTES;              // per-group activation tiles
+// A1 (conv1 operand) and X3 (conv3 operand) share storage: A1 is dead once conv1 has completed, X3 is written by
+// the conv2 epilogue.  The zero rows each of them relies on are re-written every octet (see S0 / epilogue 2).
 constexpr int TC_ACT_A1 = 0;
-constexpr int TC_ACT_A2 = TC_ACT_A1 + 2 * A1_PAR;
-constexpr int TC_ACT_X3 = TC_ACT_A2 + 2 * A2_PAR;
-constexpr int TC_ACT_G = TC_ACT_X3 + 8 * X3_LBO;
-constexpr int TC_ACT_BYTES = TC_ACT_G + 16 * G_LBO;            // 53 696
+constexpr int TC_ACT_X3 = 0;
+constexpr int TC_ACT_A2 = (2 * A1_PAR > 8 * X3_LBO ? 2 * A1_PAR : 8 * X3_LBO);
+constexpr int TC_ACT_G = TC_ACT_A2 + 2 * A2_PAR;
+constexpr int TC_ACT_BYTES = TC_ACT_G + 16 * G_LBO;            // 37 376
 constexpr int TC_SMEM = TC_OFF_ACT + TC_GROUPS * TC_ACT_BYTES;
 static_assert(TC_OFF_W % 16 == 0 && TC_OFF_ACT % 16 == 0 && TC_ACT_A2 % 16 == 0 && TC_ACT_X3 % 16 == 0 &&
                   TC_ACT_G % 16 == 0 && TC_ACT_BYTES % 16 == 0,
               "UMMA operands need 16-byte alignment");
 static_assert(TC_SMEM <= 232448, "shared memory budget");
-constexpr int TC_GROUP_COLS = 256;  // per group: conv accumulators use columns [0,128), fc1 uses [128,144)
-constexpr int TC_TMEM_COLS = TC_GROUPS * TC_GROUP_COLS;
+constexpr int TC_GROUP_COLS = 160;  // per group: conv accumulators use columns [0,128), fc1 uses [128,144)
+constexpr int TC_TMEM_COLS = 512;
+static_assert(TC_GROUPS * TC_GROUP_COLS <= TC_TMEM_COLS, "TMEM columns");
 
 struct TcArgs {
     const float* feats;  // feats[win*win_stride + coef*coef_stride + frame*frame_stride]
@@ -317,18 +320,24 @@ __device__ __forceinline__ void tc_cmvn_store(const TcArgs& a, TcWin& w, int slo
         *reinterpret_cast<uint4*>(dst) = pack_h8(lo8);
         *reinterpret_cast<uint4*>(dst + A1_LBO) = pack_h8(hi8);
     }
-    if (has1) {
+    {
+        // lane 31 holds the non-existent frame 63 (x1 == 0): it writes the zero pad row that ends the odd block
         const float lo8[8] = {x1[0], x1[1], x1[2], x1[3], x1[4], x1[5], x1[6], x1[7]};
         const float hi8[8] = {x1[8], x1[9], x1[10], x1[11], x1[12], 0.f, 0.f, 0.f};
         unsigned char* dst = sA1 + (lane & 1) * A1_PAR + (1 + 32 * slot + 16 + (lane >> 1)) * 16;
         *reinterpret_cast<uint4*>(dst) = pack_h8(lo8);
         *reinterpret_cast<uint4*>(dst + A1_LBO) = pack_h8(hi8);
     }
+    if (slot == 0 && lane == 0) {
+        // row 0 of the odd tile (x[-1] of the first window); the storage is shared with X3, so re-zero it every octet
+        *reinterpret_cast<uint4*>(sA1 + A1_PAR) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(sA1 + A1_PAR + A1_LBO) = make_uint4(0, 0, 0, 0);
+    }
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TC_OFF_BAR + 16);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TC_OFF_BAR + 32);
     float* sfc2 = reinterpret_cast<float*>(smem + TC_OFF_FC2);
     unsigned char* sW = smem + TC_OFF_W;
 
@@ -352,8 +361,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
     for (int i = tid; i < TC_W_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sW)[i] = __ldg(a.wblob + i);
     for (int i = tid; i < C * 64; i += TC_THREADS) sfc2[i] = __ldg(a.fc2 + i);
     if (tid == 0) {
-        mbar_init(reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR), 1);
-        mbar_init(reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR) + 1, 1);
+        for (int g = 0; g < TC_GROUPS; ++g) mbar_init(reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR) + g, 1);
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -376,21 +384,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
     const long long oct_stride = (long long)gridDim.x * TC_GROUPS;
     long long oct = (long long)blockIdx.x * TC_GROUPS + group;
 
-    // each warp owns two windows of the octet (slots 2*q4, 2*q4 + 1); the raw features of the NEXT octet are
-    // fetched right after this one's operand is written, so their latency hides behind the four GEMM stages
-    TcWin wa, wb;
-    if (oct < n_oct) {
-        tc_load_window(a, oct * TC_CLIPS + 2 * q4, lane, wa);
-        tc_load_window(a, oct * TC_CLIPS + 2 * q4 + 1, lane, wb);
-    }
+    // each warp owns two windows of the octet (slots 2*q4, 2*q4 + 1); the other groups' GEMM stages and epilogues
+    // hide the latency of these loads
 #pragma unroll 1
     for (; oct < n_oct; oct += oct_stride) {
         // ================= S0: CMVN two windows per warp, write A1 (fp16) =================
-        tc_cmvn_store(a, wa, 2 * q4, lane, sA1);
-        tc_cmvn_store(a, wb, 2 * q4 + 1, lane, sA1);
-        if (oct + oct_stride < n_oct) {
-            tc_load_window(a, (oct + oct_stride) * TC_CLIPS + 2 * q4, lane, wa);
-            tc_load_window(a, (oct + oct_stride) * TC_CLIPS + 2 * q4 + 1, lane, wb);
+        {
+            TcWin wa, wb;
+            tc_load_window(a, oct * TC_CLIPS + 2 * q4, lane, wa);
+            tc_load_window(a, oct * TC_CLIPS + 2 * q4 + 1, lane, wb);
+            tc_cmvn_store(a, wa, 2 * q4, lane, sA1);
+            tc_cmvn_store(a, wb, 2 * q4 + 1, lane, sA1);
         }
         fence_async_smem();
         tc_fence_before();
@@ -472,6 +476,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
             const int w = g >> 4, m = g & 15;
             const bool valid = m < 15;
             unsigned char* dst = sX3 + (1 + g) * 16;
+            if (g < 8) *reinterpret_cast<uint4*>(sX3 + g * X3_LBO) = make_uint4(0, 0, 0, 0);  // row 0 (shared with A1)
 #pragma unroll 1
             for (int hh = 0; hh < 2; ++hh) {
                 float ve[32], vo[32];
