@@ -3,7 +3,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -11,6 +13,7 @@
 #include "ww_cnn.cuh"
 #include "ww_cnn_i8.cuh"
 #include "ww_ctc.cuh"
+#include "ww_frontdsp.cuh"
 #include "ww_mfcc.cuh"
 #include "ww_tables.h"
 #ifdef WW_WITH_TC
@@ -1162,6 +1165,192 @@ extern "C" int ww_debug_tc(ww_ctx* ctx, float* dbg_dev, int* last_rescored) {
     (void)last_rescored;
     return fail(ctx, WW_ERR_UNSUPPORTED, "tensor-core CNN not built into this library");
 #endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// WAV ingestion: wav::WavHeader (main/esp_wav/esp_wav.cpp:8-139) over a memory image
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct ByteReader {
+    const unsigned char* p;
+    size_t n, pos = 0;
+    bool read(void* dst, size_t k) {  // fread(...) != count -> the reference logs and returns
+        if (pos + k > n) return false;
+        memcpy(dst, p + pos, k);
+        pos += k;
+        return true;
+    }
+};
+}  // namespace
+
+extern "C" int ww_wav_parse(const void* bytes, size_t n_bytes, int max_samples, ww_wav_info* info) {
+    if (!bytes || !info || max_samples < 0) return WW_ERR_INVALID;
+    memset(info, 0, sizeof(*info));
+    ByteReader r{static_cast<const unsigned char*>(bytes), n_bytes};
+    char riff[4], wave[4], fmt[4], tag[4];
+    // esp_wav.cpp:22-62: a wrong tag is only logged, parsing goes on; isValid() reports it later
+    if (!r.read(riff, 4) || !r.read(&info->riff_length, 4) || !r.read(wave, 4) || !r.read(fmt, 4)) return WW_ERR_INVALID;
+    // :65-93: the 16 standard fmt bytes (fmt_length is recorded, extra fmt bytes are NOT skipped)
+    if (!r.read(&info->fmt_length, 4) || !r.read(&info->audio_format, 2) || !r.read(&info->num_channels, 2) ||
+        !r.read(&info->sample_rate, 4) || !r.read(&info->byte_rate, 4) || !r.read(&info->block_align, 2) ||
+        !r.read(&info->bits_per_sample, 2))
+        return WW_ERR_INVALID;
+    // :95-121: skip chunks by their size (no pad byte) until "data"
+    bool found = false;
+    for (;;) {
+        uint32_t chunk_size;
+        if (!r.read(tag, 4) || !r.read(&chunk_size, 4)) break;
+        if (memcmp(tag, "data", 4) == 0) {
+            info->data_length = chunk_size;
+            found = true;
+            break;
+        }
+        if (chunk_size > r.n - r.pos) {  // fseek past the end succeeds on a file; the next fread then fails
+            r.pos = r.n;
+            continue;
+        }
+        r.pos += chunk_size;
+    }
+    if (!found) return WW_ERR_INVALID;  // :123-126
+    info->raw_data_pos = (uint32_t)r.pos;
+    size_t samples = info->data_length / sizeof(int16_t);  // :128-132
+    if (samples > (size_t)max_samples) samples = (size_t)max_samples;
+    const size_t present = (r.n - r.pos) / sizeof(int16_t);
+    if (samples > present) samples = present;
+    info->n_samples = (uint32_t)samples;
+    info->valid = memcmp(riff, "RIFF", 4) == 0 && memcmp(wave, "WAVE", 4) == 0 && memcmp(fmt, "fmt ", 4) == 0 &&
+                  info->audio_format == 1 && info->num_channels > 0 && info->sample_rate > 0 &&
+                  info->bits_per_sample > 0;  // esp_wav.hpp:109-118
+    return WW_OK;
+}
+
+static int wav_load_one(const char* path, int clip_samples, int16_t* dst, ww_wav_info* info_out) {
+    ww_wav_info info;
+    memset(&info, 0, sizeof(info));
+    memset(dst, 0, sizeof(int16_t) * (size_t)clip_samples);
+    FILE* f = path ? fopen(path, "rb") : nullptr;
+    int rc = WW_ERR_INVALID;
+    if (f) {
+        // header + chunk walk need random access over a few hundred bytes at most; read the file in one go
+        std::vector<unsigned char> buf;
+        if (fseek(f, 0, SEEK_END) == 0) {
+            const long sz = ftell(f);
+            if (sz > 0 && fseek(f, 0, SEEK_SET) == 0) {
+                // only the part that can matter: everything up to clip_samples past a 64 KiB header allowance
+                buf.resize((size_t)sz);
+                if (fread(buf.data(), 1, buf.size(), f) != buf.size()) buf.clear();
+            }
+        }
+        fclose(f);
+        if (!buf.empty()) {
+            rc = ww_wav_parse(buf.data(), buf.size(), clip_samples, &info);
+            if (rc == WW_OK) {
+                if (!info.valid) rc = WW_ERR_INVALID;
+                else if (info.bits_per_sample != 16) rc = WW_ERR_UNSUPPORTED;
+                else memcpy(dst, buf.data() + info.raw_data_pos, sizeof(int16_t) * (size_t)info.n_samples);
+            }
+        }
+    }
+    if (info_out) *info_out = info;
+    return rc;
+}
+
+extern "C" int ww_wav_load_batch(const char* const* paths, int n, int clip_samples, int n_threads, int16_t* pcm_host,
+                                 ww_wav_info* infos, int* status) {
+    if (!paths || n < 0 || clip_samples <= 0 || !pcm_host) return WW_ERR_INVALID;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > n) n_threads = n > 0 ? n : 1;
+    std::atomic<int> next(0), failed(0);
+    auto worker = [&]() {
+        for (;;) {
+            const int i = next.fetch_add(1);
+            if (i >= n) break;
+            const int rc = wav_load_one(paths[i], clip_samples, pcm_host + (size_t)i * clip_samples, infos ? infos + i : nullptr);
+            if (status) status[i] = rc;
+            if (rc != WW_OK) failed.fetch_add(1);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
+    return failed.load();
+}
+
+extern "C" int ww_wav_write(const char* path, const int16_t* pcm, size_t n_samples, int num_channels, int sample_rate) {
+    if (!path || (!pcm && n_samples) || num_channels <= 0 || sample_rate <= 0) return WW_ERR_INVALID;
+    // WavHeader::initialize (esp_wav.hpp:55-75) with bits_per_sample = 16, then toByteArray (:124-145)
+    const uint32_t data_length = (uint32_t)(n_samples * sizeof(int16_t));
+    const uint16_t channels = (uint16_t)num_channels, bps = 16, fmt = 1, block_align = (uint16_t)(channels * bps / 8);
+    const uint32_t sr = (uint32_t)sample_rate, byte_rate = sr * block_align, riff_length = 36 + data_length, fmt_length = 16;
+    unsigned char h[44];
+    memcpy(h, "RIFF", 4);
+    memcpy(h + 4, &riff_length, 4);
+    memcpy(h + 8, "WAVE", 4);
+    memcpy(h + 12, "fmt ", 4);
+    memcpy(h + 16, &fmt_length, 4);
+    memcpy(h + 20, &fmt, 2);
+    memcpy(h + 22, &channels, 2);
+    memcpy(h + 24, &sr, 4);
+    memcpy(h + 28, &byte_rate, 4);
+    memcpy(h + 32, &block_align, 2);
+    memcpy(h + 34, &bps, 2);
+    memcpy(h + 36, "data", 4);
+    memcpy(h + 40, &data_length, 4);
+    FILE* f = fopen(path, "wb");
+    if (!f) return WW_ERR_INVALID;
+    bool ok = fwrite(h, 1, 44, f) == 44 && (n_samples == 0 || fwrite(pcm, sizeof(int16_t), n_samples, f) == n_samples);
+    ok = fclose(f) == 0 && ok;
+    return ok ? WW_OK : WW_ERR_INVALID;
+}
+
+// ------------------------------------------------------------------------------------------------
+// front-of-frontend DSP
+// ------------------------------------------------------------------------------------------------
+extern "C" int ww_tdm_downmix(ww_ctx* ctx, const int16_t* tdm, long long n_signals, long long n_out, long long in_stride,
+                              int16_t* pcm_out, long long out_stride, ww_stream_t stream) {
+    if (!ctx) return WW_ERR_INVALID;
+    if (n_signals < 0 || n_out < 0 || in_stride < 12 * n_out || out_stride < n_out) return fail(ctx, WW_ERR_INVALID, "bad TDM geometry");
+    if (n_signals == 0 || n_out == 0) return WW_OK;
+    if (!tdm || !pcm_out) return fail(ctx, WW_ERR_INVALID, "null buffer");
+    TdmArgs a;
+    a.tdm = tdm;
+    a.in_stride = in_stride;
+    a.out = pcm_out;
+    a.out_stride = out_stride;
+    a.n_signals = n_signals;
+    a.n_out = n_out;
+    a.vec_ok = ((uintptr_t)tdm % 16 == 0) && (in_stride % 8 == 0) && ((uintptr_t)pcm_out % 8 == 0) && (out_stride % 4 == 0);
+    const long long items = n_signals * ((n_out + 3) / 4);
+    long long blocks = (items + 255) / 256;
+    const long long cap = (long long)ctx->sm_count * 16;  // 8 resident CTAs per SM, two waves
+    if (blocks > cap) blocks = cap;
+    tdm_downmix_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    CK(cudaGetLastError());
+    return WW_OK;
+}
+
+extern "C" int ww_augment_waveform(ww_ctx* ctx, const float* audio, long long n, int L, float* out, ww_stream_t stream) {
+    if (!ctx) return WW_ERR_INVALID;
+    if (n < 0 || L < 2) return fail(ctx, WW_ERR_INVALID, "bad augmentation geometry");
+    if (n == 0) return WW_OK;
+    if (!audio || !out) return fail(ctx, WW_ERR_INVALID, "null buffer");
+    AugArgs a;
+    a.audio = audio;
+    a.out = out;
+    a.n = n;
+    a.L = L;
+    a.len08 = (int)((double)L * 0.8);  // int(audio.shape[1] * speed), extract_mfcc.py:105
+    a.len12 = (int)((double)L * 1.2);
+    a.scale08 = (float)L / (float)a.len08;
+    a.scale12 = (float)L / (float)a.len12;
+    const long long items = n * L;
+    long long blocks = (items + 255) / 256;
+    const long long cap = (long long)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    augment_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    CK(cudaGetLastError());
+    return WW_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

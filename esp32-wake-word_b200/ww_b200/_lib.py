@@ -28,7 +28,16 @@ EXPORTS = [
     "ww_stream_score", "ww_stream_events", "ww_session_open", "ww_session_write", "ww_session_poll",
     "ww_session_windows", "ww_session_last_logits", "ww_session_close", "ww_ctc_greedy", "ww_ctc_loss_workspace_bytes",
     "ww_ctc_loss_fwd", "ww_ctc_loss_bwd", "ww_debug_tc", "ww_extract_mfcc", "ww_free_mfcc",
+    "ww_wav_parse", "ww_wav_load_batch", "ww_wav_write", "ww_tdm_downmix", "ww_augment_waveform",
 ]
+
+
+class WavInfo(C.Structure):
+    """ww_wav_info (include/ww_b200.h): the fields of wav::WavHeader, esp_wav.hpp:24-40."""
+    _fields_ = [("riff_length", C.c_uint32), ("fmt_length", C.c_uint32), ("audio_format", C.c_uint16),
+                ("num_channels", C.c_uint16), ("sample_rate", C.c_uint32), ("byte_rate", C.c_uint32),
+                ("block_align", C.c_uint16), ("bits_per_sample", C.c_uint16), ("data_length", C.c_uint32),
+                ("raw_data_pos", C.c_uint32), ("n_samples", C.c_uint32), ("valid", C.c_int32)]
 
 
 class WWError(RuntimeError):
@@ -90,6 +99,11 @@ def load_library():
         lib.ww_extract_mfcc.restype = C.POINTER(C.c_float)
         lib.ww_free_mfcc.argtypes = [C.POINTER(C.c_float)]
         lib.ww_free_mfcc.restype = None
+        lib.ww_wav_parse.argtypes = [vp, C.c_size_t, i32, C.POINTER(WavInfo)]
+        lib.ww_wav_load_batch.argtypes = [C.POINTER(C.c_char_p), i32, i32, i32, vp, C.POINTER(WavInfo), C.POINTER(i32)]
+        lib.ww_wav_write.argtypes = [C.c_char_p, vp, C.c_size_t, i32, i32]
+        lib.ww_tdm_downmix.argtypes = [vp, vp, i64, i64, i64, vp, i64, vp]
+        lib.ww_augment_waveform.argtypes = [vp, vp, i64, i32, vp, vp]
         _lib = lib
         return lib
 

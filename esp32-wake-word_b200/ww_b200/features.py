@@ -3,8 +3,9 @@
 Same names and argument meaning as the reference (pad_audio :7, add_random_noise :25,
 normalize_mfcc :47, augment_audio_waveform :90, extract_features :123), with the
 hot arithmetic -- pre-emphasis + T.MFCC (:171-172) and CMVN (:175) -- executed by
-libwwb200.so on the GPU.  File walking, padding and augmentation stay host PyTorch,
-as in the reference.  Batched forms (`mfcc_batch`, `cmvn_batch`) are what large jobs
+libwwb200.so on the GPU.  `extract_features` reads the WAV files with the native batched loader
+(ww_b200.wav) and augments on the GPU (ww_b200.frontdsp); the single-clip helpers below keep the
+reference's host behaviour.  Batched forms (`mfcc_batch`, `cmvn_batch`) are what large jobs
 call directly.
 """
 from __future__ import annotations
@@ -155,26 +156,42 @@ def extract_features(audio_path="./audio_data/train_data/xiaoa", label=0, is_noi
     """Reference signature (extract_mfcc.py:123): walk `audio_path`, return
     (list of [13, 63] feature tensors, list of label tensors).
 
-    All variants of all files are stacked and sent through ONE frontend launch.
+    The files are read by the native batched WAV loader (ww_b200.wav, esp_wav.cpp's parsing rules) into one
+    pinned int16 batch; padding noise, the five augmentation variants (ww_augment_waveform) and all features
+    are computed on the GPU, the features of all variants of all files in ONE frontend launch.
     """
-    clips = []
-    n_files = 0
-    for name in os.listdir(audio_path):
-        if not name.endswith(".wav"):
-            continue
-        n_files += 1
-        audio, _ = load_wav(os.path.join(audio_path, name))
-        audio = pad_audio(audio, CLIP_SAMPLES, add_noise_to_pad=add_noise_to_pad, noise_level=0.005)
-        variants = augment_audio_waveform(audio, augment_factor=3) if augment_audio else [audio]
-        for v in variants:
-            if is_noise:
-                v = add_random_noise(v, noise_level=0.01)
-            clips.append(v[0])
-    if not clips:
+    from . import frontdsp, wav
+
+    names = [n for n in os.listdir(audio_path) if n.endswith(".wav")]
+    if not names:
         return [], []
-    feats = mfcc_batch(torch.stack(clips))
+    paths = [os.path.join(audio_path, n) for n in names]
+    pcm, infos, _ = wav.load_wav_batch(paths, clip_samples=CLIP_SAMPLES)
+    n_valid = [i["n_samples"] for i in infos]
+    for k, info in enumerate(infos):
+        if info["num_channels"] != 1:  # torchaudio.load -> [C, N]; the reference's mfcc_transform(...)[0] keeps channel 0
+            mono = wav.read_wav(paths[k], max_samples=CLIP_SAMPLES * info["num_channels"])[0][::info["num_channels"]]
+            pcm[k].zero_()
+            pcm[k, :len(mono)] = torch.from_numpy(mono.copy())
+            n_valid[k] = len(mono)
+    audio = pcm.cuda(non_blocking=True).to(torch.float32) / 32768.0          # torchaudio.load normalisation
+    if add_noise_to_pad:                                                      # pad_audio(..., noise_level=0.005), :157
+        t = torch.arange(CLIP_SAMPLES, device=audio.device)[None, :]
+        tail = t >= torch.tensor(n_valid, device=audio.device)[:, None]
+        audio = torch.where(tail, torch.randn_like(audio) * 0.005, audio)
+    if augment_audio:
+        variants = frontdsp.augment_batch(audio)                              # [n, 5, L]
+        # the reference re-pads the 0.8-speed variant with pad_audio's DEFAULT (noise 0.005), :107
+        size08 = int(CLIP_SAMPLES * 0.8)
+        variants[:, 1, size08:] = torch.randn_like(variants[:, 1, size08:]) * 0.005
+        clips = variants.reshape(-1, CLIP_SAMPLES)
+    else:
+        clips = audio
+    if is_noise:
+        clips = torch.stack([add_random_noise(c[None], noise_level=0.01)[0] for c in clips])
+    feats = mfcc_batch(clips)
     feats = normalize_mfcc(feats, method=normalize_method)
     features = [f for f in feats]
     labels = [torch.tensor(label) for _ in features]
-    print(f"extracted {len(features)} MFCC features from {n_files} files (normalisation: {normalize_method})")
+    print(f"extracted {len(features)} MFCC features from {len(names)} files (normalisation: {normalize_method})")
     return features, labels

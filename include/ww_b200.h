@@ -173,6 +173,48 @@ int ww_ctc_loss_bwd(ww_ctx* ctx, const float* log_probs, long long t_stride, lon
                     const void* workspace, float* grad, long long gt_stride, long long gb_stride,
                     ww_stream_t stream);
 
+/* ---- WAV ingestion: main/esp_wav/esp_wav.cpp:8-139, esp_wav.hpp:24-213 ---------------- */
+/* The fields of wav::WavHeader after its file constructor, plus the sample count the reference reads. */
+typedef struct {
+    uint32_t riff_length;     /* esp_wav.cpp:34 */
+    uint32_t fmt_length;      /* :66 */
+    uint16_t audio_format;    /* :70 (1 = PCM) */
+    uint16_t num_channels;    /* :74 */
+    uint32_t sample_rate;     /* :78 */
+    uint32_t byte_rate;       /* :82 */
+    uint16_t block_align;     /* :86 */
+    uint16_t bits_per_sample; /* :90 */
+    uint32_t data_length;     /* :111, bytes of the data chunk */
+    uint32_t raw_data_pos;    /* :133, byte offset of the first sample */
+    uint32_t n_samples;       /* min(data_length / 2, max_samples) (:128-132), also bounded by the bytes present */
+    int32_t valid;            /* WavHeader::isValid(), esp_wav.hpp:109-118 */
+} ww_wav_info;
+/* Parse a RIFF/WAVE image held in memory with the reference's rules: fixed tag order RIFF, WAVE, "fmt " (a wrong
+ * tag is recorded in `valid` but parsing continues, esp_wav.cpp:29-62), the 16 standard fmt bytes, then chunks are
+ * skipped by their size until "data" (:95-121).  WW_ERR_INVALID when the image ends before the data chunk header
+ * (the reference logs and returns early).  Host only: no GPU needed. */
+int ww_wav_parse(const void* bytes, size_t n_bytes, int max_samples, ww_wav_info* info);
+/* Read `n` files with `n_threads` reader threads into pcm_host[n][clip_samples] int16 (pinned or pageable), each
+ * truncated / zero-padded to clip_samples as hello_world_main.cpp:196-214 and pad_audio(add_noise_to_pad=False) do.
+ * infos[n] and status[n] (WW_OK / WW_ERR_*) may be NULL.  Returns the number of files that failed. */
+int ww_wav_load_batch(const char* const* paths, int n, int clip_samples, int n_threads, int16_t* pcm_host,
+                      ww_wav_info* infos, int* status);
+/* Writer side of wav::WavHeader (esp_wav.hpp:41-75,121-213: initialize + write_info_to_file + write_data_to_file +
+ * finalize_wav_file): canonical 44-byte header, riff_length = 36 + data bytes. */
+int ww_wav_write(const char* path, const int16_t* pcm, size_t n_samples, int num_channels, int sample_rate);
+
+/* ---- front-of-frontend DSP ------------------------------------------------------------- */
+/* record_task's 4-channel TDM mix and 48 -> 16 kHz decimator (esp_wake_word_detector.cpp:103-121), bit-exact:
+ *   mono = (int16)(((L << 6) + (ref << 5) + (R << 6)) >> 7);  out[i] = (int16)((m[3i] + 2 m[3i+1] + m[3i+2]) >> 2)
+ * tdm: device [n_signals][in_stride] int16, 4 interleaved channels at 48 kHz (12 int16 per output sample);
+ * pcm_out: device [n_signals][out_stride] int16 mono 16 kHz, n_out samples per signal. */
+int ww_tdm_downmix(ww_ctx* ctx, const int16_t* tdm, long long n_signals, long long n_out, long long in_stride,
+                   int16_t* pcm_out, long long out_stride, ww_stream_t stream);
+/* augment_audio_waveform (ml_models/src/extract_mfcc.py:90-121) on padded clips: audio device fp32 [n][L] ->
+ * out device fp32 [n][5][L] = {original, speed 0.8, speed 1.2 (F.interpolate linear, align_corners=False, then
+ * pad_audio with zeros / truncation), volume 0.7, volume 1.3 (clamped to [-1, 1])}. */
+int ww_augment_waveform(ww_ctx* ctx, const float* audio, long long n, int L, float* out, ww_stream_t stream);
+
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 /* Test hook for the tensor-core CNN: `dbg_dev` (device, >= 8*31*32 + 8*15*64 + 8*128 + 8*64 floats, or NULL)
  * receives the per-layer activations of the first 8 windows of each launch; *last_rescored receives the

@@ -17,6 +17,11 @@ Modules
              numpy + torch.nn.functional.ctc_loss).
   stream.py  sliding 63-frame window scoring and refractory logic
              (main/esp_wake_word_detector/src/esp_wake_word_detector.cpp).
+  wav.py     wav::WavHeader reader / writer (main/esp_wav/esp_wav.cpp:8-139,
+             esp_wav.hpp), pinned by the reference's own esp_wav.cpp compiled into
+             oracle/_ref/libesp_wav_ref.so (tests/golden/wav_cases.npz).
+  frontdsp.py  record_task's TDM mix + 48->16 kHz decimator (cpp:103-121, numpy
+             and plain C) and augment_audio_waveform (extract_mfcc.py:90-121).
   c/         plain-C restatement of main/esp_mfcc/mfcc.c (C-MFCC, secondary
              mode) and the recipe that compiles the reference's own mfcc.c
              into oracle/_ref/ when /root/reference is present.

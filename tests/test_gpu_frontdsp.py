@@ -1,0 +1,142 @@
+"""GPU parity for the SURVEY.md 8f rank 3/4 rows: TDM down-mix (bit-exact), waveform augmentation (fp32, 1e-6),
+WAV files -> pinned int16 batch -> scores."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cnn as ocnn
+from oracle import frontdsp as ofd
+from oracle import mfcc as omfcc
+from oracle import wav as owav
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("B,n", [(1, 320), (3, 16000), (5, 1001), (2, 7), (1, 0)])
+def test_tdm_downmix_bit_exact(cuda_device, B, n):
+    """cpp:103-121: int16 wrap of the mix, floor shifts; vector path (aligned) and scalar tails."""
+    import ww_b200
+
+    rng = np.random.default_rng(100 + n)
+    x = rng.integers(-32768, 32768, size=(B, 12 * n), dtype=np.int16)
+    if n >= 3:
+        x[:, :12] = 32767           # mix overflows int16 and wraps
+        x[:, 12:24] = -32768
+    got = ww_b200.tdm_downmix(torch.from_numpy(x).to(cuda_device)).cpu().numpy()
+    want = ofd.tdm_downmix(x)
+    assert got.shape == (B, n) and got.dtype == np.int16
+    np.testing.assert_array_equal(got, want)
+    if n:
+        np.testing.assert_array_equal(got[0], ofd.tdm_downmix_c(x[0]))
+
+
+def test_tdm_downmix_unaligned_rows_and_stream(cuda_device):
+    """Row stride not a multiple of 8 elements (scalar path) and a 60 s stream processed in one call == 20 ms blocks."""
+    import ww_b200
+
+    rng = np.random.default_rng(9)
+    base = torch.from_numpy(rng.integers(-32768, 32768, size=(4, 12 * 500 + 3), dtype=np.int16)).to(cuda_device)
+    view = base[:, 1:1 + 12 * 500]          # misaligned start: the library must take the scalar path
+    got = ww_b200.tdm_downmix(view.contiguous()).cpu().numpy()
+    np.testing.assert_array_equal(got, ofd.tdm_downmix(view.cpu().numpy()))
+    n = 16000 * 60
+    s = rng.integers(-20000, 20000, size=12 * n, dtype=np.int16)
+    whole = ww_b200.tdm_downmix(torch.from_numpy(s).to(cuda_device)).cpu().numpy()
+    assert whole.shape == (n,)
+    blocks = np.concatenate([ofd.tdm_downmix(s[i:i + 3840]) for i in range(0, 3840 * 50, 3840)])
+    np.testing.assert_array_equal(whole[:blocks.size], blocks)
+    np.testing.assert_array_equal(whole, ofd.tdm_downmix_c(s))
+
+
+def test_tdm_then_frontend_matches_oracle_chain(cuda_device):
+    """TDM capture -> mono 16 kHz -> MFCC: the chain record_task feeds, against the oracle chain."""
+    import ww_b200
+
+    rng = np.random.default_rng(3)
+    t = np.arange(48000) / 48000.0
+    mic = (8000 * np.sin(2 * np.pi * 700 * t) + 500 * rng.standard_normal(48000)).astype(np.int16)
+    tdm = np.stack([mic, (mic // 3).astype(np.int16), np.roll(mic, 5), np.zeros_like(mic)], axis=1).reshape(-1)
+    pcm = ww_b200.tdm_downmix(torch.from_numpy(tdm).to(cuda_device))
+    feats = ww_b200.mfcc_batch(pcm[None]).cpu().numpy()
+    want = omfcc.mfcc_torchaudio(omfcc.pcm16_to_float(ofd.tdm_downmix(tdm)[None])).numpy()
+    assert np.abs(feats - want).max() < 1e-3
+
+
+def test_augment_matches_reference_golden_and_oracle(cuda_device):
+    """augment_audio_waveform: golden = the reference's own function output; tolerance 1e-6 abs (fp32 lerp order)."""
+    import ww_b200
+
+    d = np.load(os.path.join(ROOT, "tests", "golden", "wav_cases.npz"))
+    got = ww_b200.augment_batch(torch.from_numpy(d["aug_in"]).to(cuda_device)).cpu().numpy()
+    assert got.shape == (1, 5, 16000)
+    assert np.abs(got - d["aug_out"]).max() <= 1e-6
+    np.testing.assert_array_equal(got[:, 0], d["aug_in"])
+    np.testing.assert_array_equal(got[:, 3:], d["aug_out"][:, 3:])   # volume variants are exact
+    rng = np.random.default_rng(11)
+    x = (rng.random((37, 16000), dtype=np.float32) * 2 - 1)
+    got = ww_b200.augment_batch(torch.from_numpy(x).to(cuda_device)).cpu().numpy()
+    assert np.abs(got - ofd.augment_waveform(x)).max() <= 1e-6
+
+
+def test_wav_files_to_scores(cuda_device, xiaoa_sd, tmp_path):
+    """WAV files (shipped-clip PCM from the golden set, with junk chunks) -> load_wav_batch -> score_host:
+    same logits/decisions as scoring the PCM directly and as the oracle."""
+    import ww_b200
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_features.npz"))
+    pcm = g["pcm"]
+    paths = []
+    for i in range(pcm.shape[0]):
+        n = 16000 if i % 3 else 9000 + 500 * i          # some shorter files (zero padded by the loader)
+        body = owav.wav_bytes(pcm[i, :n])
+        if i % 2:
+            body = body[:36] + b"LIST" + (10).to_bytes(4, "little") + bytes(10) + body[36:]
+        p = tmp_path / f"c{i}.wav"
+        p.write_bytes(body)
+        paths.append(str(p))
+    batch, infos, st = ww_b200.load_wav_batch(paths)
+    assert (st == 0).all() and batch.is_pinned()
+    want_pcm = pcm.copy()
+    for i in range(pcm.shape[0]):
+        if i % 3 == 0:
+            want_pcm[i, 9000 + 500 * i:] = 0
+    np.testing.assert_array_equal(batch.numpy(), want_pcm)
+    scorer = ww_b200.WakeWordScorer(xiaoa_sd, device=0)
+    lg_h, dec_h = scorer.score_host(batch)
+    lg_d, dec_d = scorer.score(torch.from_numpy(want_pcm).to(cuda_device))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(np.asarray(dec_h), dec_d.cpu().numpy())
+    ref_f = omfcc.mfcc_torchaudio(omfcc.pcm16_to_float(want_pcm)).numpy()
+    ref_l = ocnn.forward_torch(omfcc.normalize_mfcc(ref_f, "cmvn").numpy(), xiaoa_sd)
+    assert np.abs(np.asarray(lg_h) - ref_l).max() < 1e-2
+    margin = np.abs(ref_l[:, 0]) > 1e-3
+    assert (np.asarray(dec_h).astype(bool) == ocnn.decide_python(ref_l[:, 0]))[margin].all()
+
+
+def test_extract_features_dropin(cuda_device, tmp_path):
+    """ww_b200.extract_features (the reference's signature, extract_mfcc.py:123) over a directory of WAV files:
+    equals the goldens produced by the reference's OWN extract_features (tests/golden/make_golden.py); with
+    augmentation the deterministic variants equal the oracle chain."""
+    import ww_b200
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_features.npz"))
+    n = 6
+    for i in range(n):
+        (tmp_path / f"clip_{i:02d}.wav").write_bytes(owav.wav_bytes(g["pcm"][i]))
+    (tmp_path / "notes.txt").write_text("not a wav")
+    feats, labels = ww_b200.extract_features(str(tmp_path), label=1, add_noise_to_pad=False, augment_audio=False)
+    assert len(feats) == n and all(int(l) == 1 for l in labels)
+    order = [int(name[5:7]) for name in os.listdir(tmp_path) if name.endswith(".wav")]
+    got = torch.stack(feats).cpu().numpy()
+    assert got.shape == (n, 13, 63)
+    assert np.abs(got - g["mfcc_cmvn"][order]).max() < 2e-3
+    feats5, _ = ww_b200.extract_features(str(tmp_path), add_noise_to_pad=False, augment_audio=True)
+    assert len(feats5) == 5 * n
+    got5 = torch.stack(feats5).cpu().numpy().reshape(n, 5, 13, 63)
+    aug = ofd.augment_waveform(omfcc.pcm16_to_float(g["pcm"][order]))
+    for v in (0, 2, 3, 4):   # variant 1 is re-padded with unseeded noise by the reference
+        want = omfcc.normalize_mfcc(omfcc.mfcc_torchaudio(aug[:, v]).numpy(), "cmvn").numpy()
+        assert np.abs(got5[:, v] - want).max() < 5e-3, v
