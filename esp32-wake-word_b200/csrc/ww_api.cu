@@ -1321,11 +1321,11 @@ extern "C" int ww_tdm_downmix(ww_ctx* ctx, const int16_t* tdm, long long n_signa
     a.n_signals = n_signals;
     a.n_out = n_out;
     a.vec_ok = ((uintptr_t)tdm % 16 == 0) && (in_stride % 8 == 0) && ((uintptr_t)pcm_out % 8 == 0) && (out_stride % 4 == 0);
-    const long long items = n_signals * ((n_out + 3) / 4);
-    long long blocks = (items + 255) / 256;
-    const long long cap = (long long)ctx->sm_count * 16;  // 8 resident CTAs per SM, two waves
+    const long long items = a.vec_ok ? n_signals * ((n_out + TDM_TILE_OUT - 1) / TDM_TILE_OUT) : (n_signals * n_out + 255) / 256;
+    long long blocks = items > 0 ? items : 1;
+    const long long cap = (long long)ctx->sm_count * 8;  // 8 resident 256-thread CTAs per SM, persistent over tiles
     if (blocks > cap) blocks = cap;
-    tdm_downmix_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    tdm_downmix_kernel<<<(unsigned)blocks, TDM_THREADS, 0, (cudaStream_t)stream>>>(a);
     CK(cudaGetLastError());
     return WW_OK;
 }
@@ -1344,9 +1344,10 @@ extern "C" int ww_augment_waveform(ww_ctx* ctx, const float* audio, long long n,
     a.len12 = (int)((double)L * 1.2);
     a.scale08 = (float)L / (float)a.len08;
     a.scale12 = (float)L / (float)a.len12;
-    const long long items = n * L;
+    a.vec_ok = (L % 4 == 0) && ((uintptr_t)audio % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    const long long items = a.vec_ok ? n * (L / 4) : n * L;
     long long blocks = (items + 255) / 256;
-    const long long cap = (long long)ctx->sm_count * 16;
+    const long long cap = (long long)ctx->sm_count * 8;
     if (blocks > cap) blocks = cap;
     augment_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
     CK(cudaGetLastError());

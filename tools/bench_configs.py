@@ -147,12 +147,57 @@ def cpu_stages(sd):
     return out
 
 
+def frontdsp_bench(dev):
+    """SURVEY 8f rank 3/4 rows against the HBM roofline (MEASURED_PEAKS.json hbm_gbs, else 6545.3)."""
+    import tempfile
+
+    peak = 6545.3
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    out = []
+    # TDM down-mix: 65 536 one-second captures = 25.2 GB in (> L2), 26 B per output sample
+    B, n = 65536, 16000
+    tdm = torch.randint(-32768, 32767, (B, 12 * n), dtype=torch.int16, device=dev)
+    dt = timed(lambda: ww_b200.tdm_downmix(tdm))
+    out.append({"config": "8f rank 4: TDM 4ch 48 kHz -> mono 16 kHz (ww_tdm_downmix)", "clips": B, "seconds_per_pass": dt,
+                "clips_per_s": B / dt, "algorithmic_GBps": B * n * 26 / dt / 1e9, "hbm_frac": B * n * 26 / dt / 1e9 / peak})
+    del tdm
+    # augmentation: 65 536 clips, 4 B in + 20 B out per sample
+    B = 65536
+    x = torch.rand(B, n, device=dev) * 2 - 1
+    dt = timed(lambda: ww_b200.augment_batch(x))
+    out.append({"config": "8f rank 4: augment_audio_waveform x5 (ww_augment_waveform)", "clips": B, "seconds_per_pass": dt,
+                "clips_per_s": B / dt, "algorithmic_GBps": B * n * 24 / dt / 1e9, "hbm_frac": B * n * 24 / dt / 1e9 / peak})
+    del x
+    # WAV loader (host): 4096 files of 1 s on tmpfs-or-disk, native reader threads into pinned memory
+    with tempfile.TemporaryDirectory() as td:
+        pcm = (np.random.default_rng(1).integers(-3000, 3000, size=16000)).astype(np.int16)
+        paths = []
+        for i in range(4096):
+            p = os.path.join(td, f"{i}.wav")
+            ww_b200.write_wav(p, pcm)
+            paths.append(p)
+        ww_b200.load_wav_batch(paths)
+        t0 = time.perf_counter()
+        ww_b200.load_wav_batch(paths)
+        dt = time.perf_counter() - t0
+        out.append({"config": "8f rank 3: load_wav_batch (page-cache warm, host threads)", "files": len(paths),
+                    "threads": min(32, os.cpu_count() or 1), "files_per_s": len(paths) / dt, "host_GBps": len(paths) * 32044 / dt / 1e9})
+    return out
+
+
 def main():
     dev = torch.device("cuda", 0)
     sd = bench.load_weights()
     res = []
     if "--cpu" in sys.argv:
         for r in cpu_stages(sd):
+            print(json.dumps(r), flush=True)
+        return
+    if "--frontdsp" in sys.argv:
+        for r in frontdsp_bench(dev):
             print(json.dumps(r), flush=True)
         return
     res += batch_sweep(dev, sd)
