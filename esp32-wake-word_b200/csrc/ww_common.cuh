@@ -80,6 +80,11 @@ __device__ __forceinline__ cpx p_sub_mi(cpx t, cpx d) { return p_fma(cswap(d), c
 // a * (-i)
 __device__ __forceinline__ cpx p_mul_mi(cpx a) { return p_mul(cswap(a), cpk(1.f, -1.f)); }
 // a * (c + i s)
+__device__ __forceinline__ cpx p_cmul(cpx a, float c, float s);
+__device__ __forceinline__ cpx p_cmulc(cpx a, cpx w) {
+    const float2 f = cunpk(w);
+    return p_cmul(a, f.x, f.y);
+}
 __device__ __forceinline__ cpx p_cmul(cpx a, float c, float s) { return p_fma(cswap(a), cpk(-s, s), p_mul(a, cpk(c, c))); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

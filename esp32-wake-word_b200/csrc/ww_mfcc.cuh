@@ -27,6 +27,20 @@
 #pragma once
 #include "ww_common.cuh"
 
+// Table-traffic switches, A/B-measured on B200 (262 144 clips, tools/time_frontend.py, profiles/experiments/README.md):
+//   WW_WIN_REGS     window taps in 20 registers instead of 10 LDS.64 per frame pair      26.6 -> 27.4 M clips/s (kept)
+//   WW_TW2_COMPUTE  W512^(l16+16i) = W512^l16 * W32^i (immediates) instead of 8 LDS.64   +0.2 %  (off: noise)
+//   WW_TW1_HALF     twiddles k1 >= 8 as W^(8 l16) * W^(l16 (k1-8)) instead of 4 LDS.128  -1 %    (off)
+#ifndef WW_WIN_REGS
+#define WW_WIN_REGS 1
+#endif
+#ifndef WW_TW2_COMPUTE
+#define WW_TW2_COMPUTE 0
+#endif
+#ifndef WW_TW1_HALF
+#define WW_TW1_HALF 0
+#endif
+
 namespace ww {
 
 // ---- table blob (one per feature mode, device memory, copied to smem by every CTA) ----------------
@@ -285,6 +299,24 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
 
     unsigned char* exch = smem + SM::OFF_EXCH + (warp * 2 + half) * EXCH_FRAME_BYTES;
 
+    // Per-thread constants that depend on l16 only can live in registers for the whole kernel.  Both half-warps of a
+    // warp need the same table entries, and 64/128-bit shared loads are served per half/quarter warp, so every
+    // table read costs a wavefront per frame (the kernel runs the shared-memory pipe at ~2/3 of its peak):
+    //   window: 10 packed taps (20 registers)                                              [on]
+    //   tw2:    W512^(l16 + 16 i) = W512^l16 * W32^i with W32^i as immediates              [measured, off]
+    //   tw1:    W256^(l16 k1), k1 >= 8, = W256^(8 l16) * W256^(l16 (k1 - 8))               [measured, off]
+#if WW_WIN_REGS
+    cpx wreg[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) wreg[i] = reinterpret_cast<const cpx*>(s_win)[16 * i + l16];
+#endif
+#if WW_TW2_COMPUTE
+    const float2 tw2_0 = s_tw2[l16];
+#endif
+#if WW_TW1_HALF
+    const cpx tw1_8 = cpk(s_tw1[16 * 4 + l16].x, s_tw1[16 * 4 + l16].y);
+#endif
+
     // Per-CTA software pipeline over this CTA's blocks (one CTA-wide barrier per block):
     //   iteration k:  mel(k-1) | stage PCM(k) + edge taps | FFT(k) first pass | DCT(k-1) | FFT(k) second pass | barrier
     // mel(k-1) and DCT(k-1) run between the FFT passes without waiting: P(k-1) was completed by the barrier of
@@ -470,7 +502,11 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
                 const uint32_t* p32b = reinterpret_cast<const uint32_t*>(spcm) + (base >> 1);
     #pragma unroll
                 for (int n1 = 3; n1 <= 12; ++n1) {
+#if WW_WIN_REGS
+                    const cpx w = wreg[n1 - 3];
+#else
                     const cpx w = s_winp[16 * (n1 - 3) + l16];
+#endif
                     float x0, x1, xm1;
                     if constexpr (sizeof(TIN) == 2) {
                         const uint32_t cur = p32b[16 * n1], prv = p32b[16 * n1 - 1];
@@ -492,7 +528,11 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
                 const float* ep = edge + (t == 0 ? 0 : WW_WIN) + 2 * l16;
     #pragma unroll
                 for (int n1 = 3; n1 <= 12; ++n1) {
+#if WW_WIN_REGS
+                    const cpx w = wreg[n1 - 3];
+#else
                     const cpx w = s_winp[16 * (n1 - 3) + l16];
+#endif
                     const cpx y = *reinterpret_cast<const cpx*>(ep + 32 * (n1 - 3));
                     v[n1] = p_mul(w, y);
                 }
@@ -500,12 +540,24 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
 
             // pass 1: DFT16 over n1, twiddle W256^(l16*k1), transpose through smem
             fft16<true>(v);
+#if WW_TW1_HALF
+    #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 tw = s_tw1[16 * j + l16];
+                const cpx ta = cpk(tw.x, tw.y), tb = cpk(tw.z, tw.w);
+                if (j > 0) v[2 * j] = p_cmulc(v[2 * j], ta);
+                v[2 * j + 1] = p_cmulc(v[2 * j + 1], tb);
+                v[2 * j + 8] = p_cmulc(v[2 * j + 8], j > 0 ? p_cmulc(tw1_8, ta) : tw1_8);
+                v[2 * j + 9] = p_cmulc(v[2 * j + 9], p_cmulc(tw1_8, tb));
+            }
+#else
     #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float4 tw = s_tw1[16 * j + l16];
                 if (j > 0) v[2 * j] = p_cmul(v[2 * j], tw.x, tw.y);
                 v[2 * j + 1] = p_cmul(v[2 * j + 1], tw.z, tw.w);
             }
+#endif
     #pragma unroll
             for (int k1 = 0; k1 < 16; ++k1)
                 *reinterpret_cast<cpx*>(exch + k1 * EXCH_ROW_BYTES + l16 * 8) = v[k1];
@@ -534,7 +586,16 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
                 const float2 src = cunpk(v[15 - i]);
                 cpx zb = cpk(__shfl_sync(0xffffffffu, src.x, partner, 16), __shfl_sync(0xffffffffu, src.y, partner, 16));
                 if (l16 == 0) zb = (i == 0) ? v[0] : v[(16 - i) & 15];
+#if WW_TW2_COMPUTE
+                // W512^(l16 + 16 i) = W512^l16 * W32^i
+                constexpr float W32C[8] = {1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                                           0.70710678118654752f, 0.55557023301960218f, 0.38268343236508977f, 0.19509032201612825f};
+                constexpr float W32S[8] = {0.f, -0.19509032201612825f, -0.38268343236508977f, -0.55557023301960218f,
+                                           -0.70710678118654752f, -0.83146961230254524f, -0.92387953251128674f, -0.98078528040323043f};
+                const float2 w = i == 0 ? tw2_0 : cunpk(p_cmul(cpk(tw2_0.x, tw2_0.y), W32C[i], W32S[i]));
+#else
                 const float2 w = s_tw2[k];
+#endif
                 const cpx e = p_add(za, p_conj(zb));                         // (za.x + zb.x, za.y - zb.y)
                 const cpx o = p_fma(cswap(za), cpk(1.f, -1.f), cswap(zb));   // (za.y + zb.y, zb.x - za.x)
                 const cpx tt = p_cmul(o, w.x, w.y);

@@ -11,7 +11,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libwwb200.so")
+# WW_B200_LIB selects another build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("WW_B200_LIB") or os.path.join(os.path.dirname(_HERE), "libwwb200.so")
 
 WW_OK = 0
 FEAT_PY, FEAT_ESP = 0, 1
