@@ -293,23 +293,17 @@ __device__ __forceinline__ void tc_cmvn_store(const TcArgs& a, TcWin& w, int slo
     } else if (a.cmvn_mode == CMVN_DEVICE) {
         // device-style CMVN rounds to int8: keep EXACTLY the arithmetic of cnn_fp32_kernel so that both
         // paths quantise identically
-#pragma unroll 1
-        for (int q = 0; q < WW_N_MFCC; ++q) {
-            float v0 = 0.f, v1 = 0.f;
+        // (fully unrolled: 13 independent reduction chains interleave; x0/x1 stay in named registers)
 #pragma unroll
-            for (int qq = 0; qq < WW_N_MFCC; ++qq)
-                if (qq == q) { v0 = x0[qq]; v1 = x1[qq]; }
-            v0 = lround_clamp_i8(v0);
-            v1 = has1 ? lround_clamp_i8(v1) : 0.f;
+        for (int q = 0; q < WW_N_MFCC; ++q) {
+            const float v0 = lround_clamp_i8(x0[q]);
+            const float v1 = has1 ? lround_clamp_i8(x1[q]) : 0.f;
             const float mean = warp_sum(v0 + v1) / (float)WW_WINDOW_FRAMES;
             const float d0 = v0 - mean, d1 = has1 ? v1 - mean : 0.f;
             const float ss = warp_sum(d0 * d0 + d1 * d1);
             const float den = sqrtf(ss / (float)WW_WINDOW_FRAMES) + 1e-8f;
-            const float z0 = fminf(fmaxf(lround_clamp_i8(d0 / den) * 16.f, -128.f), 127.f) * 0.0625f;
-            const float z1 = fminf(fmaxf(lround_clamp_i8(d1 / den) * 16.f, -128.f), 127.f) * 0.0625f;
-#pragma unroll
-            for (int qq = 0; qq < WW_N_MFCC; ++qq)
-                if (qq == q) { x0[qq] = z0; x1[qq] = z1; }
+            x0[q] = fminf(fmaxf(lround_clamp_i8(d0 / den) * 16.f, -128.f), 127.f) * 0.0625f;
+            x1[q] = fminf(fmaxf(lround_clamp_i8(d1 / den) * 16.f, -128.f), 127.f) * 0.0625f;
         }
     }
     // frame t -> parity tile t & 1, row 1 + 32*slot + (t >> 1); channels 0-7 -> chunk 0, 8-12 (+3 zeros) -> chunk 1

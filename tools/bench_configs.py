@@ -147,6 +147,30 @@ def cpu_stages(sd):
     return out
 
 
+def session_bench(sd, n_streams=4096, chunk=320, pushes=200):
+    """8f rank 2: push/poll sessions -- n_streams concurrent streams, one 20 ms chunk (320 samples) per push
+    (the firmware's read_mic cadence), host PCM in, hits polled.  Wall clock (the call is synchronous)."""
+    rng = np.random.default_rng(3)
+    out = []
+    for cmvn, impl in (("device", "tensor"), ("python", "tensor")):
+        ses = ww_b200.StreamSession(sd, n_streams, max_chunk_samples=chunk, device=0, cmvn=cmvn, cnn_impl=impl)
+        data = (rng.standard_normal((n_streams, chunk)) * 600).astype(np.int16)
+        for _ in range(70):          # fill the 63-frame window first
+            ses.write(data)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(pushes):
+            ses.write(data)
+            ses.poll()
+        dt = (time.perf_counter() - t0) / pushes
+        out.append({"config": "8f rank 2: streaming sessions, push 20 ms chunks for all streams + poll", "streams": n_streams,
+                    "chunk_samples": chunk, "cmvn": cmvn, "cnn_impl": impl, "ms_per_push": dt * 1e3,
+                    "realtime_streams_supported": n_streams * (chunk / 16000) / dt,
+                    "windows_per_s": n_streams * (chunk / 256.0) / dt})
+        ses.close()
+    return out
+
+
 def frontdsp_bench(dev):
     """SURVEY 8f rank 3/4 rows against the HBM roofline (MEASURED_PEAKS.json hbm_gbs, else 6545.3)."""
     import tempfile
@@ -197,7 +221,7 @@ def main():
             print(json.dumps(r), flush=True)
         return
     if "--frontdsp" in sys.argv:
-        for r in frontdsp_bench(dev):
+        for r in session_bench(sd) + frontdsp_bench(dev):
             print(json.dumps(r), flush=True)
         return
     res += batch_sweep(dev, sd)
