@@ -18,6 +18,7 @@
 #include "ww_tables.h"
 #ifdef WW_WITH_TC
 #include "ww_cnn_tc.cuh"
+#include "ww_cnn_i8_tc.cuh"
 #endif
 
 using namespace ww;
@@ -54,6 +55,8 @@ struct ww_ctx {
     signed char* i8blob = nullptr;
     I8Weights i8w{};
     bool have_i8 = false;
+    uint4* i8tc_blob = nullptr;        // int8 weights in UMMA layout (ww_cnn_i8_tc.cuh)
+    int i8_impl = WW_CNN_TENSOR;       // ww_set_option(WW_OPT_I8_IMPL)
     long long grp_windows = 0, grp_stride = 0;  // window grouping of the next CNN launch (streaming sessions)
     // fused-path scratch
     float* scratch = nullptr;          // [chunk][13][63]
@@ -280,6 +283,8 @@ extern "C" int ww_create(ww_ctx** out, int device) {
 #ifdef WW_WITH_TC
     if ((e = cudaFuncSetAttribute(cnn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)) != cudaSuccess)
         return bail(e, "cudaFuncSetAttribute(cnn_tc_kernel)");
+    if ((e = cudaFuncSetAttribute(cnn_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8T_SMEM)) != cudaSuccess)
+        return bail(e, "cudaFuncSetAttribute(cnn_i8_tc_kernel)");
     if (const char* b = getenv("WW_TC_BAND")) ctx->tc_band = (float)atof(b);
     if (const char* c = getenv("WW_CHUNK_CLIPS")) {
         const long long v = atoll(c);
@@ -296,6 +301,7 @@ extern "C" void ww_destroy(ww_ctx* ctx) {
     for (int m = 0; m < 2; ++m) cudaFree(ctx->feat[m].tables);
     cudaFree(ctx->wblob);
     cudaFree(ctx->i8blob);
+    cudaFree(ctx->i8tc_blob);
     cudaFree(ctx->scratch);
     for (int i = 0; i < 2; ++i) {
         if (ctx->hs[i]) cudaStreamDestroy(ctx->hs[i]);
@@ -313,6 +319,21 @@ extern "C" void ww_destroy(ww_ctx* ctx) {
     cudaFree(ctx->rs_count);
 #endif
     delete ctx;
+}
+
+extern "C" int ww_set_option(ww_ctx* ctx, int option, int value) {
+    if (!ctx) return WW_ERR_INVALID;
+    switch (option) {
+        case WW_OPT_I8_IMPL:
+            if (value != WW_CNN_FP32 && value != WW_CNN_TENSOR) return fail(ctx, WW_ERR_INVALID, "WW_OPT_I8_IMPL: 0 (CUDA cores) or 1 (tensor cores)");
+#ifndef WW_WITH_TC
+            if (value == WW_CNN_TENSOR) return fail(ctx, WW_ERR_UNSUPPORTED, "tensor-core kernels not built into this library");
+#endif
+            ctx->i8_impl = value;
+            return WW_OK;
+        default:
+            return fail(ctx, WW_ERR_INVALID, "unknown option");
+    }
 }
 
 extern "C" int ww_load_weights(ww_ctx* ctx, const float* conv1, const float* conv2, const float* conv3,
@@ -628,6 +649,16 @@ extern "C" int ww_quantize_weights_i8(ww_ctx* ctx, const int* exps) {
     ctx->i8blob = nullptr;
     CK(cudaMalloc(&ctx->i8blob, h.size()));
     CK(cudaMemcpy(ctx->i8blob, h.data(), h.size(), cudaMemcpyHostToDevice));
+#ifdef WW_WITH_TC
+    {
+        std::vector<unsigned char> tb;
+        i8tc_build_blob(tb, p, p + n1, p + n1 + n2, p + n1 + n2 + n3);
+        cudaFree(ctx->i8tc_blob);
+        ctx->i8tc_blob = nullptr;
+        CK(cudaMalloc(&ctx->i8tc_blob, tb.size()));
+        CK(cudaMemcpy(ctx->i8tc_blob, tb.data(), tb.size(), cudaMemcpyHostToDevice));
+    }
+#endif
     I8Weights& w = ctx->i8w;
     w.w1t = ctx->i8blob;
     w.w2t = ctx->i8blob + n1;
@@ -653,6 +684,28 @@ extern "C" int ww_cnn_forward_i8(ww_ctx* ctx, const int8_t* x, long long n_windo
     if (!ctx->have_i8) return fail(ctx, WW_ERR_NO_WEIGHTS, "int8 weights not prepared (ww_quantize_weights_i8)");
     if (n_windows == 0) return WW_OK;
     if (!x || !out || n_windows < 0) return fail(ctx, WW_ERR_INVALID, "cnn_forward_i8: bad arguments");
+#ifdef WW_WITH_TC
+    if (ctx->i8_impl == WW_CNN_TENSOR && ctx->w.num_classes <= TC_MAX_CLASSES) {
+        I8TcArgs t;
+        t.x = reinterpret_cast<const signed char*>(x);
+        t.n_windows = n_windows;
+        t.out = reinterpret_cast<signed char*>(out);
+        t.wblob = ctx->i8tc_blob;
+        t.fc2 = ctx->i8w.fc2;
+        t.num_classes = ctx->i8w.num_classes;
+        t.sh1 = ctx->i8w.sh1;
+        t.sh2 = ctx->i8w.sh2;
+        t.sh3 = ctx->i8w.sh3;
+        t.shf1 = ctx->i8w.shf1;
+        t.shf2 = ctx->i8w.shf2;
+        t.gap_num_shift = ctx->i8w.gap_num_shift;
+        const long long n_cta = ((n_windows + I8T_CLIPS - 1) / I8T_CLIPS + I8T_GROUPS - 1) / I8T_GROUPS;
+        const unsigned grid = (unsigned)(n_cta < ctx->sm_count ? n_cta : ctx->sm_count);
+        cnn_i8_tc_kernel<<<grid, I8T_THREADS, I8T_SMEM, (cudaStream_t)stream>>>(t);
+        CK(cudaGetLastError());
+        return WW_OK;
+    }
+#endif
     I8Args a;
     a.x = reinterpret_cast<const signed char*>(x);
     a.n_windows = n_windows;

@@ -34,6 +34,9 @@
 #ifndef WW_WIN_REGS
 #define WW_WIN_REGS 1
 #endif
+#ifndef WW_I2FP
+#define WW_I2FP 0
+#endif
 #ifndef WW_TW2_COMPUTE
 #define WW_TW2_COMPUTE 0
 #endif
@@ -510,9 +513,21 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
                     float x0, x1, xm1;
                     if constexpr (sizeof(TIN) == 2) {
                         const uint32_t cur = p32b[16 * n1], prv = p32b[16 * n1 - 1];
+#if WW_I2FP
+                        // sign-extend with PRMT / SHF and convert with I2FP.F32.S32 (FMA-side pipe) instead of the
+                        // quarter-rate XU conversion I2F.S16
+                        int i0, i1, im1;
+                        asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(i0) : "r"(cur));
+                        asm("prmt.b32 %0, %1, 0, 0xbb32;" : "=r"(i1) : "r"(cur));
+                        asm("prmt.b32 %0, %1, 0, 0xbb32;" : "=r"(im1) : "r"(prv));
+                        x0 = __int2float_rn(i0);
+                        x1 = __int2float_rn(i1);
+                        xm1 = __int2float_rn(im1);
+#else
                         x0 = static_cast<float>(static_cast<int16_t>(cur & 0xffffu));
                         x1 = static_cast<float>(static_cast<int16_t>(cur >> 16));
                         xm1 = static_cast<float>(static_cast<int16_t>(prv >> 16));
+#endif
                     } else {
                         const float* pf = reinterpret_cast<const float*>(spcm) + (base + 32 * n1);
                         const float2 c2 = *reinterpret_cast<const float2*>(pf);

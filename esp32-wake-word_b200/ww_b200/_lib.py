@@ -22,6 +22,7 @@ CMVN_NONE, CMVN_PY, CMVN_DEVICE = 0, 1, 2
 DECIDE_NONE, DECIDE_LOGIT, DECIDE_DEVICE = 0, 1, 2
 DECODE_KEEP_REPEATS, DECODE_COLLAPSE = 0, 1
 CNN_FP32, CNN_TENSOR = 0, 1
+OPT_I8_IMPL = 1
 
 EXPORTS = [
     "ww_version", "ww_create", "ww_destroy", "ww_last_error", "ww_load_weights", "ww_num_frames",
@@ -29,7 +30,7 @@ EXPORTS = [
     "ww_stream_score", "ww_stream_events", "ww_session_open", "ww_session_write", "ww_session_poll",
     "ww_session_windows", "ww_session_last_logits", "ww_session_close", "ww_ctc_greedy", "ww_ctc_loss_workspace_bytes",
     "ww_ctc_loss_fwd", "ww_ctc_loss_bwd", "ww_debug_tc", "ww_extract_mfcc", "ww_free_mfcc",
-    "ww_wav_parse", "ww_wav_load_batch", "ww_wav_write", "ww_tdm_downmix", "ww_augment_waveform",
+    "ww_set_option", "ww_wav_parse", "ww_wav_load_batch", "ww_wav_write", "ww_tdm_downmix", "ww_augment_waveform",
 ]
 
 
@@ -100,6 +101,7 @@ def load_library():
         lib.ww_extract_mfcc.restype = C.POINTER(C.c_float)
         lib.ww_free_mfcc.argtypes = [C.POINTER(C.c_float)]
         lib.ww_free_mfcc.restype = None
+        lib.ww_set_option.argtypes = [vp, i32, i32]
         lib.ww_wav_parse.argtypes = [vp, C.c_size_t, i32, C.POINTER(WavInfo)]
         lib.ww_wav_load_batch.argtypes = [C.POINTER(C.c_char_p), i32, i32, i32, vp, C.POINTER(WavInfo), C.POINTER(i32)]
         lib.ww_wav_write.argtypes = [C.c_char_p, vp, C.c_size_t, i32, i32]

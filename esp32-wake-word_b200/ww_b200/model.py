@@ -92,10 +92,11 @@ class LightweightKWS(nn.Module):
 XIAOA_EXPONENTS = (-4, -8, -5, -9, -5, -9, -4, -5, -9, -4, -9, -3)
 
 
-def forward_int8(state_dict, x_q, exponents=XIAOA_EXPONENTS, device=None):
+def forward_int8(state_dict, x_q, exponents=XIAOA_EXPONENTS, device=None, impl="tensor"):
     """int8 power-of-two twin of the model (what esp-dl runs on the device).
 
     x_q: int8 [B, 13, 63] at the input exponent (-4) -> int8 [B, C] at the output exponent (-3); integer exact.
+    impl: 'tensor' (tcgen05 kind::i8, default) or 'cuda' (CUDA-core integer kernel); identical results.
     """
     if not x_q.is_cuda:
         if not torch.cuda.is_available():
@@ -109,6 +110,9 @@ def forward_int8(state_dict, x_q, exponents=XIAOA_EXPONENTS, device=None):
     _push_weights(ctx, state_dict, key)
     exps = (C.c_int * 12)(*[int(e) for e in exponents])
     ctx.check(ctx.lib.ww_quantize_weights_i8(ctx.h, exps), "ww_quantize_weights_i8")
+    if impl not in ("tensor", "cuda"):
+        raise ValueError("impl must be 'tensor' or 'cuda'")
+    ctx.check(ctx.lib.ww_set_option(ctx.h, L.OPT_I8_IMPL, L.CNN_TENSOR if impl == "tensor" else L.CNN_FP32), "ww_set_option")
     out = torch.empty((x_q.shape[0], ctx.num_classes), dtype=torch.int8, device=x_q.device)
     ctx.check(ctx.lib.ww_cnn_forward_i8(ctx.h, L.ptr(x_q), x_q.shape[0], L.ptr(out), L.cur_stream(x_q.device)),
               "ww_cnn_forward_i8")

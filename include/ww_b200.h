@@ -104,6 +104,11 @@ int ww_quantize_weights_i8(ww_ctx* ctx, const int* exps);
  * esp_wake_word_detector.cpp:200-220); out: device int8 [n][num_classes] at the output exponent.
  * Integer-exact: reproduces the shipped known-answer vector ml_models/xiaoa.info:3153-3224 (-40). */
 int ww_cnn_forward_i8(ww_ctx* ctx, const int8_t* x, long long n_windows, int8_t* out, ww_stream_t stream);
+/* Context options.  WW_OPT_I8_IMPL: which kernel ww_cnn_forward_i8 launches -- WW_CNN_TENSOR (default: tcgen05
+ * kind::i8, int32 accumulators in TMEM) or WW_CNN_FP32 (here: the CUDA-core integer kernel).  Both are integer-exact
+ * and give identical results. */
+enum { WW_OPT_I8_IMPL = 1 };
+int ww_set_option(ww_ctx* ctx, int option, int value);
 
 /* ---- fused clip scoring: PCM -> MFCC -> CMVN -> CNN -> decision -------------------------------- */
 /* pcm: device [n_clips][16000].  The feature intermediate stays in an L2-sized context scratch. */

@@ -43,3 +43,35 @@ def test_device_pipeline_on_firmware_dumps(cuda_device, golden_dir, xiaoa_sd):
     want = ocnn.forward_int8(xq, xiaoa_sd)
     got = ww_b200.forward_int8(xiaoa_sd, torch.from_numpy(xq).to(cuda_device)).cpu().numpy()
     np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 33, 4096 + 5])
+def test_tensor_core_int8_equals_cuda_core_int8_and_oracle(cuda_device, xiaoa_sd, n):
+    """tcgen05 kind::i8 path (default) == CUDA-core integer kernel == oracle twin, bit for bit, including partial
+    octets and partial CTAs (window counts that are not multiples of 8 / 32)."""
+    import ww_b200
+
+    rng = np.random.default_rng(n)
+    x = rng.integers(-128, 128, size=(n, 13, 63)).astype(np.int8)
+    k = min(n, 64)
+    x[:k] = np.clip(rng.normal(0, 16, size=(k, 13, 63)).round(), -128, 127).astype(np.int8)
+    xt = torch.from_numpy(x).to(cuda_device)
+    got_tc = ww_b200.forward_int8(xiaoa_sd, xt, impl="tensor").cpu().numpy()
+    got_cc = ww_b200.forward_int8(xiaoa_sd, xt, impl="cuda").cpu().numpy()
+    np.testing.assert_array_equal(got_tc, got_cc)
+    m = min(n, 300)
+    np.testing.assert_array_equal(got_tc[:m], ocnn.forward_int8(x[:m], xiaoa_sd))
+
+
+def test_tensor_core_int8_shipped_kat_and_extremes(cuda_device, golden_dir, xiaoa_sd):
+    """The shipped known-answer vector through the tensor-core kernel, and saturating inputs (all +127 / -128)."""
+    import ww_b200
+
+    k = np.load(os.path.join(golden_dir, "kat_xiaoa_info.npz"))
+    x = np.ascontiguousarray(k["input_q"].T[None])
+    ext = np.stack([np.full((13, 63), 127, np.int8), np.full((13, 63), -128, np.int8),
+                    np.tile(np.array([127, -128], np.int8), 13 * 63 // 2 + 1)[:13 * 63].reshape(13, 63)])
+    xs = np.concatenate([x, ext])
+    got = ww_b200.forward_int8(xiaoa_sd, torch.from_numpy(xs).to(cuda_device), impl="tensor").cpu().numpy()
+    assert got[0].tolist() == [-40]
+    np.testing.assert_array_equal(got, ocnn.forward_int8(xs, xiaoa_sd))

@@ -171,6 +171,31 @@ def session_bench(sd, n_streams=4096, chunk=320, pushes=200):
     return out
 
 
+def int8_bench(dev, sd, n=1 << 18):
+    """8f rank 1: int8 power-of-two twin, windows/s on the tensor cores (kind::i8) and on the CUDA cores."""
+    import ctypes as C
+    from ww_b200 import _lib as L
+    from ww_b200.model import XIAOA_EXPONENTS, _push_weights
+
+    x = torch.randint(-128, 128, (n, 13, 63), dtype=torch.int8, device=dev)
+    ctx = L.get_context(0)
+    _push_weights(ctx, sd, ("int8-bench", 0))
+    exps = (C.c_int * 12)(*[int(e) for e in XIAOA_EXPONENTS])
+    ctx.check(ctx.lib.ww_quantize_weights_i8(ctx.h, exps), "quantize")
+    out = torch.empty((n, ctx.num_classes), dtype=torch.int8, device=dev)
+    res = []
+    ref = None
+    for name, impl in (("tensor (tcgen05 kind::i8)", L.CNN_TENSOR), ("cuda cores", L.CNN_FP32)):
+        ctx.check(ctx.lib.ww_set_option(ctx.h, L.OPT_I8_IMPL, impl), "opt")
+        dt = timed(lambda: ctx.check(ctx.lib.ww_cnn_forward_i8(ctx.h, L.ptr(x), n, L.ptr(out), L.cur_stream(dev)), "i8"))
+        same = True if ref is None else bool(torch.equal(ref, out))
+        ref = out.clone()
+        res.append({"config": "8f rank 1: int8 twin forward", "impl": name, "windows": n, "seconds_per_pass": dt,
+                    "windows_per_s": n / dt, "int8_TOPS_useful": n * 1291968 / dt / 1e12, "identical_to_previous_impl": same})
+    ctx.check(ctx.lib.ww_set_option(ctx.h, L.OPT_I8_IMPL, L.CNN_TENSOR), "opt")
+    return res
+
+
 def frontdsp_bench(dev):
     """SURVEY 8f rank 3/4 rows against the HBM roofline (MEASURED_PEAKS.json hbm_gbs, else 6545.3)."""
     import tempfile
@@ -221,7 +246,7 @@ def main():
             print(json.dumps(r), flush=True)
         return
     if "--frontdsp" in sys.argv:
-        for r in session_bench(sd) + frontdsp_bench(dev):
+        for r in int8_bench(dev, sd) + session_bench(sd) + frontdsp_bench(dev):
             print(json.dumps(r), flush=True)
         return
     res += batch_sweep(dev, sd)
