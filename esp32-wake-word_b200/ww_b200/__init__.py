@@ -6,7 +6,7 @@ libwwb200.so (hand-written sm_100a CUDA behind a C ABI, include/ww_b200.h).  No 
 from ._lib import WWError, get_context, load_library  # noqa: F401
 from .features import (add_random_noise, augment_audio_waveform, cmvn_batch, extract_features,  # noqa: F401
                        load_wav, mfcc_batch, normalize_mfcc, pad_audio)
-from .model import LightweightKWS, WakeWordScorer, forward_int8, XIAOA_EXPONENTS  # noqa: F401
+from .model import LightweightKWS, WakeWordScorer, forward_int8, score_clips_int8, XIAOA_EXPONENTS  # noqa: F401
 from .ctc import (CTCKeywordDetector, CTCLoss, ctc_greedy_decode, ctc_loss, decode_predictions,  # noqa: F401
                   greedy_batch)
 from .stream import StreamScorer, StreamSession, events, refractory_frames  # noqa: F401

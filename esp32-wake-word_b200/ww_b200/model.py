@@ -119,6 +119,25 @@ def forward_int8(state_dict, x_q, exponents=XIAOA_EXPONENTS, device=None, impl="
     return out
 
 
+def score_clips_int8(state_dict, pcm, exponents=XIAOA_EXPONENTS, threshold_percent=80.0, impl="tensor"):
+    """The DEVICE decision path end to end on the GPU: PCM -> MFCC -> int8 rounding + device CMVN
+    (esp_wake_word_detector.cpp:128-131,179-211) -> model input at exponent -4 (:216-220) -> int8 power-of-two model
+    (esp-dl export, ml_models/xiaoa.info) -> sigmoid(out * 2^-3) * 100 >= 80 (:226-228,245).
+
+    pcm: [B, 16000] int16 / float.  Returns (out_q int8 [B, C] at the output exponent, decisions uint8 [B]).
+    Everything after the float features is integer-exact.
+    """
+    from .features import cmvn_batch, mfcc_batch
+
+    feats = mfcc_batch(pcm)
+    z = cmvn_batch(feats, device_style=True)            # values k/16, already saturated to int8 at exponent -4
+    x_q = torch.round(z * 16.0).to(torch.int8)
+    out_q = forward_int8(state_dict, x_q, exponents=exponents, impl=impl)
+    logit = out_q[:, 0].to(torch.float32) * (2.0 ** int(exponents[11]))
+    dec = ((1.0 / (1.0 + torch.exp(-logit))) * 100.0 >= threshold_percent).to(torch.uint8)
+    return out_q, dec
+
+
 class WakeWordScorer:
     """PCM -> logits / decisions: the fused engine call (MFCC + CMVN + CNN + decision).
 

@@ -75,3 +75,30 @@ def test_tensor_core_int8_shipped_kat_and_extremes(cuda_device, golden_dir, xiao
     got = ww_b200.forward_int8(xiaoa_sd, torch.from_numpy(xs).to(cuda_device), impl="tensor").cpu().numpy()
     assert got[0].tolist() == [-40]
     np.testing.assert_array_equal(got, ocnn.forward_int8(xs, xiaoa_sd))
+
+
+def test_device_decision_path_end_to_end(cuda_device, xiaoa_sd):
+    """score_clips_int8: PCM -> MFCC -> int8 + device CMVN -> int8 model -> sigmoid*100 >= 80.
+    The CMVN is float arithmetic whose summation order is not pinned by the reference (sequential `variance +=` on the
+    device, esp_wake_word_detector.cpp:181-197): its int8 output may differ from the oracle's by one step where
+    (x - mean) / std lands on a rounding boundary -- bounded here at 1e-4 of the values.  From the int8 model input
+    onward everything is integer-exact."""
+    import ww_b200
+
+    pcm = om.synth_clips_int16(256, seed=77)
+    x = torch.from_numpy(pcm).to(cuda_device)
+    out_q, dec = ww_b200.score_clips_int8(xiaoa_sd, x)
+    feats = ww_b200.mfcc_batch(x)
+    xq_gpu = torch.round(ww_b200.cmvn_batch(feats, device_style=True) * 16.0).to(torch.int8).cpu().numpy()
+    _, q = om.cmvn_device(feats.cpu().numpy())
+    xq = np.clip(q.astype(np.int32) * 16, -128, 127).astype(np.int8)
+    diff = np.abs(xq_gpu.astype(np.int32) - xq.astype(np.int32))
+    assert diff.max() <= 16 and (diff != 0).mean() < 1e-4
+    want = ocnn.forward_int8(xq_gpu, xiaoa_sd)
+    np.testing.assert_array_equal(out_q.cpu().numpy(), want)
+    logit = want[:, 0].astype(np.float32) / 8.0
+    np.testing.assert_array_equal(dec.cpu().numpy().astype(bool), (1.0 / (1.0 + np.exp(-logit)) * 100.0) >= 80.0)
+    ref_f = om.mfcc_torchaudio(om.pcm16_to_float(pcm)).numpy()
+    _, q2 = om.cmvn_device(ref_f)
+    want2 = ocnn.forward_int8(np.clip(q2.astype(np.int32) * 16, -128, 127).astype(np.int8), xiaoa_sd)
+    assert (want2 == want).mean() > 0.97
