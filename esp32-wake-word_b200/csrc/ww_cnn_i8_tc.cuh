@@ -9,7 +9,7 @@
 // scoring 8 windows per iteration through conv1/conv2 (even/odd de-interleaved operands, per-thread MaxPool),
 // conv3 (channels on the TMEM lanes) and fc1.  Differences that int8 brings:
 //   * a 16-byte K chunk holds 16 channels and one MMA spans K = 32: conv1 (13 -> 16 channels) multiplies a second,
-//     arbitrary chunk by zero weights; conv2 is one MMA per tap, conv3 two, fc1 four (34 MMAs per octet, not 44)
+//     arbitrary chunk by zero weights; conv2 is one MMA per tap, conv3 two, fc1 four (28 MMAs per octet, not 44)
 //   * requantisation (ReLU, right shift with round-half-to-even, int8 saturation) happens in the TMEM epilogues;
 //     it is monotonic, so MaxPool runs first on the int32 accumulators and one requantisation serves both taps
 //   * activations are a quarter of the fp16 kernel's bytes: 27 KB per group, weights 49 KB -> four groups fit
