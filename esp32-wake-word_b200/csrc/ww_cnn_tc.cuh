@@ -4,7 +4,7 @@
 // device CMVN (esp_wake_word_detector.cpp:179-211), LightweightKWS.forward (wakeModel.py:29-34) and the
 // decision (ml_models/main.py:53, esp_wake_word_detector.cpp:226-245) for 63-frame windows.
 //
-// One persistent CTA per SM runs TC_GROUPS (3) independent 4-warp groups; each group scores EIGHT windows per iteration, so
+// One persistent CTA per SM runs TC_GROUPS (4) independent 4-warp groups; each group scores EIGHT windows per iteration, so
 // one group's TMEM epilogues (CUDA cores) overlap the other group's MMAs and waits.  Every layer is an implicit GEMM
 // issued by a single thread of the group with tcgen05.mma (kind::f16: fp16 operands, fp32 accumulation in TMEM):
 //   conv1  D[512 pos x 32]  = sum_tap A1[pos+tap][16] . W1_tap[32][16]^T     4 tiles of M=128, K=16 per tap
@@ -28,7 +28,7 @@
 
 namespace ww {
 
-constexpr int TC_GROUPS = 3;      // independent 4-warp groups per CTA
+constexpr int TC_GROUPS = 4;      // independent 4-warp groups per CTA
 constexpr int TC_THREADS = 128 * TC_GROUPS;
 constexpr int TC_CLIPS = 8;
 constexpr int TC_MAX_CLASSES = 8;
@@ -44,7 +44,9 @@ constexpr int X3_ROWS = 16 * TC_CLIPS + 2;   // 130: natural order (conv3 pools 
 constexpr int G_ROWS = 16;                   // fc1 B operand: 8 windows + 8 zero rows (N must be a multiple of 16)
 constexpr int A1_LBO = A1P_ROWS * 16, A2_LBO = A2P_ROWS * 16, X3_LBO = X3_ROWS * 16, G_LBO = G_ROWS * 16;
 constexpr int A1_PAR = 2 * A1_LBO, A2_PAR = 4 * A2_LBO;  // bytes per parity tile
-constexpr int W1_LBO = 32 * 16, W2_LBO = 64 * 16, W3_LBO = 128 * 16, WF1_LBO = 128 * 16;
+// fc1's A operand stores only its 64 real rows per K chunk: rows 64..127 of the M = 128 tile read the next chunk
+// (finite weights; one zero chunk follows the last) and produce accumulator rows nobody reads
+constexpr int W1_LBO = 32 * 16, W2_LBO = 64 * 16, W3_LBO = 128 * 16, WF1_LBO = 64 * 16;
 constexpr int W1_TAP = 2 * W1_LBO, W2_TAP = 4 * W2_LBO, W3_TAP = 8 * W3_LBO;
 
 // shared memory map (bytes).  The CTA runs TWO independent 4-warp groups, each scoring its own octet of windows
@@ -58,21 +60,25 @@ constexpr int TC_W1 = 0;
 constexpr int TC_W2 = TC_W1 + 3 * W1_TAP;
 constexpr int TC_W3 = TC_W2 + 3 * W2_TAP;
 constexpr int TC_WF1 = TC_W3 + 3 * W3_TAP;
-constexpr int TC_W_BYTES = TC_WF1 + 16 * WF1_LBO;              // 97 280
+constexpr int TC_W_BYTES = TC_WF1 + 17 * WF1_LBO;              // 81 920 (16 chunks + one zero chunk)
 constexpr int TC_OFF_ACT = TC_OFF_W + TC_W_BYTES;              // per-group activation tiles
 // A1 (conv1 operand) and X3 (conv3 operand) share storage: A1 is dead once conv1 has completed, X3 is written by
 // the conv2 epilogue.  The zero rows each of them relies on are re-written every octet (see S0 / epilogue 2).
+// G (fc1 operand, written by the conv3 epilogue) lies over the start of A2's even-position tile, which is dead
+// after conv2 and fully rewritten by the next conv1 epilogue; G's rows 8..15 (the padding of N = 16) then hold
+// stale activations that only reach accumulator columns nobody reads.
 constexpr int TC_ACT_A1 = 0;
 constexpr int TC_ACT_X3 = 0;
 constexpr int TC_ACT_A2 = (2 * A1_PAR > 8 * X3_LBO ? 2 * A1_PAR : 8 * X3_LBO);
-constexpr int TC_ACT_G = TC_ACT_A2 + 2 * A2_PAR;
-constexpr int TC_ACT_BYTES = TC_ACT_G + 16 * G_LBO;            // 37 376
+constexpr int TC_ACT_G = TC_ACT_A2;
+constexpr int TC_ACT_BYTES = TC_ACT_A2 + 2 * A2_PAR;           // 33 280
+static_assert(16 * G_LBO <= A2_PAR, "G must stay inside A2's even-position tile");
 constexpr int TC_SMEM = TC_OFF_ACT + TC_GROUPS * TC_ACT_BYTES;
 static_assert(TC_OFF_W % 16 == 0 && TC_OFF_ACT % 16 == 0 && TC_ACT_A2 % 16 == 0 && TC_ACT_X3 % 16 == 0 &&
                   TC_ACT_G % 16 == 0 && TC_ACT_BYTES % 16 == 0,
               "UMMA operands need 16-byte alignment");
 static_assert(TC_SMEM <= 232448, "shared memory budget");
-constexpr int TC_GROUP_COLS = 160;  // per group: conv accumulators use columns [0,128), fc1 uses [128,144)
+constexpr int TC_GROUP_COLS = 128;  // per group: conv accumulators use columns [0,128); fc1 reuses [0,16) after epilogue 3
 constexpr int TC_TMEM_COLS = 512;
 static_assert(TC_GROUPS * TC_GROUP_COLS <= TC_TMEM_COLS, "TMEM columns");
 
@@ -537,7 +543,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
             constexpr uint32_t idesc = umma_idesc_f16(128, 16);
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
-                umma_f16(tmem + 128, umma_desc_kmajor(sWa + TC_WF1 + ks * 2 * WF1_LBO, WF1_LBO),
+                umma_f16(tmem, umma_desc_kmajor(sWa + TC_WF1 + ks * 2 * WF1_LBO, WF1_LBO),
                          umma_desc_kmajor(sGa + ks * 2 * G_LBO, G_LBO), idesc, ks > 0);
             umma_commit(bar);
         }
@@ -547,7 +553,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
         // ---- epilogue 4: ReLU, fc2 as a warp reduction (rows 0-63 = the warps of lane quadrants 0 and 1) ----
         if (q4 < 2) {
             float h[16];
-            tmem_ld16(tmem + tlane + 128, h);
+            tmem_ld16(tmem + tlane, h);
             const int o = 32 * q4 + lane;
 #pragma unroll
             for (int c8 = 0; c8 < 8; ++c8) h[c8] = fmaxf(h[c8], 0.f);
@@ -617,7 +623,7 @@ inline void tc_build_blob(std::vector<unsigned char>& blob, const float* conv1, 
         tc_pack_operand(reinterpret_cast<__half*>(blob.data() + TC_W2 + r * W2_TAP), 64, 32, conv2 + r, 64, 32, 32 * 3, 3);
         tc_pack_operand(reinterpret_cast<__half*>(blob.data() + TC_W3 + r * W3_TAP), 128, 64, conv3 + r, 128, 64, 64 * 3, 3);
     }
-    tc_pack_operand(reinterpret_cast<__half*>(blob.data() + TC_WF1), 128, 128, fc1, 64, 128, 128, 1);
+    tc_pack_operand(reinterpret_cast<__half*>(blob.data() + TC_WF1), 64, 128, fc1, 64, 128, 128, 1);
 }
 
 }  // namespace ww
