@@ -56,6 +56,7 @@ struct ww_ctx {
     I8Weights i8w{};
     bool have_i8 = false;
     uint4* i8tc_blob = nullptr;        // int8 weights in UMMA layout (ww_cnn_i8_tc.cuh)
+    int i8_in_exp = 0, i8_out_exp = 0;  // exponents of the model input / output tensors
     int i8_impl = WW_CNN_TENSOR;       // ww_set_option(WW_OPT_I8_IMPL)
     long long grp_windows = 0, grp_stride = 0;  // window grouping of the next CNN launch (streaming sessions)
     // fused-path scratch
@@ -516,10 +517,18 @@ static int check_cnn_args(ww_ctx* ctx, int cmvn_mode, int decide_mode, int cnn_i
     if (!ctx->have_weights) return fail(ctx, WW_ERR_NO_WEIGHTS, "weights not loaded (ww_load_weights)");
     if (cmvn_mode < WW_CMVN_NONE || cmvn_mode > WW_CMVN_DEVICE) return fail(ctx, WW_ERR_INVALID, "bad cmvn_mode");
     if (decide_mode < WW_DECIDE_NONE || decide_mode > WW_DECIDE_DEVICE) return fail(ctx, WW_ERR_INVALID, "bad decide_mode");
-    if (cnn_impl != WW_CNN_FP32 && cnn_impl != WW_CNN_TENSOR) return fail(ctx, WW_ERR_INVALID, "bad cnn_impl");
+    if (cnn_impl != WW_CNN_FP32 && cnn_impl != WW_CNN_TENSOR && cnn_impl != WW_CNN_INT8)
+        return fail(ctx, WW_ERR_INVALID, "bad cnn_impl");
 #ifndef WW_WITH_TC
-    if (cnn_impl == WW_CNN_TENSOR) return fail(ctx, WW_ERR_UNSUPPORTED, "tensor-core CNN not built into this library");
+    if (cnn_impl != WW_CNN_FP32) return fail(ctx, WW_ERR_UNSUPPORTED, "tensor-core CNN not built into this library");
 #endif
+    if (cnn_impl == WW_CNN_INT8) {
+        // the device path: int8 MFCC rounding + device CMVN feed the int8 model at exponent -4 (cpp:128-131,179-220)
+        if (!ctx->have_i8) return fail(ctx, WW_ERR_NO_WEIGHTS, "int8 weights not prepared (ww_quantize_weights_i8)");
+        if (cmvn_mode != WW_CMVN_DEVICE) return fail(ctx, WW_ERR_INVALID, "WW_CNN_INT8 requires WW_CMVN_DEVICE");
+        if (ctx->i8_in_exp != -4) return fail(ctx, WW_ERR_UNSUPPORTED, "WW_CNN_INT8 expects the model input at exponent -4");
+        if (ctx->w.num_classes > TC_MAX_CLASSES) return fail(ctx, WW_ERR_UNSUPPORTED, "WW_CNN_INT8 supports at most 8 classes");
+    }
     return WW_OK;
 }
 
@@ -593,10 +602,50 @@ static int tc_forward(ww_ctx* ctx, const float* feats, long long ws, long long c
 }
 #endif
 
+#ifdef WW_WITH_TC
+static void i8tc_fill(ww_ctx* ctx, I8TcArgs& t) {
+    memset(&t, 0, sizeof(t));
+    t.wblob = ctx->i8tc_blob;
+    t.fc2 = ctx->i8w.fc2;
+    t.num_classes = ctx->i8w.num_classes;
+    t.sh1 = ctx->i8w.sh1;
+    t.sh2 = ctx->i8w.sh2;
+    t.sh3 = ctx->i8w.sh3;
+    t.shf1 = ctx->i8w.shf1;
+    t.shf2 = ctx->i8w.shf2;
+    t.gap_num_shift = ctx->i8w.gap_num_shift;
+    t.out_scale = ldexpf(1.f, ctx->i8_out_exp);
+}
+static int i8tc_launch(ww_ctx* ctx, const I8TcArgs& t, cudaStream_t st) {
+    const long long n_cta = ((t.n_windows + I8T_CLIPS - 1) / I8T_CLIPS + I8T_GROUPS - 1) / I8T_GROUPS;
+    const unsigned grid = (unsigned)(n_cta < ctx->sm_count ? n_cta : ctx->sm_count);
+    cnn_i8_tc_kernel<<<grid, I8T_THREADS, I8T_SMEM, st>>>(t);
+    CK(cudaGetLastError());
+    return WW_OK;
+}
+#endif
+
 static int run_cnn(ww_ctx* ctx, const float* feats, long long ws, long long cs, long long fs, long long n,
                    int cmvn_mode, int decide_mode, float threshold, int cnn_impl, float* logits,
                    unsigned char* decisions, cudaStream_t st) {
 #ifdef WW_WITH_TC
+    if (cnn_impl == WW_CNN_INT8) {
+        if (n == 0) return WW_OK;
+        I8TcArgs t;
+        i8tc_fill(ctx, t);
+        t.feats = feats;
+        t.win_stride = ws;
+        t.coef_stride = cs;
+        t.frame_stride = fs;
+        t.group_windows = ctx->grp_windows;
+        t.group_stride = ctx->grp_stride;
+        t.n_windows = n;
+        t.logits_f = logits;
+        t.decisions = decisions;
+        t.decide_mode = decide_mode;
+        t.threshold = threshold;
+        return i8tc_launch(ctx, t, st);
+    }
     if (cnn_impl == WW_CNN_TENSOR) {
         int rc = tc_forward(ctx, feats, ws, cs, fs, n, cmvn_mode, decide_mode, threshold, logits, decisions, st);
         return rc;
@@ -675,6 +724,8 @@ extern "C" int ww_quantize_weights_i8(ww_ctx* ctx, const int* exps) {
     if (w.sh1 < 0 || w.sh2 < 0 || w.sh3 < 0 || w.shf1 < 0 || w.shf2 < 0 || w.sh1 > 30 || w.sh2 > 30 || w.sh3 > 30 ||
         w.shf1 > 30 || w.shf2 > 30 || w.gap_num_shift < -8 || w.gap_num_shift > 8)
         return fail(ctx, WW_ERR_UNSUPPORTED, "quantize_weights_i8: unsupported exponent combination");
+    ctx->i8_in_exp = exps[0];
+    ctx->i8_out_exp = exps[11];
     ctx->have_i8 = true;
     return WW_OK;
 }
@@ -687,23 +738,11 @@ extern "C" int ww_cnn_forward_i8(ww_ctx* ctx, const int8_t* x, long long n_windo
 #ifdef WW_WITH_TC
     if (ctx->i8_impl == WW_CNN_TENSOR && ctx->w.num_classes <= TC_MAX_CLASSES) {
         I8TcArgs t;
+        i8tc_fill(ctx, t);
         t.x = reinterpret_cast<const signed char*>(x);
         t.n_windows = n_windows;
         t.out = reinterpret_cast<signed char*>(out);
-        t.wblob = ctx->i8tc_blob;
-        t.fc2 = ctx->i8w.fc2;
-        t.num_classes = ctx->i8w.num_classes;
-        t.sh1 = ctx->i8w.sh1;
-        t.sh2 = ctx->i8w.sh2;
-        t.sh3 = ctx->i8w.sh3;
-        t.shf1 = ctx->i8w.shf1;
-        t.shf2 = ctx->i8w.shf2;
-        t.gap_num_shift = ctx->i8w.gap_num_shift;
-        const long long n_cta = ((n_windows + I8T_CLIPS - 1) / I8T_CLIPS + I8T_GROUPS - 1) / I8T_GROUPS;
-        const unsigned grid = (unsigned)(n_cta < ctx->sm_count ? n_cta : ctx->sm_count);
-        cnn_i8_tc_kernel<<<grid, I8T_THREADS, I8T_SMEM, (cudaStream_t)stream>>>(t);
-        CK(cudaGetLastError());
-        return WW_OK;
+        return i8tc_launch(ctx, t, (cudaStream_t)stream);
     }
 #endif
     I8Args a;

@@ -58,9 +58,18 @@ constexpr int I8T_GROUP_COLS = 128;   // conv accumulators [0,128); fc1 reuses [
 constexpr int I8T_TMEM_COLS = 512;
 
 struct I8TcArgs {
-    const signed char* x;    // [n][13][63] int8 at the model-input exponent (coef-major)
+    const signed char* x;    // [n][13][63] int8 at the model-input exponent (coef-major), or null when `feats` is given
+    // float-feature input (the whole device path in one launch): feats[win*win_stride + coef*coef_stride +
+    // frame*frame_stride] -> int8 rounding + device CMVN (tc_cmvn_device) -> model input at exponent -4
+    const float* feats;
+    long long win_stride, coef_stride, frame_stride, group_windows, group_stride;
     long long n_windows;
-    signed char* out;        // [n][C] int8 at the output exponent
+    signed char* out;        // [n][C] int8 at the output exponent (may be null)
+    float* logits_f;         // [n][C] dequantised logits out * 2^exp_out (may be null)
+    unsigned char* decisions;  // class 0, may be null
+    int decide_mode;
+    float threshold;
+    float out_scale;         // 2^exp_out
     const uint4* wblob;      // I8_W_BYTES
     const signed char* fc2;  // [C][64]
     int num_classes;
@@ -152,21 +161,41 @@ __global__ void __launch_bounds__(I8T_THREADS, 1) cnn_i8_tc_kernel(const __grid_
     const long long oct_stride = (long long)gridDim.x * I8T_GROUPS;
 #pragma unroll 1
     for (long long oct = (long long)blockIdx.x * I8T_GROUPS + group; oct < n_oct; oct += oct_stride) {
-        // ================= S0: int8 features -> A1 rows (lane <-> frame), two windows per warp =================
+        // ================= S0: model input -> A1 rows (lane <-> frame), two windows per warp =================
+        if (a.feats) {
+            // float features: int8 rounding + device-style CMVN here, so the device path is one launch
+#pragma unroll 1
+            for (int ww_ = 0; ww_ < 2; ++ww_) {
+                const int slot = 2 * q4 + ww_;
+                TcWin w;
+                tc_load_window(a, oct * I8T_CLIPS + slot, lane, w);
+                tc_cmvn_device(w, lane);
 #pragma unroll
-        for (int ww_ = 0; ww_ < 2; ++ww_) {
-            const int slot = 2 * q4 + ww_;
-            const long long win = oct * I8T_CLIPS + slot;
-            const bool live = win < a.n_windows;
-            const signed char* src = a.x + (live ? win : 0) * (WW_N_MFCC * WW_WINDOW_FRAMES);
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int t = lane + 32 * hf;
+                    if (t >= WW_WINDOW_FRAMES) continue;
+                    int v[16];
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                const int t = lane + 32 * hf;
-                if (t >= WW_WINDOW_FRAMES) continue;   // frame 63 does not exist: its (odd-tile) row stays zero
-                int v[16];
+                    for (int q = 0; q < 16; ++q) v[q] = q < WW_N_MFCC ? (int)((hf ? w.x1[q] : w.x0[q]) * 16.f) : 0;
+                    *reinterpret_cast<uint4*>(sA1 + (t & 1) * I8_A1_PAR + (1 + 32 * slot + (t >> 1)) * 16) = pack_b16(v);
+                }
+            }
+        } else {
 #pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] = (q < WW_N_MFCC && live) ? (int)src[q * WW_WINDOW_FRAMES + t] : 0;
-                *reinterpret_cast<uint4*>(sA1 + (t & 1) * I8_A1_PAR + (1 + 32 * slot + (t >> 1)) * 16) = pack_b16(v);
+            for (int ww_ = 0; ww_ < 2; ++ww_) {
+                const int slot = 2 * q4 + ww_;
+                const long long win = oct * I8T_CLIPS + slot;
+                const bool live = win < a.n_windows;
+                const signed char* src = a.x + (live ? win : 0) * (WW_N_MFCC * WW_WINDOW_FRAMES);
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int t = lane + 32 * hf;
+                    if (t >= WW_WINDOW_FRAMES) continue;   // frame 63 does not exist: its (odd-tile) row stays zero
+                    int v[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) v[q] = (q < WW_N_MFCC && live) ? (int)src[q * WW_WINDOW_FRAMES + t] : 0;
+                    *reinterpret_cast<uint4*>(sA1 + (t & 1) * I8_A1_PAR + (1 + 32 * slot + (t >> 1)) * 16) = pack_b16(v);
+                }
             }
         }
         fence_async_smem();
@@ -328,8 +357,18 @@ __global__ void __launch_bounds__(I8T_THREADS, 1) cnn_i8_tc_kernel(const __grid_
         if (tig < 8 * C) {
             const int c8 = tig & 7, c = tig >> 3;
             const long long win = oct * I8T_CLIPS + c8;
-            if (win < a.n_windows)
-                a.out[win * C + c] = (signed char)requant_i8(part[(0 * 8 + c) * 8 + c8] + part[(1 * 8 + c) * 8 + c8], a.shf2);
+            if (win < a.n_windows) {
+                const int oq = requant_i8(part[(0 * 8 + c) * 8 + c8] + part[(1 * 8 + c) * 8 + c8], a.shf2);
+                if (a.out) a.out[win * C + c] = (signed char)oq;
+                const float s = (float)oq * a.out_scale;   // exact: int8 times a power of two
+                if (a.logits_f) a.logits_f[win * C + c] = s;
+                if (c == 0 && a.decisions) {
+                    unsigned char d = 0;
+                    if (a.decide_mode == DECIDE_LOGIT) d = s > a.threshold;
+                    else if (a.decide_mode == DECIDE_DEVICE) d = (1.f / (1.f + expf(-s)) * 100.f) >= a.threshold;
+                    a.decisions[win] = d;
+                }
+            }
         }
     }
 

@@ -242,7 +242,8 @@ struct TcWin {
     float x0[WW_N_MFCC], x1[WW_N_MFCC];
 };
 
-__device__ __forceinline__ void tc_load_window(const TcArgs& a, long long win, int lane, TcWin& w) {
+template <class ARGS>
+__device__ __forceinline__ void tc_load_window(const ARGS& a, long long win, int lane, TcWin& w) {
     const bool live = win < a.n_windows;
     const bool has1 = lane + 32 < WW_WINDOW_FRAMES;
     const float* wbase = a.feats;
@@ -257,6 +258,24 @@ __device__ __forceinline__ void tc_load_window(const TcArgs& a, long long win, i
         w.x1[q] = (live && has1) ? *p1 : 0.f;
         p0 += a.coef_stride;
         p1 += a.coef_stride;
+    }
+}
+
+// device-style CMVN (esp_wake_word_detector.cpp:128-131,179-211): int8 rounding, population std, int8 output handed
+// to the model at exponent -4.  EXACTLY the arithmetic of cnn_fp32_kernel so that all paths quantise identically;
+// fully unrolled: 13 independent reduction chains interleave.  Leaves z = k/16 (k the int8 model input) in w.
+__device__ __forceinline__ void tc_cmvn_device(TcWin& w, int lane) {
+    const bool has1 = lane + 32 < WW_WINDOW_FRAMES;
+#pragma unroll
+    for (int q = 0; q < WW_N_MFCC; ++q) {
+        const float v0 = lround_clamp_i8(w.x0[q]);
+        const float v1 = has1 ? lround_clamp_i8(w.x1[q]) : 0.f;
+        const float mean = warp_sum(v0 + v1) / (float)WW_WINDOW_FRAMES;
+        const float d0 = v0 - mean, d1 = has1 ? v1 - mean : 0.f;
+        const float ss = warp_sum(d0 * d0 + d1 * d1);
+        const float den = sqrtf(ss / (float)WW_WINDOW_FRAMES) + 1e-8f;
+        w.x0[q] = fminf(fmaxf(lround_clamp_i8(d0 / den) * 16.f, -128.f), 127.f) * 0.0625f;
+        w.x1[q] = fminf(fmaxf(lround_clamp_i8(d1 / den) * 16.f, -128.f), 127.f) * 0.0625f;
     }
 }
 
@@ -297,20 +316,7 @@ __device__ __forceinline__ void tc_cmvn_store(const TcArgs& a, TcWin& w, int slo
             x1[q] *= iq;
         }
     } else if (a.cmvn_mode == CMVN_DEVICE) {
-        // device-style CMVN rounds to int8: keep EXACTLY the arithmetic of cnn_fp32_kernel so that both
-        // paths quantise identically
-        // (fully unrolled: 13 independent reduction chains interleave; x0/x1 stay in named registers)
-#pragma unroll
-        for (int q = 0; q < WW_N_MFCC; ++q) {
-            const float v0 = lround_clamp_i8(x0[q]);
-            const float v1 = has1 ? lround_clamp_i8(x1[q]) : 0.f;
-            const float mean = warp_sum(v0 + v1) / (float)WW_WINDOW_FRAMES;
-            const float d0 = v0 - mean, d1 = has1 ? v1 - mean : 0.f;
-            const float ss = warp_sum(d0 * d0 + d1 * d1);
-            const float den = sqrtf(ss / (float)WW_WINDOW_FRAMES) + 1e-8f;
-            x0[q] = fminf(fmaxf(lround_clamp_i8(d0 / den) * 16.f, -128.f), 127.f) * 0.0625f;
-            x1[q] = fminf(fmaxf(lround_clamp_i8(d1 / den) * 16.f, -128.f), 127.f) * 0.0625f;
-        }
+        tc_cmvn_device(w, lane);
     }
     // frame t -> parity tile t & 1, row 1 + 32*slot + (t >> 1); channels 0-7 -> chunk 0, 8-12 (+3 zeros) -> chunk 1
     {

@@ -21,7 +21,7 @@ LAYOUT_COEF_MAJOR, LAYOUT_FRAME_MAJOR = 0, 1
 CMVN_NONE, CMVN_PY, CMVN_DEVICE = 0, 1, 2
 DECIDE_NONE, DECIDE_LOGIT, DECIDE_DEVICE = 0, 1, 2
 DECODE_KEEP_REPEATS, DECODE_COLLAPSE = 0, 1
-CNN_FP32, CNN_TENSOR = 0, 1
+CNN_FP32, CNN_TENSOR, CNN_INT8 = 0, 1, 2
 OPT_I8_IMPL = 1
 
 EXPORTS = [

@@ -21,7 +21,21 @@ LN4 = math.log(4.0)
 _tokens = itertools.count(1)  # unique per weight owner: id() values are recycled after garbage collection
 
 
-def _push_weights(ctx, sd, owner_key):
+_IMPL = {"fp32": L.CNN_FP32, "tensor": L.CNN_TENSOR, "int8": L.CNN_INT8}
+# ml_models/xiaoa.info:3139-3150 (input, w1, act1, w2, act2, w3, act3, gap, w_fc1, act_fc1, w_fc2, output)
+XIAOA_EXPONENTS = (-4, -8, -5, -9, -5, -9, -4, -5, -9, -4, -9, -3)
+
+
+def _impl_code(name):
+    try:
+        return _IMPL[name]
+    except KeyError:
+        raise ValueError(f"cnn_impl must be one of {sorted(_IMPL)}") from None
+
+
+def _push_weights(ctx, sd, owner_key, int8_exponents=None):
+    """Make `sd` the context's weight set (no-op when it already is).  int8_exponents: also prepare the int8
+    power-of-two twin (cnn_impl='int8')."""
     if getattr(ctx, "weights_owner", None) == owner_key:
         return
     arrs = []
@@ -38,6 +52,9 @@ def _push_weights(ctx, sd, owner_key):
     ptrs = [a.ctypes.data_as(C.c_void_p) for a in arrs]
     ctx.check(ctx.lib.ww_load_weights(ctx.h, *ptrs, int(C_out)), "ww_load_weights")
     ctx.num_classes = int(C_out)
+    if int8_exponents is not None:
+        exps = (C.c_int * 12)(*[int(e) for e in int8_exponents])
+        ctx.check(ctx.lib.ww_quantize_weights_i8(ctx.h, exps), "ww_quantize_weights_i8")
     ctx.weights_owner = owner_key
 
 
@@ -82,14 +99,11 @@ class LightweightKWS(nn.Module):
         _push_weights(ctx, self.state_dict(), self._weights_key())
         B = x.shape[0]
         out = torch.empty((B, ctx.num_classes), dtype=torch.float32, device=x.device)
-        impl = L.CNN_TENSOR if self.cnn_impl == "tensor" else L.CNN_FP32
+        impl = _impl_code(self.cnn_impl)
         ctx.check(ctx.lib.ww_cnn_forward(ctx.h, L.ptr(x), 13 * 63, 63, 1, B, L.CMVN_NONE, L.DECIDE_NONE, 0.0,
                                          impl, L.ptr(out), None, L.cur_stream(x.device)), "ww_cnn_forward")
         return out
 
-
-# per-tensor exponents of the shipped export: ml_models/xiaoa.info:3139-3150
-XIAOA_EXPONENTS = (-4, -8, -5, -9, -5, -9, -4, -5, -9, -4, -9, -3)
 
 
 def forward_int8(state_dict, x_q, exponents=XIAOA_EXPONENTS, device=None, impl="tensor"):
@@ -119,22 +133,19 @@ def forward_int8(state_dict, x_q, exponents=XIAOA_EXPONENTS, device=None, impl="
     return out
 
 
-def score_clips_int8(state_dict, pcm, exponents=XIAOA_EXPONENTS, threshold_percent=80.0, impl="tensor"):
+def score_clips_int8(state_dict, pcm, exponents=XIAOA_EXPONENTS, threshold_percent=80.0):
     """The DEVICE decision path end to end on the GPU: PCM -> MFCC -> int8 rounding + device CMVN
     (esp_wake_word_detector.cpp:128-131,179-211) -> model input at exponent -4 (:216-220) -> int8 power-of-two model
     (esp-dl export, ml_models/xiaoa.info) -> sigmoid(out * 2^-3) * 100 >= 80 (:226-228,245).
 
-    pcm: [B, 16000] int16 / float.  Returns (out_q int8 [B, C] at the output exponent, decisions uint8 [B]).
-    Everything after the float features is integer-exact.
+    pcm: CUDA [B, 16000] int16 / float.  Returns (out_q int8 [B, C] at the output exponent, decisions uint8 [B]).
+    Two launches: the frontend and the kind::i8 tensor-core kernel (CMVN fused into its first stage); everything
+    after the float features is integer-exact.
     """
-    from .features import cmvn_batch, mfcc_batch
-
-    feats = mfcc_batch(pcm)
-    z = cmvn_batch(feats, device_style=True)            # values k/16, already saturated to int8 at exponent -4
-    x_q = torch.round(z * 16.0).to(torch.int8)
-    out_q = forward_int8(state_dict, x_q, exponents=exponents, impl=impl)
-    logit = out_q[:, 0].to(torch.float32) * (2.0 ** int(exponents[11]))
-    dec = ((1.0 / (1.0 + torch.exp(-logit))) * 100.0 >= threshold_percent).to(torch.uint8)
+    sc = WakeWordScorer(state_dict, cmvn="device", decision="device", cnn_impl="int8", int8_exponents=exponents)
+    sc.threshold = float(threshold_percent)
+    logits, dec = sc.score(pcm)
+    out_q = torch.round(logits * (2.0 ** -int(exponents[11]))).to(torch.int8)   # exact: logits are out_q * 2^exp
     return out_q, dec
 
 
@@ -146,9 +157,15 @@ class WakeWordScorer:
     (esp_wake_word_detector.cpp:179-211,226-245).
     """
 
-    def __init__(self, state_dict, device=None, cmvn="python", decision="python", cnn_impl="fp32"):
+    def __init__(self, state_dict, device=None, cmvn="python", decision="python", cnn_impl="fp32",
+                 int8_exponents=XIAOA_EXPONENTS):
+        """cnn_impl: 'fp32' (exact, CUDA cores), 'tensor' (tcgen05 fp16 + fp32 re-score near the threshold) or
+        'int8' (the device model: int8 power-of-two twin on tcgen05 kind::i8; needs cmvn='device')."""
         self.ctx = L.get_context(device)
         self.sd = state_dict
+        self._i8 = tuple(int8_exponents) if cnn_impl == "int8" else None
+        if cnn_impl == "int8" and cmvn != "device":
+            raise ValueError("cnn_impl='int8' is the device path: use cmvn='device'")
         self.cmvn = {"none": L.CMVN_NONE, "python": L.CMVN_PY, "device": L.CMVN_DEVICE}[cmvn]
         if decision == "python":
             self.decide, self.threshold = L.DECIDE_LOGIT, 0.0
@@ -156,16 +173,16 @@ class WakeWordScorer:
             self.decide, self.threshold = L.DECIDE_DEVICE, 80.0
         else:
             raise ValueError(decision)
-        self.cnn_impl = L.CNN_TENSOR if cnn_impl == "tensor" else L.CNN_FP32
+        self.cnn_impl = _impl_code(cnn_impl)
         self._key = ("scorer", next(_tokens))
-        _push_weights(self.ctx, self.sd, self._key)
+        _push_weights(self.ctx, self.sd, self._key, self._i8)
 
     @classmethod
     def from_onnx(cls, path, **kw):
         return cls(load_kws_state_dict(path), **kw)
 
     def _prep(self):
-        _push_weights(self.ctx, self.sd, self._key)
+        _push_weights(self.ctx, self.sd, self._key, self._i8)
 
     def score(self, pcm):
         """pcm: CUDA [B, 16000] int16 or float32 -> (logits [B, C], decisions uint8 [B])."""

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .model import _push_weights, _tokens
+from .model import XIAOA_EXPONENTS, _impl_code, _push_weights, _tokens
 
 WINDOW = 63
 LN4 = math.log(4.0)  # sigmoid(x)*100 >= 80  <=>  x >= ln 4
@@ -26,16 +26,18 @@ def refractory_frames(seconds=5.0, hop=256, sr=16000):
 
 
 class StreamScorer:
-    def __init__(self, state_dict, device=None, cmvn="device", cnn_impl="fp32"):
+    def __init__(self, state_dict, device=None, cmvn="device", cnn_impl="fp32", int8_exponents=XIAOA_EXPONENTS):
+        """cnn_impl 'int8' = the firmware's own model (int8 power-of-two twin, needs cmvn='device')."""
         self.ctx = L.get_context(device)
         self.sd = state_dict
         self.cmvn = {"none": L.CMVN_NONE, "python": L.CMVN_PY, "device": L.CMVN_DEVICE}[cmvn]
-        self.cnn_impl = L.CNN_TENSOR if cnn_impl == "tensor" else L.CNN_FP32
+        self.cnn_impl = _impl_code(cnn_impl)
+        self._i8 = tuple(int8_exponents) if cnn_impl == "int8" else None
         self._key = ("stream", next(_tokens))
 
     def score(self, pcm):
         """pcm: CUDA [N] int16 / float32 -> (features [13, T], logits [T-62, C])."""
-        _push_weights(self.ctx, self.sd, self._key)
+        _push_weights(self.ctx, self.sd, self._key, self._i8)
         if not pcm.is_cuda or pcm.dim() != 1:
             raise ValueError("StreamScorer.score expects a 1-D CUDA tensor")
         pcm = pcm.contiguous()
@@ -86,13 +88,13 @@ class StreamSession:
     """
 
     def __init__(self, state_dict, n_streams, max_chunk_samples=16000, device=None, cmvn="device", cnn_impl="fp32",
-                 threshold_logit=LN4, warmup=64, refractory=None):
+                 threshold_logit=LN4, warmup=64, refractory=None, int8_exponents=XIAOA_EXPONENTS):
         self.ctx = L.get_context(device)
         self._key = ("session", next(_tokens))
-        _push_weights(self.ctx, state_dict, self._key)
+        _push_weights(self.ctx, state_dict, self._key, tuple(int8_exponents) if cnn_impl == "int8" else None)
         self.n_streams = int(n_streams)
         cm = {"none": L.CMVN_NONE, "python": L.CMVN_PY, "device": L.CMVN_DEVICE}[cmvn]
-        impl = L.CNN_TENSOR if cnn_impl == "tensor" else L.CNN_FP32
+        impl = _impl_code(cnn_impl)
         if refractory is None:
             refractory = refractory_frames()
         h = C.c_void_p()

@@ -56,7 +56,12 @@ enum {
     WW_DECODE_KEEP_REPEATS = 0, /* CTCKeywordDetector.ctc_greedy_decode, ml_models/test.py:201-217 */
     WW_DECODE_COLLAPSE = 1      /* THCHS30Trainer.decode_predictions, ml_models/ctc.py:453-471 */
 };
-enum { WW_CNN_FP32 = 0, WW_CNN_TENSOR = 1 };
+enum {
+    WW_CNN_FP32 = 0,   /* exact fp32, CUDA cores */
+    WW_CNN_TENSOR = 1, /* tcgen05 kind::f16 + fp32 re-score near the threshold */
+    WW_CNN_INT8 = 2    /* the DEVICE model: int8 power-of-two twin on tcgen05 kind::i8 fed by int8 rounding + device CMVN
+                          (requires WW_CMVN_DEVICE and ww_quantize_weights_i8); logits are out_q * 2^exp_out, exactly */
+};
 
 #define WW_CLIP_SAMPLES 16000
 #define WW_N_MFCC 13

@@ -102,3 +102,42 @@ def test_device_decision_path_end_to_end(cuda_device, xiaoa_sd):
     _, q2 = om.cmvn_device(ref_f)
     want2 = ocnn.forward_int8(np.clip(q2.astype(np.int32) * 16, -128, 127).astype(np.int8), xiaoa_sd)
     assert (want2 == want).mean() > 0.97
+
+
+def test_int8_impl_through_scorer_stream_and_session(cuda_device, xiaoa_sd):
+    """cnn_impl='int8' (CMVN fused into the kind::i8 kernel) == the three-launch composition (ww_cmvn device ->
+    int8 -> ww_cnn_forward_i8) exactly, for clips, for the sliding windows of a stream and for push/poll sessions."""
+    import ww_b200
+
+    pcm = om.synth_clips_int16(300, seed=5)
+    x = torch.from_numpy(pcm).to(cuda_device)
+    sc = ww_b200.WakeWordScorer(xiaoa_sd, cmvn="device", decision="device", cnn_impl="int8")
+    logits, dec = sc.score(x)
+    feats = ww_b200.mfcc_batch(x)
+    xq = torch.round(ww_b200.cmvn_batch(feats, device_style=True) * 16.0).to(torch.int8)
+    want_q = ww_b200.forward_int8(xiaoa_sd, xq).cpu().numpy()
+    np.testing.assert_array_equal(logits.cpu().numpy(), want_q.astype(np.float32) / 8.0)
+    np.testing.assert_array_equal(dec.cpu().numpy().astype(bool),
+                                  (1.0 / (1.0 + np.exp(-want_q[:, 0].astype(np.float32) / 8.0)) * 100.0) >= 80.0)
+    with pytest.raises(ValueError):
+        ww_b200.WakeWordScorer(xiaoa_sd, cmvn="python", cnn_impl="int8")
+    # stream: windows are strided views of the feature matrix
+    stream = torch.from_numpy(om.synth_clips_int16(6, seed=9).reshape(-1)).to(cuda_device)
+    ss = ww_b200.StreamScorer(xiaoa_sd, cmvn="device", cnn_impl="int8")
+    f, lg = ss.score(stream)
+    T = f.shape[1]
+    wins = f.unfold(1, 63, 1).permute(1, 0, 2).contiguous()                    # [T-62, 13, 63]
+    xq = torch.round(ww_b200.cmvn_batch(wins, device_style=True) * 16.0).to(torch.int8)
+    want = ww_b200.forward_int8(xiaoa_sd, xq).cpu().numpy().astype(np.float32) / 8.0
+    assert lg.shape[0] == T - 62
+    np.testing.assert_array_equal(lg.cpu().numpy(), want)
+    # sessions: chunked pushes reproduce the whole-stream logits
+    n_streams = 3
+    data = om.synth_clips_int16(n_streams * 4, seed=21).reshape(n_streams, -1)
+    ses = ww_b200.StreamSession(xiaoa_sd, n_streams, max_chunk_samples=4000, cmvn="device", cnn_impl="int8")
+    got = [ses.write(data[:, i:i + 4000]) for i in range(0, data.shape[1], 4000)]
+    got = np.concatenate([g for g in got if g.shape[1]], axis=1)
+    ses.close()
+    for k in range(n_streams):
+        _, lgk = ss.score(torch.from_numpy(data[k]).to(cuda_device))
+        np.testing.assert_array_equal(got[k], lgk.cpu().numpy()[:got.shape[1]])

@@ -44,7 +44,7 @@ def stream_bench(dev, sd, seconds=3600, impl="tensor"):
     pcm = torch.round(torch.clamp(x, -1, 32767 / 32768) * 32767).to(torch.int16)
     del x, burst, t
     out = []
-    for cmvn in ("device", "python"):
+    for cmvn, impl in (("device", impl), ("python", impl), ("device", "int8")):
         sc = ww_b200.StreamScorer(sd, device=0, cmvn=cmvn, cnn_impl=impl)
         dt = timed(lambda: sc.score(pcm))
         feats, logits = sc.score(pcm)
@@ -196,6 +196,19 @@ def int8_bench(dev, sd, n=1 << 18):
     return res
 
 
+def device_path_bench(dev, sd, n=1 << 18):
+    """The device decision path over clips: frontend + (int8 rounding, device CMVN, int8 model, decision) in the
+    kind::i8 kernel, against the float model with device CMVN."""
+    pcm = bench.synth_pcm(n, dev, 1234)
+    out = []
+    for impl in ("int8", "tensor"):
+        sc = ww_b200.WakeWordScorer(sd, device=0, cmvn="device", decision="device", cnn_impl=impl)
+        dt = timed(lambda: sc.score(pcm))
+        out.append({"config": "device decision path over clips (device CMVN, sigmoid*100 >= 80)", "cnn_impl": impl, "clips": n,
+                    "seconds_per_pass": dt, "clips_per_s": n / dt})
+    return out
+
+
 def frontdsp_bench(dev):
     """SURVEY 8f rank 3/4 rows against the HBM roofline (MEASURED_PEAKS.json hbm_gbs, else 6545.3)."""
     import tempfile
@@ -246,7 +259,7 @@ def main():
             print(json.dumps(r), flush=True)
         return
     if "--frontdsp" in sys.argv:
-        for r in int8_bench(dev, sd) + session_bench(sd) + frontdsp_bench(dev):
+        for r in int8_bench(dev, sd) + device_path_bench(dev, sd) + session_bench(sd) + frontdsp_bench(dev):
             print(json.dumps(r), flush=True)
         return
     res += batch_sweep(dev, sd)
