@@ -164,11 +164,13 @@ __global__ void __launch_bounds__(I8T_THREADS, 1) cnn_i8_tc_kernel(const __grid_
         // ================= S0: model input -> A1 rows (lane <-> frame), two windows per warp =================
         if (a.feats) {
             // float features: int8 rounding + device-style CMVN here, so the device path is one launch
-#pragma unroll 1
+            TcWin w2[2];
+            tc_load_window(a, oct * I8T_CLIPS + 2 * q4, lane, w2[0]);       // both windows' loads in flight
+            tc_load_window(a, oct * I8T_CLIPS + 2 * q4 + 1, lane, w2[1]);
+#pragma unroll
             for (int ww_ = 0; ww_ < 2; ++ww_) {
                 const int slot = 2 * q4 + ww_;
-                TcWin w;
-                tc_load_window(a, oct * I8T_CLIPS + slot, lane, w);
+                TcWin& w = w2[ww_];
                 tc_cmvn_device(w, lane);
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
