@@ -109,42 +109,9 @@ def batch_sweep(dev, sd):
 
 
 def cpu_stages(sd):
-    """configs[0]: the reference's CPU path per stage (oracle port), B in {1, 200, 4096, 16384}, all threads and 1."""
-    from oracle import cnn as ocnn
-    from oracle import mfcc as omfcc
-
-    out = []
-    try:
-        ncpu = len(os.sched_getaffinity(0))
-    except Exception:
-        ncpu = os.cpu_count()
-    for threads in (ncpu, 1):
-        torch.set_num_threads(threads)
-        for B in (1, 200, 4096, 16384):
-            if threads == 1 and B > 4096:
-                continue
-            pcm = bench.synth_pcm(B, "cpu", 1234, chunk=4096)
-            x = pcm.to(torch.float32) / 32768.0
-
-            def best(fn, n=5):
-                fn(); fn()
-                ts = []
-                for _ in range(n):
-                    t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
-                return min(ts), float(np.median(ts))
-
-            feats = omfcc.mfcc_torchaudio(x)
-            z = omfcc.normalize_mfcc(feats, "cmvn")
-            zn = z.numpy()
-            t_m = best(lambda: omfcc.mfcc_torchaudio(x))
-            t_c = best(lambda: ocnn.forward_torch(omfcc.normalize_mfcc(feats, "cmvn").numpy(), sd))
-            t_e = best(lambda: bench.cpu_reference_step(pcm, sd))
-            out.append({"config": "configs[0] reference CPU path (oracle port), per stage", "threads": threads,
-                        "cpus": ncpu, "clips": B, "mfcc_clips_per_s_best": B / t_m[0], "mfcc_clips_per_s_median": B / t_m[1],
-                        "cmvn_cnn_clips_per_s_best": B / t_c[0], "end_to_end_clips_per_s_best": B / t_e[0],
-                        "end_to_end_clips_per_s_median": B / t_e[1]})
-            del zn
-    return out
+    """configs[0]: per-stage timing of the reference's CPU path -- lives in bench.py's cpu_baseline leg (the only
+    place outside tests/ that may run the oracle)."""
+    return bench.cpu_baseline_stages(sd)
 
 
 def session_bench(sd, n_streams=4096, chunk=320, pushes=200):
