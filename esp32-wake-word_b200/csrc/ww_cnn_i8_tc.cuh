@@ -97,8 +97,18 @@ __device__ __forceinline__ int rq_pos(int acc, int shift, int hm1) {
     if (shift <= 0) return min(127, acc << (-shift));
     return min(127, (acc + hm1 + ((acc >> shift) & 1)) >> shift);
 }
-__device__ __forceinline__ uint32_t pack_b4(int a, int b, int c, int d) {
-    return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(d & 0xff) << 24);
+// four int32 -> four int8 with saturation, two I2IP.S8.S32.SAT: cvt.pack puts sat(a) in byte 1, sat(b) in byte 0 and
+// the low half of c above them
+__device__ __forceinline__ uint32_t pack_b4(int x0, int x1, int x2, int x3) {
+    uint32_t t, d;
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(x3), "r"(x2), "r"(0));
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x1), "r"(x0), "r"(t));
+    return d;
+}
+// rq_pos without the clamp: the saturating pack that follows applies it
+__device__ __forceinline__ int rq_pos_nosat(int acc, int shift, int hm1) {
+    if (shift <= 0) return acc << (-shift);
+    return (acc + hm1 + ((acc >> shift) & 1)) >> shift;
 }
 __device__ __forceinline__ uint4 pack_b16(const int* v) {
     return make_uint4(pack_b4(v[0], v[1], v[2], v[3]), pack_b4(v[4], v[5], v[6], v[7]), pack_b4(v[8], v[9], v[10], v[11]),
@@ -233,7 +243,7 @@ __global__ void __launch_bounds__(I8T_THREADS, 1) cnn_i8_tc_kernel(const __grid_
             const int w = g >> 5, j = g & 31;
             int mine[32];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) mine[c] = rq_pos(max(max(ve[c], vo[c]), 0), sh1, hm1_1);
+            for (int c = 0; c < 32; ++c) mine[c] = rq_pos_nosat(max(max(ve[c], vo[c]), 0), sh1, hm1_1);
             if (j < 31) {
                 unsigned char* dst = sA2 + (j & 1) * I8_A2_PAR + (1 + 16 * w + (j >> 1)) * 16;
                 *reinterpret_cast<uint4*>(dst) = pack_b16(mine);
@@ -272,7 +282,7 @@ __global__ void __launch_bounds__(I8T_THREADS, 1) cnn_i8_tc_kernel(const __grid_
                 tmem_ld32x2_i(tmem + tlane + 32 * hh, tmem + tlane + 64 + 32 * hh, ve, vo);
                 int mine[32];
 #pragma unroll
-                for (int c = 0; c < 32; ++c) mine[c] = valid ? rq_pos(max(max(ve[c], vo[c]), 0), sh2, hm1_2) : 0;
+                for (int c = 0; c < 32; ++c) mine[c] = valid ? rq_pos_nosat(max(max(ve[c], vo[c]), 0), sh2, hm1_2) : 0;
                 *reinterpret_cast<uint4*>(dst + (2 * hh) * I8_X3_LBO) = pack_b16(mine);
                 *reinterpret_cast<uint4*>(dst + (2 * hh + 1) * I8_X3_LBO) = pack_b16(mine + 16);
             }

@@ -497,7 +497,9 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
             const TIN* spcm = reinterpret_cast<const TIN*>(pcm_buf + half * SM::HALF_STRIDE);
             const int org = half ? org1 : org0;
             const float pre = a.preemph;
+#if !WW_WIN_REGS
             const cpx* s_winp = reinterpret_cast<const cpx*>(s_win);
+#endif
             if (interior) {
                 // complex point m = 16*n1 + l16 (n1 = 3..12) <-> samples fo + 2m, fo + 2m + 1
                 const int base = fo - org + 2 * l16;  // smem sample index of m = l16 (even: fo - org is a multiple of 8)
