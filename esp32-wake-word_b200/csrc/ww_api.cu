@@ -1192,10 +1192,23 @@ extern "C" int ww_ctc_loss_fwd(ww_ctx* ctx, const float* log_probs, long long t_
         CK(cudaGetLastError());
         return WW_OK;
     }
+    const int K = ctc_lp(S) / 32;
+    const unsigned grid = (unsigned)((B + CTC_WARPS - 1) / CTC_WARPS);
+    if (K <= 4) {  // states and labels in registers, gathers prefetched CTC_PF steps ahead
+        const size_t smem_pf = (size_t)CTC_WARPS * (2 * (32 * K + 2) + CTC_PF * 32 * K) * sizeof(float);
+        switch (K) {
+            case 1: ctc_loss_fwd_pf_kernel<1><<<grid, CTC_WARPS * 32, smem_pf, (cudaStream_t)stream>>>(a); break;
+            case 2: ctc_loss_fwd_pf_kernel<2><<<grid, CTC_WARPS * 32, smem_pf, (cudaStream_t)stream>>>(a); break;
+            case 3: ctc_loss_fwd_pf_kernel<3><<<grid, CTC_WARPS * 32, smem_pf, (cudaStream_t)stream>>>(a); break;
+            default: ctc_loss_fwd_pf_kernel<4><<<grid, CTC_WARPS * 32, smem_pf, (cudaStream_t)stream>>>(a); break;
+        }
+        CK(cudaGetLastError());
+        return WW_OK;
+    }
     const size_t smem = (size_t)CTC_WARPS * 2 * ctc_lp(S) * sizeof(float);
     if (smem > 48 * 1024)
         CK(cudaFuncSetAttribute(ctc_loss_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ctc_loss_fwd_kernel<<<(B + CTC_WARPS - 1) / CTC_WARPS, CTC_WARPS * 32, smem, (cudaStream_t)stream>>>(a);
+    ctc_loss_fwd_kernel<<<grid, CTC_WARPS * 32, smem, (cudaStream_t)stream>>>(a);
     CK(cudaGetLastError());
     return WW_OK;
 }
@@ -1230,13 +1243,28 @@ extern "C" int ww_ctc_loss_bwd(ww_ctx* ctx, const float* log_probs, long long t_
         long long blocks = (rows + 7) / 8;
         const long long cap = (long long)ctx->sm_count * 8;
         if (blocks > cap) blocks = cap;
+        a.fill_vec = (C % 4 == 0) && ((uintptr_t)log_probs % 16 == 0) && ((uintptr_t)grad % 16 == 0) && (t_stride % 4 == 0) &&
+                     (b_stride % 4 == 0) && (gt_stride % 4 == 0) && (gb_stride % 4 == 0);
         ctc_grad_fill_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
         CK(cudaGetLastError());
+    }
+    const int K = ctc_lp(S) / 32;
+    const unsigned grid = (unsigned)((B + CTC_WARPS - 1) / CTC_WARPS);
+    if (K <= 4) {
+        const size_t smem_pf = (size_t)CTC_WARPS * (3 * (32 * K + 2) + 2 * CTC_PF * 32 * K + 3 * S) * sizeof(float);
+        switch (K) {
+            case 1: ctc_loss_bwd_pf_kernel<1><<<grid, CTC_WARPS * 32, smem_pf, (cudaStream_t)stream>>>(a); break;
+            case 2: ctc_loss_bwd_pf_kernel<2><<<grid, CTC_WARPS * 32, smem_pf, (cudaStream_t)stream>>>(a); break;
+            case 3: ctc_loss_bwd_pf_kernel<3><<<grid, CTC_WARPS * 32, smem_pf, (cudaStream_t)stream>>>(a); break;
+            default: ctc_loss_bwd_pf_kernel<4><<<grid, CTC_WARPS * 32, smem_pf, (cudaStream_t)stream>>>(a); break;
+        }
+        CK(cudaGetLastError());
+        return WW_OK;
     }
     const size_t smem = (size_t)CTC_WARPS * (2 * ctc_lp(S) + 3 * S) * sizeof(float);
     if (smem > 48 * 1024)
         CK(cudaFuncSetAttribute(ctc_loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ctc_loss_bwd_kernel<<<(B + CTC_WARPS - 1) / CTC_WARPS, CTC_WARPS * 32, smem, (cudaStream_t)stream>>>(a);
+    ctc_loss_bwd_kernel<<<grid, CTC_WARPS * 32, smem, (cudaStream_t)stream>>>(a);
     CK(cudaGetLastError());
     return WW_OK;
 }

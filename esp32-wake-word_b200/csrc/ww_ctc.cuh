@@ -117,6 +117,7 @@ struct CtcLossArgs {
     float* grad;            // grad[t*gt_stride + b*gb_stride + c] (backward only)
     long long gt_stride, gb_stride;
     int skip_fill;          // backward: grad rows were pre-filled with exp(lp)*go by ctc_grad_fill_kernel
+    int fill_vec;           // fill kernel: 16-byte vector path is legal (alignment and C % 4 checked on the host)
 };
 
 __device__ __forceinline__ float lse3(float a, float b, float c) {
@@ -260,6 +261,11 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_bwd_kernel(const CtcL
         ndup += __popc(m);
     }
     __syncwarp();
+    bool blank_in_tgt = false;
+    for (int i0 = 0; i0 < Sb; i0 += 32) {
+        const int i = i0 + lane;
+        blank_in_tgt |= __any_sync(0xffffffffu, i < Sb && tgt[i] == a.blank);
+    }
 
     int cur = 0;
     for (int t = Tb - 1; t >= 0; --t) {
@@ -319,8 +325,9 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_bwd_kernel(const CtcL
         if (lane == 0) {
             // a target label equal to the blank index is folded into the blank class as PyTorch does
             float tot = blank_m;
-            for (int i = 0; i < Sb; ++i)
-                if (first[i] == i && tgt[i] == a.blank) tot = lse2(tot, acc[i]);
+            if (blank_in_tgt)
+                for (int i = 0; i < Sb; ++i)
+                    if (first[i] == i && tgt[i] == a.blank) tot = lse2(tot, acc[i]);
             const float lpv = row[a.blank];
             grow[a.blank] = (expf(lpv) - expf(tot + nll - lpv)) * go;
         }
@@ -328,6 +335,328 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_bwd_kernel(const CtcL
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Prefetching variants for 2S+1 <= 32*K (K <= 4): same arithmetic as ctc_loss_fwd_kernel / ctc_loss_bwd_kernel,
+// but every lane keeps its K extended states (label, skip flag) in registers and the gathers that do NOT depend on
+// the recursion -- lp[t][label] (and alpha[t][s] in the backward pass) -- are issued CTC_PF time steps ahead with
+// 4-byte cp.async copies into a shared-memory ring.  The warp-per-utterance recursion is a dependent chain over T;
+// without the prefetch each step waits for a global gather (1.9 us / step forward, 6.2 us backward at T = 801,
+// C = 4096).  A register ring does not work: a warp has six scoreboards, so waiting for any shared-memory or MUFU
+// result also waits for the outstanding prefetch loads (measured: 50 % long-scoreboard stalls); cp.async groups are
+// tracked separately.
+// ------------------------------------------------------------------------------------------------
+constexpr int CTC_PF = 8;
+
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int K>
+__global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_fwd_pf_kernel(const CtcLossArgs a) {
+    extern __shared__ float ctc_sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long b = (long long)blockIdx.x * CTC_WARPS + warp;
+    if (b >= a.B) return;
+    constexpr int Lp = 32 * K;
+    constexpr int PER_WARP = 2 * (Lp + 2) + CTC_PF * Lp;
+    float* buf = ctc_sm + warp * PER_WARP + 2;       // two leading pad cells: prev[s-1], prev[s-2] need no branch
+    float* ring = ctc_sm + warp * PER_WARP + 2 * (Lp + 2);   // [CTC_PF][Lp] gathered lp[t][label of state s]
+    const int Tb = min(max(a.in_len[b], 0), a.T);
+    const int Sb = min(max(a.tgt_len[b], 0), a.S);
+    const int L = 2 * Sb + 1;
+    const int Lw = 2 * a.S + 1;
+    const int* tgt = a.targets + b * (long long)a.S;
+    const float* base = a.lp + b * a.b_stride;
+    float* al = a.alpha + b * (long long)a.T * Lw;
+    const float NEG = -CUDART_INF_F;
+
+    if (Tb == 0) {
+        if (lane == 0) {
+            float v = Sb == 0 ? 0.f : CUDART_INF_F;
+            if (a.zero_infinity && v == CUDART_INF_F) v = 0.f;
+            a.nll[b] = v;
+        }
+        return;
+    }
+    int lab[K];
+    bool live[K], skip[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int s = lane + 32 * k;
+        live[k] = s < L;
+        lab[k] = (live[k] && (s & 1)) ? tgt[s >> 1] : a.blank;
+        skip[k] = live[k] && (s & 1) && s >= 3 && tgt[s >> 1] != tgt[(s >> 1) - 1];
+    }
+    float* b0 = buf;
+    float* b1 = buf + Lp + 2;
+    if (lane < 2) {
+        b0[-1 - lane] = NEG;
+        b1[-1 - lane] = NEG;
+    }
+    // t = 0
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int s = lane + 32 * k;
+        float v = NEG;
+        if (s == 0) v = base[a.blank];
+        else if (s == 1 && L > 1) v = base[tgt[0]];
+        b0[s] = v;
+        if (live[k]) al[s] = v;
+    }
+    __syncwarp();
+    // ring slot (t - 1) % CTC_PF holds the gathered log-probs of step t; one cp.async group per step
+#pragma unroll
+    for (int p = 0; p < CTC_PF; ++p) {
+        const int t = 1 + p;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (t < Tb && live[k]) cp_async4(ring + p * Lp + lane + 32 * k, base + (long long)t * a.t_stride + lab[k]);
+        cp_async_commit();
+    }
+    int cur = 0;
+    for (int t0 = 1; t0 < Tb; t0 += CTC_PF) {
+#pragma unroll
+        for (int p = 0; p < CTC_PF; ++p) {
+            const int t = t0 + p;
+            if (t < Tb) {   // warp-uniform
+                const float* prev = cur ? b1 : b0;
+                float* next = cur ? b0 : b1;
+                cp_async_wait<CTC_PF - 1>();   // the group of step t has landed (each lane reads only what it copied)
+                float lpv[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) lpv[k] = live[k] ? ring[p * Lp + lane + 32 * k] : 0.f;
+                // refill this slot for step t + CTC_PF (independent of the recursion)
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int tn = t + CTC_PF;
+                    if (tn < Tb && live[k]) cp_async4(ring + p * Lp + lane + 32 * k, base + (long long)tn * a.t_stride + lab[k]);
+                }
+                cp_async_commit();
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int s = lane + 32 * k;
+                    float v = NEG;
+                    if (live[k]) {
+                        const float a0 = prev[s], a1 = prev[s - 1];
+                        const float a2 = skip[k] ? prev[s - 2] : NEG;
+                        v = lse3(a0, a1, a2) + lpv[k];
+                        al[(long long)t * Lw + s] = v;
+                    }
+                    next[s] = v;
+                }
+                cur ^= 1;
+                __syncwarp();
+            }
+        }
+    }
+    cp_async_wait<0>();
+    if (lane == 0) {
+        const float* fin = cur ? b1 : b0;
+        float ll = fin[L - 1];
+        if (L > 1) ll = lse2(ll, fin[L - 2]);
+        float v = -ll;
+        if (a.zero_infinity && v == CUDART_INF_F) v = 0.f;
+        a.nll[b] = v;
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_bwd_pf_kernel(const CtcLossArgs a) {
+    extern __shared__ float ctc_sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long b = (long long)blockIdx.x * CTC_WARPS + warp;
+    if (b >= a.B) return;
+    constexpr int Lp = 32 * K;
+    const int per_warp = 3 * (Lp + 2) + 2 * CTC_PF * Lp + 3 * a.S;
+    float* buf = ctc_sm + warp * per_warp;           // beta double buffer, two trailing pad cells each
+    float* lps = buf + 2 * (Lp + 2);                 // [Lp] lp[t][label of state s] of the current step
+    float* ring_lp = lps + (Lp + 2);                 // [CTC_PF][Lp] prefetched lp[t][label]
+    float* ring_al = ring_lp + CTC_PF * Lp;          // [CTC_PF][Lp] prefetched alpha[t][s]
+    float* acc = ring_al + CTC_PF * Lp;              // [S] per-label log-sum of alpha*beta
+    int* first = reinterpret_cast<int*>(acc + a.S);  // [S] first occurrence of the same label
+    int* dups = first + a.S;                         // [S] positions whose label occurred before
+    const int Tb = min(max(a.in_len[b], 0), a.T);
+    const int Sb = min(max(a.tgt_len[b], 0), a.S);
+    const int L = 2 * Sb + 1;
+    const int Lw = 2 * a.S + 1;
+    const int* tgt = a.targets + b * (long long)a.S;
+    const float* base = a.lp + b * a.b_stride;
+    const float* al = a.alpha + b * (long long)a.T * Lw;
+    float* gbase = a.grad + b * a.gb_stride;
+    const float NEG = -CUDART_INF_F;
+
+    float nll;
+    {
+        float ll = NEG;
+        if (Tb > 0) {
+            ll = al[(long long)(Tb - 1) * Lw + L - 1];
+            if (L > 1) ll = lse2(ll, al[(long long)(Tb - 1) * Lw + L - 2]);
+        } else if (Sb == 0) {
+            ll = 0.f;
+        }
+        nll = -ll;
+    }
+    const float go = a.grad_out ? a.grad_out[b] : 1.f;
+    const bool dead = (a.zero_infinity && nll == CUDART_INF_F);
+    const int t_live = dead ? 0 : Tb;
+    if (!a.skip_fill) {
+        for (int t = t_live; t < a.T; ++t) {
+            float* grow = gbase + (long long)t * a.gt_stride;
+            for (int c = lane; c < a.C; c += 32) grow[c] = 0.f;
+        }
+    }
+    if (t_live == 0) return;
+
+    int ndup = 0;
+    for (int i0 = 0; i0 < Sb; i0 += 32) {
+        const int i = i0 + lane;
+        int f = i;
+        if (i < Sb) {
+            const int li = tgt[i];
+            for (int j = 0; j < i; ++j)
+                if (tgt[j] == li) { f = j; break; }
+            first[i] = f;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, i < Sb && f != i);
+        if (i < Sb && f != i) dups[ndup + __popc(m & ((1u << lane) - 1u))] = i;
+        ndup += __popc(m);
+    }
+    bool blank_in_tgt = false;
+    for (int i0 = 0; i0 < Sb; i0 += 32) {
+        const int i = i0 + lane;
+        blank_in_tgt |= __any_sync(0xffffffffu, i < Sb && tgt[i] == a.blank);
+    }
+    int lab[K];
+    bool live[K], skip[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int s = lane + 32 * k;
+        live[k] = s < L;
+        lab[k] = (live[k] && (s & 1)) ? tgt[s >> 1] : a.blank;
+        skip[k] = live[k] && (s & 1) && s + 2 < L && tgt[s >> 1] != tgt[(s >> 1) + 1];
+    }
+    // labels this lane patches: i = lane + 32 j (first occurrences that are not the blank index), else -1
+    int patch_c[2];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int i = lane + 32 * j;
+        patch_c[j] = (i < Sb && first[i] == i && tgt[i] != a.blank) ? tgt[i] : -1;
+    }
+    float* b0 = buf;
+    float* b1 = buf + Lp + 2;
+    if (lane < 2) {
+        b0[Lp + lane] = NEG;
+        b1[Lp + lane] = NEG;
+    }
+    __syncwarp();
+
+#pragma unroll
+    for (int p = 0; p < CTC_PF; ++p) {
+        const int t = Tb - 1 - p;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (t >= 0 && live[k]) {
+                cp_async4(ring_lp + p * Lp + lane + 32 * k, base + (long long)t * a.t_stride + lab[k]);
+                cp_async4(ring_al + p * Lp + lane + 32 * k, al + (long long)t * Lw + lane + 32 * k);
+            }
+        cp_async_commit();
+    }
+    int cur = 0;
+    for (int t0 = Tb - 1; t0 >= 0; t0 -= CTC_PF) {
+#pragma unroll
+        for (int p = 0; p < CTC_PF; ++p) {
+            const int t = t0 - p;
+            if (t >= 0) {   // warp-uniform
+                float* grow = gbase + (long long)t * a.gt_stride;
+                const float* nxt = cur ? b1 : b0;
+                float* now = cur ? b0 : b1;
+                cp_async_wait<CTC_PF - 1>();
+                float lpv[K], alv[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    lpv[k] = live[k] ? ring_lp[p * Lp + lane + 32 * k] : 0.f;
+                    alv[k] = live[k] ? ring_al[p * Lp + lane + 32 * k] : 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int tn = t - CTC_PF;
+                    if (tn >= 0 && live[k]) {
+                        cp_async4(ring_lp + p * Lp + lane + 32 * k, base + (long long)tn * a.t_stride + lab[k]);
+                        cp_async4(ring_al + p * Lp + lane + 32 * k, al + (long long)tn * Lw + lane + 32 * k);
+                    }
+                }
+                cp_async_commit();
+                float blank_m = NEG;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int s = lane + 32 * k;
+                    float v = NEG;
+                    if (live[k]) {
+                        if (t == Tb - 1) {
+                            v = (s == L - 1 || s == L - 2) ? lpv[k] : NEG;
+                        } else {
+                            const float c0 = nxt[s];
+                            const float c1 = s + 1 < L ? nxt[s + 1] : NEG;
+                            const float c2 = skip[k] ? nxt[s + 2] : NEG;
+                            v = lse3(c0, c1, c2) + lpv[k];
+                        }
+                        const float ab = alv[k] + v;
+                        if (s & 1) acc[s >> 1] = ab;
+                        else blank_m = lse2(blank_m, ab);
+                        lps[s] = lpv[k];
+                    }
+                    now[s] = v;
+                }
+                cur ^= 1;
+                {
+                    float m = blank_m;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                    float e = (m == NEG) ? 0.f : expf(blank_m - m);
+                    e = warp_sum(e);
+                    blank_m = (m == NEG) ? NEG : logf(e) + m;
+                }
+                if (!a.skip_fill) {
+                    const float* row = base + (long long)t * a.t_stride;
+                    for (int c = lane; c < a.C; c += 32) grow[c] = expf(row[c]) * go;
+                }
+                __syncwarp();
+                if (ndup) {
+                    if (lane == 0)
+                        for (int d = 0; d < ndup; ++d) acc[first[dups[d]]] = lse2(acc[first[dups[d]]], acc[dups[d]]);
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {   // Sb <= 2 * K * 16 - 1 <= 63: at most two labels per lane
+                    const int i = lane + 32 * j;
+                    if (patch_c[j] >= 0) {
+                        const float l = lps[2 * i + 1];
+                        grow[patch_c[j]] = (expf(l) - expf(acc[i] + nll - l)) * go;
+                    }
+                }
+                if (lane == 0) {
+                    // a target label equal to the blank index is folded into the blank class as PyTorch does (rare:
+                    // the scan over the labels runs only for utterances that contain one)
+                    float tot = blank_m;
+                    if (blank_in_tgt)
+                        for (int i = 0; i < Sb; ++i)
+                            if (first[i] == i && tgt[i] == a.blank) tot = lse2(tot, acc[i]);
+                    const float l = lps[0];
+                    grow[a.blank] = (expf(l) - expf(tot + nll - l)) * go;
+                }
+                __syncwarp();
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
 
 // ------------------------------------------------------------------------------------------------
 // Short-target specialisation (S <= 3, i.e. at most 7 extended states -- the reference's keyword shapes
@@ -494,7 +823,20 @@ __global__ void __launch_bounds__(256) ctc_grad_fill_kernel(const CtcLossArgs a)
         }
         const float* row = a.lp + b * a.b_stride + (long long)t * a.t_stride;
         float* grow = a.grad + b * a.gb_stride + (long long)t * a.gt_stride;
-        if (scale == 0.f) {
+        if (a.fill_vec) {
+            // rows are 16-byte aligned and C % 4 == 0: 16-byte streaming loads / stores
+            const float4* r4 = reinterpret_cast<const float4*>(row);
+            float4* g4 = reinterpret_cast<float4*>(grow);
+            const int n4 = a.C >> 2;
+            if (scale == 0.f) {
+                for (int c = lane; c < n4; c += 32) __stcs(g4 + c, make_float4(0.f, 0.f, 0.f, 0.f));
+            } else {
+                for (int c = lane; c < n4; c += 32) {
+                    const float4 v = __ldcs(r4 + c);
+                    __stcs(g4 + c, make_float4(expf(v.x) * scale, expf(v.y) * scale, expf(v.z) * scale, expf(v.w) * scale));
+                }
+            }
+        } else if (scale == 0.f) {
             for (int c = lane; c < a.C; c += 32) grow[c] = 0.f;
         } else {
             for (int c = lane; c < a.C; c += 32) grow[c] = expf(row[c]) * scale;

@@ -97,7 +97,8 @@ def _rand_problem(T, B, C, S, seed, full_len=False):
     return lp.astype(np.float32), tg, il, tl
 
 
-@pytest.mark.parametrize("T,B,C,S", [(63, 64, 3, 1), (63, 200, 3, 2), (50, 9, 20, 7), (120, 5, 50, 40), (801, 2, 300, 32)])
+@pytest.mark.parametrize("T,B,C,S", [(63, 64, 3, 1), (63, 200, 3, 2), (50, 9, 20, 7), (120, 5, 50, 40), (801, 2, 300, 32),
+                                     (200, 4, 100, 63), (300, 3, 200, 70), (37, 6, 64, 15), (5, 3, 8, 4)])
 @pytest.mark.parametrize("reduction", ["mean", "none"])
 def test_ctc_loss_fwd_bwd_vs_torch(cuda_device, T, B, C, S, reduction):
     """loss rtol 1e-5, grad atol 1e-5 against torch.nn.functional.ctc_loss on CPU.
