@@ -1237,7 +1237,9 @@ extern "C" int ww_ctc_loss_bwd(ww_ctx* ctx, const float* log_probs, long long t_
         return WW_OK;
     }
     a.skip_fill = C >= 64 ? 1 : 0;
-    if (a.skip_fill) {
+    const int K = ctc_lp(S) / 32;
+    const unsigned grid = (unsigned)((B + CTC_WARPS - 1) / CTC_WARPS);
+    auto launch_fill = [&]() -> int {
         // wide vocabulary: the exp(lp) fill is a bandwidth-bound pass over all T*B rows, not warp-per-utterance work
         long long rows = (long long)T * B;
         long long blocks = (rows + 7) / 8;
@@ -1247,9 +1249,12 @@ extern "C" int ww_ctc_loss_bwd(ww_ctx* ctx, const float* log_probs, long long t_
                      (b_stride % 4 == 0) && (gt_stride % 4 == 0) && (gb_stride % 4 == 0);
         ctc_grad_fill_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
         CK(cudaGetLastError());
+        return WW_OK;
+    };
+    if (a.skip_fill) {
+        rc = launch_fill();
+        if (rc) return rc;
     }
-    const int K = ctc_lp(S) / 32;
-    const unsigned grid = (unsigned)((B + CTC_WARPS - 1) / CTC_WARPS);
     if (K <= 4) {
         const size_t smem_pf = (size_t)CTC_WARPS * (3 * (32 * K + 2) + 2 * CTC_PF * 32 * K + 3 * S) * sizeof(float);
         switch (K) {

@@ -131,6 +131,19 @@ __device__ __forceinline__ float lse2(float a, float b) {
     return logf(expf(a - m) + expf(b - m)) + m;
 }
 
+// MUFU-based variants for the prefetching kernels (ex2.approx / lg2.approx: ~3e-7 absolute per call on sums in [1, 3],
+// far below the fp32 resolution of alpha/beta themselves, whose magnitude reaches 1e3..1e4 at T = 801)
+__device__ __forceinline__ float lse3f(float a, float b, float c) {
+    float m = fmaxf(a, fmaxf(b, c));
+    if (m == -CUDART_INF_F) m = 0.f;
+    return __logf(__expf(a - m) + __expf(b - m) + __expf(c - m)) + m;
+}
+__device__ __forceinline__ float lse2f(float a, float b) {
+    float m = fmaxf(a, b);
+    if (m == -CUDART_INF_F) return -CUDART_INF_F;
+    return __logf(__expf(a - m) + __expf(b - m)) + m;
+}
+
 // dynamic smem per warp: 2*Lp floats (double-buffered alpha/beta row), Lp = 2S+1 rounded up to 32,
 // plus (backward) S floats label accumulators and 2*S ints (first-occurrence map, duplicate list)
 __host__ __device__ inline int ctc_lp(int S) { return ((2 * S + 1 + 31) / 32) * 32; }
@@ -384,14 +397,18 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_fwd_pf_kernel(const C
         }
         return;
     }
+    // per-state flags live in ONE integer register (bit k: state is live, bit 8+k: the skip transition exists):
+    // as bools they become long-lived predicates, ptxas runs out of the 7 predicate registers and spills them to
+    // local memory, and the reload sits on the recursion's critical path behind the outstanding cp.async traffic
     int lab[K];
-    bool live[K], skip[K];
+    unsigned flags = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int s = lane + 32 * k;
-        live[k] = s < L;
-        lab[k] = (live[k] && (s & 1)) ? tgt[s >> 1] : a.blank;
-        skip[k] = live[k] && (s & 1) && s >= 3 && tgt[s >> 1] != tgt[(s >> 1) - 1];
+        const bool lv = s < L;
+        lab[k] = (lv && (s & 1)) ? tgt[s >> 1] : a.blank;
+        if (lv) flags |= 1u << k;
+        if (lv && (s & 1) && s >= 3 && tgt[s >> 1] != tgt[(s >> 1) - 1]) flags |= 256u << k;
     }
     float* b0 = buf;
     float* b1 = buf + Lp + 2;
@@ -407,7 +424,7 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_fwd_pf_kernel(const C
         if (s == 0) v = base[a.blank];
         else if (s == 1 && L > 1) v = base[tgt[0]];
         b0[s] = v;
-        if (live[k]) al[s] = v;
+        if (((flags >> k) & 1u)) al[s] = v;
     }
     __syncwarp();
     // ring slot (t - 1) % CTC_PF holds the gathered log-probs of step t; one cp.async group per step
@@ -416,44 +433,40 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_fwd_pf_kernel(const C
         const int t = 1 + p;
 #pragma unroll
         for (int k = 0; k < K; ++k)
-            if (t < Tb && live[k]) cp_async4(ring + p * Lp + lane + 32 * k, base + (long long)t * a.t_stride + lab[k]);
+            if (t < Tb && ((flags >> k) & 1u)) cp_async4(ring + p * Lp + lane + 32 * k, base + (long long)t * a.t_stride + lab[k]);
         cp_async_commit();
     }
     int cur = 0;
-    for (int t0 = 1; t0 < Tb; t0 += CTC_PF) {
+#pragma unroll 1
+    for (int t = 1; t < Tb; ++t) {
+        const int p = (t - 1) & (CTC_PF - 1);
+        const float* prev = cur ? b1 : b0;
+        float* next = cur ? b0 : b1;
+        cp_async_wait<CTC_PF - 1>();   // the group of step t has landed (each lane reads only what it copied)
+        float lpv[K];
 #pragma unroll
-        for (int p = 0; p < CTC_PF; ++p) {
-            const int t = t0 + p;
-            if (t < Tb) {   // warp-uniform
-                const float* prev = cur ? b1 : b0;
-                float* next = cur ? b0 : b1;
-                cp_async_wait<CTC_PF - 1>();   // the group of step t has landed (each lane reads only what it copied)
-                float lpv[K];
+        for (int k = 0; k < K; ++k) lpv[k] = ((flags >> k) & 1u) ? ring[p * Lp + lane + 32 * k] : 0.f;
+        // refill this slot for step t + CTC_PF (independent of the recursion)
 #pragma unroll
-                for (int k = 0; k < K; ++k) lpv[k] = live[k] ? ring[p * Lp + lane + 32 * k] : 0.f;
-                // refill this slot for step t + CTC_PF (independent of the recursion)
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const int tn = t + CTC_PF;
-                    if (tn < Tb && live[k]) cp_async4(ring + p * Lp + lane + 32 * k, base + (long long)tn * a.t_stride + lab[k]);
-                }
-                cp_async_commit();
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const int s = lane + 32 * k;
-                    float v = NEG;
-                    if (live[k]) {
-                        const float a0 = prev[s], a1 = prev[s - 1];
-                        const float a2 = skip[k] ? prev[s - 2] : NEG;
-                        v = lse3(a0, a1, a2) + lpv[k];
-                        al[(long long)t * Lw + s] = v;
-                    }
-                    next[s] = v;
-                }
-                cur ^= 1;
-                __syncwarp();
-            }
+        for (int k = 0; k < K; ++k) {
+            const int tn = t + CTC_PF;
+            if (tn < Tb && ((flags >> k) & 1u)) cp_async4(ring + p * Lp + lane + 32 * k, base + (long long)tn * a.t_stride + lab[k]);
         }
+        cp_async_commit();
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int s = lane + 32 * k;
+            float v = NEG;
+            if (((flags >> k) & 1u)) {
+                const float a0 = prev[s], a1 = prev[s - 1];
+                const float a2 = ((flags >> (8 + k)) & 1u) ? prev[s - 2] : NEG;
+                v = lse3f(a0, a1, a2) + lpv[k];
+                al[(long long)t * Lw + s] = v;
+            }
+            next[s] = v;
+        }
+        cur ^= 1;
+        __syncwarp();
     }
     cp_async_wait<0>();
     if (lane == 0) {
@@ -533,13 +546,14 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_bwd_pf_kernel(const C
         blank_in_tgt |= __any_sync(0xffffffffu, i < Sb && tgt[i] == a.blank);
     }
     int lab[K];
-    bool live[K], skip[K];
+    unsigned flags = 0;   // bit k: state live, bit 8+k: skip transition (one register, not predicates: see the forward kernel)
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int s = lane + 32 * k;
-        live[k] = s < L;
-        lab[k] = (live[k] && (s & 1)) ? tgt[s >> 1] : a.blank;
-        skip[k] = live[k] && (s & 1) && s + 2 < L && tgt[s >> 1] != tgt[(s >> 1) + 1];
+        const bool lv = s < L;
+        lab[k] = (lv && (s & 1)) ? tgt[s >> 1] : a.blank;
+        if (lv) flags |= 1u << k;
+        if (lv && (s & 1) && s + 2 < L && tgt[s >> 1] != tgt[(s >> 1) + 1]) flags |= 256u << k;
     }
     // labels this lane patches: i = lane + 32 j (first occurrences that are not the blank index), else -1
     int patch_c[2];
@@ -562,18 +576,18 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_bwd_pf_kernel(const C
         const int t = Tb - 1 - p;
 #pragma unroll
         for (int k = 0; k < K; ++k)
-            if (t >= 0 && live[k]) {
+            if (t >= 0 && ((flags >> k) & 1u)) {
                 cp_async4(ring_lp + p * Lp + lane + 32 * k, base + (long long)t * a.t_stride + lab[k]);
                 cp_async4(ring_al + p * Lp + lane + 32 * k, al + (long long)t * Lw + lane + 32 * k);
             }
         cp_async_commit();
     }
     int cur = 0;
-    for (int t0 = Tb - 1; t0 >= 0; t0 -= CTC_PF) {
-#pragma unroll
-        for (int p = 0; p < CTC_PF; ++p) {
-            const int t = t0 - p;
-            if (t >= 0) {   // warp-uniform
+#pragma unroll 1
+    for (int t = Tb - 1; t >= 0; --t) {
+        {
+            {
+                const int p = (Tb - 1 - t) & (CTC_PF - 1);
                 float* grow = gbase + (long long)t * a.gt_stride;
                 const float* nxt = cur ? b1 : b0;
                 float* now = cur ? b0 : b1;
@@ -581,13 +595,13 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_bwd_pf_kernel(const C
                 float lpv[K], alv[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    lpv[k] = live[k] ? ring_lp[p * Lp + lane + 32 * k] : 0.f;
-                    alv[k] = live[k] ? ring_al[p * Lp + lane + 32 * k] : 0.f;
+                    lpv[k] = ((flags >> k) & 1u) ? ring_lp[p * Lp + lane + 32 * k] : 0.f;
+                    alv[k] = ((flags >> k) & 1u) ? ring_al[p * Lp + lane + 32 * k] : 0.f;
                 }
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     const int tn = t - CTC_PF;
-                    if (tn >= 0 && live[k]) {
+                    if (tn >= 0 && ((flags >> k) & 1u)) {
                         cp_async4(ring_lp + p * Lp + lane + 32 * k, base + (long long)tn * a.t_stride + lab[k]);
                         cp_async4(ring_al + p * Lp + lane + 32 * k, al + (long long)tn * Lw + lane + 32 * k);
                     }
@@ -598,18 +612,18 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_bwd_pf_kernel(const C
                 for (int k = 0; k < K; ++k) {
                     const int s = lane + 32 * k;
                     float v = NEG;
-                    if (live[k]) {
+                    if (((flags >> k) & 1u)) {
                         if (t == Tb - 1) {
                             v = (s == L - 1 || s == L - 2) ? lpv[k] : NEG;
                         } else {
                             const float c0 = nxt[s];
                             const float c1 = s + 1 < L ? nxt[s + 1] : NEG;
-                            const float c2 = skip[k] ? nxt[s + 2] : NEG;
-                            v = lse3(c0, c1, c2) + lpv[k];
+                            const float c2 = ((flags >> (8 + k)) & 1u) ? nxt[s + 2] : NEG;
+                            v = lse3f(c0, c1, c2) + lpv[k];
                         }
                         const float ab = alv[k] + v;
                         if (s & 1) acc[s >> 1] = ab;
-                        else blank_m = lse2(blank_m, ab);
+                        else blank_m = lse2f(blank_m, ab);
                         lps[s] = lpv[k];
                     }
                     now[s] = v;
@@ -619,9 +633,9 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_bwd_pf_kernel(const C
                     float m = blank_m;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-                    float e = (m == NEG) ? 0.f : expf(blank_m - m);
+                    float e = (m == NEG) ? 0.f : __expf(blank_m - m);
                     e = warp_sum(e);
-                    blank_m = (m == NEG) ? NEG : logf(e) + m;
+                    blank_m = (m == NEG) ? NEG : __logf(e) + m;
                 }
                 if (!a.skip_fill) {
                     const float* row = base + (long long)t * a.t_stride;
@@ -638,7 +652,7 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_bwd_pf_kernel(const C
                     const int i = lane + 32 * j;
                     if (patch_c[j] >= 0) {
                         const float l = lps[2 * i + 1];
-                        grow[patch_c[j]] = (expf(l) - expf(acc[i] + nll - l)) * go;
+                        grow[patch_c[j]] = (__expf(l) - __expf(acc[i] + nll - l)) * go;
                     }
                 }
                 if (lane == 0) {
@@ -649,7 +663,7 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_bwd_pf_kernel(const C
                         for (int i = 0; i < Sb; ++i)
                             if (first[i] == i && tgt[i] == a.blank) tot = lse2(tot, acc[i]);
                     const float l = lps[0];
-                    grow[a.blank] = (expf(l) - expf(tot + nll - l)) * go;
+                    grow[a.blank] = (__expf(l) - __expf(tot + nll - l)) * go;
                 }
                 __syncwarp();
             }
