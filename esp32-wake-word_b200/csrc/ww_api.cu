@@ -949,6 +949,7 @@ struct ww_session {
     int16_t* d_pcm[2] = {nullptr, nullptr};
     float* d_feat[2] = {nullptr, nullptr};
     float* d_logits = nullptr;
+    int16_t* d_tdm = nullptr;  // 4-channel 48 kHz staging of ww_session_write_tdm (allocated on first use)
     int pcm_cur = 0, feat_cur = 0;
     long long g0 = 0;          // global sample index of column 0 of d_pcm[cur]
     int tail_len = 0;          // valid samples in d_pcm[cur] per stream
@@ -1007,6 +1008,7 @@ extern "C" void ww_session_close(ww_session* s) {
     cudaSetDevice(s->ctx->device);
     for (int i = 0; i < 2; ++i) {
         cudaFree(s->d_pcm[i]);
+        if (i == 0) cudaFree(s->d_tdm);
         cudaFree(s->d_feat[i]);
     }
     cudaFree(s->d_logits);
@@ -1019,17 +1021,44 @@ extern "C" long long ww_session_windows(const ww_session* s) {
     return s->t_done >= WW_WINDOW_FRAMES ? s->t_done - (WW_WINDOW_FRAMES - 1) : 0;
 }
 
+static int session_advance(ww_session* s, int chunk_samples);
+
 extern "C" int ww_session_write(ww_session* s, const int16_t* pcm_host, int chunk_samples) {
     if (!s) return WW_ERR_INVALID;
     ww_ctx* ctx = s->ctx;
     if (!pcm_host || chunk_samples < 1 || chunk_samples > s->max_chunk || chunk_samples % 8 != 0)
         return fail(ctx, WW_ERR_INVALID, "session_write: chunk must be a positive multiple of 8 samples <= max_chunk_samples");
     CK(cudaSetDevice(ctx->device));
+    // append the chunk behind the retained tail of every stream
+    CK(cudaMemcpy2DAsync(s->d_pcm[s->pcm_cur] + s->tail_len, sizeof(int16_t) * s->pcm_cap, pcm_host,
+                         sizeof(int16_t) * chunk_samples, sizeof(int16_t) * chunk_samples, s->n_streams, cudaMemcpyHostToDevice,
+                         s->st));
+    return session_advance(s, chunk_samples);
+}
+
+extern "C" int ww_session_write_tdm(ww_session* s, const int16_t* tdm_host, int chunk_samples) {
+    if (!s) return WW_ERR_INVALID;
+    ww_ctx* ctx = s->ctx;
+    if (!tdm_host || chunk_samples < 1 || chunk_samples > s->max_chunk || chunk_samples % 8 != 0)
+        return fail(ctx, WW_ERR_INVALID, "session_write_tdm: chunk must be a positive multiple of 8 output samples <= max_chunk_samples");
+    CK(cudaSetDevice(ctx->device));
+    const size_t per_stream = (size_t)12 * s->max_chunk;
+    if (!s->d_tdm) CK(cudaMalloc(&s->d_tdm, sizeof(int16_t) * per_stream * s->n_streams));
+    // what read_mic delivers (esp_wake_word_detector.cpp:92-95): 4 interleaved channels at 48 kHz
+    CK(cudaMemcpy2DAsync(s->d_tdm, sizeof(int16_t) * per_stream, tdm_host, sizeof(int16_t) * 12 * chunk_samples,
+                         sizeof(int16_t) * 12 * chunk_samples, s->n_streams, cudaMemcpyHostToDevice, s->st));
+    // record_task's mix + decimator (cpp:103-121) straight into the PCM ring, behind the retained tail
+    int rc = ww_tdm_downmix(ctx, s->d_tdm, s->n_streams, chunk_samples, (long long)per_stream,
+                            s->d_pcm[s->pcm_cur] + s->tail_len, s->pcm_cap, s->st);
+    if (rc) return rc;
+    return session_advance(s, chunk_samples);
+}
+
+// everything after the new chunk is in place: new frames, new windows, hit logic, tails
+static int session_advance(ww_session* s, int chunk_samples) {
+    ww_ctx* ctx = s->ctx;
     const int S = s->n_streams, C = ctx->w.num_classes;
     int16_t* pcm = s->d_pcm[s->pcm_cur];
-    // append the chunk behind the retained tail of every stream
-    CK(cudaMemcpy2DAsync(pcm + s->tail_len, sizeof(int16_t) * s->pcm_cap, pcm_host, sizeof(int16_t) * chunk_samples,
-                         sizeof(int16_t) * chunk_samples, S, cudaMemcpyHostToDevice, s->st));
     const int L = s->tail_len + chunk_samples;
     s->n_samples += chunk_samples;
     // frames whose 320 taps are complete: 256 t + 159 < n_samples

@@ -27,7 +27,7 @@ OPT_I8_IMPL = 1
 EXPORTS = [
     "ww_version", "ww_create", "ww_destroy", "ww_last_error", "ww_load_weights", "ww_num_frames",
     "ww_mfcc_batch", "ww_cmvn", "ww_cnn_forward", "ww_quantize_weights_i8", "ww_cnn_forward_i8", "ww_score_clips", "ww_score_clips_host",
-    "ww_stream_score", "ww_stream_events", "ww_session_open", "ww_session_write", "ww_session_poll",
+    "ww_stream_score", "ww_stream_events", "ww_session_open", "ww_session_write", "ww_session_write_tdm", "ww_session_poll",
     "ww_session_windows", "ww_session_last_logits", "ww_session_close", "ww_ctc_greedy", "ww_ctc_loss_workspace_bytes",
     "ww_ctc_loss_fwd", "ww_ctc_loss_bwd", "ww_debug_tc", "ww_extract_mfcc", "ww_free_mfcc",
     "ww_set_option", "ww_wav_parse", "ww_wav_load_batch", "ww_wav_write", "ww_tdm_downmix", "ww_augment_waveform",
@@ -82,6 +82,7 @@ def load_library():
         lib.ww_stream_events.restype = i64
         lib.ww_session_open.argtypes = [vp, i32, i32, i32, i32, f32, i32, i32, C.POINTER(vp)]
         lib.ww_session_write.argtypes = [vp, vp, i32]
+        lib.ww_session_write_tdm.argtypes = [vp, vp, i32]
         lib.ww_session_poll.argtypes = [vp, vp, i64]
         lib.ww_session_poll.restype = i64
         lib.ww_session_windows.argtypes = [vp]

@@ -121,6 +121,25 @@ class StreamSession:
             return np.zeros((self.n_streams, 0, self.ctx.num_classes), np.float32)
         return np.ctypeslib.as_array(p, shape=(self.n_streams, n, self.ctx.num_classes)).copy()
 
+    def write_tdm(self, tdm):
+        """tdm: int16 [n_streams, 12 * n] -- what the firmware's read_mic delivers (4 interleaved channels at 48 kHz,
+        esp_wake_word_detector.cpp:92-95).  The mix + 48 -> 16 kHz decimator of record_task (cpp:103-121) run on the
+        GPU; equivalent to write(tdm_downmix(tdm)).  Returns the logits of the newly scored windows."""
+        if isinstance(tdm, torch.Tensor):
+            tdm = tdm.cpu().numpy()
+        tdm = np.ascontiguousarray(tdm, dtype=np.int16)
+        if tdm.ndim != 2 or tdm.shape[0] != self.n_streams or tdm.shape[1] % 12:
+            raise ValueError("write_tdm() expects int16 [n_streams, 12 * n]")
+        if getattr(self.ctx, "weights_owner", None) != self._key:
+            raise L.WWError("another model's weights were loaded into this context while the session was open")
+        self.ctx.check(self.ctx.lib.ww_session_write_tdm(self.h, tdm.ctypes.data_as(C.c_void_p), tdm.shape[1] // 12),
+                       "ww_session_write_tdm")
+        p = C.POINTER(C.c_float)()
+        n = self.ctx.lib.ww_session_last_logits(self.h, C.byref(p))
+        if n <= 0:
+            return np.zeros((self.n_streams, 0, self.ctx.num_classes), np.float32)
+        return np.ctypeslib.as_array(p, shape=(self.n_streams, n, self.ctx.num_classes)).copy()
+
     def poll(self, max_hits=4096):
         buf = (_Hit * max_hits)()
         n = self.ctx.lib.ww_session_poll(self.h, buf, max_hits)

@@ -153,6 +153,10 @@ int ww_session_open(ww_ctx* ctx, int n_streams, int max_chunk_samples, int cmvn_
                     float threshold_logit, int warmup_frames, int refractory_frames, ww_session** out);
 /* pcm_host: [n_streams][chunk_samples] int16; computes the newly completed frames, scores the new windows */
 int ww_session_write(ww_session* s, const int16_t* pcm_host, int chunk_samples);
+/* same, fed with what read_mic delivers: tdm_host [n_streams][12 * chunk_samples] int16 (4 interleaved channels at
+ * 48 kHz, esp_wake_word_detector.cpp:92-95); record_task's mix and decimator (cpp:103-121) run on the GPU and yield
+ * chunk_samples 16 kHz samples per stream */
+int ww_session_write_tdm(ww_session* s, const int16_t* tdm_host, int chunk_samples);
 /* drain up to max_hits pending WAKE_WORD_DETECTED events; returns how many were written */
 long long ww_session_poll(ww_session* s, ww_hit* hits, long long max_hits);
 /* windows scored so far per stream */

@@ -140,3 +140,40 @@ def test_extract_features_dropin(cuda_device, tmp_path):
     for v in (0, 2, 3, 4):   # variant 1 is re-padded with unseeded noise by the reference
         want = omfcc.normalize_mfcc(omfcc.mfcc_torchaudio(aug[:, v]).numpy(), "cmvn").numpy()
         assert np.abs(got5[:, v] - want).max() < 5e-3, v
+
+
+def test_firmware_chain_tdm_sessions_int8(cuda_device, xiaoa_sd):
+    """The firmware's whole live path as a batch service: read_mic's TDM chunks (20 ms = 3840 int16 per stream) ->
+    mix + decimator -> MFCC -> int8 + device CMVN -> int8 model -> hits, through push/poll sessions.  Pushing TDM
+    chunks must equal pushing the oracle's down-mixed PCM, and both must equal whole-stream scoring."""
+    import ww_b200
+
+    rng = np.random.default_rng(17)
+    n_streams, seconds = 3, 3
+    n16 = 16000 * seconds
+    t = np.arange(3 * n16) / 48000.0
+    tdm = np.zeros((n_streams, 3 * n16, 4), dtype=np.int16)
+    for k in range(n_streams):
+        mic = (6000 * np.sin(2 * np.pi * (300 + 170 * k) * t) + 900 * rng.standard_normal(3 * n16)).astype(np.int16)
+        tdm[k, :, 0] = mic
+        tdm[k, :, 1] = mic // 4
+        tdm[k, :, 2] = np.roll(mic, 7)
+        tdm[k, :, 3] = rng.integers(-100, 100, size=3 * n16)
+    tdm = tdm.reshape(n_streams, -1)
+    pcm = ofd.tdm_downmix(tdm)                                    # oracle mono 16 kHz [n_streams, n16]
+    a = ww_b200.StreamSession(xiaoa_sd, n_streams, max_chunk_samples=320, cmvn="device", cnn_impl="int8")
+    got_a = [a.write_tdm(tdm[:, 12 * i:12 * (i + 320)]) for i in range(0, n16, 320)]
+    hits_a = a.poll()
+    a.close()
+    b = ww_b200.StreamSession(xiaoa_sd, n_streams, max_chunk_samples=320, cmvn="device", cnn_impl="int8")
+    got_b = [b.write(pcm[:, i:i + 320]) for i in range(0, n16, 320)]
+    hits_b = b.poll()
+    b.close()
+    la = np.concatenate([g for g in got_a if g.shape[1]], axis=1)
+    lb = np.concatenate([g for g in got_b if g.shape[1]], axis=1)
+    np.testing.assert_array_equal(la, lb)
+    assert [tuple(h) for h in hits_a] == [tuple(h) for h in hits_b]
+    ss = ww_b200.StreamScorer(xiaoa_sd, cmvn="device", cnn_impl="int8")
+    for k in range(n_streams):
+        _, lg = ss.score(torch.from_numpy(pcm[k]).to(cuda_device))
+        np.testing.assert_array_equal(la[k], lg.cpu().numpy()[:la.shape[1]])
