@@ -99,3 +99,39 @@ def test_one_hour_stream_periodic(cuda_device, xiaoa_sd):
             assert d.max() < 1e-2
         else:
             assert np.mean(d > 2e-3) < 0.03
+
+
+def test_full_size_front_dsp_and_int8_properties(cuda_device, xiaoa_sd):
+    """Full-size, size-independent checks of the 8f kernels.
+    TDM down-mix: 16 384 one-second captures (6.3 GB) built from a period of 64 that the oracle pins; the integer
+    kernel must be position-invariant and linear in the sense the arithmetic allows (a capture whose three used
+    channels are all zero maps to silence; channel 3 never matters).
+    int8 twin: 2^18 windows, tensor-core kernel == CUDA-core kernel bit for bit, periodic input pins position
+    invariance, the oracle pins one period."""
+    import ww_b200
+    from oracle import frontdsp as ofd
+
+    rng = np.random.default_rng(42)
+    period, n = 64, 16384
+    base = rng.integers(-32768, 32768, size=(period, 12 * 16000), dtype=np.int16)
+    base[1].reshape(-1, 4)[:, :3] = 0                      # silent capture, junk only in the unused channel
+    tdm = torch.from_numpy(base).to(cuda_device).repeat(n // period, 1)
+    out = ww_b200.tdm_downmix(tdm)
+    assert out.shape == (n, 16000)
+    np.testing.assert_array_equal(out[:period].cpu().numpy(), ofd.tdm_downmix(base))
+    assert torch.equal(out.view(-1, period, 16000)[0], out.view(-1, period, 16000)[-1])
+    assert torch.equal(out.view(-1, period, 16000)[0], out.view(-1, period, 16000)[(n // period) // 2])
+    assert int(out[1].abs().max()) == 0
+    t2 = tdm[:period].clone()
+    t2.view(period, -1, 4)[:, :, 3] = 777                 # channel 3 is ignored (cpp:104-106)
+    assert torch.equal(ww_b200.tdm_downmix(t2), out[:period])
+    del tdm, out, t2
+
+    nw, per = 1 << 18, 512
+    xb = rng.integers(-128, 128, size=(per, 13, 63)).astype(np.int8)
+    x = torch.from_numpy(xb).to(cuda_device).repeat(nw // per, 1, 1)
+    y_tc = ww_b200.forward_int8(xiaoa_sd, x, impl="tensor")
+    y_cc = ww_b200.forward_int8(xiaoa_sd, x, impl="cuda")
+    assert torch.equal(y_tc, y_cc)
+    assert torch.equal(y_tc.view(-1, per)[0], y_tc.view(-1, per)[-1])
+    np.testing.assert_array_equal(y_tc[:per].cpu().numpy(), ocnn.forward_int8(xb, xiaoa_sd))
