@@ -84,3 +84,25 @@ def write_wav(path: str, pcm, sample_rate: int = 16000, num_channels: int = 1) -
     rc = lib.ww_wav_write(os.fspath(path).encode(), a.ctypes.data_as(C.c_void_p), a.size, int(num_channels), int(sample_rate))
     if rc != L.WW_OK:
         raise L.WWError(f"ww_wav_write({path}) failed ({rc})")
+
+
+def score_wav_dir(path, state_dict, device_path=False, threads=None):
+    """Score every *.wav of a directory -- the offline check the firmware runs over /flash/*.wav
+    (main/hello_world_main.cpp:168-280: load, 63-frame MFCC, model, tally).
+
+    device_path=False: float model, python CMVN, sigmoid(out) > 0.5 (ml_models/main.py:53);
+    device_path=True:  int8 rounding + device CMVN + int8 esp-dl model + sigmoid*100 >= 80
+                       (esp_wake_word_detector.cpp:128-131,179-258).
+    Returns (names, logits [n, C], decisions uint8 [n], number of positives)."""
+    from .model import WakeWordScorer
+
+    names = sorted(n for n in os.listdir(path) if n.endswith(".wav"))
+    if not names:
+        return [], np.zeros((0, 1), np.float32), np.zeros((0,), np.uint8), 0
+    pcm, _, _ = load_wav_batch([os.path.join(path, n) for n in names], threads=threads)
+    if device_path:
+        sc = WakeWordScorer(state_dict, cmvn="device", decision="device", cnn_impl="int8")
+    else:
+        sc = WakeWordScorer(state_dict, cmvn="python", decision="python", cnn_impl="tensor")
+    logits, dec = sc.score_host(pcm)
+    return names, logits, dec, int(dec.sum())

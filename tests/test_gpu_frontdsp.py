@@ -177,3 +177,22 @@ def test_firmware_chain_tdm_sessions_int8(cuda_device, xiaoa_sd):
     for k in range(n_streams):
         _, lg = ss.score(torch.from_numpy(pcm[k]).to(cuda_device))
         np.testing.assert_array_equal(la[k], lg.cpu().numpy()[:la.shape[1]])
+
+
+def test_score_wav_dir_float_and_device_paths(cuda_device, xiaoa_sd, tmp_path):
+    """hello_world_main.cpp's test_model loop (WAV directory -> tally) on both decision paths."""
+    import ww_b200
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_features.npz"))
+    n = g["pcm"].shape[0]
+    for i in range(n):
+        (tmp_path / f"w{i:02d}.wav").write_bytes(owav.wav_bytes(g["pcm"][i]))
+    names, logits, dec, pos = ww_b200.score_wav_dir(str(tmp_path), xiaoa_sd)
+    assert names == [f"w{i:02d}.wav" for i in range(n)] and pos == int(dec.sum())
+    assert np.abs(logits - g["logits"]).max() < 1e-2                      # the reference's own logits
+    margin = np.abs(g["logits"][:, 0]) > 1e-2
+    assert (dec.astype(bool) == (g["logits"][:, 0] > 0))[margin].all()
+    names2, lq, dec2, pos2 = ww_b200.score_wav_dir(str(tmp_path), xiaoa_sd, device_path=True)
+    out_q, dec_ref = ww_b200.score_clips_int8(xiaoa_sd, torch.from_numpy(g["pcm"]).to(cuda_device))
+    np.testing.assert_array_equal(lq * 8.0, out_q.cpu().numpy().astype(np.float32))
+    np.testing.assert_array_equal(dec2, dec_ref.cpu().numpy())
