@@ -954,7 +954,8 @@ struct ww_session {
     long long g0 = 0;          // global sample index of column 0 of d_pcm[cur]
     int tail_len = 0;          // valid samples in d_pcm[cur] per stream
     int pcm_cap = 0, feat_cap = 0, max_new = 0;
-    std::vector<float> h_logits;
+    float* h_logits = nullptr;   // pinned: [n_streams][max_new][C], so the D2H of every push is asynchronous DMA
+    size_t h_logits_n = 0;       // floats valid after the last write
     std::vector<long long> reset_f;  // per stream: first frame index after the last ring reset
     std::vector<ww_hit> hits;
     cudaStream_t st = nullptr;
@@ -998,6 +999,7 @@ extern "C" int ww_session_open(ww_ctx* ctx, int n_streams, int max_chunk_samples
         if ((e = cudaMemset(s->d_feat[i], 0, sizeof(float) * (size_t)n_streams * WW_N_MFCC * s->feat_cap)) != cudaSuccess) return bail(e, "cudaMemset");
     }
     if ((e = cudaMalloc(&s->d_logits, sizeof(float) * (size_t)n_streams * s->max_new * ctx->w.num_classes)) != cudaSuccess) return bail(e, "cudaMalloc session logits");
+    if ((e = cudaMallocHost((void**)&s->h_logits, sizeof(float) * (size_t)n_streams * s->max_new * ctx->w.num_classes)) != cudaSuccess) return bail(e, "cudaMallocHost session logits");
     if ((e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     *out = s;
     return WW_OK;
@@ -1012,6 +1014,7 @@ extern "C" void ww_session_close(ww_session* s) {
         cudaFree(s->d_feat[i]);
     }
     cudaFree(s->d_logits);
+    if (s->h_logits) cudaFreeHost(s->h_logits);
     if (s->st) cudaStreamDestroy(s->st);
     delete s;
 }
@@ -1087,8 +1090,7 @@ static int session_advance(ww_session* s, int chunk_samples) {
             ctx->grp_stride = 0;
             if (rc) return rc;
             n_win_total = (long long)S * n_win;
-            s->h_logits.resize((size_t)n_win_total * C);
-            CK(cudaMemcpyAsync(s->h_logits.data(), s->d_logits, sizeof(float) * (size_t)n_win_total * C, cudaMemcpyDeviceToHost,
+            CK(cudaMemcpyAsync(s->h_logits, s->d_logits, sizeof(float) * (size_t)n_win_total * C, cudaMemcpyDeviceToHost,
                                s->st));
         }
     }
@@ -1103,7 +1105,7 @@ static int session_advance(ww_session* s, int chunk_samples) {
     CK(cudaStreamSynchronize(s->st));
     s->pcm_cur ^= 1;
     if (n_new > 0) s->feat_cur ^= 1;
-    if (n_win <= 0) s->h_logits.clear();
+    s->h_logits_n = n_win > 0 ? (size_t)n_win_total * C : 0;
     s->g0 = g0_next;
     s->tail_len = keep;
     // host-side hit logic per stream (esp_wake_word_detector.cpp:38-44,245-258)
@@ -1141,8 +1143,8 @@ extern "C" long long ww_session_poll(ww_session* s, ww_hit* hits, long long max_
 /* last scored logits of the most recent write: [n_streams][n_new_windows][C] (host); returns n_new_windows */
 extern "C" long long ww_session_last_logits(const ww_session* s, const float** logits) {
     if (!s || !logits) return WW_ERR_INVALID;
-    *logits = s->h_logits.data();
-    return s->n_streams ? (long long)(s->h_logits.size() / ((size_t)s->n_streams * s->ctx->w.num_classes)) : 0;
+    *logits = s->h_logits;
+    return s->n_streams ? (long long)(s->h_logits_n / ((size_t)s->n_streams * s->ctx->w.num_classes)) : 0;
 }
 
 // ------------------------------------------------------------------------------------------------
