@@ -1173,6 +1173,23 @@ extern "C" int ww_ctc_greedy(ww_ctx* ctx, const float* log_probs, long long t_st
     a.keyword = keyword;
     a.K = keyword_len;
     a.hits = hits;
+    a.pre_argmax = 0;
+    a.vec_ok = 0;
+    if (C > 32 && T > 0) {
+        // wide vocabulary: a bandwidth-bound pass computes every frame's argmax into the label buffer, the
+        // warp-per-utterance kernel then only compacts it
+        a.vec_ok = (C % 4 == 0) && ((uintptr_t)log_probs % 16 == 0) && (t_stride % 4 == 0) && (b_stride % 4 == 0);
+        const long long rows = (long long)B * T;
+        long long blocks = (rows + 7) / 8;
+        const int elems = a.vec_ok ? C / 4 : C;   // 16-byte (or 4-byte) elements per row
+        const long long cap = (long long)ctx->sm_count * (elems > 16 ? 8 : 16);
+        if (blocks > cap) blocks = cap;
+        if (elems > 16) ctc_argmax_rows_kernel<32><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+        else if (elems > 8) ctc_argmax_rows_kernel<16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+        else ctc_argmax_rows_kernel<8><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+        CK(cudaGetLastError());
+        a.pre_argmax = 1;
+    }
     ctc_greedy_kernel<<<(B + CTC_WARPS - 1) / CTC_WARPS, CTC_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     CK(cudaGetLastError());
     return WW_OK;

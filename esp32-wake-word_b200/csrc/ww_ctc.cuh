@@ -25,6 +25,8 @@ struct GreedyArgs {
     const int* keyword;    // optional [K] label ids
     int K;
     unsigned char* hits;   // optional [B]
+    int pre_argmax;        // 1: labels[b][t] already holds the per-frame argmax (ctc_argmax_rows_kernel); compact in place
+    int vec_ok;            // argmax kernel: rows are 16-byte aligned and C % 4 == 0
 };
 
 constexpr int CTC_WARPS = 4;
@@ -54,6 +56,10 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_greedy_kernel(const Greedy
                     if (v > best) { best = v; idx = c; }
                 }
             }
+        } else if (a.pre_argmax) {
+            // wide vocabulary: the argmax of every frame was computed by the bandwidth-bound row kernel into the label
+            // buffer itself; compaction below never writes past the frames already read (pos <= tb)
+            if (t < Tb) idx = lab[t];
         } else {
             // warp per frame, lanes stride the classes (coalesced); first index wins ties
             const int nt = min(32, Tb - tb);
@@ -96,6 +102,60 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_greedy_kernel(const Greedy
         }
         hit = __any_sync(0xffffffffu, hit);
         if (lane == 0) a.hits[b] = hit ? 1 : 0;
+    }
+}
+
+// Wide-vocabulary best path, step 1: argmax of every (b, t) row -- one warp per row, grid stride over all B*T rows,
+// 16-byte streaming loads; first index wins ties (torch.argmax).  T*C*4 bytes per utterance, HBM-bound.  A warp per
+// UTTERANCE (ctc_greedy_kernel alone) walks its T rows one after the other and reaches 3.5 % of HBM bandwidth at
+// B = 256, T = 801, C = 4096.
+// LPR = lanes per row: a power of two in [8, 32] that covers the row with one 16-byte (or 4-byte) element per lane when it
+// is short, so that narrow vocabularies (C = 64: 16 float4) keep all 32 lanes busy with 2-4 rows per warp
+template <int LPR>
+__global__ void __launch_bounds__(256) ctc_argmax_rows_kernel(const GreedyArgs a) {
+    const int lane = threadIdx.x & 31;
+    constexpr int lpr = LPR;
+    constexpr int rpw = 32 / lpr;                 // rows per warp iteration
+    const int sub = lane / lpr, l = lane % lpr;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long rows = (long long)a.B * a.T;
+    for (long long r0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * rpw; r0 < rows; r0 += warps * rpw) {
+        const long long r = r0 + sub;
+        const bool in = r < rows;
+        const long long b = in ? r / a.T : 0;
+        const int t = (int)(in ? r - b * a.T : 0);
+        const bool live = in && !(a.lengths && t >= min(max(a.lengths[b], 0), a.T));
+        const float* row = a.lp + b * a.b_stride + (long long)t * a.t_stride;
+        float best = -CUDART_INF_F;
+        int bi = 0x7fffffff;
+        if (live) {
+            if (a.vec_ok) {
+                const float4* r4 = reinterpret_cast<const float4*>(row);
+                const int n4 = a.C >> 2;
+                for (int c4 = l; c4 < n4; c4 += lpr) {
+                    const float4 v = __ldcs(r4 + c4);
+                    const int c = 4 * c4;
+                    if (v.x > best || bi == 0x7fffffff) { best = v.x; bi = c; }
+                    if (v.y > best) { best = v.y; bi = c + 1; }
+                    if (v.z > best) { best = v.z; bi = c + 2; }
+                    if (v.w > best) { best = v.w; bi = c + 3; }
+                }
+            } else {
+                for (int c = l; c < a.C; c += lpr) {
+                    const float v = row[c];
+                    if (v > best || bi == 0x7fffffff) { best = v; bi = c; }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {   // segmented butterfly: partners stay inside the row's lane group
+            if (o < lpr) {                   // warp-uniform
+                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+        }
+        if (live && l == 0) a.labels[b * (long long)a.T + t] = bi;
     }
 }
 

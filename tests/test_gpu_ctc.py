@@ -24,7 +24,7 @@ def test_decoders_against_reference_goldens(cuda_device, golden_dir, i):
     assert ww_b200.decode_predictions(lp, chars) == list(g[f"collapse{i}"])
 
 
-@pytest.mark.parametrize("B,T,C", [(1, 1, 2), (37, 63, 3), (5, 100, 40), (3, 33, 4096), (2, 64, 33)])
+@pytest.mark.parametrize("B,T,C", [(1, 1, 2), (37, 63, 3), (5, 100, 40), (3, 33, 4096), (2, 64, 33), (4, 257, 68), (7, 200, 130)])
 @pytest.mark.parametrize("mode", ["collapse", "keep_repeats"])
 def test_greedy_batch_vs_oracle(cuda_device, B, T, C, mode):
     import ww_b200

@@ -86,6 +86,28 @@ def ctc_bench(dev, T, B, C, S, seed=777):
             "algorithmic_GBps": bytes_alg / d_ours / 1e9}
 
 
+def greedy_bench(dev):
+    """a11/a12: CTC best-path decode, bandwidth-bound argmax over [B, T, C] log-probs (T*C*4 bytes per utterance)."""
+    peak = 6545.3
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    out = []
+    for (B, T, C) in ((256, 801, 4096), (1 << 20, 63, 3), (4096, 801, 64)):
+        lp = torch.randn((B, T, C), device=dev)
+        dt = timed(lambda: ww_b200.greedy_batch(lp, mode="collapse"))
+        t0 = time.perf_counter()
+        torch.argmax(lp, dim=-1)
+        torch.cuda.synchronize()
+        dt_t = timed(lambda: torch.argmax(lp, dim=-1))
+        gb = B * T * C * 4 / 1e9
+        out.append({"config": f"a12 CTC greedy decode B={B} T={T} C={C}", "seq_per_s": B / dt, "algorithmic_GBps": gb / dt,
+                    "hbm_frac": gb / dt / peak, "torch_argmax_only_GBps": gb / dt_t})
+        del lp
+    return out
+
+
 def batch_sweep(dev, sd):
     """configs[2]: per-GPU batch-size sweep of the fused scorer (tensor CNN) and the frontend alone."""
     out = []
@@ -227,7 +249,7 @@ def main():
             print(json.dumps(r), flush=True)
         return
     if "--frontdsp" in sys.argv:
-        for r in int8_bench(dev, sd) + device_path_bench(dev, sd) + session_bench(sd) + frontdsp_bench(dev):
+        for r in greedy_bench(dev) + int8_bench(dev, sd) + device_path_bench(dev, sd) + session_bench(sd) + frontdsp_bench(dev):
             print(json.dumps(r), flush=True)
         return
     res += batch_sweep(dev, sd)
