@@ -509,8 +509,30 @@ extern "C" int ww_cmvn(ww_ctx* ctx, const float* feats, long long n_windows, int
     if (n_windows == 0) return WW_OK;
     if (!feats || !out || n_windows < 0) return fail(ctx, WW_ERR_INVALID, "cmvn: bad arguments");
     if (cmvn_mode < WW_CMVN_NONE || cmvn_mode > WW_CMVN_DEVICE) return fail(ctx, WW_ERR_INVALID, "cmvn: bad mode");
+#ifdef WW_WITH_TC
+    {
+        // dedicated bandwidth-bound kernel (a warp per window); the fp32 CNN kernel's CMVN stage is the fallback
+        CmvnArgs a;
+        a.feats = feats;
+        a.out = out;
+        a.n_windows = n_windows;
+        a.cmvn_mode = cmvn_mode;
+        a.win_stride = WW_N_MFCC * WW_WINDOW_FRAMES;
+        a.coef_stride = WW_WINDOW_FRAMES;
+        a.frame_stride = 1;
+        a.group_windows = 0;
+        a.group_stride = 0;
+        long long blocks = (n_windows + 7) / 8;
+        const long long cap = (long long)ctx->sm_count * 8;
+        if (blocks > cap) blocks = cap;
+        cmvn_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+        CK(cudaGetLastError());
+        return WW_OK;
+    }
+#else
     return launch_cnn_fp32(ctx, feats, WW_N_MFCC * WW_WINDOW_FRAMES, WW_WINDOW_FRAMES, 1, n_windows, nullptr, nullptr,
                            cmvn_mode, WW_DECIDE_NONE, 0.f, nullptr, nullptr, out, (cudaStream_t)stream);
+#endif
 }
 
 static int check_cnn_args(ww_ctx* ctx, int cmvn_mode, int decide_mode, int cnn_impl) {

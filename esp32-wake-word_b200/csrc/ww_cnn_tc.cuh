@@ -609,6 +609,64 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
     }
 }
 
+// ---- stand-alone CMVN (normalize_mfcc / device CMVN over [n][13][63] windows) ------------------------------
+// ww_cmvn's kernel: a warp per window, grid stride, lane <-> frame.  6 552 bytes per window (read + write): bound by
+// HBM.  Python style is the exact formula of extract_mfcc.py:47-88 (true divisions, unbiased std, std == 0 -> 1);
+// device style is tc_cmvn_device, i.e. bit-identical to what the CNN kernels feed their first layer.
+struct CmvnArgs {
+    const float* feats;   // [n][13][63]
+    float* out;           // [n][13][63]
+    long long n_windows;
+    int cmvn_mode;
+    // tc_load_window's view of the windows
+    long long win_stride, coef_stride, frame_stride, group_windows, group_stride;
+};
+
+__global__ void __launch_bounds__(256) cmvn_rows_kernel(const CmvnArgs a) {
+    const int lane = threadIdx.x & 31;
+    const bool has1 = lane + 32 < WW_WINDOW_FRAMES;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long win = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); win < a.n_windows; win += warps) {
+        TcWin w;
+        tc_load_window(a, win, lane, w);
+        if (a.cmvn_mode == CMVN_PY) {
+            float v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = q < WW_N_MFCC ? w.x0[q] + w.x1[q] : 0.f;
+            const float tot = reduce16(v, lane) / (float)WW_WINDOW_FRAMES;   // lane 2q: mean of coefficient q
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                if (q < WW_N_MFCC) {
+                    const float mean = __shfl_sync(0xffffffffu, tot, 2 * q);
+                    w.x0[q] -= mean;
+                    w.x1[q] = has1 ? w.x1[q] - mean : 0.f;
+                    v[q] = fmaf(w.x0[q], w.x0[q], w.x1[q] * w.x1[q]);
+                } else {
+                    v[q] = 0.f;
+                }
+            }
+            const float ss = reduce16(v, lane);
+            float sd = sqrtf(ss / (float)(WW_WINDOW_FRAMES - 1));
+            if (sd == 0.f) sd = 1.f;
+            const float den = sd + 1e-8f;
+#pragma unroll
+            for (int q = 0; q < WW_N_MFCC; ++q) {
+                const float dq = __shfl_sync(0xffffffffu, den, 2 * q);
+                w.x0[q] = w.x0[q] / dq;
+                w.x1[q] = w.x1[q] / dq;
+            }
+        } else if (a.cmvn_mode == CMVN_DEVICE) {
+            tc_cmvn_device(w, lane);
+        }
+        float* o = a.out + win * (long long)(WW_N_MFCC * WW_WINDOW_FRAMES) + lane;
+#pragma unroll
+        for (int q = 0; q < WW_N_MFCC; ++q) {
+            o[q * WW_WINDOW_FRAMES] = w.x0[q];
+            if (has1) o[q * WW_WINDOW_FRAMES + 32] = w.x1[q];
+        }
+    }
+}
+
 // ---- host: fp16 weight blob in UMMA K-major layout ---------------------------------------------------
 // element (row n, k) of a [rows x K] operand: byte (k/8)*rows*16 + n*16 + (k%8)*2
 inline void tc_pack_operand(__half* dst, int rows, int K_padded, const float* src, int src_rows, int src_K,

@@ -86,6 +86,26 @@ def ctc_bench(dev, T, B, C, S, seed=777):
             "algorithmic_GBps": bytes_alg / d_ours / 1e9}
 
 
+def cmvn_bench(dev, n=1 << 18):
+    """a8: stand-alone CMVN (normalize_mfcc) over [n, 13, 63] windows, 6 552 B per window; and the feature-extraction
+    chain mfcc_batch + normalize_mfcc that extract_features runs."""
+    peak = 6545.3
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    feats = torch.randn((n, 13, 63), device=dev) * 10 - 20
+    out = []
+    for dev_style in (False, True):
+        dt = timed(lambda: ww_b200.cmvn_batch(feats, device_style=dev_style))
+        out.append({"config": "a8 stand-alone CMVN (ww_cmvn)", "style": "device" if dev_style else "python", "windows": n,
+                    "windows_per_s": n / dt, "algorithmic_GBps": n * 6552 / dt / 1e9, "hbm_frac": n * 6552 / dt / 1e9 / peak})
+    pcm = bench.synth_pcm(n, dev, 1234)
+    dt = timed(lambda: ww_b200.normalize_mfcc(ww_b200.mfcc_batch(pcm), "cmvn"))
+    out.append({"config": "feature extraction chain: mfcc_batch + normalize_mfcc('cmvn')", "clips": n, "clips_per_s": n / dt})
+    return out
+
+
 def greedy_bench(dev):
     """a11/a12: CTC best-path decode, bandwidth-bound argmax over [B, T, C] log-probs (T*C*4 bytes per utterance)."""
     peak = 6545.3
@@ -249,7 +269,7 @@ def main():
             print(json.dumps(r), flush=True)
         return
     if "--frontdsp" in sys.argv:
-        for r in greedy_bench(dev) + int8_bench(dev, sd) + device_path_bench(dev, sd) + session_bench(sd) + frontdsp_bench(dev):
+        for r in cmvn_bench(dev) + greedy_bench(dev) + int8_bench(dev, sd) + device_path_bench(dev, sd) + session_bench(sd) + frontdsp_bench(dev):
             print(json.dumps(r), flush=True)
         return
     res += batch_sweep(dev, sd)
