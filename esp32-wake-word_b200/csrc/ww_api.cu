@@ -16,6 +16,7 @@
 #include "ww_frontdsp.cuh"
 #include "ww_mfcc.cuh"
 #include "ww_tables.h"
+#include "ww_tables_esp.h"
 #ifdef WW_WITH_TC
 #include "ww_cnn_tc.cuh"
 #include "ww_cnn_i8_tc.cuh"
@@ -26,6 +27,7 @@ using namespace ww;
 #define WW_VERSION_NUM 100
 
 struct FeatMode {
+    bool generated = false;   // the compiled-in mel / DCT code (ww_mel_py.inc / ww_mel_esp.inc) matches these tables
     uint4* tables = nullptr;  // device blob
     float dct[WW_N_MELS * WW_N_MFCC];
     int origin_off;
@@ -94,7 +96,26 @@ static int cuda_fail(ww_ctx* c, cudaError_t e, const char* what) {
 struct HostTables {
     std::vector<unsigned char> blob;
     float dct[WW_N_MELS * WW_N_MFCC];
+    // sparse filterbank as built (for ww_debug_esp_tables and the generated-code checksum)
+    std::vector<int> start, len;
+    std::vector<float> w, bias;
+    float window[WW_WIN];
 };
+
+// FNV-1a over the bit patterns of the tables the generated ESP mel/DCT code (ww_mel_esp.inc) was made from
+static uint32_t tables_checksum(const HostTables& t) {
+    uint32_t h = 2166136261u;
+    auto mix = [&](const void* p, size_t n) {
+        const unsigned char* b = static_cast<const unsigned char*>(p);
+        for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 16777619u;
+    };
+    mix(t.start.data(), t.start.size() * sizeof(int));
+    mix(t.len.data(), t.len.size() * sizeof(int));
+    mix(t.w.data(), t.w.size() * sizeof(float));
+    mix(t.bias.data(), t.bias.size() * sizeof(float));
+    mix(t.dct, sizeof(t.dct));
+    return h;
+}
 
 static void fill_common(HostTables& t, const float* window320, float preemph, const std::vector<int>& start,
                         const std::vector<int>& len, const std::vector<int>& off, const std::vector<float>& w,
@@ -199,6 +220,11 @@ static bool build_esp_tables(HostTables& t) {
     }
     if ((int)w.size() > MEL_W_CAP) return false;
     fill_common(t, window, 0.97f, start, len, off, w, bias);
+    t.start = start;
+    t.len = len;
+    t.w = w;
+    t.bias = bias;
+    memcpy(t.window, window, sizeof(t.window));
     const int n = n_filters;
     for (int k = 0; k < WW_N_MFCC; ++k) {
         const float scale = (k == 0) ? sqrtf(1.0f / n) : sqrtf(2.0f / n);
@@ -209,6 +235,24 @@ static bool build_esp_tables(HostTables& t) {
     }
     return true;
 }
+
+#ifndef WW_ESP_TABLES_STUB
+// the same tables as compile-time constants (ww_tables_esp.h, generated from build_esp_tables on the build machine)
+static bool load_esp_tables(HostTables& t) {
+    std::vector<int> start(WW_ESP_MEL_START, WW_ESP_MEL_START + 40), len(WW_ESP_MEL_LEN, WW_ESP_MEL_LEN + 40),
+        off(WW_ESP_MEL_OFF, WW_ESP_MEL_OFF + 40);
+    std::vector<float> w(WW_ESP_MEL_W, WW_ESP_MEL_W + WW_ESP_MEL_NNZ), bias(WW_ESP_MEL_BIAS, WW_ESP_MEL_BIAS + 40);
+    if ((int)w.size() > MEL_W_CAP) return false;
+    fill_common(t, WW_ESP_WINDOW, 0.97f, start, len, off, w, bias);
+    t.start = start;
+    t.len = len;
+    t.w = w;
+    t.bias = bias;
+    memcpy(t.window, WW_ESP_WINDOW, sizeof(t.window));
+    memcpy(t.dct, WW_ESP_DCT, sizeof(t.dct));
+    return true;
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // context
@@ -253,7 +297,11 @@ extern "C" int ww_create(ww_ctx** out, int device) {
 
     HostTables ht[2];
     build_py_tables(ht[0]);
-    const bool esp_ok = build_esp_tables(ht[1]);
+#ifdef WW_ESP_TABLES_STUB
+    const bool esp_ok = build_esp_tables(ht[1]);   // bootstrap build: computed here, table-driven kernel
+#else
+    const bool esp_ok = load_esp_tables(ht[1]);    // the constants ww_mel_esp.inc was generated from
+#endif
     for (int m = 0; m < 2; ++m) {
         if (m == 1 && !esp_ok) continue;
         if ((e = cudaMalloc(&ctx->feat[m].tables, TB_BYTES)) != cudaSuccess) return bail(e, "cudaMalloc tables");
@@ -261,6 +309,9 @@ extern "C" int ww_create(ww_ctx** out, int device) {
             return bail(e, "cudaMemcpy tables");
         memcpy(ctx->feat[m].dct, ht[m].dct, sizeof(ht[m].dct));
     }
+    ctx->feat[0].generated = true;  // ww_mel_py.inc and the PY tables come from the same generator run
+    // ww_mel_esp.inc was generated from build_esp_tables() on the build machine; libm differences would show here
+    ctx->feat[1].generated = esp_ok && tables_checksum(ht[1]) == WW_MEL_ESP_CHECKSUM;  // false only in a bootstrap build
     ctx->feat[0].origin_off = -256;
     ctx->feat[0].reflect = 1;
     ctx->feat[0].mode_pscale = 1.0f;
@@ -276,10 +327,12 @@ extern "C" int ww_create(ww_ctx** out, int device) {
 #define WW_SET_SMEM(K, S)                                                                                  \
     if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, S)) != cudaSuccess)       \
         return bail(e, "cudaFuncSetAttribute(" #K ")");
-    WW_SET_SMEM((mfcc_kernel<int16_t, true>), (MfccSmem<int16_t, true>::TOTAL))
-    WW_SET_SMEM((mfcc_kernel<int16_t, false>), (MfccSmem<int16_t, false>::TOTAL))
-    WW_SET_SMEM((mfcc_kernel<float, true>), (MfccSmem<float, true>::TOTAL))
-    WW_SET_SMEM((mfcc_kernel<float, false>), (MfccSmem<float, false>::TOTAL))
+    WW_SET_SMEM((mfcc_kernel<int16_t, MEL_PY>), (MfccSmem<int16_t, MEL_PY>::TOTAL))
+    WW_SET_SMEM((mfcc_kernel<int16_t, MEL_ESP>), (MfccSmem<int16_t, MEL_ESP>::TOTAL))
+    WW_SET_SMEM((mfcc_kernel<int16_t, MEL_TABLE>), (MfccSmem<int16_t, MEL_TABLE>::TOTAL))
+    WW_SET_SMEM((mfcc_kernel<float, MEL_PY>), (MfccSmem<float, MEL_PY>::TOTAL))
+    WW_SET_SMEM((mfcc_kernel<float, MEL_ESP>), (MfccSmem<float, MEL_ESP>::TOTAL))
+    WW_SET_SMEM((mfcc_kernel<float, MEL_TABLE>), (MfccSmem<float, MEL_TABLE>::TOTAL))
 #undef WW_SET_SMEM
 #ifdef WW_WITH_TC
     if ((e = cudaFuncSetAttribute(cnn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)) != cudaSuccess)
@@ -433,14 +486,19 @@ static int launch_mfcc_ex(ww_ctx* ctx, const void* pcm, int pcm_type, long long 
     a.n_blocks = total_blocks;
     const long long resident = 2LL * ctx->sm_count;  // persistent: two CTAs per SM walk over the blocks
     const unsigned grid = (unsigned)(total_blocks < resident ? total_blocks : resident);
-    const bool py = feat_mode == WW_FEAT_PY;  // PY filterbank is compiled in (ww_mel_py.inc); others are table-driven
+    // generated mel / DCT code (weights as immediates) when it matches the tables of this mode, else table-driven
+    const int mel = !fm.generated ? MEL_TABLE : (feat_mode == WW_FEAT_PY ? MEL_PY : MEL_ESP);
+#define WW_LAUNCH_MFCC(T, M) mfcc_kernel<T, M><<<grid, MFCC_THREADS, MfccSmem<T, M>::TOTAL, st>>>(a)
     if (pcm_type == WW_PCM_S16) {
-        if (py) mfcc_kernel<int16_t, true><<<grid, MFCC_THREADS, MfccSmem<int16_t, true>::TOTAL, st>>>(a);
-        else mfcc_kernel<int16_t, false><<<grid, MFCC_THREADS, MfccSmem<int16_t, false>::TOTAL, st>>>(a);
+        if (mel == MEL_PY) WW_LAUNCH_MFCC(int16_t, MEL_PY);
+        else if (mel == MEL_ESP) WW_LAUNCH_MFCC(int16_t, MEL_ESP);
+        else WW_LAUNCH_MFCC(int16_t, MEL_TABLE);
     } else {
-        if (py) mfcc_kernel<float, true><<<grid, MFCC_THREADS, MfccSmem<float, true>::TOTAL, st>>>(a);
-        else mfcc_kernel<float, false><<<grid, MFCC_THREADS, MfccSmem<float, false>::TOTAL, st>>>(a);
+        if (mel == MEL_PY) WW_LAUNCH_MFCC(float, MEL_PY);
+        else if (mel == MEL_ESP) WW_LAUNCH_MFCC(float, MEL_ESP);
+        else WW_LAUNCH_MFCC(float, MEL_TABLE);
     }
+#undef WW_LAUNCH_MFCC
     CK(cudaGetLastError());
     return WW_OK;
 }
@@ -1360,6 +1418,23 @@ extern "C" int ww_debug_tc(ww_ctx* ctx, float* dbg_dev, int* last_rescored) {
     (void)last_rescored;
     return fail(ctx, WW_ERR_UNSUPPORTED, "tensor-core CNN not built into this library");
 #endif
+}
+
+// host-only: the C-MFCC tables as build_esp_tables() makes them on this machine (tools/gen_tables.py --esp turns them
+// into ww_mel_esp.inc).  fb is dense [40][257]; returns the checksum the generated code must carry, 0 on failure.
+extern "C" unsigned int ww_debug_esp_tables(float* window320, float* fb_dense, float* bias40, float* dct_40x13) {
+    HostTables t;
+    if (!build_esp_tables(t)) return 0;
+    if (window320) memcpy(window320, t.window, sizeof(t.window));
+    if (fb_dense) {
+        memset(fb_dense, 0, sizeof(float) * WW_N_MELS * WW_N_BINS);
+        size_t o = 0;
+        for (int j = 0; j < WW_N_MELS; ++j)
+            for (int i = 0; i < t.len[j]; ++i) fb_dense[(size_t)j * WW_N_BINS + t.start[j] + i] = t.w[o++];
+    }
+    if (bias40) memcpy(bias40, t.bias.data(), sizeof(float) * WW_N_MELS);
+    if (dct_40x13) memcpy(dct_40x13, t.dct, sizeof(t.dct));
+    return tables_checksum(t);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -170,7 +170,11 @@ constexpr int MFCC_FRAMES = 32;   // frames per CTA (lane <-> frame in the mel /
 constexpr int P_STRIDE = 257;     // floats per frame of power spectrum (odd: conflict-free lane <-> frame reads)
 constexpr int TB_BYTES_PY = TB_MELW_OFF;  // the PY path needs no mel tables in smem
 
-template <typename TIN, bool PYMEL>
+// MEL: 0 = table-driven filterbank / DCT from the blob (any contiguous-support filter set), 1 = generated PY code
+// (ww_mel_py.inc), 2 = generated ESP code (ww_mel_esp.inc): weights as FFMA immediates, no mel tables in smem
+constexpr int MEL_TABLE = 0, MEL_PY = 1, MEL_ESP = 2;
+
+template <typename TIN, int MEL>
 struct MfccSmem {
     static constexpr int FRAMES = MFCC_FRAMES;
     // the block is staged as two halves of 16 frames: 15*256 + 320 taps + 8 lead samples each
@@ -182,8 +186,8 @@ struct MfccSmem {
     static_assert(HALF_STRIDE % 16 == 0 && HALF_STRIDE % 128 == 64, "half-warp bank stagger");
     // int16 PCM on the PY path is double-buffered (the next block is prefetched by TMA while this one is
     // transformed); the other variants are single-buffered to keep two CTAs per SM
-    static constexpr int PCM_BUFS = (sizeof(TIN) == 2 && PYMEL) ? 2 : 1;
-    static constexpr int TAB_BYTES = PYMEL ? TB_BYTES_PY : TB_BYTES;
+    static constexpr int PCM_BUFS = (sizeof(TIN) == 2 && MEL != MEL_TABLE) ? 2 : 1;
+    static constexpr int TAB_BYTES = MEL != MEL_TABLE ? TB_BYTES_PY : TB_BYTES;
     static constexpr int OFF_BAR = 0;
     static constexpr int OFF_TAB = 32;
     static constexpr int OFF_PCM = OFF_TAB + TAB_BYTES;
@@ -194,11 +198,12 @@ struct MfccSmem {
     static constexpr int TOTAL = OFF_EDGE + 2 * WW_WIN * 4;
     static_assert(OFF_PCM % 16 == 0 && OFF_EXCH % 16 == 0 && OFF_P % 16 == 0, "smem alignment");
     // two CTAs per SM need TOTAL <= 115712 B; only the (float PCM, table-driven mel) variant exceeds it
-    static_assert(TOTAL <= 115712 || (!PYMEL && sizeof(TIN) == 4), "two CTAs per SM must fit");
+    static_assert(TOTAL <= 115712 || (MEL == MEL_TABLE && sizeof(TIN) == 4), "two CTAs per SM must fit");
 };
 
 #include "ww_mel_py.inc"
-static_assert(WW_MEL_PY_GROUPS == MFCC_WARPS, "one generated mel group per warp");
+#include "ww_mel_esp.inc"
+static_assert(WW_MEL_PY_GROUPS == MFCC_WARPS && WW_MEL_ESP_GROUPS == MFCC_WARPS, "one generated mel group per warp");
 
 // DCT of one frame for the coefficient subset {G0, G0+G, ...}: weights are immediate constant operands.
 template <int G, int G0>
@@ -229,9 +234,9 @@ struct DctDispatch<G, G> {
     static __device__ __forceinline__ void run(int, const MfccArgs&, const float*, float*) {}
 };
 
-template <typename TIN, bool PYMEL>
+template <typename TIN, int MEL>
 __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_constant__ MfccArgs a) {
-    using SM = MfccSmem<TIN, PYMEL>;
+    using SM = MfccSmem<TIN, MEL>;
     constexpr int FRAMES = MFCC_FRAMES;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
@@ -345,7 +350,7 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
                 const float pscale = a.pscale, log_offset = a.log_offset;
                 const float* prow = pw + lane * P_STRIDE;
                 float* lrow = lm + lane * LM_STRIDE;
-                if constexpr (PYMEL) {
+                if constexpr (MEL == MEL_PY) {
                     switch (warp) {
                         case 0: mel_py_group<0>(prow, lrow, pscale, log_offset); break;
                         case 1: mel_py_group<1>(prow, lrow, pscale, log_offset); break;
@@ -355,6 +360,18 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
                         case 5: mel_py_group<5>(prow, lrow, pscale, log_offset); break;
                         case 6: mel_py_group<6>(prow, lrow, pscale, log_offset); break;
                         default: mel_py_group<7>(prow, lrow, pscale, log_offset); break;
+                    }
+                } else if constexpr (MEL == MEL_ESP) {
+                    const float log_floor = a.log_floor;
+                    switch (warp) {
+                        case 0: mel_esp_group<0>(prow, lrow, pscale, log_floor, log_offset); break;
+                        case 1: mel_esp_group<1>(prow, lrow, pscale, log_floor, log_offset); break;
+                        case 2: mel_esp_group<2>(prow, lrow, pscale, log_floor, log_offset); break;
+                        case 3: mel_esp_group<3>(prow, lrow, pscale, log_floor, log_offset); break;
+                        case 4: mel_esp_group<4>(prow, lrow, pscale, log_floor, log_offset); break;
+                        case 5: mel_esp_group<5>(prow, lrow, pscale, log_floor, log_offset); break;
+                        case 6: mel_esp_group<6>(prow, lrow, pscale, log_floor, log_offset); break;
+                        default: mel_esp_group<7>(prow, lrow, pscale, log_floor, log_offset); break;
                     }
                 } else {
                     // table-driven filterbank (weights broadcast from smem): any contiguous-support filter set
@@ -460,7 +477,7 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
                     if (t < n_frames) {
                         float* outp = a.out + prev_sig * a.out_sig_stride + (long long)t * a.out_frame_stride;
                         const float* lrow = lm + lane * LM_STRIDE;
-                        if constexpr (PYMEL) {
+                        if constexpr (MEL == MEL_PY) {
                             const long long cs = a.out_coef_stride;
                             switch (warp) {
                                 case 0: dct_py_group<0>(lrow, outp, cs); break;
@@ -471,6 +488,18 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
                                 case 5: dct_py_group<5>(lrow, outp, cs); break;
                                 case 6: dct_py_group<6>(lrow, outp, cs); break;
                                 default: dct_py_group<7>(lrow, outp, cs); break;
+                            }
+                        } else if constexpr (MEL == MEL_ESP) {
+                            const long long cs = a.out_coef_stride;
+                            switch (warp) {
+                                case 0: dct_esp_group<0>(lrow, outp, cs); break;
+                                case 1: dct_esp_group<1>(lrow, outp, cs); break;
+                                case 2: dct_esp_group<2>(lrow, outp, cs); break;
+                                case 3: dct_esp_group<3>(lrow, outp, cs); break;
+                                case 4: dct_esp_group<4>(lrow, outp, cs); break;
+                                case 5: dct_esp_group<5>(lrow, outp, cs); break;
+                                case 6: dct_esp_group<6>(lrow, outp, cs); break;
+                                default: dct_esp_group<7>(lrow, outp, cs); break;
                             }
                         } else {
                             DctDispatch<MFCC_WARPS, 0>::run(warp, a, lrow, outp);

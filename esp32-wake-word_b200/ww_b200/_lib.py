@@ -29,7 +29,7 @@ EXPORTS = [
     "ww_mfcc_batch", "ww_cmvn", "ww_cnn_forward", "ww_quantize_weights_i8", "ww_cnn_forward_i8", "ww_score_clips", "ww_score_clips_host",
     "ww_stream_score", "ww_stream_events", "ww_session_open", "ww_session_write", "ww_session_write_tdm", "ww_session_poll",
     "ww_session_windows", "ww_session_last_logits", "ww_session_close", "ww_ctc_greedy", "ww_ctc_loss_workspace_bytes",
-    "ww_ctc_loss_fwd", "ww_ctc_loss_bwd", "ww_debug_tc", "ww_extract_mfcc", "ww_free_mfcc",
+    "ww_ctc_loss_fwd", "ww_ctc_loss_bwd", "ww_debug_tc", "ww_debug_esp_tables", "ww_extract_mfcc", "ww_free_mfcc",
     "ww_set_option", "ww_wav_parse", "ww_wav_load_batch", "ww_wav_write", "ww_tdm_downmix", "ww_augment_waveform",
 ]
 
@@ -98,6 +98,8 @@ def load_library():
         lib.ww_ctc_loss_bwd.argtypes = [vp, vp, i64, i64, i32, i32, i32, vp, i32, vp, vp, i32, i32, vp, vp, vp,
                                         i64, i64, vp]
         lib.ww_debug_tc.argtypes = [vp, vp, vp]
+        lib.ww_debug_esp_tables.argtypes = [vp, vp, vp, vp]
+        lib.ww_debug_esp_tables.restype = C.c_uint
         lib.ww_extract_mfcc.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32]
         lib.ww_extract_mfcc.restype = C.POINTER(C.c_float)
         lib.ww_free_mfcc.argtypes = [C.POINTER(C.c_float)]

@@ -234,6 +234,10 @@ int ww_augment_waveform(ww_ctx* ctx, const float* audio, long long n, int L, flo
  * receives the per-layer activations of the first 8 windows of each launch; *last_rescored receives the
  * number of windows the previous launch handed to the exact fp32 kernel. */
 int ww_debug_tc(ww_ctx* ctx, float* dbg_dev, int* last_rescored);
+/* Host-only: the C-MFCC (mfcc.c) tables as this machine builds them -- window [320], dense filterbank [40][257], per-filter
+ * epsilon bias [40], DCT [40][13] (any pointer may be NULL).  Returns their checksum (0 on failure); the generated
+ * kernel code of the ESP mode (csrc/ww_mel_esp.inc, tools/gen_tables.py --esp) is used only when it carries the same one. */
+unsigned int ww_debug_esp_tables(float* window320, float* fb_dense, float* bias40, float* dct_40x13);
 
 /* ---- drop-in for main/esp_mfcc/mfcc.h:10-17 ---------------------------------------------------- */
 /* Same signature and ownership as the reference's extract_mfcc(): returns a malloc'd
