@@ -515,6 +515,9 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
             const bool valid = t < n_frames;
             const int fo = WW_HOP * t + origin_off;  // signal sample index of frame point n = 0
             const bool interior = valid && (fo + 95 >= 0) && (fo + 415 < L);
+            // both frames of this warp lie past the end of the signal (short signals, streaming sessions that add one or
+            // two frames per push): nothing to transform; their power rows stay stale and their outputs are never stored
+            if (!__any_sync(0xffffffffu, valid)) continue;
             float* ps = pw + fl * P_STRIDE;
 
             cpx v[16];
