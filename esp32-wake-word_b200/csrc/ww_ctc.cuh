@@ -667,7 +667,9 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_bwd_pf_kernel(const C
                     }
                 }
                 cp_async_commit();
-                float blank_m = NEG;
+                // posterior mass of the blank class, summed directly: exp(alpha + beta + nll - lp) <= 1 for every state,
+                // so no log-sum-exp (max butterfly + log) is needed on the way to the gradient
+                float blank_e = 0.f;
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     const int s = lane + 32 * k;
@@ -683,20 +685,13 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_bwd_pf_kernel(const C
                         }
                         const float ab = alv[k] + v;
                         if (s & 1) acc[s >> 1] = ab;
-                        else blank_m = lse2f(blank_m, ab);
+                        else blank_e += __expf(ab + nll - lpv[k]);
                         lps[s] = lpv[k];
                     }
                     now[s] = v;
                 }
                 cur ^= 1;
-                {
-                    float m = blank_m;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-                    float e = (m == NEG) ? 0.f : __expf(blank_m - m);
-                    e = warp_sum(e);
-                    blank_m = (m == NEG) ? NEG : __logf(e) + m;
-                }
+                blank_e = warp_sum(blank_e);
                 if (!a.skip_fill) {
                     const float* row = base + (long long)t * a.t_stride;
                     for (int c = lane; c < a.C; c += 32) grow[c] = expf(row[c]) * go;
@@ -718,12 +713,12 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_bwd_pf_kernel(const C
                 if (lane == 0) {
                     // a target label equal to the blank index is folded into the blank class as PyTorch does (rare:
                     // the scan over the labels runs only for utterances that contain one)
-                    float tot = blank_m;
+                    const float l = lps[0];
+                    float tot = blank_e;
                     if (blank_in_tgt)
                         for (int i = 0; i < Sb; ++i)
-                            if (first[i] == i && tgt[i] == a.blank) tot = lse2(tot, acc[i]);
-                    const float l = lps[0];
-                    grow[a.blank] = (__expf(l) - __expf(tot + nll - l)) * go;
+                            if (first[i] == i && tgt[i] == a.blank) tot += __expf(acc[i] + nll - l);
+                    grow[a.blank] = (__expf(l) - tot) * go;
                 }
                 __syncwarp();
             }
