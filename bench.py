@@ -396,7 +396,8 @@ def run_ours(args):
     e2e_val = world * eb / float(te.item())
 
     if rank == 0:
-        chunks = (B + 65535) // 65536
+        chunk = int(os.environ.get("WW_CHUNK_CLIPS", "131072"))  # ww_api.cu kScratchClips: clips per fused frontend + CNN pair
+        chunks = (B + chunk - 1) // chunk
         per_chunk = 3 if cnn_impl == "tensor" else 2  # frontend + CNN (+ fp32 re-score of borderline clips)
         launches = args.steps * (chunks * per_chunk + (1 if n_utt else 0))
         cpu = None
