@@ -60,6 +60,7 @@ struct ww_ctx {
     uint4* i8tc_blob = nullptr;        // int8 weights in UMMA layout (ww_cnn_i8_tc.cuh)
     int i8_in_exp = 0, i8_out_exp = 0;  // exponents of the model input / output tensors
     int i8_impl = WW_CNN_TENSOR;       // ww_set_option(WW_OPT_I8_IMPL)
+    int opt_generic_frontend = 0;      // ww_set_option(WW_OPT_GENERIC_FRONTEND)
     long long grp_windows = 0, grp_stride = 0;  // window grouping of the next CNN launch (streaming sessions)
     // fused-path scratch
     float* scratch = nullptr;          // [chunk][13][63]
@@ -333,6 +334,8 @@ extern "C" int ww_create(ww_ctx** out, int device) {
     WW_SET_SMEM((mfcc_kernel<float, MEL_PY>), (MfccSmem<float, MEL_PY>::TOTAL))
     WW_SET_SMEM((mfcc_kernel<float, MEL_ESP>), (MfccSmem<float, MEL_ESP>::TOTAL))
     WW_SET_SMEM((mfcc_kernel<float, MEL_TABLE>), (MfccSmem<float, MEL_TABLE>::TOTAL))
+    WW_SET_SMEM((mfcc_kernel<int16_t, MEL_PY, true>), (MfccSmem<int16_t, MEL_PY>::TOTAL))
+    WW_SET_SMEM((mfcc_kernel<float, MEL_PY, true>), (MfccSmem<float, MEL_PY>::TOTAL))
 #undef WW_SET_SMEM
 #ifdef WW_WITH_TC
     if ((e = cudaFuncSetAttribute(cnn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)) != cudaSuccess)
@@ -384,6 +387,9 @@ extern "C" int ww_set_option(ww_ctx* ctx, int option, int value) {
             if (value == WW_CNN_TENSOR) return fail(ctx, WW_ERR_UNSUPPORTED, "tensor-core kernels not built into this library");
 #endif
             ctx->i8_impl = value;
+            return WW_OK;
+        case WW_OPT_GENERIC_FRONTEND:
+            ctx->opt_generic_frontend = value != 0;
             return WW_OK;
         default:
             return fail(ctx, WW_ERR_INVALID, "unknown option");
@@ -481,6 +487,8 @@ static int launch_mfcc_ex(ww_ctx* ctx, const void* pcm, int pcm_type, long long 
     a.log_floor = fm.log_floor;
     a.log_offset = fm.log_offset;
     a.preemph = 0.97f;
+    a.pm1[0] = 1.0f;
+    a.pm1[1] = -1.0f;
     memcpy(a.dct, fm.dct, sizeof(a.dct));
     const long long total_blocks = n_signals * a.blocks_per_sig;
     a.n_blocks = total_blocks;
@@ -488,8 +496,16 @@ static int launch_mfcc_ex(ww_ctx* ctx, const void* pcm, int pcm_type, long long 
     const unsigned grid = (unsigned)(total_blocks < resident ? total_blocks : resident);
     // generated mel / DCT code (weights as immediates) when it matches the tables of this mode, else table-driven
     const int mel = !fm.generated ? MEL_TABLE : (feat_mode == WW_FEAT_PY ? MEL_PY : MEL_ESP);
+    // whole 1 s clips in the PY layout: the instantiation with the launch shape frozen at compile time (same bits)
+    const bool clip_shape = mel == MEL_PY && a.use_bulk && n_samples == CLIP_SAMPLES && sig_stride == CLIP_SAMPLES &&
+                            n_frames == CLIP_FRAMES && origin_off == CLIP_ORIGIN && reflect == 1 &&
+                            oss == (long long)WW_N_MFCC * CLIP_FRAMES && ocs == CLIP_FRAMES && ofs == 1 &&
+                            !ctx->opt_generic_frontend;
 #define WW_LAUNCH_MFCC(T, M) mfcc_kernel<T, M><<<grid, MFCC_THREADS, MfccSmem<T, M>::TOTAL, st>>>(a)
-    if (pcm_type == WW_PCM_S16) {
+    if (clip_shape) {
+        if (pcm_type == WW_PCM_S16) mfcc_kernel<int16_t, MEL_PY, true><<<grid, MFCC_THREADS, MfccSmem<int16_t, MEL_PY>::TOTAL, st>>>(a);
+        else mfcc_kernel<float, MEL_PY, true><<<grid, MFCC_THREADS, MfccSmem<float, MEL_PY>::TOTAL, st>>>(a);
+    } else if (pcm_type == WW_PCM_S16) {
         if (mel == MEL_PY) WW_LAUNCH_MFCC(int16_t, MEL_PY);
         else if (mel == MEL_ESP) WW_LAUNCH_MFCC(int16_t, MEL_ESP);
         else WW_LAUNCH_MFCC(int16_t, MEL_TABLE);

@@ -81,6 +81,7 @@ struct MfccArgs {
     float log_floor;          // lm = log(max(mel + bias, floor) + offset)
     float log_offset;
     float preemph;            // 0.97
+    float pm1[2];             // {1, -1}: a run-time value so that it stays in one register pair (see the kernel)
     float dct[WW_N_MELS * WW_N_MFCC];  // row-major [40][13]; lives in the parameter constant bank
 };
 
@@ -234,7 +235,14 @@ struct DctDispatch<G, G> {
     static __device__ __forceinline__ void run(int, const MfccArgs&, const float*, float*) {}
 };
 
-template <typename TIN, int MEL>
+// CLIP = true is the same kernel with the launch shape of the headline workload frozen at compile time (whole 1 s
+// clips of the PY feature mode: 16 000 contiguous samples, 63 frames, two blocks per clip, reflect padding, TMA-legal
+// alignment, [B][13][63] output): the per-block bookkeeping (block -> signal mapping, staging spans, edge-frame tests,
+// output addressing) that every warp repeats for every block folds into constants.  The arithmetic is untouched, so
+// both instantiations produce identical bits; the host picks CLIP when the launch arguments match (launch_mfcc_ex).
+constexpr int CLIP_SAMPLES = 16000, CLIP_FRAMES = 63, CLIP_ORIGIN = -256;
+
+template <typename TIN, int MEL, bool CLIP = false>
 __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_constant__ MfccArgs a) {
     using SM = MfccSmem<TIN, MEL>;
     constexpr int FRAMES = MFCC_FRAMES;
@@ -247,10 +255,15 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int half = lane >> 4, l16 = lane & 15;
 
-    const int L = a.n_samples;
-    const int n_frames = a.n_frames;
-    const int origin_off = a.origin_off;
-    const bool use_bulk = a.use_bulk != 0;
+    const int L = CLIP ? CLIP_SAMPLES : a.n_samples;
+    const int n_frames = CLIP ? CLIP_FRAMES : a.n_frames;
+    const int origin_off = CLIP ? CLIP_ORIGIN : a.origin_off;
+    const bool use_bulk = CLIP ? true : a.use_bulk != 0;
+    const long long sig_stride = CLIP ? (long long)CLIP_SAMPLES : a.sig_stride;
+    const long long out_sig_stride = CLIP ? (long long)(WW_N_MFCC * CLIP_FRAMES) : a.out_sig_stride;
+    const long long out_coef_stride = CLIP ? (long long)CLIP_FRAMES : a.out_coef_stride;
+    const long long out_frame_stride = CLIP ? 1LL : a.out_frame_stride;
+    const int reflect = CLIP ? 1 : a.reflect;
     constexpr int NBUF = SM::PCM_BUFS;
     uint64_t* bars = bar;  // one mbarrier per PCM buffer
 
@@ -258,7 +271,7 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
     // one thread: TMA both halves of block (signal sg, block-in-signal bi) into buffer `buf`
     auto stage_block = [&](long long sg, int bi, int buf) {
         const int bt0 = bi * FRAMES;
-        const TIN* gs = reinterpret_cast<const TIN*>(a.pcm) + sg * a.sig_stride;
+        const TIN* gs = reinterpret_cast<const TIN*>(a.pcm) + sg * sig_stride;
         int lo[2], n[2];
         for (int h = 0; h < 2; ++h) {
             const int org = WW_HOP * (bt0 + 16 * h) + origin_off + 88;
@@ -292,7 +305,7 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
     __syncthreads();
     const long long first = blockIdx.x, stride = gridDim.x;
     // (signal, block-in-signal) of the current block, advanced incrementally: no 64-bit division in the loop
-    const int bps = a.blocks_per_sig;
+    const int bps = CLIP ? (CLIP_FRAMES + FRAMES - 1) / FRAMES : a.blocks_per_sig;
     const int stride_q = (int)gridDim.x / bps, stride_r = (int)gridDim.x % bps;
     long long sig_cur = first / bps;
     int bi_cur = (int)(first - sig_cur * bps);
@@ -321,6 +334,10 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
 #if WW_TW2_COMPUTE
     const float2 tw2_0 = s_tw2[l16];
 #endif
+    // {1, -1} comes from the launch arguments so that it lives in one register pair for the whole kernel: as a
+    // compile-time constant it is re-materialised from a uniform register with two MOVs in front of every packed
+    // instruction whose other two operands are broadcast scalars
+    const cpx pm1 = cpk(a.pm1[0], a.pm1[1]);
 #if WW_TW1_HALF
     const cpx tw1_8 = cpk(s_tw1[16 * 4 + l16].x, s_tw1[16 * 4 + l16].y);
 #endif
@@ -424,7 +441,7 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
                 }
             } else {
                 // unaligned / odd-length signals: cooperative copy instead of TMA
-                const TIN* gsig = reinterpret_cast<const TIN*>(a.pcm) + sig * a.sig_stride;
+                const TIN* gsig = reinterpret_cast<const TIN*>(a.pcm) + sig * sig_stride;
                 for (int h = 0; h < 2; ++h) {
                     const int org = h ? org1 : org0;
                     const int lo_h = org < 0 ? 0 : org;
@@ -444,7 +461,6 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
             const bool has1 = (t_tail >= t0) && (t_tail < t0 + FRAMES) && (t_tail < n_frames) && (t_tail > 0 || !has0);
             block_has_edge = has0 || has1;
             if (block_has_edge) {
-                const int reflect = a.reflect;
                 const float pre = a.preemph;
     #pragma unroll 1
                 for (int slot = has0 ? 0 : 1; slot <= (has1 ? 1 : 0); ++slot) {
@@ -475,10 +491,10 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
                 {
                     const int t = prev_t0 + lane;
                     if (t < n_frames) {
-                        float* outp = a.out + prev_sig * a.out_sig_stride + (long long)t * a.out_frame_stride;
+                        float* outp = a.out + prev_sig * out_sig_stride + (long long)t * out_frame_stride;
                         const float* lrow = lm + lane * LM_STRIDE;
                         if constexpr (MEL == MEL_PY) {
-                            const long long cs = a.out_coef_stride;
+                            const long long cs = out_coef_stride;
                             switch (warp) {
                                 case 0: dct_py_group<0>(lrow, outp, cs); break;
                                 case 1: dct_py_group<1>(lrow, outp, cs); break;
@@ -490,7 +506,7 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
                                 default: dct_py_group<7>(lrow, outp, cs); break;
                             }
                         } else if constexpr (MEL == MEL_ESP) {
-                            const long long cs = a.out_coef_stride;
+                            const long long cs = out_coef_stride;
                             switch (warp) {
                                 case 0: dct_esp_group<0>(lrow, outp, cs); break;
                                 case 1: dct_esp_group<1>(lrow, outp, cs); break;
@@ -645,13 +661,17 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
 #else
                 const float2 w = s_tw2[k];
 #endif
-                const cpx e = p_add(za, p_conj(zb));                         // (za.x + zb.x, za.y - zb.y)
-                const cpx o = p_fma(cswap(za), cpk(1.f, -1.f), cswap(zb));   // (za.y + zb.y, zb.x - za.x)
-                const cpx tt = p_cmul(o, w.x, w.y);
-                const cpx x1 = p_add(e, tt), x2 = p_sub(e, tt);
-                const float2 q1 = cunpk(p_mul(x1, x1)), q2 = cunpk(p_mul(x2, x2));
-                ps[k] = q1.x + q1.y;
-                ps[256 - k] = q2.x + q2.y;
+                const cpx e = p_add(za, p_conj(zb));                 // (za.x + zb.x, za.y - zb.y)
+                const cpx o = p_fma(cswap(za), pm1, cswap(zb));      // (za.y + zb.y, zb.x - za.x)
+                const float2 ef = cunpk(e), tf = cunpk(p_cmul(o, w.x, w.y));
+                // X[k] = e + tt, X[256-k] = conj(e - tt): real parts {e.x + tt.x, e.x - tt.x} and imaginary parts
+                // {e.y + tt.y, e.y - tt.y} as packed pairs (scalar operands are broadcast by the instruction), so the
+                // two power bins come out of one FMUL2 + one FFMA2
+                const cpx xr = p_fma(cpk(tf.x, tf.x), pm1, cpk(ef.x, ef.x));
+                const cpx xi = p_fma(cpk(tf.y, tf.y), pm1, cpk(ef.y, ef.y));
+                const float2 pp = cunpk(p_fma(xi, xi, p_mul(xr, xr)));
+                ps[k] = pp.x;
+                ps[256 - k] = pp.y;
             }
             if (l16 == 0) {
                 const float2 z8 = cunpk(v[8]);

@@ -23,6 +23,7 @@ DECIDE_NONE, DECIDE_LOGIT, DECIDE_DEVICE = 0, 1, 2
 DECODE_KEEP_REPEATS, DECODE_COLLAPSE = 0, 1
 CNN_FP32, CNN_TENSOR, CNN_INT8 = 0, 1, 2
 OPT_I8_IMPL = 1
+OPT_GENERIC_FRONTEND = 2
 
 EXPORTS = [
     "ww_version", "ww_create", "ww_destroy", "ww_last_error", "ww_load_weights", "ww_num_frames",

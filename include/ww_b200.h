@@ -111,8 +111,10 @@ int ww_quantize_weights_i8(ww_ctx* ctx, const int* exps);
 int ww_cnn_forward_i8(ww_ctx* ctx, const int8_t* x, long long n_windows, int8_t* out, ww_stream_t stream);
 /* Context options.  WW_OPT_I8_IMPL: which kernel ww_cnn_forward_i8 launches -- WW_CNN_TENSOR (default: tcgen05
  * kind::i8, int32 accumulators in TMEM) or WW_CNN_FP32 (here: the CUDA-core integer kernel).  Both are integer-exact
- * and give identical results. */
-enum { WW_OPT_I8_IMPL = 1 };
+ * and give identical results.
+ * WW_OPT_GENERIC_FRONTEND: 1 makes whole-clip launches use the run-time-shaped frontend kernel instead of the
+ * instantiation with the 1 s clip shape frozen at compile time (identical results; for A/B timing and tests). */
+enum { WW_OPT_I8_IMPL = 1, WW_OPT_GENERIC_FRONTEND = 2 };
 int ww_set_option(ww_ctx* ctx, int option, int value);
 
 /* ---- fused clip scoring: PCM -> MFCC -> CMVN -> CNN -> decision -------------------------------- */

@@ -138,3 +138,23 @@ def test_extract_mfcc_c_shim(cuda_device):
     lib.ww_free_mfcc(p)
     assert np.abs(got - oesp.esp_mfcc_port(x)).max() < 2e-3
     assert not lib.ww_extract_mfcc(x.ctypes.data, 16000, 8000, 320, 256, 512, 40, 13)  # unsupported params
+
+
+@pytest.mark.parametrize("dtype", ["int16", "float32"])
+def test_clip_shape_instantiation_matches_generic_kernel_bitwise(cuda_device, dtype):
+    """Whole 1 s clips run on the instantiation with the launch shape frozen at compile time; the run-time-shaped
+    kernel (WW_OPT_GENERIC_FRONTEND) must give the same bits, for 1, an odd number and many clips."""
+    import ww_b200
+    from ww_b200 import _lib as L
+
+    ctx = L.get_context(torch.device(cuda_device).index or 0)
+    for n in (1, 37, 1024):
+        pcm = om.synth_clips_int16(n, seed=99 + n)
+        x = torch.from_numpy(pcm if dtype == "int16" else om.pcm16_to_float(pcm)).to(cuda_device)
+        fast = _gpu_mfcc(x)
+        ctx.check(ctx.lib.ww_set_option(ctx.h, L.OPT_GENERIC_FRONTEND, 1), "ww_set_option")
+        try:
+            generic = _gpu_mfcc(x)
+        finally:
+            ctx.check(ctx.lib.ww_set_option(ctx.h, L.OPT_GENERIC_FRONTEND, 0), "ww_set_option")
+        assert np.array_equal(fast.view(np.uint32), generic.view(np.uint32))
