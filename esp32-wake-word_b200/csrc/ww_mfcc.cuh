@@ -28,12 +28,10 @@
 #include "ww_common.cuh"
 
 // Table-traffic switches, A/B-measured on B200 (262 144 clips, tools/time_frontend.py, profiles/experiments/README.md):
-//   WW_WIN_REGS     window taps in 20 registers instead of 10 LDS.64 per frame pair      26.6 -> 27.4 M clips/s (kept)
+//   window taps in 20 registers instead of 10 LDS.64 per frame pair                      26.6 -> 27.4 M clips/s (kept,
+//                   no switch any more: the taps are read from global memory once and never staged in smem)
 //   WW_TW2_COMPUTE  W512^(l16+16i) = W512^l16 * W32^i (immediates) instead of 8 LDS.64   +0.2 %  (off: noise)
 //   WW_TW1_HALF     twiddles k1 >= 8 as W^(8 l16) * W^(l16 (k1-8)) instead of 4 LDS.128  -1 %    (off)
-#ifndef WW_WIN_REGS
-#define WW_WIN_REGS 1
-#endif
 #ifndef WW_I2FP
 #define WW_I2FP 0
 #endif
@@ -60,7 +58,20 @@ constexpr int MFCC_THREADS = 256;
 constexpr int MFCC_WARPS = MFCC_THREADS / 32;
 constexpr int EXCH_ROW_BYTES = 144;                    // 16 complex + 16 B pad: conflict-free LDS.128
 constexpr int EXCH_FRAME_BYTES = 16 * EXCH_ROW_BYTES;  // 2304 (>= 257 complex for the natural-order pass)
-constexpr int LM_STRIDE = 41;                          // floats per frame of log-mel
+// Rows of the power-spectrum and log-mel buffers (lane <-> frame in the mel / DCT stages).  The generated mel / DCT
+// code reads its row with 16-byte loads: rows are 16-byte aligned with a stride of 4 (mod 32) words, which makes the
+// eight lanes of a quarter-warp hit disjoint banks, and the rows of frames 16..31 are shifted by another 16 words so
+// that the two half-warps of an FFT warp (frames t and t + 16, scalar stores along k) stay on disjoint banks too.
+// The table-driven fallback reads scalars and keeps odd strides.
+template <int MEL>
+struct MfccRows {
+    static constexpr bool VEC = MEL != 0;
+    static constexpr int P_STRIDE = VEC ? 260 : 257;
+    static constexpr int P_HALF_SHIFT = VEC ? 16 : 0;
+    static constexpr int P_FLOATS = 32 * P_STRIDE + P_HALF_SHIFT;
+    static constexpr int LM_STRIDE = VEC ? 44 : 41;
+    static __device__ __forceinline__ int p_row(int fl) { return fl * P_STRIDE + (fl >> 4) * P_HALF_SHIFT; }
+};
 
 struct MfccArgs {
     const void* pcm;          // [n_signals][sig_stride] samples
@@ -168,7 +179,6 @@ __device__ __forceinline__ float emph_sample(const TIN* spcm, int lo, int s, int
 }
 
 constexpr int MFCC_FRAMES = 32;   // frames per CTA (lane <-> frame in the mel / DCT phases)
-constexpr int P_STRIDE = 257;     // floats per frame of power spectrum (odd: conflict-free lane <-> frame reads)
 constexpr int TB_BYTES_PY = TB_MELW_OFF;  // the PY path needs no mel tables in smem
 
 // MEL: 0 = table-driven filterbank / DCT from the blob (any contiguous-support filter set), 1 = generated PY code
@@ -188,16 +198,18 @@ struct MfccSmem {
     // int16 PCM on the PY path is double-buffered (the next block is prefetched by TMA while this one is
     // transformed); the other variants are single-buffered to keep two CTAs per SM
     static constexpr int PCM_BUFS = (sizeof(TIN) == 2 && MEL != MEL_TABLE) ? 2 : 1;
-    static constexpr int TAB_BYTES = MEL != MEL_TABLE ? TB_BYTES_PY : TB_BYTES;
+    // the window taps (head of the blob) live in registers and are never staged: smem holds blob[TB_TW1_OFF ..)
+    static constexpr int TAB_SKIP = TB_TW1_OFF;
+    static constexpr int TAB_BYTES = (MEL != MEL_TABLE ? TB_BYTES_PY : TB_BYTES) - TAB_SKIP;
     static constexpr int OFF_BAR = 0;
     static constexpr int OFF_TAB = 32;
     static constexpr int OFF_PCM = OFF_TAB + TAB_BYTES;
     static constexpr int OFF_EXCH = OFF_PCM + PCM_BUFS * PCM_BYTES;
     static constexpr int OFF_P = OFF_EXCH + MFCC_WARPS * 2 * EXCH_FRAME_BYTES;
-    static constexpr int OFF_LM = OFF_P + FRAMES * P_STRIDE * 4;
-    static constexpr int OFF_EDGE = OFF_LM + FRAMES * LM_STRIDE * 4;   // 2 x 320 pre-emphasised edge-frame samples
+    static constexpr int OFF_LM = OFF_P + MfccRows<MEL>::P_FLOATS * 4;
+    static constexpr int OFF_EDGE = OFF_LM + FRAMES * MfccRows<MEL>::LM_STRIDE * 4;   // 2 x 320 pre-emphasised edge-frame samples
     static constexpr int TOTAL = OFF_EDGE + 2 * WW_WIN * 4;
-    static_assert(OFF_PCM % 16 == 0 && OFF_EXCH % 16 == 0 && OFF_P % 16 == 0, "smem alignment");
+    static_assert(OFF_PCM % 16 == 0 && OFF_EXCH % 16 == 0 && OFF_P % 16 == 0 && OFF_LM % 16 == 0, "smem alignment");
     // two CTAs per SM need TOTAL <= 115712 B; only the (float PCM, table-driven mel) variant exceeds it
     static_assert(TOTAL <= 115712 || (MEL == MEL_TABLE && sizeof(TIN) == 4), "two CTAs per SM must fit");
 };
@@ -248,7 +260,8 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
     constexpr int FRAMES = MFCC_FRAMES;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
-    const unsigned char* tab = smem + SM::OFF_TAB;
+    using ROWS = MfccRows<MEL>;
+    const unsigned char* tab = smem + SM::OFF_TAB - SM::TAB_SKIP;  // tab + TB_x_OFF for x = TW1, TW2, MELW, MELM
     float* pw = reinterpret_cast<float*>(smem + SM::OFF_P);
     float* lm = reinterpret_cast<float*>(smem + SM::OFF_LM);
 
@@ -300,7 +313,7 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
     // tables -> smem (once per persistent CTA)
     {
         uint4* dst = reinterpret_cast<uint4*>(smem + SM::OFF_TAB);
-        for (int i = tid; i < SM::TAB_BYTES / 16; i += MFCC_THREADS) dst[i] = __ldg(a.tables + i);
+        for (int i = tid; i < SM::TAB_BYTES / 16; i += MFCC_THREADS) dst[i] = __ldg(a.tables + SM::TAB_SKIP / 16 + i);
     }
     __syncthreads();
     const long long first = blockIdx.x, stride = gridDim.x;
@@ -314,7 +327,6 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
     float* edge = reinterpret_cast<float*>(smem + SM::OFF_EDGE);
     const int t_tail = (L - origin_off - 416) / WW_HOP + 1;  // first frame whose taps run past the signal end
 
-    const float2* s_win = reinterpret_cast<const float2*>(tab + TB_WIN_OFF);
     const float4* s_tw1 = reinterpret_cast<const float4*>(tab + TB_TW1_OFF);
     const float2* s_tw2 = reinterpret_cast<const float2*>(tab + TB_TW2_OFF);
 
@@ -326,11 +338,10 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
     //   window: 10 packed taps (20 registers)                                              [on]
     //   tw2:    W512^(l16 + 16 i) = W512^l16 * W32^i with W32^i as immediates              [measured, off]
     //   tw1:    W256^(l16 k1), k1 >= 8, = W256^(8 l16) * W256^(l16 (k1 - 8))               [measured, off]
-#if WW_WIN_REGS
     cpx wreg[10];
 #pragma unroll
-    for (int i = 0; i < 10; ++i) wreg[i] = reinterpret_cast<const cpx*>(s_win)[16 * i + l16];
-#endif
+    for (int i = 0; i < 10; ++i)
+        wreg[i].v = __ldg(reinterpret_cast<const unsigned long long*>(a.tables) + TB_WIN_OFF / 8 + 16 * i + l16);
 #if WW_TW2_COMPUTE
     const float2 tw2_0 = s_tw2[l16];
 #endif
@@ -365,8 +376,8 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
             // mel + log: lane <-> frame, warp <-> filter range
             {
                 const float pscale = a.pscale, log_offset = a.log_offset;
-                const float* prow = pw + lane * P_STRIDE;
-                float* lrow = lm + lane * LM_STRIDE;
+                const float* prow = pw + ROWS::p_row(lane);
+                float* lrow = lm + lane * ROWS::LM_STRIDE;
                 if constexpr (MEL == MEL_PY) {
                     switch (warp) {
                         case 0: mel_py_group<0>(prow, lrow, pscale, log_offset); break;
@@ -492,7 +503,7 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
                     const int t = prev_t0 + lane;
                     if (t < n_frames) {
                         float* outp = a.out + prev_sig * out_sig_stride + (long long)t * out_frame_stride;
-                        const float* lrow = lm + lane * LM_STRIDE;
+                        const float* lrow = lm + lane * ROWS::LM_STRIDE;
                         if constexpr (MEL == MEL_PY) {
                             const long long cs = out_coef_stride;
                             switch (warp) {
@@ -534,7 +545,7 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
             // both frames of this warp lie past the end of the signal (short signals, streaming sessions that add one or
             // two frames per push): nothing to transform; their power rows stay stale and their outputs are never stored
             if (!__any_sync(0xffffffffu, valid)) continue;
-            float* ps = pw + fl * P_STRIDE;
+            float* ps = pw + ROWS::p_row(fl);
 
             cpx v[16];
     #pragma unroll
@@ -545,9 +556,6 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
             const TIN* spcm = reinterpret_cast<const TIN*>(pcm_buf + half * SM::HALF_STRIDE);
             const int org = half ? org1 : org0;
             const float pre = a.preemph;
-#if !WW_WIN_REGS
-            const cpx* s_winp = reinterpret_cast<const cpx*>(s_win);
-#endif
             if (interior) {
                 // complex point m = 16*n1 + l16 (n1 = 3..12) <-> samples fo + 2m, fo + 2m + 1
                 const int base = fo - org + 2 * l16;  // smem sample index of m = l16 (even: fo - org is a multiple of 8)
@@ -555,11 +563,7 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
                 const uint32_t* p32b = reinterpret_cast<const uint32_t*>(spcm) + (base >> 1);
     #pragma unroll
                 for (int n1 = 3; n1 <= 12; ++n1) {
-#if WW_WIN_REGS
                     const cpx w = wreg[n1 - 3];
-#else
-                    const cpx w = s_winp[16 * (n1 - 3) + l16];
-#endif
                     float x0, x1, xm1;
                     if constexpr (sizeof(TIN) == 2) {
                         const uint32_t cur = p32b[16 * n1], prv = p32b[16 * n1 - 1];
@@ -593,11 +597,7 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
                 const float* ep = edge + (t == 0 ? 0 : WW_WIN) + 2 * l16;
     #pragma unroll
                 for (int n1 = 3; n1 <= 12; ++n1) {
-#if WW_WIN_REGS
                     const cpx w = wreg[n1 - 3];
-#else
-                    const cpx w = s_winp[16 * (n1 - 3) + l16];
-#endif
                     const cpx y = *reinterpret_cast<const cpx*>(ep + 32 * (n1 - 3));
                     v[n1] = p_mul(w, y);
                 }
