@@ -498,8 +498,10 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
                     mbar_wait(&bars[2], mel_uses & 1);
                     mel_pending = false;
                 }
-                // DCT: lane <-> frame, warp <-> coefficient pair {warp, warp + 8}; stores coalesced along time
-                {
+                // DCT: lane <-> frame, four of the warps <-> three or four coefficients each (the generated code's
+                // WW_DCT_*_WARP_MASK; every DCT warp reads the whole log-mel row); stores coalesced along time
+                constexpr unsigned dct_warps = MEL == MEL_PY ? WW_DCT_PY_WARP_MASK : MEL == MEL_ESP ? WW_DCT_ESP_WARP_MASK : 0xffu;
+                if ((dct_warps >> warp) & 1u) {
                     const int t = prev_t0 + lane;
                     if (t < n_frames) {
                         float* outp = a.out + prev_sig * out_sig_stride + (long long)t * out_frame_stride;
