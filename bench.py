@@ -39,8 +39,8 @@ UNIT = "clips/s"
 FRONTEND_BYTES_PER_CLIP = 16000 * 2 + 13 * 63 * 4  # 35 276
 FUSED_BYTES_PER_CLIP = 16000 * 2 + 5
 # dram__bytes_read.sum + dram__bytes_write.sum of mfcc_kernel<int16, PY> per clip, from the `ncu --set full` capture
-# profiles/r1_ncu_mfcc_kernel.txt (2.0974 GB + 212.0 MB over a 65 536-clip launch): traffic == algorithmic bytes
-FRONTEND_DRAM_BYTES_PER_CLIP_NCU = (2.097426e9 + 211.971328e6) / 65536
+# profiles/r1_ncu_mfcc_kernel.txt (2.0977 GB + 211.0 MB over a 65 536-clip launch): traffic == algorithmic bytes
+FRONTEND_DRAM_BYTES_PER_CLIP_NCU = (2.097739e9 + 210.983680e6) / 65536
 UTT = 63  # windows per CTC utterance
 CPU_BATCH = 200
 
