@@ -1,4 +1,5 @@
 // libwwb200.so -- C ABI over the sm_100a kernels (see include/ww_b200.h for the contract).
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1041,7 +1042,8 @@ struct ww_session {
     int warmup = 64, refractory = 313;
     long long n_samples = 0;   // samples received per stream
     long long t_done = 0;      // frames computed per stream
-    // device: PCM tail + chunk (ping-pong), feature history 62 + new frames (ping-pong), logits
+    // device: PCM history + chunk and feature history 62 + new frames, both appended in place; the retained part is
+    // moved to the front of the other buffer only when the room behind it is used up (every few dozen pushes)
     int16_t* d_pcm[2] = {nullptr, nullptr};
     float* d_feat[2] = {nullptr, nullptr};
     float* d_logits = nullptr;
@@ -1049,6 +1051,7 @@ struct ww_session {
     int pcm_cur = 0, feat_cur = 0;
     long long g0 = 0;          // global sample index of column 0 of d_pcm[cur]
     int tail_len = 0;          // valid samples in d_pcm[cur] per stream
+    int feat_base = 0;         // column of d_feat[cur] where the 62-frame history starts
     int pcm_cap = 0, feat_cap = 0, max_new = 0;
     float* h_logits = nullptr;   // pinned: [n_streams][max_new][C], so the D2H of every push is asynchronous DMA
     size_t h_logits_n = 0;       // floats valid after the last write
@@ -1079,9 +1082,10 @@ extern "C" int ww_session_open(ww_ctx* ctx, int n_streams, int max_chunk_samples
     s->thr = threshold_logit;
     s->warmup = warmup_frames;
     s->refractory = refractory_frames;
-    s->pcm_cap = kSessTail + max_chunk_samples;
     s->max_new = (kSessTail + max_chunk_samples) / WW_HOP + 2;
-    s->feat_cap = ((WW_WINDOW_FRAMES - 1) + s->max_new + 3) / 4 * 4;
+    // room behind the retained tail / history: chunks and frames are appended until it is used up
+    s->pcm_cap = kSessTail + std::max(4 * max_chunk_samples, 8192);
+    s->feat_cap = ((WW_WINDOW_FRAMES - 1) + std::max(4 * s->max_new, 128) + 3) / 4 * 4;
     s->reset_f.assign(n_streams, 0);
     auto bail = [&](cudaError_t e, const char* what) {
         cuda_fail(ctx, e, what);
@@ -1163,7 +1167,7 @@ static int session_advance(ww_session* s, int chunk_samples) {
     // frames whose 320 taps are complete: 256 t + 159 < n_samples
     const long long t_count = s->n_samples >= 160 ? (s->n_samples - 160) / WW_HOP + 1 : 0;
     const int n_new = (int)(t_count - s->t_done);
-    float* feat = s->d_feat[s->feat_cur];
+    float* feat = s->d_feat[s->feat_cur] + s->feat_base;
     const int H = WW_WINDOW_FRAMES - 1;  // 62 frames of history in front of the new ones
     long long n_win_total = 0;
     int j_lo = 0, n_win = 0;
@@ -1190,20 +1194,35 @@ static int session_advance(ww_session* s, int chunk_samples) {
                                s->st));
         }
     }
-    // retain what the next frames need: PCM from align8(256 t_count - 161), features: the last 62 frames
+    // retain what the next frames need: PCM from align8(256 t_count - 161), features: the last 62 frames.  Both stay
+    // where they are while the next push still fits behind them; otherwise they move to the front of the other buffer
     const long long g0_next = t_count == 0 ? 0 : ((WW_HOP * t_count - 161) / 8) * 8;
+    const bool move_pcm = L + s->max_chunk > s->pcm_cap;
     const int keep = (int)(s->g0 + L - g0_next);
-    CK(cudaMemcpy2DAsync(s->d_pcm[s->pcm_cur ^ 1], sizeof(int16_t) * s->pcm_cap, pcm + (g0_next - s->g0),
-                         sizeof(int16_t) * s->pcm_cap, sizeof(int16_t) * keep, S, cudaMemcpyDeviceToDevice, s->st));
-    if (n_new > 0)
-        CK(cudaMemcpy2DAsync(s->d_feat[s->feat_cur ^ 1], sizeof(float) * s->feat_cap, feat + n_new, sizeof(float) * s->feat_cap,
-                             sizeof(float) * H, (size_t)S * WW_N_MFCC, cudaMemcpyDeviceToDevice, s->st));
+    if (move_pcm)
+        CK(cudaMemcpy2DAsync(s->d_pcm[s->pcm_cur ^ 1], sizeof(int16_t) * s->pcm_cap, pcm + (g0_next - s->g0),
+                             sizeof(int16_t) * s->pcm_cap, sizeof(int16_t) * keep, S, cudaMemcpyDeviceToDevice, s->st));
+    const int feat_base_next = s->feat_base + (n_new > 0 ? n_new : 0);
+    const bool move_feat = feat_base_next + H + s->max_new > s->feat_cap;
+    if (move_feat)
+        CK(cudaMemcpy2DAsync(s->d_feat[s->feat_cur ^ 1], sizeof(float) * s->feat_cap, s->d_feat[s->feat_cur] + feat_base_next,
+                             sizeof(float) * s->feat_cap, sizeof(float) * H, (size_t)S * WW_N_MFCC, cudaMemcpyDeviceToDevice,
+                             s->st));
     CK(cudaStreamSynchronize(s->st));
-    s->pcm_cur ^= 1;
-    if (n_new > 0) s->feat_cur ^= 1;
+    if (move_pcm) {
+        s->pcm_cur ^= 1;
+        s->g0 = g0_next;
+        s->tail_len = keep;
+    } else {
+        s->tail_len = L;
+    }
+    if (move_feat) {
+        s->feat_cur ^= 1;
+        s->feat_base = 0;
+    } else {
+        s->feat_base = feat_base_next;
+    }
     s->h_logits_n = n_win > 0 ? (size_t)n_win_total * C : 0;
-    s->g0 = g0_next;
-    s->tail_len = keep;
     // host-side hit logic per stream (esp_wake_word_detector.cpp:38-44,245-258)
     if (n_win > 0) {
         for (int g = 0; g < S; ++g) {
