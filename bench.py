@@ -90,6 +90,48 @@ def synth_pcm(n_clips, device, seed, chunk=32768, pin=False):
 
 
 # ------------------------------------------------------------------------------------------------
+# host placement for the e2e leg at N > 1: each rank's pinned buffers on the NUMA node its GPU hangs off
+# ------------------------------------------------------------------------------------------------
+def bind_host_to_gpu_node(local):
+    """Prefer host memory (and CPUs, when the process is allowed any there) of the GPU's own NUMA node, so that the
+    eight H2D streams of an eight-rank run do not all read one socket's DRAM across the inter-socket link.
+    Everything here is best effort: a container without the topology files, or without permission for
+    set_mempolicy, leaves the process as it was.  Returns what was done, for the JSON line."""
+    import ctypes
+    import torch
+
+    info = {"node": None, "mempolicy": "unchanged", "cpus": len(os.sched_getaffinity(0))}
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        node = int(open(base + "/numa_node").read().strip())
+        info["node"] = node
+        if node < 0:
+            return info
+        try:
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = ctypes.c_ulong(1 << node)
+            MPOL_PREFERRED, SYS_set_mempolicy = 1, 238            # x86_64
+            rc = libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(8 * ctypes.sizeof(mask)))
+            info["mempolicy"] = "preferred" if rc == 0 else "errno %d" % ctypes.get_errno()
+        except Exception as e:  # noqa: BLE001
+            info["mempolicy"] = "failed: %s" % type(e).__name__
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            if part:
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        mine = cpus & os.sched_getaffinity(0)
+        if mine:
+            os.sched_setaffinity(0, mine)
+            info["cpus"] = len(mine)
+    except Exception as e:  # noqa: BLE001
+        info["error"] = "%s: %s" % (type(e).__name__, e)
+    return info
+
+
+# ------------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
@@ -274,6 +316,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a GPU (ww_b200 has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    host_numa = bind_host_to_gpu_node(local) if world > 1 and not os.environ.get("WW_NO_NUMA_BIND") else None
     if world > 1:
         # keep stdout to the single JSON line: NCCL's version banner goes to stderr
         os.environ["NCCL_DEBUG"] = os.environ.get("WW_NCCL_DEBUG", "WARN")
@@ -394,6 +437,13 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = world * eb / float(te.item())
+    if host_numa is not None:
+        # every rank's placement: [NUMA node of its GPU (-1 unknown), memory policy set, CPUs it may run on]
+        mine = torch.tensor([-1 if host_numa["node"] is None else host_numa["node"],
+                             1 if host_numa["mempolicy"] == "preferred" else 0, host_numa["cpus"]], device=dev)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        host_numa = dict(host_numa, per_rank=[[int(v) for v in t.tolist()] for t in every])
 
     if rank == 0:
         chunk = int(os.environ.get("WW_CHUNK_CLIPS", "131072"))  # ww_api.cu kScratchClips: clips per fused frontend + CNN pair
@@ -413,7 +463,8 @@ def run_ours(args):
             "config": workload_config(args, world),
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": eb * 32000, "d2h_bytes_per_step": eb * 5,
-                    "clips_per_step_per_gpu": eb, "api": "WakeWordScorer.score_host -> ww_score_clips_host (pinned host "
+                    "clips_per_step_per_gpu": eb, "host_numa": host_numa,
+                    "api": "WakeWordScorer.score_host -> ww_score_clips_host (pinned host "
                     "PCM in, host logits+decisions out)"},
             "gpu_launches": launches,
             "roofline": roof,
