@@ -140,6 +140,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.nv_rows, self._halt = [], threading.Event()
 
     def start(self):
         try:
@@ -149,6 +150,29 @@ class ClockSampler:
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
+        # NVML directly as well (30 ms period; 10 ms costs the timed region about 1 %): nvidia-smi's loop gives only a couple of rows inside a 0.2 s region
+        self.nv_rows, self._halt = [], threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def poll():
+                while not self._halt.is_set():
+                    try:
+                        self.nv_rows.append((time.time(), pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), mx,
+                                             int(get_reasons(h))))
+                    except Exception:
+                        return
+                    time.sleep(0.03)
+
+            threading.Thread(target=poll, daemon=True).start()
+        except Exception:
+            pass
 
     def _read(self):
         for line in self.proc.stdout:
@@ -171,6 +195,15 @@ class ClockSampler:
                         reasons.add(nm)
             except Exception:
                 pass
+        self._halt.set()
+        # NVML reason bits (nvml.h): sw_power_cap 0x4, hw_slowdown 0x8, sw_thermal 0x20, hw_thermal 0x40
+        bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        for ts, c, m, mask in list(self.nv_rows):
+            if ts < t0 or ts > t1:
+                continue
+            sm.append(float(c))
+            mx.append(float(m))
+            reasons.update(nm for nm, b in bits.items() if mask & b)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
