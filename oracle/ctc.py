@@ -14,8 +14,8 @@ Restated reference code:
   ml_models/ctc.py:369,393-401  nn.CTCLoss(blank=0)  (reduction='mean')
 
 The three decoders cannot be imported from the reference (both scripts train
-at import time and need librosa/matplotlib), so they are restated verbatim in
-behaviour.  The loss is pinned by PyTorch itself: `ctc_loss_torch` calls
+at import time and need librosa/matplotlib), so their behaviour is restated in our own
+code.  The loss is pinned by PyTorch itself: `ctc_loss_torch` calls
 torch.nn.functional.ctc_loss on CPU; `ctc_loss_numpy64` is an independent
 alpha/beta implementation checked against it (tests/test_oracle_ctc.py).
 The reference holds no golden CTC vectors.

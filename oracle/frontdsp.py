@@ -7,7 +7,7 @@
 
 Pinning: the integer path has no float freedom -- numpy restatement == plain-C port on random and extreme inputs
 (tests/test_oracle_frontdsp.py), including the int16 wrap of the mix for |weighted >> 7| > 32767.  The reference's
-.cpp cannot be compiled here (FreeRTOS / esp-dl / I2S dependencies), so the C port restates lines 103-121 verbatim.
+.cpp cannot be compiled here (FreeRTOS / esp-dl / I2S dependencies), so the C port restates lines 103-121 operation by operation.
 augment_waveform is checked against the reference's own function imported from /root/reference when present.
 """
 from __future__ import annotations
