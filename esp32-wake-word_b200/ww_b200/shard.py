@@ -57,3 +57,21 @@ def stream_segments(n_samples: int, world: int):
         s1 = min(n_samples, HOP * (w1 + WINDOW - 2) + 256) if w1 > w0 else s0
         out.append((s0, s1, w0, w1 - w0))
     return out
+
+
+def ctc_mean_across_ranks(nll: torch.Tensor, target_lengths, group=None):
+    """`reduction='mean'` of nn.CTCLoss (ml_models/test.py:89, ml_models/ctc.py:369: per-utterance loss / target
+    length, then the batch mean) when the utterances of one batch are sharded over the ranks.
+
+    nll: this rank's per-utterance losses [B_local] (`ctc_loss(..., reduction='none')`).  One all-reduce of two
+    scalars (sum of loss/length, utterance count) is the only exchange.  Returns (loss, global_mean):
+    `loss` = this rank's share, sum_local(nll_i / len_i) / N_global — differentiable, and the sum over ranks of its
+    gradients (what the weight-gradient all-reduce computes) is the gradient of the global mean; `global_mean` is
+    the detached value every rank reports."""
+    tl = torch.as_tensor(target_lengths).to(device=nll.device, dtype=nll.dtype).clamp_min(1)
+    local = (nll / tl).sum()
+    stats = torch.stack([local.detach(), torch.tensor(float(nll.numel()), device=nll.device, dtype=nll.dtype)])
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+    n_global = stats[1].clamp_min(1)
+    return local / n_global, stats[0] / n_global

@@ -66,3 +66,45 @@ def test_stream_segments_cover_windows_with_halo():
         assert s0 <= max(first - 1, 0) and s1 >= min(last + 1, n)
     # halo: consecutive segments overlap by 62 frames plus context
     assert segs[0][1] - segs[1][0] == 62 * 256 + 513 - 256 or segs[0][1] > segs[1][0]
+
+
+def _ctc_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # the same 7-utterance batch on every rank (seeded); each rank owns a contiguous range of utterances
+        g = torch.Generator().manual_seed(5)
+        T, B, C, S = 63, 7, 3, 2
+        lp_all = torch.randn((T, B, C), generator=g).log_softmax(-1)
+        tg_all = torch.randint(1, C, (B, S), generator=g)
+        tl_all = torch.tensor([1, 2, 2, 1, 2, 1, 2])
+        il_all = torch.full((B,), T)
+        # single-process reference: nn.CTCLoss(reduction='mean') over the whole batch
+        lp_ref = lp_all.clone().requires_grad_(True)
+        want = torch.nn.functional.ctc_loss(lp_ref, tg_all, il_all, tl_all, blank=0, reduction="mean")
+        want.backward()
+        a, b = shard.shard_range(B, rank, world)
+        lp = lp_all[:, a:b].clone().requires_grad_(True)
+        nll = torch.nn.functional.ctc_loss(lp, tg_all[a:b], il_all[a:b], tl_all[a:b], blank=0, reduction="none")
+        loss, mean = shard.ctc_mean_across_ranks(nll, tl_all[a:b])
+        loss.backward()
+        ok = torch.allclose(mean, want.detach(), rtol=1e-6, atol=1e-7)
+        ok = ok and torch.allclose(lp.grad, lp_ref.grad[:, a:b], rtol=1e-5, atol=1e-7)
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_ctc_mean_equals_single_process_mean():
+    """8e: utterances sharded over two ranks; one 2-scalar all-reduce reproduces reduction='mean' and its gradient."""
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_ctc_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world))
+
+
+def test_ctc_mean_single_process_is_plain_mean():
+    nll = torch.tensor([2.0, 3.0, 8.0], requires_grad=True)
+    loss, mean = shard.ctc_mean_across_ranks(nll, [1, 0, 4])      # a zero target length is clamped like torch does
+    assert torch.allclose(loss, torch.tensor((2.0 + 3.0 + 2.0) / 3)) and torch.allclose(mean, loss.detach())
