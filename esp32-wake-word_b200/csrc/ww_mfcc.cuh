@@ -41,13 +41,6 @@
 #ifndef WW_TW1_HALF
 #define WW_TW1_HALF 0
 #endif
-// WW_TW1_REGS = R: the first R of the 8 inter-pass twiddle quads (lane constants) live in registers instead of
-// being re-read from smem for every frame pair (R LDS.128 = 4 R wavefronts per pair, 128 R of the 6.0 k wavefronts
-// per clip).  Prepared at the end of round 1, not yet measured on the GPU: the clip instantiation compiles to
-// 114 registers for R = 2 and 117 for R = 3 (116 for R = 0), no spills; the default build is unchanged (same SASS).
-#ifndef WW_TW1_REGS
-#define WW_TW1_REGS 0
-#endif
 
 namespace ww {
 
@@ -359,11 +352,6 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
 #if WW_TW1_HALF
     const cpx tw1_8 = cpk(s_tw1[16 * 4 + l16].x, s_tw1[16 * 4 + l16].y);
 #endif
-#if WW_TW1_REGS > 0
-    float4 tw1r[WW_TW1_REGS];
-    #pragma unroll
-    for (int j = 0; j < WW_TW1_REGS; ++j) tw1r[j] = s_tw1[16 * j + l16];
-#endif
 
     // Per-CTA software pipeline over this CTA's blocks (one CTA-wide barrier per block):
     //   iteration k:  mel(k-1) | stage PCM(k) + edge taps | FFT(k) first pass | DCT(k-1) | FFT(k) second pass | barrier
@@ -632,11 +620,7 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
 #else
     #pragma unroll
             for (int j = 0; j < 8; ++j) {
-#if WW_TW1_REGS > 0
-                const float4 tw = j < WW_TW1_REGS ? tw1r[j < WW_TW1_REGS ? j : 0] : s_tw1[16 * j + l16];
-#else
                 const float4 tw = s_tw1[16 * j + l16];
-#endif
                 if (j > 0) v[2 * j] = p_cmul(v[2 * j], tw.x, tw.y);
                 v[2 * j + 1] = p_cmul(v[2 * j + 1], tw.z, tw.w);
             }
