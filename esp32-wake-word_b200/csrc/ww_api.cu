@@ -1700,3 +1700,33 @@ extern "C" float* ww_extract_mfcc(const float* signal, int signal_len, int sampl
 }
 
 extern "C" void ww_free_mfcc(float* mfcc) { free(mfcc); }
+
+// mfcc.c:530-553: a float accumulator in array order, exactly as the reference sums
+extern "C" long long ww_analyze_mfcc_range(const float* mfcc_host, long long size, const char* label, ww_mfcc_range* out) {
+    if (!mfcc_host || size <= 0) return WW_ERR_INVALID;
+    float lo = INFINITY, hi = -INFINITY, sum = 0.f;
+    long long valid = 0;
+    for (long long i = 0; i < size; ++i) {
+        const float v = mfcc_host[i];
+        if (std::isnan(v) || std::isinf(v)) continue;
+        if (v < lo) lo = v;
+        if (v > hi) hi = v;
+        sum += v;
+        ++valid;
+    }
+    if (out) {
+        out->min_val = lo;
+        out->max_val = hi;
+        out->avg = valid > 0 ? sum / (float)valid : 0.f;
+        out->valid = valid;
+        out->size = size;
+    }
+    if (label) {
+        if (valid > 0)
+            fprintf(stderr, "%s MFCC Range: min=%.6f, max=%.6f, avg=%.6f, valid=%lld/%lld\n", label, lo, hi, sum / (float)valid,
+                    valid, size);
+        else
+            fprintf(stderr, "%s MFCC: No valid values\n", label);
+    }
+    return valid;
+}

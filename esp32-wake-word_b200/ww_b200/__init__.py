@@ -4,8 +4,8 @@ Mirrors the reference's `ml_models` entry points (feature, model-forward and CTC
 libwwb200.so (hand-written sm_100a CUDA behind a C ABI, include/ww_b200.h).  No CPU fallback.
 """
 from ._lib import WWError, get_context, load_library  # noqa: F401
-from .features import (add_random_noise, augment_audio_waveform, cmvn_batch, extract_features,  # noqa: F401
-                       load_wav, mfcc_batch, normalize_mfcc, pad_audio)
+from .features import (add_random_noise, analyze_mfcc_range, augment_audio_waveform, cmvn_batch,  # noqa: F401
+                       extract_features, load_wav, mfcc_batch, normalize_mfcc, pad_audio)
 from .model import LightweightKWS, WakeWordScorer, forward_int8, score_clips_int8, XIAOA_EXPONENTS  # noqa: F401
 from .ctc import (CTCKeywordDetector, CTCLoss, ctc_greedy_decode, ctc_loss, decode_predictions,  # noqa: F401
                   greedy_batch)

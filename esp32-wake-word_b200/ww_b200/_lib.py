@@ -30,7 +30,7 @@ EXPORTS = [
     "ww_mfcc_batch", "ww_cmvn", "ww_cnn_forward", "ww_quantize_weights_i8", "ww_cnn_forward_i8", "ww_score_clips", "ww_score_clips_host",
     "ww_stream_score", "ww_stream_events", "ww_session_open", "ww_session_write", "ww_session_write_tdm", "ww_session_poll",
     "ww_session_windows", "ww_session_last_logits", "ww_session_close", "ww_ctc_greedy", "ww_ctc_loss_workspace_bytes",
-    "ww_ctc_loss_fwd", "ww_ctc_loss_bwd", "ww_debug_tc", "ww_debug_esp_tables", "ww_extract_mfcc", "ww_free_mfcc",
+    "ww_ctc_loss_fwd", "ww_ctc_loss_bwd", "ww_debug_tc", "ww_debug_esp_tables", "ww_extract_mfcc", "ww_free_mfcc", "ww_analyze_mfcc_range",
     "ww_set_option", "ww_wav_parse", "ww_wav_load_batch", "ww_wav_write", "ww_tdm_downmix", "ww_augment_waveform",
 ]
 
@@ -41,6 +41,12 @@ class WavInfo(C.Structure):
                 ("num_channels", C.c_uint16), ("sample_rate", C.c_uint32), ("byte_rate", C.c_uint32),
                 ("block_align", C.c_uint16), ("bits_per_sample", C.c_uint16), ("data_length", C.c_uint32),
                 ("raw_data_pos", C.c_uint32), ("n_samples", C.c_uint32), ("valid", C.c_int32)]
+
+
+class MfccRange(C.Structure):
+    """ww_mfcc_range (include/ww_b200.h): what analyze_mfcc_range (mfcc.c:530-553) logs."""
+    _fields_ = [("min_val", C.c_float), ("max_val", C.c_float), ("avg", C.c_float), ("valid", C.c_longlong),
+                ("size", C.c_longlong)]
 
 
 class WWError(RuntimeError):
@@ -105,6 +111,8 @@ def load_library():
         lib.ww_extract_mfcc.restype = C.POINTER(C.c_float)
         lib.ww_free_mfcc.argtypes = [C.POINTER(C.c_float)]
         lib.ww_free_mfcc.restype = None
+        lib.ww_analyze_mfcc_range.argtypes = [vp, i64, C.c_char_p, C.POINTER(MfccRange)]
+        lib.ww_analyze_mfcc_range.restype = i64
         lib.ww_set_option.argtypes = [vp, i32, i32]
         lib.ww_wav_parse.argtypes = [vp, C.c_size_t, i32, C.POINTER(WavInfo)]
         lib.ww_wav_load_batch.argtypes = [C.POINTER(C.c_char_p), i32, i32, i32, vp, C.POINTER(WavInfo), C.POINTER(i32)]

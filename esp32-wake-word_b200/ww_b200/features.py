@@ -127,6 +127,22 @@ def cmvn_batch(feats, device_style=False):
     return out
 
 
+def analyze_mfcc_range(mfcc, label=None):
+    """analyze_mfcc_range of main/esp_mfcc/mfcc.h:16 (mfcc.c:530-553): min / max / mean over the finite values of a
+    feature array (host work; a CUDA tensor is copied back first).  With `label` the reference's log line goes to
+    stderr.  Returns {"min", "max", "avg", "valid", "size"}; `valid` = 0 means no finite value."""
+    import ctypes as C
+
+    x = mfcc.detach().cpu().numpy() if isinstance(mfcc, torch.Tensor) else np.asarray(mfcc)
+    x = np.ascontiguousarray(x, dtype=np.float32).ravel()
+    out = L.MfccRange()
+    n = L.load_library().ww_analyze_mfcc_range(x.ctypes.data_as(C.c_void_p), x.size,
+                                               None if label is None else str(label).encode(), C.byref(out))
+    if n < 0:
+        raise L.WWError(f"ww_analyze_mfcc_range failed ({n}): empty array")
+    return {"min": out.min_val, "max": out.max_val, "avg": out.avg, "valid": int(out.valid), "size": int(out.size)}
+
+
 def normalize_mfcc(mfcc, method="standardization"):
     """Reference signature: mfcc [13, T] (or [B, 13, T]) -> normalised tensor of the same shape.
 

@@ -250,6 +250,18 @@ float* ww_extract_mfcc(const float* signal, int signal_len, int sampling_rate, i
                        int n_fft, int n_filters, int n_mfcc);
 void ww_free_mfcc(float* mfcc);
 
+/* analyze_mfcc_range() of main/esp_mfcc/mfcc.h:16 (mfcc.c:530-553): minimum, maximum and mean over the finite
+ * values of a HOST feature array, NaN / Inf skipped.  The reference only logs the line
+ * "<label> MFCC Range: min=…, max=…, avg=…, valid=n/size" (ESP_LOGI; ESP_LOGE "No valid values" when none is
+ * finite); here the same line goes to stderr when `label` is not NULL and the numbers are returned through `out`
+ * (may be NULL).  Returns the number of finite values, or WW_ERR_INVALID for a NULL array or size <= 0 (the
+ * reference returns silently).  Host only: no context, no GPU. */
+typedef struct {
+    float min_val, max_val, avg;
+    long long valid, size;
+} ww_mfcc_range;
+long long ww_analyze_mfcc_range(const float* mfcc_host, long long size, const char* label, ww_mfcc_range* out);
+
 #ifdef __cplusplus
 }
 #endif

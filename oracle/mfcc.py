@@ -198,6 +198,30 @@ def mfcc_numpy64(x, tables="fp64", return_intermediates=False):
 # ----------------------------------------------------------------------------
 # normalisation
 # ----------------------------------------------------------------------------
+def analyze_range(mfcc):
+    """analyze_mfcc_range, main/esp_mfcc/mfcc.c:530-553: min / max / mean over the finite values with a FLOAT
+    accumulator in array order (the mean of a long array drifts accordingly), and the line the reference logs.
+    Pinned by tests/golden/analyze_range.npz (the reference's own function, tests/golden/make_golden_range.py)."""
+    x = np.asarray(mfcc, np.float32).ravel()
+    ok = np.isfinite(x)
+    v = x[ok]
+    if v.size == 0:
+        return {"min": np.inf, "max": -np.inf, "avg": 0.0, "valid": 0, "size": int(x.size)}
+    total = np.float32(0.0)
+    # sequential float32 sum (np.sum is pairwise and would hide the drift)
+    total = np.add.accumulate(v, dtype=np.float32)[-1]
+    return {"min": float(v.min()), "max": float(v.max()), "avg": float(np.float32(total) / np.float32(v.size)),
+            "valid": int(v.size), "size": int(x.size)}
+
+
+def analyze_range_line(label, r):
+    """The ESP_LOGI / ESP_LOGE text of mfcc.c:548-551."""
+    if r["valid"] == 0:
+        return "E %s MFCC: No valid values" % label
+    return "%s MFCC Range: min=%.6f, max=%.6f, avg=%.6f, valid=%d/%d" % (label, r["min"], r["max"], r["avg"], r["valid"],
+                                                                          r["size"])
+
+
 def normalize_mfcc(mfcc, method="standardization"):
     """extract_mfcc.py:47-88.  mfcc: [..., 13, T] (torch tensor or ndarray).
 

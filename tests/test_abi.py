@@ -92,3 +92,32 @@ def test_refractory_frames():
     import ww_b200
 
     assert ww_b200.refractory_frames() == ostream.refractory_frames() == 313
+
+
+def test_analyze_mfcc_range_logs_what_the_reference_logs(lib, capfd):
+    """ww_analyze_mfcc_range (host only, no GPU) against the golden log lines of the reference's own
+    analyze_mfcc_range (main/esp_mfcc/mfcc.c:530-553): same float accumulator, same text, NaN / Inf skipped."""
+    import ctypes as C
+
+    from oracle import mfcc as omfcc
+    from ww_b200 import _lib as L
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "analyze_range.npz"))
+    for name in [k[2:] for k in g.files if k.startswith("x_")]:
+        x = np.ascontiguousarray(g["x_" + name], np.float32)
+        out = L.MfccRange()
+        n = lib.ww_analyze_mfcc_range(x.ctypes.data_as(C.c_void_p), x.size, name.encode(), C.byref(out))
+        want = str(g["line_" + name])
+        logged = capfd.readouterr().err.strip()
+        if want.startswith("E "):
+            assert n == 0 and out.valid == 0 and logged == want[2:]
+        else:
+            assert logged == want
+            r = {"min": out.min_val, "max": out.max_val, "avg": out.avg, "valid": out.valid, "size": out.size}
+            assert omfcc.analyze_range_line(name, r) == want and n == out.valid
+    assert lib.ww_analyze_mfcc_range(None, 5, None, None) < 0          # the reference returns silently
+    x = np.zeros(4, np.float32)
+    assert lib.ww_analyze_mfcc_range(x.ctypes.data_as(C.c_void_p), 0, None, None) < 0
+    import ww_b200
+    assert ww_b200.analyze_mfcc_range(np.array([1.0, np.nan, 3.0], np.float32)) == \
+        {"min": 1.0, "max": 3.0, "avg": 2.0, "valid": 2, "size": 3}

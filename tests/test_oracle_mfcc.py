@@ -80,3 +80,14 @@ def test_synth_is_deterministic():
     b = om.synth_clips_int16(4, seed=1234, start_index=4)
     assert (a[4:] == b).all()
     assert (a[3, 9000:] == 0).all() and a[3, :9000].any()
+
+
+def test_analyze_range_matches_the_references_own_log_lines():
+    """oracle.mfcc.analyze_range against what the reference's analyze_mfcc_range (mfcc.c:530-553) logged for the same
+    arrays (tests/golden/analyze_range.npz, made by tests/golden/make_golden_range.py from the reference's mfcc.c)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "analyze_range.npz"))
+    names = [k[2:] for k in g.files if k.startswith("x_")]
+    assert len(names) == 6
+    for name in names:
+        r = om.analyze_range(g["x_" + name])
+        assert om.analyze_range_line(name, r) == str(g["line_" + name]), name
