@@ -1701,6 +1701,61 @@ extern "C" float* ww_extract_mfcc(const float* signal, int signal_len, int sampl
 
 extern "C" void ww_free_mfcc(float* mfcc) { free(mfcc); }
 
+// ------------------------------------------------------------------------------------------------
+// host ring buffer (main/ring_buffer/ring_buffer.h:17-33, intended semantics of ring_buffer.c:57-117)
+// ------------------------------------------------------------------------------------------------
+struct ww_ring {
+    std::vector<float> buf;
+    int head = 0;   // index of the oldest retained value
+    int count = 0;  // retained values (<= buf.size())
+};
+
+extern "C" int ww_ring_create(ww_ring** out, int buffer_len) {
+    if (!out) return WW_ERR_INVALID;
+    *out = nullptr;
+    if (buffer_len < 1 || buffer_len > 65535) return WW_ERR_INVALID;  // uint16_t buffer_len in the reference
+    ww_ring* r = new (std::nothrow) ww_ring();
+    if (!r) return WW_ERR_NOMEM;
+    r->buf.assign((size_t)buffer_len, 0.f);
+    *out = r;
+    return WW_OK;
+}
+
+extern "C" void ww_ring_delete(ww_ring* r) { delete r; }
+
+extern "C" int ww_ring_count(const ww_ring* r) { return r ? r->count : WW_ERR_INVALID; }
+
+extern "C" int ww_ring_write(ww_ring* r, const float* data, long long data_len) {
+    if (!r || !data || data_len <= 0) return WW_ERR_INVALID;
+    const int n = (int)r->buf.size();
+    if (data_len > n) {  // only the last buffer_len values survive
+        data += data_len - n;
+        data_len = n;
+    }
+    int tail = r->head + r->count;  // next write position
+    if (tail >= n) tail -= n;
+    const int first = std::min<long long>(data_len, n - tail);
+    memcpy(r->buf.data() + tail, data, sizeof(float) * (size_t)first);
+    memcpy(r->buf.data(), data + first, sizeof(float) * (size_t)(data_len - first));
+    const long long total = (long long)r->count + data_len;
+    if (total > n) {  // the oldest values were overwritten
+        r->head = (int)((r->head + (total - n)) % n);
+        r->count = n;
+    } else {
+        r->count = (int)total;
+    }
+    return WW_OK;
+}
+
+extern "C" int ww_ring_read(const ww_ring* r, float* data, int data_len) {
+    if (!r || !data || data_len <= 0 || data_len > r->count) return WW_ERR_INVALID;
+    const int n = (int)r->buf.size();
+    const int first = std::min(data_len, n - r->head);
+    memcpy(data, r->buf.data() + r->head, sizeof(float) * (size_t)first);
+    memcpy(data + first, r->buf.data(), sizeof(float) * (size_t)(data_len - first));
+    return WW_OK;
+}
+
 // mfcc.c:530-553: a float accumulator in array order, exactly as the reference sums
 extern "C" long long ww_analyze_mfcc_range(const float* mfcc_host, long long size, const char* label, ww_mfcc_range* out) {
     if (!mfcc_host || size <= 0) return WW_ERR_INVALID;

@@ -9,7 +9,7 @@ from .features import (add_random_noise, analyze_mfcc_range, augment_audio_wavef
 from .model import LightweightKWS, WakeWordScorer, forward_int8, score_clips_int8, XIAOA_EXPONENTS  # noqa: F401
 from .ctc import (CTCKeywordDetector, CTCLoss, ctc_greedy_decode, ctc_loss, decode_predictions,  # noqa: F401
                   greedy_batch)
-from .stream import StreamScorer, StreamSession, events, refractory_frames  # noqa: F401
+from .stream import RingBuffer, StreamScorer, StreamSession, events, refractory_frames  # noqa: F401
 from .onnx_reader import load_kws_state_dict, read_initializers  # noqa: F401
 from .wav import load_wav_batch, parse_wav, read_wav, score_wav_dir, write_wav  # noqa: F401
 from .frontdsp import augment_batch, tdm_downmix  # noqa: F401

@@ -30,7 +30,7 @@ EXPORTS = [
     "ww_mfcc_batch", "ww_cmvn", "ww_cnn_forward", "ww_quantize_weights_i8", "ww_cnn_forward_i8", "ww_score_clips", "ww_score_clips_host",
     "ww_stream_score", "ww_stream_events", "ww_session_open", "ww_session_write", "ww_session_write_tdm", "ww_session_poll",
     "ww_session_windows", "ww_session_last_logits", "ww_session_close", "ww_ctc_greedy", "ww_ctc_loss_workspace_bytes",
-    "ww_ctc_loss_fwd", "ww_ctc_loss_bwd", "ww_debug_tc", "ww_debug_esp_tables", "ww_extract_mfcc", "ww_free_mfcc", "ww_analyze_mfcc_range",
+    "ww_ctc_loss_fwd", "ww_ctc_loss_bwd", "ww_debug_tc", "ww_debug_esp_tables", "ww_extract_mfcc", "ww_free_mfcc", "ww_analyze_mfcc_range", "ww_ring_create", "ww_ring_delete", "ww_ring_write", "ww_ring_read", "ww_ring_count",
     "ww_set_option", "ww_wav_parse", "ww_wav_load_batch", "ww_wav_write", "ww_tdm_downmix", "ww_augment_waveform",
 ]
 
@@ -113,6 +113,12 @@ def load_library():
         lib.ww_free_mfcc.restype = None
         lib.ww_analyze_mfcc_range.argtypes = [vp, i64, C.c_char_p, C.POINTER(MfccRange)]
         lib.ww_analyze_mfcc_range.restype = i64
+        lib.ww_ring_create.argtypes = [C.POINTER(vp), i32]
+        lib.ww_ring_delete.argtypes = [vp]
+        lib.ww_ring_delete.restype = None
+        lib.ww_ring_write.argtypes = [vp, vp, i64]
+        lib.ww_ring_read.argtypes = [vp, vp, i32]
+        lib.ww_ring_count.argtypes = [vp]
         lib.ww_set_option.argtypes = [vp, i32, i32]
         lib.ww_wav_parse.argtypes = [vp, C.c_size_t, i32, C.POINTER(WavInfo)]
         lib.ww_wav_load_batch.argtypes = [C.POINTER(C.c_char_p), i32, i32, i32, vp, C.POINTER(WavInfo), C.POINTER(i32)]

@@ -159,3 +159,44 @@ class StreamSession:
             self.close()
         except Exception:
             pass
+
+
+class RingBuffer:
+    """Host float ring, drop-in for main/ring_buffer/ring_buffer.h:17-33 (`create_rinbuffer` / `write_rinbuffer` /
+    `read_rinbuffer` / `delete_ringbuffer`): keeps the last `buffer_len` values written; `read(n)` returns the oldest
+    n retained values without consuming them (ring_buffer.c:57-117, intended semantics).  Host only."""
+
+    def __init__(self, buffer_len):
+        self._lib = L.load_library()
+        self._h = C.c_void_p()
+        rc = self._lib.ww_ring_create(C.byref(self._h), int(buffer_len))
+        if rc != 0:
+            raise L.WWError(f"ww_ring_create failed ({rc}): buffer_len must be 1..65535")
+        self.buffer_len = int(buffer_len)
+
+    def write(self, data):
+        x = np.ascontiguousarray(np.asarray(data, dtype=np.float32).ravel())
+        rc = self._lib.ww_ring_write(self._h, x.ctypes.data_as(C.c_void_p), x.size)
+        if rc != 0:
+            raise L.WWError(f"ww_ring_write failed ({rc}): empty write")
+
+    def __len__(self):
+        return int(self._lib.ww_ring_count(self._h))
+
+    def read(self, n):
+        out = np.empty(int(n), np.float32)
+        rc = self._lib.ww_ring_read(self._h, out.ctypes.data_as(C.c_void_p), int(n))
+        if rc != 0:
+            raise L.WWError(f"ww_ring_read failed ({rc}): {n} values asked, {len(self)} held")
+        return out
+
+    def close(self):
+        if self._h:
+            self._lib.ww_ring_delete(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -262,6 +262,22 @@ typedef struct {
 } ww_mfcc_range;
 long long ww_analyze_mfcc_range(const float* mfcc_host, long long size, const char* label, ww_mfcc_range* out);
 
+/* ---- host ring buffer: drop-in for main/ring_buffer/ring_buffer.h:17-33 ------------------------------------- */
+/* The float ring the firmware stages samples / frames in, with the semantics ring_buffer.c:57-117 intends: a write
+ * appends and, once the ring is full, overwrites the oldest values, so the ring always holds the last `buffer_len`
+ * values written (a write longer than the ring keeps its last buffer_len values, ring_buffer.c:63-66); a read copies
+ * the OLDEST data_len retained values in writing order without consuming them (read_rinbuffer takes a const ring)
+ * and fails when fewer are held.  The reference's own code cannot serve as the checker: create_rinbuffer sets
+ * end_p = -1 (ring_buffer.c:33), so its first write copies to buffer - 1, and the wrap branch of read_rinbuffer
+ * re-reads past start_p (ring_buffer.c:113-114) -- the oracle is oracle/stream.py:RingModel (parity unpinned).
+ * Host only, no context, no GPU.  Returns WW_OK or WW_ERR_INVALID (RINBUF_ERROR = -1 in the reference). */
+typedef struct ww_ring ww_ring;
+int ww_ring_create(ww_ring** out, int buffer_len);                       /* create_rinbuffer */
+void ww_ring_delete(ww_ring* r);                                          /* delete_ringbuffer */
+int ww_ring_write(ww_ring* r, const float* data, long long data_len);    /* write_rinbuffer */
+int ww_ring_read(const ww_ring* r, float* data, int data_len);           /* read_rinbuffer */
+int ww_ring_count(const ww_ring* r);                                      /* ringbuf_data_count (static there) */
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,3 +77,30 @@ def events(logits, threshold_logit=LN4, warmup=64, refractory=None, window=WINDO
                 continue
         f += 1
     return hits
+
+
+class RingModel:
+    """The float ring of main/ring_buffer/ring_buffer.h:17-33 with the semantics ring_buffer.c:57-117 intends
+    (keep the last `buffer_len` values written; read = the oldest `n` retained values, not consumed).
+
+    PARITY UNPINNED: the reference's own implementation cannot produce goldens -- create_rinbuffer sets end_p = -1
+    (ring_buffer.c:33), so the first write lands at buffer - 1, and read_rinbuffer's wrap branch copies from
+    start_p + remain instead of 0 (ring_buffer.c:113-114).  The scenario of its ring_buffer_test_simple
+    (ring_buffer.c:120-200: create 10, write 3, read 3, write 7, read 3) is replayed in tests/test_abi.py."""
+
+    def __init__(self, buffer_len):
+        from collections import deque
+
+        self.buffer_len = int(buffer_len)
+        self.q = deque(maxlen=self.buffer_len)
+
+    def write(self, data):
+        self.q.extend(np.asarray(data, np.float32).tolist())
+
+    def count(self):
+        return len(self.q)
+
+    def read(self, n):
+        if n <= 0 or n > len(self.q):
+            return None                      # RINBUF_ERROR
+        return np.array(list(self.q)[:n], np.float32)

@@ -121,3 +121,50 @@ def test_analyze_mfcc_range_logs_what_the_reference_logs(lib, capfd):
     import ww_b200
     assert ww_b200.analyze_mfcc_range(np.array([1.0, np.nan, 3.0], np.float32)) == \
         {"min": 1.0, "max": 3.0, "avg": 2.0, "valid": 2, "size": 3}
+
+
+def test_ring_buffer_replays_the_references_own_test_scenario(lib):
+    """ring_buffer_test_simple (main/ring_buffer/ring_buffer.c:120-200): create 10, write 3, read 3, write 7 (now
+    full), read 3 -- with the intended keep-last-N / non-consuming-read semantics."""
+    import ww_b200
+
+    r = ww_b200.RingBuffer(10)
+    r.write([1.1, 2.2, 3.3])
+    assert len(r) == 3
+    np.testing.assert_array_equal(r.read(3), np.array([1.1, 2.2, 3.3], np.float32))
+    assert len(r) == 3                                           # read_rinbuffer takes a const ring: nothing consumed
+    r.write([4.4, 5.5, 6.6, 7.7, 8.8, 9.9, 10.10])
+    assert len(r) == 10
+    np.testing.assert_array_equal(r.read(3), np.array([1.1, 2.2, 3.3], np.float32))
+    r.write([11.0])                                              # full: the oldest value goes
+    np.testing.assert_array_equal(r.read(10), np.array([2.2, 3.3, 4.4, 5.5, 6.6, 7.7, 8.8, 9.9, 10.10, 11.0], np.float32))
+    with pytest.raises(ww_b200.WWError):
+        r.read(11)                                               # more than held: RINBUF_ERROR
+    with pytest.raises(ww_b200.WWError):
+        r.write([])
+    r.close()
+    with pytest.raises(ww_b200.WWError):
+        ww_b200.RingBuffer(0)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_ring_buffer_matches_the_oracle_model_on_random_traffic(lib, seed):
+    import ww_b200
+
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 200))
+    r, m = ww_b200.RingBuffer(n), ostream.RingModel(n)
+    for _ in range(300):
+        k = int(rng.integers(1, 3 * n))                          # also writes longer than the ring (ring_buffer.c:63-66)
+        x = rng.standard_normal(k).astype(np.float32)
+        r.write(x)
+        m.write(x)
+        assert len(r) == m.count()
+        q = int(rng.integers(1, n + 2))
+        want = m.read(q)
+        if want is None:
+            with pytest.raises(ww_b200.WWError):
+                r.read(q)
+        else:
+            np.testing.assert_array_equal(r.read(q), want)
+    r.close()
