@@ -1,5 +1,8 @@
 // libwwb200.so -- C ABI over the sm_100a kernels (see include/ww_b200.h for the contract).
 #include <algorithm>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1476,22 +1479,45 @@ extern "C" unsigned int ww_debug_esp_tables(float* window320, float* fb_dense, f
 // WAV ingestion: wav::WavHeader (main/esp_wav/esp_wav.cpp:8-139) over a memory image
 // ------------------------------------------------------------------------------------------------
 namespace {
+// A file of n bytes of which the first `have` are in memory (have == n for a whole image).  A read that lies inside
+// the file but past the part in memory sets `starved`: the caller then has to come back with more of the file.
 struct ByteReader {
     const unsigned char* p;
-    size_t n, pos = 0;
+    size_t n, have, pos = 0;
+    bool starved = false;
     bool read(void* dst, size_t k) {  // fread(...) != count -> the reference logs and returns
         if (pos + k > n) return false;
+        if (pos + k > have) {
+            starved = true;
+            return false;
+        }
         memcpy(dst, p + pos, k);
         pos += k;
         return true;
     }
 };
+
+// the parser proper: `bytes` holds the first `have` bytes of a file of `n_bytes`; *starved reports that the header
+// walk needed bytes beyond `have` (then the result is not valid)
+int wav_parse_prefix(const void* bytes, size_t have, size_t n_bytes, int max_samples, ww_wav_info* info, bool* starved);
 }  // namespace
 
 extern "C" int ww_wav_parse(const void* bytes, size_t n_bytes, int max_samples, ww_wav_info* info) {
     if (!bytes || !info || max_samples < 0) return WW_ERR_INVALID;
+    bool starved = false;
+    return wav_parse_prefix(bytes, n_bytes, n_bytes, max_samples, info, &starved);
+}
+
+namespace {
+int wav_parse_prefix(const void* bytes, size_t have, size_t n_bytes, int max_samples, ww_wav_info* info, bool* starved) {
     memset(info, 0, sizeof(*info));
-    ByteReader r{static_cast<const unsigned char*>(bytes), n_bytes};
+    *starved = false;
+    ByteReader r{static_cast<const unsigned char*>(bytes), n_bytes, have < n_bytes ? have : n_bytes};
+    struct Flag {  // every exit reports whether the walk ran out of in-memory bytes
+        ByteReader& r;
+        bool* out;
+        ~Flag() { *out = r.starved; }
+    } flag{r, starved};
     char riff[4], wave[4], fmt[4], tag[4];
     // esp_wav.cpp:22-62: a wrong tag is only logged, parsing goes on; isValid() reports it later
     if (!r.read(riff, 4) || !r.read(&info->riff_length, 4) || !r.read(wave, 4) || !r.read(fmt, 4)) return WW_ERR_INVALID;
@@ -1528,8 +1554,67 @@ extern "C" int ww_wav_parse(const void* bytes, size_t n_bytes, int max_samples, 
                   info->bits_per_sample > 0;  // esp_wav.hpp:109-118
     return WW_OK;
 }
+}  // namespace
 
+static int wav_load_one_whole(const char* path, int clip_samples, int16_t* dst, ww_wav_info* info_out);
+
+// One file into its row of the batch.  Fast path: open, fstat, one pread of the first 4 KiB (header and chunk walk),
+// then the samples are read straight into the destination row -- no staging buffer, no second copy, only the padding
+// behind a short file is zeroed.  A header that does not fit the prefix (large LIST / junk chunks in front of
+// "data") takes the whole-file path.
 static int wav_load_one(const char* path, int clip_samples, int16_t* dst, ww_wav_info* info_out) {
+    constexpr size_t kPrefix = 4096;
+    ww_wav_info info;
+    memset(&info, 0, sizeof(info));
+    int rc = WW_ERR_INVALID;
+    const int fd = path ? open(path, O_RDONLY | O_CLOEXEC) : -1;
+    struct stat st;
+    if (fd >= 0 && fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+        unsigned char head[kPrefix];
+        const size_t fsz = (size_t)st.st_size, want = fsz < kPrefix ? fsz : kPrefix;
+        size_t have = 0;
+        while (have < want) {
+            const ssize_t k = pread(fd, head + have, want - have, (off_t)have);
+            if (k <= 0) break;
+            have += (size_t)k;
+        }
+        if (have == want) {
+            bool starved = false;
+            rc = wav_parse_prefix(head, have, fsz, clip_samples, &info, &starved);
+            if (starved) {
+                close(fd);
+                return wav_load_one_whole(path, clip_samples, dst, info_out);
+            }
+            if (rc == WW_OK) {
+                if (!info.valid) rc = WW_ERR_INVALID;
+                else if (info.bits_per_sample != 16) rc = WW_ERR_UNSUPPORTED;
+                else {
+                    const size_t bytes = sizeof(int16_t) * (size_t)info.n_samples, pos = info.raw_data_pos;
+                    size_t done = pos < have ? std::min(bytes, have - pos) : 0;
+                    memcpy(dst, head + pos, done);
+                    while (done < bytes) {
+                        const ssize_t k = pread(fd, reinterpret_cast<unsigned char*>(dst) + done, bytes - done, (off_t)(pos + done));
+                        if (k <= 0) break;
+                        done += (size_t)k;
+                    }
+                    if (done == bytes) {
+                        memset(dst + info.n_samples, 0, sizeof(int16_t) * (size_t)(clip_samples - (int)info.n_samples));
+                        close(fd);
+                        if (info_out) *info_out = info;
+                        return WW_OK;
+                    }
+                    rc = WW_ERR_INVALID;  // the file shrank under us
+                }
+            }
+        }
+    }
+    if (fd >= 0) close(fd);
+    memset(dst, 0, sizeof(int16_t) * (size_t)clip_samples);
+    if (info_out) *info_out = info;
+    return rc;
+}
+
+static int wav_load_one_whole(const char* path, int clip_samples, int16_t* dst, ww_wav_info* info_out) {
     ww_wav_info info;
     memset(&info, 0, sizeof(info));
     memset(dst, 0, sizeof(int16_t) * (size_t)clip_samples);

@@ -149,3 +149,45 @@ def test_product_wav_load_batch_and_write(wwlib, cases, tmp_path):
     assert mine == bytes(ref)
     back, _ = wwlib.read_wav(str(wp))
     np.testing.assert_array_equal(back, d["written_pcm"])
+
+
+def test_product_wav_loader_prefix_and_whole_file_paths(wwlib, tmp_path):
+    """The batch loader parses the first 4 KiB and reads the samples straight into the batch row; a header that does
+    not fit the prefix (big LIST / junk chunks in front of "data") takes the whole-file path.  Both against the
+    oracle (and the reference's own parser where it is built), for data chunks at every side of the 4 KiB mark."""
+    rng = np.random.default_rng(21)
+
+    def image(junk_sizes, n_samples, truncate=0):
+        pcm = rng.integers(-30000, 30000, n_samples).astype(np.int16)
+        body = b"".join(b"JUNK" + struct.pack("<I", k) + bytes(rng.integers(0, 256, k, dtype=np.uint8)) for k in junk_sizes)
+        fmt = struct.pack("<4sIHHIIHH", b"fmt ", 16, 1, 1, 16000, 32000, 2, 16)
+        data = b"data" + struct.pack("<I", 2 * n_samples) + pcm.tobytes()
+        riff = b"WAVE" + fmt + body + data
+        img = b"RIFF" + struct.pack("<I", len(riff)) + riff
+        return img[: len(img) - truncate] if truncate else img
+
+    cases = {
+        "no_junk": image([], 16000),
+        "junk_3000": image([3000], 16000),                 # data starts inside the prefix, runs far beyond it
+        "junk_4044": image([4044], 16000),                 # "data" tag + size end exactly at byte 4096
+        "junk_4045": image([4045], 16000),                 # the size field straddles the prefix end -> whole-file path
+        "junk_10000_x2": image([10000, 7000], 12000),      # header far beyond the prefix, short clip (padding)
+        "short_700": image([100], 700),                    # whole file inside the prefix
+        "truncated": image([2000], 16000, truncate=5001),  # fewer sample bytes than the data chunk announces
+        "long": image([5000], 40000),                      # longer than a clip: truncated to 16000
+    }
+    paths = []
+    for name, img in cases.items():
+        p = tmp_path / (name + ".wav")
+        p.write_bytes(img)
+        paths.append(str(p))
+    pcm, infos, st = wwlib.load_wav_batch(paths, threads=4, pinned=False)
+    assert (st == 0).all()
+    for i, (name, img) in enumerate(cases.items()):
+        want = owav.parse(img)
+        np.testing.assert_array_equal(pcm[i].numpy(), owav.load_clip(img), err_msg=name)
+        for k in ("n_samples", "raw_data_pos", "data_length", "riff_length"):
+            assert infos[i][k] == want[k], (name, k)
+        if owav.have_ref():
+            ref = owav.ref_parse(paths[i])
+            assert ref["raw_data_pos"] == infos[i]["raw_data_pos"] and ref["data_length"] == infos[i]["data_length"], name
