@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <fcntl.h>
 #include <sys/stat.h>
+#include <sys/uio.h>
 #include <unistd.h>
 #include <cmath>
 #include <cstdio>
@@ -1568,6 +1569,27 @@ static int wav_load_one(const char* path, int clip_samples, int16_t* dst, ww_wav
     memset(&info, 0, sizeof(info));
     int rc = WW_ERR_INVALID;
     const int fd = path ? open(path, O_RDONLY | O_CLOEXEC) : -1;
+    // The common file -- canonical 44-byte header, at least one clip of samples -- in ONE read: the header lands in
+    // `canon`, the samples directly in the batch row.  Anything else (other header length, shorter file, not a
+    // regular file) falls through to the general path below, which rewrites the whole row.
+    if (fd >= 0) {
+        unsigned char canon[44];
+        const size_t clip_bytes = sizeof(int16_t) * (size_t)clip_samples;
+        struct iovec iov[2] = {{canon, sizeof(canon)}, {dst, clip_bytes}};
+        const ssize_t got = preadv(fd, iov, 2, 0);
+        if (got == (ssize_t)(sizeof(canon) + clip_bytes)) {
+            bool starved = false;
+            // the file is at least this long; its exact length cannot matter once a whole clip is present
+            const int prc = wav_parse_prefix(canon, sizeof(canon), sizeof(canon) + clip_bytes, clip_samples, &info, &starved);
+            if (!starved && prc == WW_OK && info.valid && info.bits_per_sample == 16 && info.raw_data_pos == sizeof(canon) &&
+                info.n_samples == (uint32_t)clip_samples) {
+                close(fd);
+                if (info_out) *info_out = info;
+                return WW_OK;
+            }
+            memset(&info, 0, sizeof(info));
+        }
+    }
     struct stat st;
     if (fd >= 0 && fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
         unsigned char head[kPrefix];
