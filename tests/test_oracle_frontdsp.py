@@ -191,3 +191,37 @@ def test_product_wav_loader_prefix_and_whole_file_paths(wwlib, tmp_path):
         if owav.have_ref():
             ref = owav.ref_parse(paths[i])
             assert ref["raw_data_pos"] == infos[i]["raw_data_pos"] and ref["data_length"] == infos[i]["data_length"], name
+
+
+def test_product_wav_loader_single_read_path_rejections(wwlib, tmp_path):
+    """Files long enough for the loader's one-read path whose 44 header bytes do not allow it: the row must come out
+    as the general path (and the oracle) says -- no stale bytes of the speculative read."""
+    rng = np.random.default_rng(22)
+    pcm = rng.integers(-30000, 30000, 20000).astype(np.int16)
+
+    def canonical(n_samples, bits=16, riff=b"RIFF", tail=b""):
+        h = riff + struct.pack("<I", 36 + 2 * n_samples) + b"WAVE" + \
+            struct.pack("<4sIHHIIHH", b"fmt ", 16, 1, 1, 16000, 32000, 2, bits) + b"data" + struct.pack("<I", 2 * n_samples)
+        return h + pcm[:n_samples].tobytes() + tail
+
+    trailer = b"LIST" + struct.pack("<I", 30000) + bytes(rng.integers(1, 256, 30000, dtype=np.uint8))
+    cases = {
+        "ok_exact": (canonical(16000), 0),
+        "ok_long_with_trailer": (canonical(20000, tail=trailer), 0),
+        "short_data_long_file": (canonical(9000, tail=trailer), 0),      # 9000 samples, then non-audio bytes
+        "bits_8_long": (canonical(20000, bits=8), None),
+        "bad_riff_long": (canonical(20000, riff=b"RIFX"), None),
+    }
+    paths = []
+    for name, (img, _) in cases.items():
+        p = tmp_path / (name + ".wav")
+        p.write_bytes(img)
+        paths.append(str(p))
+    got, infos, st = wwlib.load_wav_batch(paths, threads=2, pinned=False, strict=False)
+    for i, (name, (img, want_status)) in enumerate(cases.items()):
+        if want_status is None:
+            assert st[i] != 0 and int(got[i].abs().sum()) == 0, name
+        else:
+            assert st[i] == 0, name
+            np.testing.assert_array_equal(got[i].numpy(), owav.load_clip(img), err_msg=name)
+            assert infos[i]["n_samples"] == owav.parse(img)["n_samples"], name
