@@ -183,9 +183,10 @@ def extract_features(audio_path="./audio_data/train_data/xiaoa", label=0, is_noi
         return [], []
     paths = [os.path.join(audio_path, n) for n in names]
     pcm, infos, _ = wav.load_wav_batch(paths, clip_samples=CLIP_SAMPLES)
-    n_valid = [i["n_samples"] for i in infos]
-    for k, info in enumerate(infos):
-        if info["num_channels"] != 1:  # torchaudio.load -> [C, N]; the reference's mfcc_transform(...)[0] keeps channel 0
+    n_valid = infos.field("n_samples").tolist()
+    for k in np.nonzero(infos.field("num_channels") != 1)[0].tolist():
+        info = infos[k]
+        if True:  # torchaudio.load -> [C, N]; the reference's mfcc_transform(...)[0] keeps channel 0
             mono = wav.read_wav(paths[k], max_samples=CLIP_SAMPLES * info["num_channels"])[0][::info["num_channels"]]
             pcm[k].zero_()
             pcm[k, :len(mono)] = torch.from_numpy(mono.copy())

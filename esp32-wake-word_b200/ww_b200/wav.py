@@ -23,6 +23,31 @@ def _info_dict(info: L.WavInfo) -> dict:
     return {name: int(getattr(info, name)) for name, _ in L.WavInfo._fields_}
 
 
+class WavInfos:
+    """The headers of a loaded batch: behaves like the list of header dicts it replaces (`len`, indexing and
+    iteration give dicts) without building a dict per file up front; `field(name)` is the whole column as a numpy
+    array (`infos.field("n_samples")`)."""
+
+    def __init__(self, raw, n):
+        self._raw = raw                                   # keeps the ctypes array alive
+        self._a = np.frombuffer(raw, dtype=np.dtype(L.WavInfo))[:n] if n else np.zeros(0, np.dtype(L.WavInfo))
+
+    def __len__(self):
+        return int(self._a.shape[0])
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        row = self._a[i]
+        return {name: int(row[name]) for name in self._a.dtype.names}
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def field(self, name):
+        return self._a[name]
+
+
 def parse_wav(data: bytes, max_samples: int = CLIP_SAMPLES) -> dict:
     """Header fields of a WAV image in memory (WavHeader's file constructor).  Raises on a truncated image or a
     missing data chunk (the reference logs an error and leaves the header unusable)."""
@@ -49,18 +74,26 @@ def read_wav(path: str, max_samples: int = CLIP_SAMPLES):
 
 
 def load_wav_batch(paths, clip_samples: int = CLIP_SAMPLES, threads: int | None = None, pinned: bool | None = None,
-                   strict: bool = True):
+                   strict: bool = True, out: torch.Tensor | None = None):
     """Read `paths` into one int16 tensor [n, clip_samples] (truncated / zero padded), in native reader threads.
 
     Returns (pcm, infos, status): `pcm` is pinned when CUDA is available (so the H2D copy of score_host is
-    asynchronous), `infos` a list of header dicts, `status` an int32 numpy array (0 = ok).  With strict=True a
-    failed file raises."""
+    asynchronous), `infos` the headers (`WavInfos`: a sequence of header dicts, `.field(name)` for a column), `status` an int32 numpy array (0 = ok).  With strict=True a
+    failed file raises.  `out` (int16 CPU tensor with room for [n, clip_samples], contiguous) is filled instead of a
+    fresh allocation: a job that walks a large directory in batches reuses one (pinned) buffer and pays the page
+    faults of 32 KB per file only once."""
     lib = L.load_library()
     paths = [os.fspath(p) for p in paths]
     n = len(paths)
     if pinned is None:
         pinned = torch.cuda.is_available()
-    pcm = torch.zeros((n, clip_samples), dtype=torch.int16, pin_memory=bool(pinned))
+    # every row is written in full by the loader (samples + zero padding, or zeros for a failed file)
+    if out is not None:
+        if out.dtype != torch.int16 or out.is_cuda or not out.is_contiguous() or out.numel() < n * clip_samples:
+            raise ValueError("out must be a contiguous int16 CPU tensor with at least n * clip_samples elements")
+        pcm = out.view(-1)[: n * clip_samples].view(n, clip_samples)
+    else:
+        pcm = torch.empty((n, clip_samples), dtype=torch.int16, pin_memory=bool(pinned))
     infos = (L.WavInfo * max(n, 1))()
     status = (C.c_int * max(n, 1))()
     arr = (C.c_char_p * max(n, 1))(*[p.encode() for p in paths])
@@ -73,7 +106,7 @@ def load_wav_batch(paths, clip_samples: int = CLIP_SAMPLES, threads: int | None 
     if strict and failed:
         bad = [paths[i] for i in range(n) if st[i] != 0]
         raise L.WWError(f"{failed} WAV file(s) could not be loaded: {bad[:5]}")
-    return pcm, [_info_dict(infos[i]) for i in range(n)], st
+    return pcm, WavInfos(infos, n), st
 
 
 def write_wav(path: str, pcm, sample_rate: int = 16000, num_channels: int = 1) -> None:

@@ -225,3 +225,23 @@ def test_product_wav_loader_single_read_path_rejections(wwlib, tmp_path):
             assert st[i] == 0, name
             np.testing.assert_array_equal(got[i].numpy(), owav.load_clip(img), err_msg=name)
             assert infos[i]["n_samples"] == owav.parse(img)["n_samples"], name
+
+
+def test_product_wav_loader_reuses_a_caller_buffer(wwlib, cases, tmp_path):
+    import torch
+
+    d, imgs = cases
+    names = ["canonical_9000", "exact_16000", "long_20000"]
+    paths = []
+    for name in names:
+        p = tmp_path / (name + ".wav")
+        p.write_bytes(imgs[name])
+        paths.append(str(p))
+    buf = torch.full((8, 16000), 77, dtype=torch.int16)           # stale content must not survive
+    pcm, infos, st = wwlib.load_wav_batch(paths, pinned=False, out=buf)
+    assert pcm.data_ptr() == buf.data_ptr() and tuple(pcm.shape) == (3, 16000) and (st == 0).all()
+    for i, name in enumerate(names):
+        np.testing.assert_array_equal(pcm[i].numpy(), owav.load_clip(imgs[name]), err_msg=name)
+    assert infos.field("n_samples").tolist() == [9000, 16000, 16000] and len(infos) == 3
+    with pytest.raises(ValueError):
+        wwlib.load_wav_batch(paths, pinned=False, out=torch.zeros((2, 16000), dtype=torch.int16))
