@@ -167,6 +167,24 @@ def normalize_mfcc(mfcc, method="standardization"):
     return mfcc
 
 
+def _load_clip_batch(paths):
+    """Host part of extract_features: the files as one int16 batch [n, 16000] (pinned where CUDA exists) and the
+    number of real samples per row.  Multi-channel files keep channel 0 only (torchaudio.load gives [C, N] and the
+    reference's `mfcc_transform(...)[0]` keeps the first channel, extract_mfcc.py:154-172)."""
+    from . import wav
+
+    pcm, infos, _ = wav.load_wav_batch(paths, clip_samples=CLIP_SAMPLES)
+    n_valid = infos.field("n_samples").tolist()
+    channels = infos.field("num_channels")
+    for k in np.nonzero(channels != 1)[0].tolist():
+        c = int(channels[k])
+        mono = wav.read_wav(paths[k], max_samples=CLIP_SAMPLES * c)[0][::c]
+        pcm[k].zero_()
+        pcm[k, :len(mono)] = torch.from_numpy(mono.copy())
+        n_valid[k] = len(mono)
+    return pcm, n_valid
+
+
 def extract_features(audio_path="./audio_data/train_data/xiaoa", label=0, is_noise=False,
                      add_noise_to_pad=True, augment_audio=True, normalize_method="cmvn"):
     """Reference signature (extract_mfcc.py:123): walk `audio_path`, return
@@ -176,21 +194,13 @@ def extract_features(audio_path="./audio_data/train_data/xiaoa", label=0, is_noi
     pinned int16 batch; padding noise, the five augmentation variants (ww_augment_waveform) and all features
     are computed on the GPU, the features of all variants of all files in ONE frontend launch.
     """
-    from . import frontdsp, wav
+    from . import frontdsp
 
     names = [n for n in os.listdir(audio_path) if n.endswith(".wav")]
     if not names:
         return [], []
     paths = [os.path.join(audio_path, n) for n in names]
-    pcm, infos, _ = wav.load_wav_batch(paths, clip_samples=CLIP_SAMPLES)
-    n_valid = infos.field("n_samples").tolist()
-    for k in np.nonzero(infos.field("num_channels") != 1)[0].tolist():
-        info = infos[k]
-        if True:  # torchaudio.load -> [C, N]; the reference's mfcc_transform(...)[0] keeps channel 0
-            mono = wav.read_wav(paths[k], max_samples=CLIP_SAMPLES * info["num_channels"])[0][::info["num_channels"]]
-            pcm[k].zero_()
-            pcm[k, :len(mono)] = torch.from_numpy(mono.copy())
-            n_valid[k] = len(mono)
+    pcm, n_valid = _load_clip_batch(paths)
     audio = pcm.cuda(non_blocking=True).to(torch.float32) / 32768.0          # torchaudio.load normalisation
     if add_noise_to_pad:                                                      # pad_audio(..., noise_level=0.005), :157
         t = torch.arange(CLIP_SAMPLES, device=audio.device)[None, :]
