@@ -168,3 +168,22 @@ def test_ring_buffer_matches_the_oracle_model_on_random_traffic(lib, seed):
         else:
             np.testing.assert_array_equal(r.read(q), want)
     r.close()
+
+
+def test_null_handles_are_rejected_without_touching_the_gpu(lib):
+    """Every entry point that takes a context / session / ring checks it before anything else (no GPU here)."""
+    import ctypes as C
+
+    out = C.c_void_p()
+    assert lib.ww_session_open(None, 4, 320, 1, 1, C.c_float(0.0), 64, 313, C.byref(out)) < 0 and not out.value
+    x = np.zeros(320, np.int16)
+    assert lib.ww_session_write(None, x.ctypes.data_as(C.c_void_p), 320) < 0
+    assert lib.ww_session_write_tdm(None, x.ctypes.data_as(C.c_void_p), 24) < 0
+    assert lib.ww_session_poll(None, None, 0) < 0
+    assert lib.ww_session_windows(None) < 0
+    lib.ww_session_close(None)                                   # like free(NULL)
+    assert lib.ww_ring_write(None, x.ctypes.data_as(C.c_void_p), 4) < 0
+    assert lib.ww_ring_read(None, x.ctypes.data_as(C.c_void_p), 4) < 0
+    assert lib.ww_ring_count(None) < 0
+    lib.ww_ring_delete(None)
+    assert lib.ww_score_clips_host(None, x.ctypes.data_as(C.c_void_p), 0, 1, 1, 1, C.c_float(0.0), 1, None, None) < 0
