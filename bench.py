@@ -41,13 +41,30 @@ FUSED_BYTES_PER_CLIP = 16000 * 2 + 5
 # dram__bytes_read.sum + dram__bytes_write.sum of mfcc_kernel<int16, PY> per clip, from the `ncu --set full` capture
 # profiles/r1_ncu_mfcc_kernel.txt (2.0977 GB + 211.0 MB over a 65 536-clip launch): traffic == algorithmic bytes
 FRONTEND_DRAM_BYTES_PER_CLIP_NCU = (2.097739e9 + 210.983680e6) / 65536
+# executed warp instructions and shared-memory wavefronts per clip of the same kernel (ncu, same capture family;
+# profiles/r2_ncu_mfcc_kernel.txt when present, else round 1's): the issue ports (4 warp-instructions/clk/SM) and the
+# shared-memory pipe (1 wavefront/clk/SM) are what the kernel is actually limited by, so their fractions are reported
+# beside the HBM one
+FRONTEND_WARP_INSTR_PER_CLIP = 1375739280 / 65536
+FRONTEND_SMEM_WAVEFRONTS_PER_CLIP = 432555572 / 65536
 UTT = 63  # windows per CTC utterance
 CPU_BATCH = 200
+PARITY_DISTINCT = 65536   # exact-match check on >= 65 536 distinct clips per GPU
+PARITY_STRIDED = 4096     # strided subset of the timed clips
+PARITY_MARGIN = 2e-3      # |oracle logit - threshold| below which a float pipeline cannot promise the oracle's decision
 
 
 def load_weights():
     d = np.load(os.path.join(ROOT, "tests", "golden", "xiaoa_weights.npz"))
     return {k: d[k] for k in d.files}
+
+
+_SM_MHZ = [None]
+
+
+def measured_sm_mhz():
+    """SM clock sampled under load during the timed region (set by run_ours before the roofline leg)."""
+    return _SM_MHZ[0]
 
 
 def measured_peaks():
@@ -321,13 +338,50 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def parity_check(ctx, L, pcm_dev, logits_dev, dec_dev, idx, sd, sp, threads):
+    """The oracle (torchaudio MFCC + normalize_mfcc + LightweightKWS, the reference's own calls) over clips `idx` of the
+    TIMED device PCM, against what the timed step left in `logits_dev` / `dec_dev` for those clips, and against the
+    frontend's features for them.  Checker only: nothing here is timed or shipped."""
+    import torch
+
+    from oracle import cnn as ocnn
+    from oracle import mfcc as omfcc
+
+    torch.set_num_threads(max(1, threads))
+    sub = pcm_dev[idx].contiguous()
+    n = sub.shape[0]
+    feats = torch.empty((n, 13, 63), dtype=torch.float32, device=pcm_dev.device)
+    ctx.check(ctx.lib.ww_mfcc_batch(ctx.h, L.ptr(sub), L.PCM_S16, n, 16000, 16000, L.FEAT_PY, L.LAYOUT_COEF_MAJOR,
+                                    L.ptr(feats), sp), "ww_mfcc_batch(parity)")
+    got_f = feats.cpu().numpy()
+    got_l = logits_dev[idx, 0].cpu().numpy()
+    got_d = dec_dev[idx].cpu().numpy().astype(bool)
+    host = sub.cpu()
+    f_err, l_err, mism, mism_out, near = 0.0, 0.0, 0, 0, 0
+    for c0 in range(0, n, 4096):
+        x = host[c0:c0 + 4096].to(torch.float32) / 32768.0
+        f = omfcc.mfcc_torchaudio(x)
+        z = omfcc.normalize_mfcc(f, "cmvn")
+        want = ocnn.forward_torch(z.numpy(), sd)[:, 0]
+        wd = ocnn.decide_python(want)
+        f_err = max(f_err, float(np.abs(f.numpy() - got_f[c0:c0 + 4096]).max()))
+        l_err = max(l_err, float(np.abs(want - got_l[c0:c0 + 4096]).max()))
+        bad = wd != got_d[c0:c0 + 4096]
+        clear = np.abs(want) > PARITY_MARGIN
+        mism += int(bad.sum())
+        mism_out += int((bad & clear).sum())
+        near += int((~clear).sum())
+    return {"n": n, "feature_max_abs": f_err, "logit_max_abs": l_err, "decision_mismatches": mism,
+            "decision_mismatches_outside_margin": mism_out, "near_threshold": near}
+
+
 def workload_config(args, n):
     return {"workload": "configs[2]: fused MFCC(esp_mfcc/ml_models params: 320/256/512, 40 mel, 13 cep) + CMVN + "
                         "xiaoa.onnx LightweightKWS CNN + sigmoid>0.5 decision + CTC best-path/keyword over 63-window "
                         "utterances, clip-sharded",
             "clips_per_gpu": args.clips, "global_clips": args.clips * n, "clip_samples": 16000, "pcm": "int16",
-            "cnn_impl": args.cnn + (" (tcgen05 kind::f16, fp32 accumulate in TMEM; clips within 0.03 of the threshold "
-                                    "are re-scored by the fp32 kernel)" if args.cnn == "tensor" else ""),
+            "cnn_impl": args.cnn + (" (tcgen05 kind::f16, fp32 accumulate in TMEM; clips inside the guard band calibrated "
+                                    "for the loaded weights are re-scored by the fp32 kernel)" if args.cnn == "tensor" else ""),
             "parallelism": f"dp{n} (clip shards, no hot-path collective)",
             "l2_policy": "inputs (32 KB/clip x clips) exceed L2; no flush needed"}
 
@@ -350,21 +404,19 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     host_numa = bind_host_to_gpu_node(local) if world > 1 and not os.environ.get("WW_NO_NUMA_BIND") else None
+    # stdout carries the ONE JSON line and nothing else: for the rest of the run fd 1 points at stderr (NCCL's INFO
+    # lines, library banners), and the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # keep stdout to the single JSON line: NCCL's version banner goes to stderr
-        os.environ["NCCL_DEBUG"] = os.environ.get("WW_NCCL_DEBUG", "WARN")
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=dev)
-            warm = torch.zeros(1, device=dev)
-            dist.all_reduce(warm)  # creates the communicator (and prints whatever NCCL wants to print)
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
+        # the communicator's own account of itself (ranks, transport, NVLS) goes to stderr so that it can be checked
+        os.environ.setdefault("NCCL_DEBUG", os.environ.get("WW_NCCL_DEBUG", "INFO"))
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        dist.init_process_group("nccl", device_id=dev)
+        warm = torch.zeros(1, device=dev)
+        dist.all_reduce(warm)  # creates the communicator
+        torch.cuda.synchronize()
     sd = load_weights()
     cnn_impl = args.cnn
     scorer = ww_b200.WakeWordScorer(sd, device=local, cmvn="python", decision="python", cnn_impl=cnn_impl)
@@ -420,6 +472,8 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms_max = float(tt.item())
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    if clocks and clocks.get("sm_mhz"):
+        _SM_MHZ[0] = clocks["sm_mhz"]
     ms_per_step = ms_max / args.steps
     value = world * B / (ms_per_step * 1e-3)
 
@@ -446,12 +500,27 @@ def run_ours(args):
         fms = f0.elapsed_time(f1) / reps
         peak, how = measured_peaks()
         ach = rb * FRONTEND_BYTES_PER_CLIP / (fms * 1e-3) / 1e9
+        sm_clk = 1e6 * (measured_sm_mhz() or 1965.0)
+        n_sm = torch.cuda.get_device_properties(local).multi_processor_count
         roof = {"bound": "hbm", "kernel": "mfcc_kernel<int16, PY> (frontend alone, 1 persistent launch over %d clips)" % rb,
                 "achieved": ach, "peak": peak, "peak_source": how, "unit": "GB/s", "frac": ach / peak,
                 "traffic": FRONTEND_DRAM_BYTES_PER_CLIP_NCU * rb, "traffic_source": "profiles/r1_ncu_mfcc_kernel.txt "
                 "(ncu --set full, per-clip DRAM bytes x clips of this launch)", "algorithmic_bytes": rb * FRONTEND_BYTES_PER_CLIP,
                 "ms_per_launch": fms, "clips_per_s": rb / (fms * 1e-3),
-                "algorithmic_bytes_per_clip": FRONTEND_BYTES_PER_CLIP}
+                "algorithmic_bytes_per_clip": FRONTEND_BYTES_PER_CLIP,
+                # the kernel's real limiters, same launch: per-clip counts from the ncu capture x live clips/s over the
+                # per-SM peak at the SM clock sampled under load
+                "other_bounds": [
+                    {"bound": "issue", "achieved": FRONTEND_WARP_INSTR_PER_CLIP * rb / (fms * 1e-3) / (n_sm * sm_clk),
+                     "peak": 4.0, "unit": "warp-instr/clk/SM",
+                     "frac": FRONTEND_WARP_INSTR_PER_CLIP * rb / (fms * 1e-3) / (n_sm * sm_clk) / 4.0,
+                     "per_clip": FRONTEND_WARP_INSTR_PER_CLIP, "source": "smsp__inst_executed.sum / clips (ncu)"},
+                    {"bound": "shared-memory pipe", "achieved": FRONTEND_SMEM_WAVEFRONTS_PER_CLIP * rb / (fms * 1e-3) / (n_sm * sm_clk),
+                     "peak": 1.0, "unit": "wavefronts/clk/SM",
+                     "frac": FRONTEND_SMEM_WAVEFRONTS_PER_CLIP * rb / (fms * 1e-3) / (n_sm * sm_clk),
+                     "per_clip": FRONTEND_SMEM_WAVEFRONTS_PER_CLIP,
+                     "source": "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum / clips (ncu)"}],
+                "sm_clock_hz_used": sm_clk}
         del feats
 
     # ---- e2e: host buffers through the public call ---------------------------------------------------
@@ -467,9 +536,30 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_dt = (time.perf_counter() - t0) / args.steps
     te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+    per_rank_e2e = [te.clone() for _ in range(world)]
     if world > 1:
+        dist.all_gather(per_rank_e2e, te)
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    per_rank_e2e = [float(t.item()) for t in per_rank_e2e]
     e2e_val = world * eb / float(te.item())
+    # the ceiling of that leg: the same pinned buffer copied host -> device by every rank at once, no kernels
+    d_sink = torch.empty_like(host, device=dev)
+    for _ in range(2):
+        d_sink.copy_(host, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(3, args.steps)):
+        d_sink.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_dt = (time.perf_counter() - t0) / max(3, args.steps)
+    th = torch.tensor([h2d_dt], dtype=torch.float64, device=dev)
+    per_rank_h2d = [th.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank_h2d, th)
+        dist.all_reduce(th, op=dist.ReduceOp.MAX)
+    per_rank_h2d = [eb * 32000 / float(t.item()) / 1e9 for t in per_rank_h2d]
+    h2d_ceiling_gbs = world * eb * 32000 / float(th.item()) / 1e9
+    del d_sink
     if host_numa is not None:
         # every rank's placement: [NUMA node of its GPU (-1 unknown), memory policy set, CPUs it may run on]
         mine = torch.tensor([-1 if host_numa["node"] is None else host_numa["node"],
@@ -477,6 +567,54 @@ def run_ours(args):
         every = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(every, mine)
         host_numa = dict(host_numa, per_rank=[[int(v) for v in t.tolist()] for t in every])
+
+    # ---- parity of the measured run (outside every timed region) --------------------------------------
+    # `logits` / `dec` still hold what the LAST timed step wrote for this rank's B clips.  Checked against the oracle:
+    # a strided subset over all of them and the first PARITY_DISTINCT clips (every synthetic clip is distinct)
+    parity = None
+    if not args.no_parity:
+        try:
+            ncpu = len(os.sched_getaffinity(0))
+        except Exception:
+            ncpu = os.cpu_count() or 1
+        rescored = int(ctx.lib.ww_tc_rescored_total(ctx.h, 0)) if cnn_impl == "tensor" else 0
+        stride = max(1, B // PARITY_STRIDED)
+        idx_s = torch.arange(0, B, stride, device=dev)[:PARITY_STRIDED]
+        idx_d = torch.arange(0, min(B, args.parity_clips), device=dev)
+        ps = parity_check(ctx, L, pcm, logits, dec, idx_s, sd, sp, ncpu // world)
+        pd = parity_check(ctx, L, pcm, logits, dec, idx_d, sd, sp, ncpu // world)
+        # the e2e leg's own outputs, on the host clips it scored
+        ne = min(eb, 2048)
+        pe_l = torch.from_numpy(lh[:ne].copy()).to(dev)
+        pe_d = torch.from_numpy(dh[:ne].copy()).to(dev)
+        pe = parity_check(ctx, L, host[:ne].to(dev), pe_l, pe_d, torch.arange(ne, device=dev), sd, sp, ncpu // world)
+        mine = torch.tensor([ps["n"] + pd["n"] + pe["n"],
+                             ps["decision_mismatches"] + pd["decision_mismatches"] + pe["decision_mismatches"],
+                             ps["decision_mismatches_outside_margin"] + pd["decision_mismatches_outside_margin"] +
+                             pe["decision_mismatches_outside_margin"],
+                             ps["near_threshold"] + pd["near_threshold"] + pe["near_threshold"], rescored],
+                            dtype=torch.float64, device=dev)
+        mx = torch.tensor([max(ps["feature_max_abs"], pd["feature_max_abs"], pe["feature_max_abs"]),
+                           max(ps["logit_max_abs"], pd["logit_max_abs"], pe["logit_max_abs"])], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(mine, op=dist.ReduceOp.SUM)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        band = ctx.tc_band_info() if cnn_impl == "tensor" else None
+        parity = {"oracle": "oracle/mfcc.py mfcc_torchaudio + normalize_mfcc('cmvn') + oracle/cnn.py forward_torch "
+                            "(the reference's torchaudio / torch calls), fp32 on the host",
+                  "what": "clips of the TIMED device PCM against the logits / decisions the last timed step wrote for them "
+                          f"(per rank: {ps['n']} strided over all clips + the first {pd['n']} clips, all distinct) and "
+                          f"{pe['n']} clips of the e2e leg against its host outputs",
+                  "n_checked": int(mine[0].item()), "feature_max_abs": float(mx[0].item()), "feature_tolerance": 1e-3,
+                  "logit_max_abs": float(mx[1].item()),
+                  "decision_mismatches": int(mine[1].item()),
+                  "decision_mismatches_outside_margin": int(mine[2].item()),
+                  "near_threshold_excluded": int(mine[3].item()), "margin": PARITY_MARGIN,
+                  "rescored": int(mine[4].item()),
+                  "rescored_note": "windows the tcgen05 path handed to the exact fp32 kernel over ALL steps of this run "
+                                   "(warm-up, timed, e2e), summed over ranks",
+                  "tc_band": band,
+                  "ok": bool(mine[2].item() == 0 and mx[0].item() < 1e-3)}
 
     if rank == 0:
         chunk = int(os.environ.get("WW_CHUNK_CLIPS", "131072"))  # ww_api.cu kScratchClips: clips per fused frontend + CNN pair
@@ -497,17 +635,27 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": eb * 32000, "d2h_bytes_per_step": eb * 5,
                     "clips_per_step_per_gpu": eb, "host_numa": host_numa,
+                    "per_rank_s_per_step": per_rank_e2e,
+                    "h2d_gbs": e2e_val * 32000 / 1e9,
+                    "h2d_ceiling_gbs": h2d_ceiling_gbs, "h2d_ceiling_per_rank_gbs": per_rank_h2d,
+                    "h2d_ceiling_how": "every rank copies the same pinned buffer host->device at once, no kernels, "
+                                       "max-over-ranks wall time",
+                    "frac_of_h2d_ceiling": e2e_val * 32000 / 1e9 / h2d_ceiling_gbs,
                     "api": "WakeWordScorer.score_host -> ww_score_clips_host (pinned host "
                     "PCM in, host logits+decisions out)"},
             "gpu_launches": launches,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "parity": parity,
             "positives": int(dec.sum().item()), "keyword_hits": int(hits[:n_utt].sum().item()) if n_utt else 0,
             "fused_hbm_frac": (value / world) * FUSED_BYTES_PER_CLIP / 1e9 / measured_peaks()[0],
         }
-        print(json.dumps(line), flush=True)
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        sys.stderr.write("bench.py: PARITY FAILURE in the measured run: %s\n" % json.dumps(parity))
+        raise SystemExit(3)
 
 
 def main():
@@ -523,6 +671,9 @@ def main():
     ap.add_argument("--cnn", default="tensor", choices=["fp32", "tensor"],
                     help="tensor: tcgen05 fp16-operand CNN + exact fp32 re-score of borderline clips (default)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the measured run")
+    ap.add_argument("--parity-clips", type=int, default=PARITY_DISTINCT,
+                    help="distinct clips per rank checked against the oracle (plus a 4096-clip strided subset)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -14,18 +14,19 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/ww_b200.h"
 #include "ww_cnn.cuh"
 #include "ww_cnn_i8.cuh"
 #include "ww_ctc.cuh"
 #include "ww_frontdsp.cuh"
 #include "ww_mfcc.cuh"
+#include "ww_norm.cuh"
 #include "ww_tables.h"
 #include "ww_tables_esp.h"
-#ifdef WW_WITH_TC
 #include "ww_cnn_tc.cuh"
 #include "ww_cnn_i8_tc.cuh"
-#endif
 
 using namespace ww;
 
@@ -50,14 +51,20 @@ struct ww_ctx {
     float* wblob = nullptr;
     CnnWeights w{};
     bool have_weights = false;
-#ifdef WW_WITH_TC
     uint4* tc_blob = nullptr;       // fp16 weights in UMMA layout (ww_cnn_tc.cuh)
     long long* rs_list = nullptr;   // windows to re-score in fp32
     int* rs_count = nullptr;
+    unsigned long long* rs_total = nullptr;  // windows handed to the fp32 kernel since the last ww_tc_rescored_total(reset)
     long long rs_cap = 0;
-    float tc_band = 0.03f;          // |logit - threshold| below which the fp32 kernel decides
+    // guard band of the fp16-operand path, set by ww_load_weights (tc_calibrate): |tensor logit - fp32 logit| <=
+    // tc_beta * ||window||_F.  tc_beta = min(8 x the largest ratio seen on the calibration set, the rigorous bound)
+    float tc_beta = 0.f, tc_beta_cal = 0.f, tc_beta_rig = 0.f;
+    float tc_norm_limit = 0.f;      // windows with a larger norm could leave the fp16 range in some layer (rigorous)
+    bool tc_ok = false;             // false: every tensor-path call runs the fp32 kernel (calibration saw non-finite logits)
+    float tc_band_override = -1.f;  // WW_TC_BAND (absolute, experiments only)
     float* tc_dbg = nullptr;
-#endif
+    long long chunk_clips = 0;      // clips per frontend + CNN pair of the fused path (WW_CHUNK_CLIPS)
+    std::atomic<int> busy{0};       // ww_score_clips* share one feature scratch per context: one call at a time
     std::vector<float> host_w[5];      // fp32 weights as loaded (for the int8 twin's quantisation)
     signed char* i8blob = nullptr;
     I8Weights i8w{};
@@ -70,6 +77,9 @@ struct ww_ctx {
     // fused-path scratch
     float* scratch = nullptr;          // [chunk][13][63]
     long long scratch_clips = 0;
+    cudaEvent_t scratch_ev = nullptr;  // recorded after the last use of `scratch`; a call on another stream waits for it
+    cudaStream_t scratch_stream = nullptr;
+    bool scratch_used = false;
     // host-buffer path
     cudaStream_t hs[2] = {nullptr, nullptr};
     cudaEvent_t hev[2] = {nullptr, nullptr};
@@ -81,6 +91,18 @@ struct ww_ctx {
     unsigned char* h_dec[2] = {nullptr, nullptr};
     long long host_chunk = 0;
     size_t host_chunk_bytes = 0;
+    int host_classes = 0;              // class count d_logits / h_logits were sized for
+};
+
+static int tc_calibrate(ww_ctx* ctx);
+static void free_host_path(ww_ctx* ctx);
+
+// NVTX ranges around the host-visible stages (load / H2D / frontend / CNN / D2H): the counterpart of the reference's
+// esp_timer_get_time() deltas around CMVN and model->run() (esp_wake_word_detector.cpp:177,213,222-234).  Header-only
+// NVTX v3: a no-op unless a profiler is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
 };
 
 static int fail(ww_ctx* c, int code, const std::string& msg) {
@@ -270,7 +292,7 @@ extern "C" const char* ww_last_error(const ww_ctx* ctx) { return ctx ? ctx->err.
 // Feature scratch of the fused path: frontend and CNN run chunk by chunk so the [13,63] features never leave
 // the device as a full [B,13,63] tensor.  Measured on B200 (tools/sweep_chunks.sh): 8192 -> 17.0, 16384 -> 17.9,
 // 32768 -> 18.3, 65536 -> 18.5 M clips/s; the host-buffer pipeline keeps 16384-clip chunks for copy overlap.
-static long long kScratchClips = 131072;  // WW_CHUNK_CLIPS overrides (sweep: 65536 -> 25.25, 131072 -> 25.49, 262144 -> 25.35 M clips/s)
+static const long long kScratchClips = 131072;  // WW_CHUNK_CLIPS overrides (sweep: 65536 -> 25.25, 131072 -> 25.49, 262144 -> 25.35 M clips/s)
 static const long long kHostChunkClips = 16384;
 
 extern "C" int ww_create(ww_ctx** out, int device) {
@@ -342,17 +364,16 @@ extern "C" int ww_create(ww_ctx** out, int device) {
     WW_SET_SMEM((mfcc_kernel<int16_t, MEL_PY, true>), (MfccSmem<int16_t, MEL_PY>::TOTAL))
     WW_SET_SMEM((mfcc_kernel<float, MEL_PY, true>), (MfccSmem<float, MEL_PY>::TOTAL))
 #undef WW_SET_SMEM
-#ifdef WW_WITH_TC
     if ((e = cudaFuncSetAttribute(cnn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)) != cudaSuccess)
         return bail(e, "cudaFuncSetAttribute(cnn_tc_kernel)");
     if ((e = cudaFuncSetAttribute(cnn_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8T_SMEM)) != cudaSuccess)
         return bail(e, "cudaFuncSetAttribute(cnn_i8_tc_kernel)");
-    if (const char* b = getenv("WW_TC_BAND")) ctx->tc_band = (float)atof(b);
+    if (const char* b = getenv("WW_TC_BAND")) ctx->tc_band_override = (float)atof(b);
+    ctx->chunk_clips = kScratchClips;
     if (const char* c = getenv("WW_CHUNK_CLIPS")) {
         const long long v = atoll(c);
-        if (v >= 256 && v <= (1LL << 22)) kScratchClips = v;
+        if (v >= 256 && v <= (1LL << 22)) ctx->chunk_clips = v;
     }
-#endif
     *out = ctx;
     return WW_OK;
 }
@@ -365,21 +386,16 @@ extern "C" void ww_destroy(ww_ctx* ctx) {
     cudaFree(ctx->i8blob);
     cudaFree(ctx->i8tc_blob);
     cudaFree(ctx->scratch);
+    if (ctx->scratch_ev) cudaEventDestroy(ctx->scratch_ev);
     for (int i = 0; i < 2; ++i) {
         if (ctx->hs[i]) cudaStreamDestroy(ctx->hs[i]);
         if (ctx->hev[i]) cudaEventDestroy(ctx->hev[i]);
-        if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
-        cudaFree(ctx->d_pcm[i]);
-        cudaFree(ctx->d_logits[i]);
-        cudaFree(ctx->d_dec[i]);
-        if (ctx->h_logits[i]) cudaFreeHost(ctx->h_logits[i]);
-        if (ctx->h_dec[i]) cudaFreeHost(ctx->h_dec[i]);
     }
-#ifdef WW_WITH_TC
+    free_host_path(ctx);
     cudaFree(ctx->tc_blob);
     cudaFree(ctx->rs_list);
     cudaFree(ctx->rs_count);
-#endif
+    cudaFree(ctx->rs_total);
     delete ctx;
 }
 
@@ -388,9 +404,6 @@ extern "C" int ww_set_option(ww_ctx* ctx, int option, int value) {
     switch (option) {
         case WW_OPT_I8_IMPL:
             if (value != WW_CNN_FP32 && value != WW_CNN_TENSOR) return fail(ctx, WW_ERR_INVALID, "WW_OPT_I8_IMPL: 0 (CUDA cores) or 1 (tensor cores)");
-#ifndef WW_WITH_TC
-            if (value == WW_CNN_TENSOR) return fail(ctx, WW_ERR_UNSUPPORTED, "tensor-core kernels not built into this library");
-#endif
             ctx->i8_impl = value;
             return WW_OK;
         case WW_OPT_GENERIC_FRONTEND:
@@ -438,16 +451,17 @@ extern "C" int ww_load_weights(ww_ctx* ctx, const float* conv1, const float* con
     ctx->host_w[3].assign(fc1, fc1 + n4);
     ctx->host_w[4].assign(fc2, fc2 + n5);
     ctx->have_i8 = false;
-#ifdef WW_WITH_TC
     {
         std::vector<unsigned char> blob;
         tc_build_blob(blob, conv1, conv2, conv3, fc1);
         if (!ctx->tc_blob) CK(cudaMalloc(&ctx->tc_blob, TC_W_BYTES));
         CK(cudaMemcpy(ctx->tc_blob, blob.data(), TC_W_BYTES, cudaMemcpyHostToDevice));
     }
-#endif
     ctx->have_weights = true;
-    return WW_OK;
+    // the host-buffer path sizes its logit buffers by class count: drop them when the model changes shape
+    if (ctx->host_classes != num_classes) free_host_path(ctx);
+    // measure the fp16-operand path against the exact kernel for THESE weights (guard band, fp16-range limit)
+    return tc_calibrate(ctx);
 }
 
 extern "C" int ww_num_frames(int feat_mode, int n_samples) {
@@ -556,7 +570,8 @@ extern "C" int ww_mfcc_batch(ww_ctx* ctx, const void* pcm, int pcm_type, long lo
 // ------------------------------------------------------------------------------------------------
 static int launch_cnn_fp32(ww_ctx* ctx, const float* feats, long long ws, long long cs, long long fs, long long n,
                            const long long* index, const int* index_count, int cmvn_mode, int decide_mode,
-                           float threshold, float* logits, unsigned char* decisions, float* norm_out, cudaStream_t st) {
+                           float threshold, float* logits, unsigned char* decisions, float* norm_out, cudaStream_t st,
+                           unsigned grid_override = 0) {
     CnnArgs a;
     a.feats = feats;
     a.win_stride = ws;
@@ -567,6 +582,7 @@ static int launch_cnn_fp32(ww_ctx* ctx, const float* feats, long long ws, long l
     a.group_stride = ctx->grp_stride;
     a.index = index;
     a.index_count = index_count;
+    a.index_total = index ? ctx->rs_total : nullptr;
     a.cmvn_mode = cmvn_mode;
     a.decide_mode = decide_mode;
     a.threshold = threshold;
@@ -577,6 +593,7 @@ static int launch_cnn_fp32(ww_ctx* ctx, const float* feats, long long ws, long l
     if (n == 0) return WW_OK;
     long long grid = (long long)ctx->sm_count * 8;
     if (grid > n) grid = n;
+    if (grid_override) grid = grid_override;
     cnn_fp32_kernel<<<(unsigned)grid, CNN_THREADS, 0, st>>>(a);
     CK(cudaGetLastError());
     return WW_OK;
@@ -588,7 +605,6 @@ extern "C" int ww_cmvn(ww_ctx* ctx, const float* feats, long long n_windows, int
     if (n_windows == 0) return WW_OK;
     if (!feats || !out || n_windows < 0) return fail(ctx, WW_ERR_INVALID, "cmvn: bad arguments");
     if (cmvn_mode < WW_CMVN_NONE || cmvn_mode > WW_CMVN_DEVICE) return fail(ctx, WW_ERR_INVALID, "cmvn: bad mode");
-#ifdef WW_WITH_TC
     {
         // dedicated bandwidth-bound kernel (a warp per window); the fp32 CNN kernel's CMVN stage is the fallback
         CmvnArgs a;
@@ -608,10 +624,32 @@ extern "C" int ww_cmvn(ww_ctx* ctx, const float* feats, long long n_windows, int
         CK(cudaGetLastError());
         return WW_OK;
     }
-#else
-    return launch_cnn_fp32(ctx, feats, WW_N_MFCC * WW_WINDOW_FRAMES, WW_WINDOW_FRAMES, 1, n_windows, nullptr, nullptr,
-                           cmvn_mode, WW_DECIDE_NONE, 0.f, nullptr, nullptr, out, (cudaStream_t)stream);
-#endif
+}
+
+extern "C" int ww_normalize_rows(ww_ctx* ctx, const float* x, long long n_rows, int T, long long row_stride, int method,
+                                 float* out, ww_stream_t stream) {
+    if (!ctx) return WW_ERR_INVALID;
+    if (n_rows == 0 || T == 0) return WW_OK;
+    if (!x || !out || n_rows < 0 || T < 0 || row_stride < T) return fail(ctx, WW_ERR_INVALID, "normalize_rows: bad arguments");
+    if (method != WW_NORM_STANDARD && method != WW_NORM_MINMAX) return fail(ctx, WW_ERR_INVALID, "normalize_rows: bad method");
+    NormArgs a;
+    a.x = x;
+    a.out = out;
+    a.n_rows = n_rows;
+    a.row_stride = row_stride;
+    a.T = T;
+    a.method = method;
+    const long long cap = (long long)ctx->sm_count * 8;
+    if (T <= 512) {  // a warp per row
+        long long blocks = (n_rows + 7) / 8;
+        if (blocks > cap) blocks = cap;
+        normalize_rows_kernel<32><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    } else {
+        const long long blocks = n_rows < cap ? n_rows : cap;
+        normalize_rows_kernel<256><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    }
+    CK(cudaGetLastError());
+    return WW_OK;
 }
 
 static int check_cnn_args(ww_ctx* ctx, int cmvn_mode, int decide_mode, int cnn_impl) {
@@ -620,9 +658,6 @@ static int check_cnn_args(ww_ctx* ctx, int cmvn_mode, int decide_mode, int cnn_i
     if (decide_mode < WW_DECIDE_NONE || decide_mode > WW_DECIDE_DEVICE) return fail(ctx, WW_ERR_INVALID, "bad decide_mode");
     if (cnn_impl != WW_CNN_FP32 && cnn_impl != WW_CNN_TENSOR && cnn_impl != WW_CNN_INT8)
         return fail(ctx, WW_ERR_INVALID, "bad cnn_impl");
-#ifndef WW_WITH_TC
-    if (cnn_impl != WW_CNN_FP32) return fail(ctx, WW_ERR_UNSUPPORTED, "tensor-core CNN not built into this library");
-#endif
     if (cnn_impl == WW_CNN_INT8) {
         // the device path: int8 MFCC rounding + device CMVN feed the int8 model at exponent -4 (cpp:128-131,179-220)
         if (!ctx->have_i8) return fail(ctx, WW_ERR_NO_WEIGHTS, "int8 weights not prepared (ww_quantize_weights_i8)");
@@ -633,23 +668,15 @@ static int check_cnn_args(ww_ctx* ctx, int cmvn_mode, int decide_mode, int cnn_i
     return WW_OK;
 }
 
-#ifdef WW_WITH_TC
-// tensor-core forward + exact fp32 re-score of the windows that land within tc_band of the threshold
-static int tc_forward(ww_ctx* ctx, const float* feats, long long ws, long long cs, long long fs, long long n,
-                      int cmvn_mode, int decide_mode, float threshold, float* logits, unsigned char* decisions,
-                      cudaStream_t st) {
-    if (ctx->w.num_classes > TC_MAX_CLASSES)
-        return fail(ctx, WW_ERR_UNSUPPORTED, "tensor-core CNN supports at most 8 classes");
-    if (n == 0) return WW_OK;
-    const bool rescoring = decisions && decide_mode != WW_DECIDE_NONE;
-    if (rescoring && ctx->rs_cap < n) {
-        cudaFree(ctx->rs_list);
-        ctx->rs_list = nullptr;
-        ctx->rs_cap = 0;
-        if (!ctx->rs_count) CK(cudaMalloc(&ctx->rs_count, sizeof(int)));
-        CK(cudaMalloc(&ctx->rs_list, sizeof(long long) * (size_t)n));
-        ctx->rs_cap = n;
-    }
+// ---- tensor-core forward + exact fp32 re-score of the windows inside the guard band ------------------------------
+// ||z||_F of a window after CMVN: python style makes every coefficient row sum to N - 1 = 62 (or 0 for a constant row),
+// device style rounds a population-normalised row (norm sqrt(63)) to integers (+- 0.5 per value, saturation shrinks it)
+static const float kNormPy = 28.3901391f;      // sqrt(13 * 62)
+static const float kNormDevice = 42.9243521f;  // 1.5 * sqrt(13 * 63)
+
+static int tc_launch(ww_ctx* ctx, const float* feats, long long ws, long long cs, long long fs, long long n,
+                     int cmvn_mode, int decide_mode, float threshold, float thr0, float thr1, float band, float band_rel,
+                     float* logits, unsigned char* decisions, long long* rescore_list, cudaStream_t st) {
     TcArgs a;
     a.feats = feats;
     a.win_stride = ws;
@@ -661,49 +688,309 @@ static int tc_forward(ww_ctx* ctx, const float* feats, long long ws, long long c
     a.cmvn_mode = cmvn_mode;
     a.decide_mode = decide_mode;
     a.threshold = threshold;
-    a.thr_logit = decide_mode == WW_DECIDE_DEVICE ? logf(threshold / (100.f - threshold)) : threshold;
-    a.band = ctx->tc_band;
+    a.thr0 = thr0;
+    a.thr1 = thr1;
+    a.band = band;
+    a.band_rel = band_rel;
+    a.norm_limit = ctx->tc_norm_limit;
     a.logits = logits;
     a.decisions = decisions;
-    a.rescore_list = rescoring ? ctx->rs_list : nullptr;
+    a.rescore_list = rescore_list;
     a.rescore_count = ctx->rs_count;
     a.wblob = ctx->tc_blob;
     a.fc2 = ctx->w.fc2;
     a.num_classes = ctx->w.num_classes;
     a.dbg = ctx->tc_dbg;
-    if (rescoring) CK(cudaMemsetAsync(ctx->rs_count, 0, sizeof(int), st));
     const long long n_cta = ((n + TC_CLIPS - 1) / TC_CLIPS + TC_GROUPS - 1) / TC_GROUPS;
     const unsigned grid = (unsigned)(n_cta < ctx->sm_count ? n_cta : ctx->sm_count);
     cnn_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(a);
     CK(cudaGetLastError());
-    if (rescoring) {
-        CnnArgs r;
-        r.feats = feats;
-        r.win_stride = ws;
-        r.coef_stride = cs;
-        r.frame_stride = fs;
-        r.n_windows = n;  // capacity; the device-side count bounds the loop
-        r.group_windows = ctx->grp_windows;
-        r.group_stride = ctx->grp_stride;
-        r.index = ctx->rs_list;
-        r.index_count = ctx->rs_count;
-        r.cmvn_mode = cmvn_mode;
-        r.decide_mode = decide_mode;
-        r.threshold = threshold;
-        r.logits = logits;
-        r.decisions = decisions;
-        r.norm_out = nullptr;
-        r.w = ctx->w;
-        long long g = 64;  // the list is short (windows within tc_band of the threshold)
-        if (g > n) g = n;
-        cnn_fp32_kernel<<<(unsigned)g, CNN_THREADS, 0, st>>>(r);
-        CK(cudaGetLastError());
-    }
     return WW_OK;
 }
-#endif
 
-#ifdef WW_WITH_TC
+// Decisions AND logits near a decision threshold are those of the fp32 kernel: every window whose tensor-path logit
+// could, within the calibrated error of the fp16 operands, lie on the other side of a threshold is recomputed
+// exactly.  With DECIDE_NONE both rules of the reference are protected (sigmoid > 0.5 <=> logit > 0,
+// ml_models/main.py:53; sigmoid*100 >= 80 <=> logit >= ln 4, esp_wake_word_detector.cpp:226-228,245), so a caller
+// that thresholds the returned logits itself (LightweightKWS.forward + torch.sigmoid(out) > 0.5) gets the fp32
+// path's decisions too.
+static int tc_forward(ww_ctx* ctx, const float* feats, long long ws, long long cs, long long fs, long long n,
+                      int cmvn_mode, int decide_mode, float threshold, float* logits, unsigned char* decisions,
+                      cudaStream_t st) {
+    if (ctx->w.num_classes > TC_MAX_CLASSES)
+        return fail(ctx, WW_ERR_UNSUPPORTED, "tensor-core CNN supports at most 8 classes");
+    if (n == 0) return WW_OK;
+    const float norm_mode = cmvn_mode == WW_CMVN_PY ? kNormPy : (cmvn_mode == WW_CMVN_DEVICE ? kNormDevice : 0.f);
+    if (!ctx->tc_ok || norm_mode > ctx->tc_norm_limit)  // weights for which fp16 operands are not trustworthy
+        return launch_cnn_fp32(ctx, feats, ws, cs, fs, n, nullptr, nullptr, cmvn_mode, decide_mode, threshold, logits,
+                               decisions, nullptr, st);
+    if (ctx->rs_cap < n) {
+        cudaFree(ctx->rs_list);
+        ctx->rs_list = nullptr;
+        ctx->rs_cap = 0;
+        CK(cudaMalloc(&ctx->rs_list, sizeof(long long) * (size_t)n));
+        ctx->rs_cap = n;
+    }
+    if (!ctx->rs_count) CK(cudaMalloc(&ctx->rs_count, sizeof(int)));
+    if (!ctx->rs_total) {
+        CK(cudaMalloc(&ctx->rs_total, sizeof(unsigned long long)));
+        CK(cudaMemset(ctx->rs_total, 0, sizeof(unsigned long long)));
+    }
+    const float ln4 = 1.38629436f;
+    float thr0 = 0.f, thr1 = ln4;
+    if (decide_mode == WW_DECIDE_LOGIT) thr0 = thr1 = threshold;
+    else if (decide_mode == WW_DECIDE_DEVICE) thr0 = thr1 = logf(threshold / (100.f - threshold));
+    float band = ctx->tc_beta * norm_mode, band_rel = cmvn_mode == WW_CMVN_NONE ? ctx->tc_beta : 0.f;
+    if (ctx->tc_band_override >= 0.f) {
+        band = ctx->tc_band_override;
+        band_rel = 0.f;
+    }
+    CK(cudaMemsetAsync(ctx->rs_count, 0, sizeof(int), st));
+    int rc = tc_launch(ctx, feats, ws, cs, fs, n, cmvn_mode, decide_mode, threshold, thr0, thr1, band, band_rel, logits,
+                       decisions, ctx->rs_list, st);
+    if (rc) return rc;
+    long long g = (long long)ctx->sm_count * 2;  // the list is short; blocks beyond the device-side count exit at once
+    if (g > n) g = n;
+    return launch_cnn_fp32(ctx, feats, ws, cs, fs, n /* capacity */, ctx->rs_list, ctx->rs_count, cmvn_mode,
+                           decide_mode, threshold, logits, decisions, nullptr, st, (unsigned)g);
+}
+
+// ---- calibration of the tensor path against the exact kernel, for the weights just loaded ------------------------
+// (a) rigorous part, from the weights alone.  Frobenius-norm recursion through the bias-free network with
+//     L_l >= the operator norm of layer l (a k = 3 convolution is [W_0 W_1 W_2] applied to the im2col'ed input, whose
+//     norm is at most sqrt(3) ||x||_F; ReLU, MaxPool are 1-Lipschitz; the average over 7 steps divides by sqrt(7)).
+//     sigma_max(A) <= tr((A A^T)^32)^(1/64) is an upper bound that needs no eigen-solver.  This gives
+//       - tc_norm_limit: no activation the tensor path stores as fp16 can exceed 65504 while ||x||_F <= tc_norm_limit;
+//       - tc_beta_rig:   |tensor logit - exact logit| <= tc_beta_rig ||x||_F for ANY input (u = 2^-11 per fp16
+//                        rounding, the actual fp16 weight perturbation, K 2^-22 per accumulation).  It assumes the
+//                        worst alignment in every layer and is 500-1000x the observed error (3.5 logits for
+//                        xiaoa.onnx with CMVN input) -- a filter that re-scores everything.
+// (b) measured part.  4096 deterministic windows (white, coloured, single hot frames, square waves, full-scale
+//     signs, the CMVN extreme point, smooth drifts, raw-MFCC-like rows) go through both kernels, fed as they are and
+//     through the python CMVN; tc_beta_cal = 8 x max |tensor logit - fp32 logit| / ||x||_F.  The error is a sum of
+//     ~1e4 independent roundings, so the largest of 8192 samples is ~4 sigma and the band ~30 sigma.
+// The band used is min(a, b); non-finite calibration logits switch the tensor path off for these weights.
+static double sigma_ub(const std::vector<double>& A, int rows, int cols) {
+    std::vector<double> G((size_t)rows * rows, 0.0), H((size_t)rows * rows);
+    for (int i = 0; i < rows; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double acc = 0.0;
+            for (int k = 0; k < cols; ++k) acc += A[(size_t)i * cols + k] * A[(size_t)j * cols + k];
+            G[(size_t)i * rows + j] = G[(size_t)j * rows + i] = acc;
+        }
+    double t0 = 0.0;
+    for (int i = 0; i < rows; ++i) t0 += G[(size_t)i * rows + i];
+    if (!(t0 > 0.0)) return 0.0;
+    for (double& v : G) v /= t0;
+    double logscale = 0.0;
+    const int squarings = 5;  // p = 32
+    for (int sq = 0; sq < squarings; ++sq) {
+        for (int i = 0; i < rows; ++i)
+            for (int j = 0; j <= i; ++j) {
+                double acc = 0.0;
+                for (int k = 0; k < rows; ++k) acc += G[(size_t)i * rows + k] * G[(size_t)k * rows + j];
+                H[(size_t)i * rows + j] = H[(size_t)j * rows + i] = acc;
+            }
+        double t = 0.0;
+        for (int i = 0; i < rows; ++i) t += H[(size_t)i * rows + i];
+        if (!(t > 0.0)) return sqrt(t0);  // cannot happen for a PSD matrix with positive trace; Frobenius bound
+        for (size_t i = 0; i < G.size(); ++i) G[i] = H[i] / t;
+        logscale = 2.0 * logscale + log(t);
+    }
+    return sqrt(t0 * exp(logscale / 32.0));
+}
+
+static float fp16_round(float v) { return __half2float(__float2half_rn(v)); }
+
+static int tc_calibrate(ww_ctx* ctx) {
+    ctx->tc_ok = false;
+    ctx->tc_beta = ctx->tc_beta_cal = ctx->tc_beta_rig = 0.f;
+    ctx->tc_norm_limit = 0.f;
+    const int C = ctx->w.num_classes;
+    if (C > TC_MAX_CLASSES) return WW_OK;  // such models always run the fp32 kernel
+    // ---- (a) rigorous bounds
+    const int O[4] = {32, 64, 128, 64}, I[4] = {13, 32, 64, 128}, K[5] = {39, 96, 192, 128, 64};
+    double Lb[5], Db[4], Fb[5];
+    for (int l = 0; l < 4; ++l) {
+        const bool conv = l < 3;
+        const int cols = conv ? 3 * I[l] : I[l];
+        std::vector<double> A((size_t)O[l] * cols), dA(A.size());
+        double fro = 0.0;
+        for (size_t i = 0; i < A.size(); ++i) {   // torch [O][I][3] flattened is already [O][3 I] up to a column permutation
+            const float w = ctx->host_w[l][i];
+            A[i] = w;
+            dA[i] = (double)fp16_round(w) - (double)w;
+            fro += (double)w * w;
+        }
+        const double f = conv ? sqrt(3.0) : 1.0;
+        Lb[l] = f * sigma_ub(A, O[l], cols);
+        Db[l] = f * sigma_ub(dA, O[l], cols);
+        Fb[l] = f * sqrt(fro);
+    }
+    {
+        std::vector<double> A((size_t)C * 64);
+        double fro = 0.0;
+        for (size_t i = 0; i < A.size(); ++i) {
+            A[i] = ctx->host_w[4][i];
+            fro += A[i] * A[i];
+        }
+        Lb[4] = sigma_ub(A, C, 64);
+        Fb[4] = sqrt(fro);
+    }
+    const double u = ldexp(1.0, -11);
+    double a = 1.0, e = (u + ldexp(1.0, -21)) * a, amax = 1.0;
+    for (int l = 0; l < 3; ++l) {
+        e = (Lb[l] + Db[l]) * e + Db[l] * a + 2.0 * K[l] * ldexp(1.0, -22) * Fb[l] * a;
+        a = Lb[l] * a;
+        if (l < 2) {
+            e += u * (a + e);
+            amax = std::max(amax, a);
+        }
+    }
+    a /= sqrt(7.0);
+    e /= sqrt(7.0);
+    e += u * (a + e);
+    amax = std::max(amax, a);
+    e = (Lb[3] + Db[3]) * e + Db[3] * a + 2.0 * K[3] * ldexp(1.0, -22) * Fb[3] * a;
+    a = Lb[3] * a;
+    e = Lb[4] * e + 2.0 * K[4] * ldexp(1.0, -24) * Fb[4] * a;
+    ctx->tc_beta_rig = (float)e;
+    ctx->tc_norm_limit = (float)(0.99 * 65504.0 / amax);
+    if (!std::isfinite(ctx->tc_beta_rig) || !std::isfinite(ctx->tc_norm_limit) || !(ctx->tc_norm_limit > 0.f)) {
+        ctx->tc_norm_limit = 0.f;
+        return WW_OK;
+    }
+
+    // ---- (b) measured part
+    const int N = 4096, W = WW_N_MFCC * WW_WINDOW_FRAMES;
+    std::vector<float> x((size_t)N * W);
+    uint64_t rng = 0x9E3779B97F4A7C15ull;
+    auto uni = [&]() {  // xorshift64*, (0, 1)
+        rng ^= rng >> 12;
+        rng ^= rng << 25;
+        rng ^= rng >> 27;
+        return (float)(((rng * 0x2545F4914F6CDD1Dull) >> 40) + 0.5) * (1.0f / 16777216.0f);
+    };
+    auto gauss = [&]() { return (uni() + uni() + uni() + uni() - 2.0f) * 1.7320508f; };  // variance 1
+    for (int w = 0; w < N; ++w) {
+        float* xw = x.data() + (size_t)w * W;
+        const int kind = w & 7;
+        for (int q = 0; q < WW_N_MFCC; ++q) {
+            float* r = xw + q * WW_WINDOW_FRAMES;
+            const int T = WW_WINDOW_FRAMES;
+            switch (kind) {
+                case 0: for (int t = 0; t < T; ++t) r[t] = gauss(); break;
+                case 1: {
+                    const float sc = powf(10.f, 2.f * uni() - 1.f), off = 4.f * gauss();
+                    for (int t = 0; t < T; ++t) r[t] = off + sc * gauss();
+                } break;
+                case 2: {
+                    const int hot = (int)(uni() * T) % T;
+                    for (int t = 0; t < T; ++t) r[t] = 0.f;
+                    r[hot] = 8.f * gauss();
+                } break;
+                case 3: {
+                    const int per = 1 + (int)(uni() * 8), ph = (int)(uni() * 16);
+                    const float amp = 0.25f + 4.f * uni();
+                    for (int t = 0; t < T; ++t) r[t] = (((t + ph) / per) & 1) ? amp : -amp;
+                } break;
+                case 4: for (int t = 0; t < T; ++t) r[t] = uni() < 0.5f ? -7.8f : 7.8f; break;
+                case 5: {
+                    const int hot = (int)(uni() * T) % T;
+                    for (int t = 0; t < T; ++t) r[t] = -0.125988f;
+                    r[hot] = 7.811249f;
+                } break;
+                case 6: {
+                    float acc = 0.f;
+                    for (int t = 0; t < T; ++t) {
+                        acc = 0.9f * acc + gauss();
+                        r[t] = acc;
+                    }
+                } break;
+                default: {
+                    const float base = q == 0 ? -40.f + 10.f * gauss() : 0.f, sc = 12.f / (1.f + q);
+                    for (int t = 0; t < T; ++t) r[t] = base + sc * gauss();
+                } break;
+            }
+        }
+    }
+    float *d_x = nullptr, *d_a = nullptr, *d_b = nullptr;
+    std::vector<float> la((size_t)N * C), lb((size_t)N * C);
+    double ratio = 0.0;
+    bool finite = true;
+    int rc = WW_OK;
+    cudaError_t ce;
+    if ((ce = cudaMalloc(&d_x, x.size() * sizeof(float))) != cudaSuccess ||
+        (ce = cudaMalloc(&d_a, la.size() * sizeof(float))) != cudaSuccess ||
+        (ce = cudaMalloc(&d_b, lb.size() * sizeof(float))) != cudaSuccess ||
+        (ce = cudaMemcpy(d_x, x.data(), x.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) {
+        rc = cuda_fail(ctx, ce, "tc_calibrate: buffers");
+    }
+    const long long gw = ctx->grp_windows, gs = ctx->grp_stride;
+    ctx->grp_windows = ctx->grp_stride = 0;
+    for (int pass = 0; pass < 2 && rc == WW_OK; ++pass) {
+        const int mode = pass == 0 ? WW_CMVN_NONE : WW_CMVN_PY;
+        rc = launch_cnn_fp32(ctx, d_x, W, WW_WINDOW_FRAMES, 1, N, nullptr, nullptr, mode, WW_DECIDE_NONE, 0.f, d_a, nullptr,
+                             nullptr, nullptr);
+        if (rc == WW_OK)
+            rc = tc_launch(ctx, d_x, W, WW_WINDOW_FRAMES, 1, N, mode, WW_DECIDE_NONE, 0.f, 0.f, 0.f, 0.f, 0.f, d_b, nullptr,
+                           nullptr, nullptr);
+        if (rc != WW_OK) break;
+        if ((ce = cudaMemcpy(la.data(), d_a, la.size() * sizeof(float), cudaMemcpyDeviceToHost)) != cudaSuccess ||
+            (ce = cudaMemcpy(lb.data(), d_b, lb.size() * sizeof(float), cudaMemcpyDeviceToHost)) != cudaSuccess) {
+            rc = cuda_fail(ctx, ce, "tc_calibrate: read back");
+            break;
+        }
+        for (int w = 0; w < N; ++w) {
+            double nx = kNormPy;
+            if (mode == WW_CMVN_NONE) {
+                nx = 0.0;
+                const float* xw = x.data() + (size_t)w * W;
+                for (int i = 0; i < W; ++i) nx += (double)xw[i] * xw[i];
+                nx = sqrt(nx);
+                if (nx > ctx->tc_norm_limit) continue;  // such windows never trust the tensor path
+            }
+            for (int c = 0; c < C; ++c) {
+                const float va = la[(size_t)w * C + c], vb = lb[(size_t)w * C + c];
+                if (!std::isfinite(va) || !std::isfinite(vb)) finite = false;
+                else if (nx > 0.0) ratio = std::max(ratio, fabs((double)va - (double)vb) / nx);
+            }
+        }
+    }
+    ctx->grp_windows = gw;
+    ctx->grp_stride = gs;
+    cudaFree(d_x);
+    cudaFree(d_a);
+    cudaFree(d_b);
+    if (rc != WW_OK) return rc;
+    ctx->tc_beta_cal = (float)(8.0 * ratio) + 1e-9f;
+    ctx->tc_beta = std::min(ctx->tc_beta_cal, ctx->tc_beta_rig);
+    ctx->tc_ok = finite && std::isfinite(ctx->tc_beta);
+    return WW_OK;
+}
+
+// windows the tensor path has handed to the exact kernel since the counter was last reset (synchronises the device)
+extern "C" long long ww_tc_rescored_total(ww_ctx* ctx, int reset) {
+    if (!ctx) return WW_ERR_INVALID;
+    if (!ctx->rs_total) return 0;
+    unsigned long long v = 0;
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+        cudaMemcpy(&v, ctx->rs_total, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return WW_ERR_CUDA;
+    if (reset && cudaMemset(ctx->rs_total, 0, sizeof(v)) != cudaSuccess) return WW_ERR_CUDA;
+    return (long long)v;
+}
+
+extern "C" int ww_tc_band_info(const ww_ctx* ctx, float* beta, float* beta_calibrated, float* beta_rigorous,
+                               float* norm_limit) {
+    if (!ctx) return WW_ERR_INVALID;
+    if (beta) *beta = ctx->tc_beta;
+    if (beta_calibrated) *beta_calibrated = ctx->tc_beta_cal;
+    if (beta_rigorous) *beta_rigorous = ctx->tc_beta_rig;
+    if (norm_limit) *norm_limit = ctx->tc_norm_limit;
+    return ctx->tc_ok ? 1 : 0;
+}
+
 static void i8tc_fill(ww_ctx* ctx, I8TcArgs& t) {
     memset(&t, 0, sizeof(t));
     t.wblob = ctx->i8tc_blob;
@@ -724,12 +1011,10 @@ static int i8tc_launch(ww_ctx* ctx, const I8TcArgs& t, cudaStream_t st) {
     CK(cudaGetLastError());
     return WW_OK;
 }
-#endif
 
 static int run_cnn(ww_ctx* ctx, const float* feats, long long ws, long long cs, long long fs, long long n,
                    int cmvn_mode, int decide_mode, float threshold, int cnn_impl, float* logits,
                    unsigned char* decisions, cudaStream_t st) {
-#ifdef WW_WITH_TC
     if (cnn_impl == WW_CNN_INT8) {
         if (n == 0) return WW_OK;
         I8TcArgs t;
@@ -751,7 +1036,6 @@ static int run_cnn(ww_ctx* ctx, const float* feats, long long ws, long long cs, 
         int rc = tc_forward(ctx, feats, ws, cs, fs, n, cmvn_mode, decide_mode, threshold, logits, decisions, st);
         return rc;
     }
-#endif
     return launch_cnn_fp32(ctx, feats, ws, cs, fs, n, nullptr, nullptr, cmvn_mode, decide_mode, threshold, logits,
                            decisions, nullptr, st);
 }
@@ -794,27 +1078,8 @@ extern "C" int ww_quantize_weights_i8(ww_ctx* ctx, const int* exps) {
     trq(ctx->host_w[2], p + n1 + n2, 128, 64, exps[5]);
     for (int i = 0; i < n4; ++i) p[n1 + n2 + n3 + i] = q(ctx->host_w[3][i], exps[8]);
     for (int i = 0; i < n5; ++i) p[n1 + n2 + n3 + n4 + i] = q(ctx->host_w[4][i], exps[10]);
-    CK(cudaSetDevice(ctx->device));
-    cudaFree(ctx->i8blob);
-    ctx->i8blob = nullptr;
-    CK(cudaMalloc(&ctx->i8blob, h.size()));
-    CK(cudaMemcpy(ctx->i8blob, h.data(), h.size(), cudaMemcpyHostToDevice));
-#ifdef WW_WITH_TC
-    {
-        std::vector<unsigned char> tb;
-        i8tc_build_blob(tb, p, p + n1, p + n1 + n2, p + n1 + n2 + n3);
-        cudaFree(ctx->i8tc_blob);
-        ctx->i8tc_blob = nullptr;
-        CK(cudaMalloc(&ctx->i8tc_blob, tb.size()));
-        CK(cudaMemcpy(ctx->i8tc_blob, tb.data(), tb.size(), cudaMemcpyHostToDevice));
-    }
-#endif
-    I8Weights& w = ctx->i8w;
-    w.w1t = ctx->i8blob;
-    w.w2t = ctx->i8blob + n1;
-    w.w3t = ctx->i8blob + n1 + n2;
-    w.fc1 = ctx->i8blob + n1 + n2 + n3;
-    w.fc2 = ctx->i8blob + n1 + n2 + n3 + n4;
+    // validate the exponent combination BEFORE anything of the previous quantisation is replaced
+    I8Weights w{};
     w.num_classes = C;
     w.sh1 = exps[2] - (exps[0] + exps[1]);
     w.sh2 = exps[4] - (exps[2] + exps[3]);
@@ -825,6 +1090,26 @@ extern "C" int ww_quantize_weights_i8(ww_ctx* ctx, const int* exps) {
     if (w.sh1 < 0 || w.sh2 < 0 || w.sh3 < 0 || w.shf1 < 0 || w.shf2 < 0 || w.sh1 > 30 || w.sh2 > 30 || w.sh3 > 30 ||
         w.shf1 > 30 || w.shf2 > 30 || w.gap_num_shift < -8 || w.gap_num_shift > 8)
         return fail(ctx, WW_ERR_UNSUPPORTED, "quantize_weights_i8: unsupported exponent combination");
+    CK(cudaSetDevice(ctx->device));
+    ctx->have_i8 = false;  // from here on the old blobs are being replaced
+    cudaFree(ctx->i8blob);
+    ctx->i8blob = nullptr;
+    CK(cudaMalloc(&ctx->i8blob, h.size()));
+    CK(cudaMemcpy(ctx->i8blob, h.data(), h.size(), cudaMemcpyHostToDevice));
+    {
+        std::vector<unsigned char> tb;
+        i8tc_build_blob(tb, p, p + n1, p + n1 + n2, p + n1 + n2 + n3);
+        cudaFree(ctx->i8tc_blob);
+        ctx->i8tc_blob = nullptr;
+        CK(cudaMalloc(&ctx->i8tc_blob, tb.size()));
+        CK(cudaMemcpy(ctx->i8tc_blob, tb.data(), tb.size(), cudaMemcpyHostToDevice));
+    }
+    w.w1t = ctx->i8blob;
+    w.w2t = ctx->i8blob + n1;
+    w.w3t = ctx->i8blob + n1 + n2;
+    w.fc1 = ctx->i8blob + n1 + n2 + n3;
+    w.fc2 = ctx->i8blob + n1 + n2 + n3 + n4;
+    ctx->i8w = w;
     ctx->i8_in_exp = exps[0];
     ctx->i8_out_exp = exps[11];
     ctx->have_i8 = true;
@@ -836,7 +1121,6 @@ extern "C" int ww_cnn_forward_i8(ww_ctx* ctx, const int8_t* x, long long n_windo
     if (!ctx->have_i8) return fail(ctx, WW_ERR_NO_WEIGHTS, "int8 weights not prepared (ww_quantize_weights_i8)");
     if (n_windows == 0) return WW_OK;
     if (!x || !out || n_windows < 0) return fail(ctx, WW_ERR_INVALID, "cnn_forward_i8: bad arguments");
-#ifdef WW_WITH_TC
     if (ctx->i8_impl == WW_CNN_TENSOR && ctx->w.num_classes <= TC_MAX_CLASSES) {
         I8TcArgs t;
         i8tc_fill(ctx, t);
@@ -845,7 +1129,6 @@ extern "C" int ww_cnn_forward_i8(ww_ctx* ctx, const int8_t* x, long long n_windo
         t.out = reinterpret_cast<signed char*>(out);
         return i8tc_launch(ctx, t, (cudaStream_t)stream);
     }
-#endif
     I8Args a;
     a.x = reinterpret_cast<const signed char*>(x);
     a.n_windows = n_windows;
@@ -863,10 +1146,26 @@ extern "C" int ww_cnn_forward_i8(ww_ctx* ctx, const int8_t* x, long long n_windo
 // ------------------------------------------------------------------------------------------------
 static int ensure_scratch(ww_ctx* ctx) {
     if (ctx->scratch) return WW_OK;
-    CK(cudaMalloc(&ctx->scratch, (size_t)kScratchClips * WW_N_MFCC * WW_WINDOW_FRAMES * sizeof(float)));
-    ctx->scratch_clips = kScratchClips;
+    CK(cudaMalloc(&ctx->scratch, (size_t)ctx->chunk_clips * WW_N_MFCC * WW_WINDOW_FRAMES * sizeof(float)));
+    ctx->scratch_clips = ctx->chunk_clips;
+    CK(cudaEventCreateWithFlags(&ctx->scratch_ev, cudaEventDisableTiming));
     return WW_OK;
 }
+
+// One fused call at a time per context from the host's point of view (the feature scratch, the re-score list and the
+// host-path buffers are context-owned): a second thread entering while one is inside gets WW_ERR_BUSY instead of a race.
+// Calls that follow each other on DIFFERENT streams are ordered on the device through scratch_ev.
+struct BusyGuard {
+    ww_ctx* c;
+    bool ok;
+    explicit BusyGuard(ww_ctx* ctx) : c(ctx) {
+        int zero = 0;
+        ok = c->busy.compare_exchange_strong(zero, 1);
+    }
+    ~BusyGuard() {
+        if (ok) c->busy.store(0);
+    }
+};
 
 static int score_clips_dev(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_clips, int cmvn_mode,
                            int decide_mode, float threshold, int cnn_impl, float* logits, unsigned char* decisions,
@@ -875,14 +1174,31 @@ static int score_clips_dev(ww_ctx* ctx, const void* pcm, int pcm_type, long long
     if (rc) return rc;
     const size_t esz = pcm_type == WW_PCM_S16 ? 2 : 4;
     const int C = ctx->w.num_classes;
+    if (ctx->scratch_used && ctx->scratch_stream != st) CK(cudaStreamWaitEvent(st, ctx->scratch_ev, 0));
+    struct Mark {  // every exit leaves the scratch's last use recorded on this stream
+        ww_ctx* c;
+        cudaStream_t st;
+        ~Mark() {
+            if (cudaEventRecord(c->scratch_ev, st) == cudaSuccess) {
+                c->scratch_stream = st;
+                c->scratch_used = true;
+            }
+        }
+    } mark{ctx, st};
     for (long long c0 = 0; c0 < n_clips; c0 += ctx->scratch_clips) {
         const long long nc = (n_clips - c0) < ctx->scratch_clips ? (n_clips - c0) : ctx->scratch_clips;
         const char* p = (const char*)pcm + (size_t)c0 * WW_CLIP_SAMPLES * esz;
-        rc = launch_mfcc(ctx, p, pcm_type, nc, WW_CLIP_SAMPLES, WW_CLIP_SAMPLES, WW_FEAT_PY, ctx->scratch,
-                         WW_N_MFCC * WW_WINDOW_FRAMES, WW_WINDOW_FRAMES, 1, st);
+        {
+            NvtxRange r("ww:frontend");
+            rc = launch_mfcc(ctx, p, pcm_type, nc, WW_CLIP_SAMPLES, WW_CLIP_SAMPLES, WW_FEAT_PY, ctx->scratch,
+                             WW_N_MFCC * WW_WINDOW_FRAMES, WW_WINDOW_FRAMES, 1, st);
+        }
         if (rc) return rc;
-        rc = run_cnn(ctx, ctx->scratch, WW_N_MFCC * WW_WINDOW_FRAMES, WW_WINDOW_FRAMES, 1, nc, cmvn_mode, decide_mode,
-                     threshold, cnn_impl, logits + c0 * C, decisions ? decisions + c0 : nullptr, st);
+        {
+            NvtxRange r("ww:cmvn+cnn+decision");
+            rc = run_cnn(ctx, ctx->scratch, WW_N_MFCC * WW_WINDOW_FRAMES, WW_WINDOW_FRAMES, 1, nc, cmvn_mode, decide_mode,
+                         threshold, cnn_impl, logits + c0 * C, decisions ? decisions + c0 : nullptr, st);
+        }
         if (rc) return rc;
     }
     return WW_OK;
@@ -897,31 +1213,55 @@ extern "C" int ww_score_clips(ww_ctx* ctx, const void* pcm, int pcm_type, long l
     if (pcm_type != WW_PCM_S16 && pcm_type != WW_PCM_F32) return fail(ctx, WW_ERR_INVALID, "score_clips: bad pcm_type");
     int rc = check_cnn_args(ctx, cmvn_mode, decide_mode, cnn_impl);
     if (rc) return rc;
+    BusyGuard guard(ctx);
+    if (!guard.ok) return WW_ERR_BUSY;  // ctx->err belongs to the call that is inside
     return score_clips_dev(ctx, pcm, pcm_type, n_clips, cmvn_mode, decide_mode, threshold, cnn_impl, logits, decisions,
                            (cudaStream_t)stream);
 }
 
+static void free_host_path(ww_ctx* ctx) {
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
+        cudaFree(ctx->d_pcm[i]);
+        cudaFree(ctx->d_logits[i]);
+        cudaFree(ctx->d_dec[i]);
+        if (ctx->h_logits[i]) cudaFreeHost(ctx->h_logits[i]);
+        if (ctx->h_dec[i]) cudaFreeHost(ctx->h_dec[i]);
+        ctx->h_pin[i] = nullptr;
+        ctx->d_pcm[i] = nullptr;
+        ctx->d_logits[i] = nullptr;
+        ctx->d_dec[i] = nullptr;
+        ctx->h_logits[i] = nullptr;
+        ctx->h_dec[i] = nullptr;
+    }
+    ctx->host_chunk = 0;
+    ctx->host_chunk_bytes = 0;
+    ctx->host_classes = 0;
+}
+
+// Buffers of the host-buffer path: two pinned PCM staging chunks, two device PCM chunks, logits / decisions per chunk on
+// both sides.  Everything is sized for (chunk, sample width, class count); a change of any of them (ww_load_weights
+// with another num_classes frees the set) rebuilds it.
 static int ensure_host_path(ww_ctx* ctx, size_t esz) {
     const long long chunk = kHostChunkClips;
     const size_t bytes = (size_t)chunk * WW_CLIP_SAMPLES * esz;
-    if (ctx->host_chunk == chunk && ctx->host_chunk_bytes >= bytes) return WW_OK;
+    const int C = ctx->w.num_classes;
+    if (ctx->host_chunk == chunk && ctx->host_chunk_bytes >= bytes && ctx->host_classes == C) return WW_OK;
+    free_host_path(ctx);
+    const size_t lb = (size_t)chunk * sizeof(float) * (size_t)C;
     for (int i = 0; i < 2; ++i) {
         if (!ctx->hs[i]) CK(cudaStreamCreateWithFlags(&ctx->hs[i], cudaStreamNonBlocking));
         if (!ctx->hev[i]) CK(cudaEventCreateWithFlags(&ctx->hev[i], cudaEventDisableTiming));
-        if (ctx->h_pin[i]) { cudaFreeHost(ctx->h_pin[i]); ctx->h_pin[i] = nullptr; }
-        cudaFree(ctx->d_pcm[i]); ctx->d_pcm[i] = nullptr;
         CK(cudaMallocHost(&ctx->h_pin[i], bytes));
         CK(cudaMalloc(&ctx->d_pcm[i], bytes));
-        if (!ctx->d_logits[i]) {
-            const size_t lb = (size_t)chunk * sizeof(float) * (size_t)ctx->w.num_classes;
-            CK(cudaMalloc(&ctx->d_logits[i], lb));
-            CK(cudaMalloc(&ctx->d_dec[i], (size_t)chunk));
-            CK(cudaMallocHost((void**)&ctx->h_logits[i], lb));
-            CK(cudaMallocHost((void**)&ctx->h_dec[i], (size_t)chunk));
-        }
+        CK(cudaMalloc(&ctx->d_logits[i], lb));
+        CK(cudaMalloc(&ctx->d_dec[i], (size_t)chunk));
+        CK(cudaMallocHost((void**)&ctx->h_logits[i], lb));
+        CK(cudaMallocHost((void**)&ctx->h_dec[i], (size_t)chunk));
     }
     ctx->host_chunk = chunk;
     ctx->host_chunk_bytes = bytes;
+    ctx->host_classes = C;
     return WW_OK;
 }
 
@@ -934,6 +1274,9 @@ extern "C" int ww_score_clips_host(ww_ctx* ctx, const void* pcm_host, int pcm_ty
     if (pcm_type != WW_PCM_S16 && pcm_type != WW_PCM_F32) return fail(ctx, WW_ERR_INVALID, "score_clips_host: bad pcm_type");
     int rc = check_cnn_args(ctx, cmvn_mode, decide_mode, cnn_impl);
     if (rc) return rc;
+    BusyGuard guard(ctx);
+    if (!guard.ok) return WW_ERR_BUSY;
+    NvtxRange whole("ww_score_clips_host");
     CK(cudaSetDevice(ctx->device));
     const size_t esz = pcm_type == WW_PCM_S16 ? 2 : 4;
     rc = ensure_host_path(ctx, esz);
@@ -955,6 +1298,7 @@ extern "C" int ww_score_clips_host(ww_ctx* ctx, const void* pcm_host, int pcm_ty
             const long long kk = k - 2;
             const int b = (int)(kk & 1);
             const long long c0 = kk * chunk, nc = (n_clips - c0) < chunk ? (n_clips - c0) : chunk;
+            NvtxRange r("ww:retire(d2h wait + copy out)");
             CK(cudaStreamSynchronize(ctx->hs[b]));
             memcpy(logits_host + c0 * C, ctx->h_logits[b], (size_t)nc * C * sizeof(float));
             if (decisions_host) memcpy(decisions_host + c0, ctx->h_dec[b], (size_t)nc);
@@ -964,6 +1308,7 @@ extern "C" int ww_score_clips_host(ww_ctx* ctx, const void* pcm_host, int pcm_ty
             const long long c0 = k * chunk, nc = (n_clips - c0) < chunk ? (n_clips - c0) : chunk;
             const size_t bytes = (size_t)nc * WW_CLIP_SAMPLES * esz;
             const char* src = (const char*)pcm_host + (size_t)c0 * WW_CLIP_SAMPLES * esz;
+            NvtxRange r("ww:h2d+enqueue");
             if (pinned) {
                 CK(cudaMemcpyAsync(ctx->d_pcm[b], src, bytes, cudaMemcpyHostToDevice, ctx->hs[b]));
             } else {
@@ -987,22 +1332,57 @@ extern "C" int ww_score_clips_host(ww_ctx* ctx, const void* pcm_host, int pcm_ty
 // ------------------------------------------------------------------------------------------------
 // streaming
 // ------------------------------------------------------------------------------------------------
-extern "C" int ww_stream_score(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_samples, int cmvn_mode,
-                               int cnn_impl, float* feats_work, float* logits, ww_stream_t stream) {
+// Frames [first_frame, first_frame + n_frames) of a stream of `stream_len` samples, computed from a buffer that holds the
+// samples [first_sample, first_sample + n_samples) of it, and every 63-frame window made of them.  Frame t of the
+// stream is centred on sample 256 t: it reads samples 256 t - 160 .. 256 t + 159 and, for the pre-emphasis, the one
+// before; torch.stft's reflect padding exists only at the two true ends of the stream, so a segment in the middle
+// must simply carry its halo (checked below).  The frontend is entered with the origin that keeps the frame phase of
+// the whole stream -- the same mechanism the streaming sessions use.
+extern "C" int ww_stream_score_segment(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_samples,
+                                       long long first_sample, long long stream_len, long long first_frame,
+                                       long long n_frames, int cmvn_mode, int cnn_impl, float* feats_work, float* logits,
+                                       ww_stream_t stream) {
     if (!ctx) return WW_ERR_INVALID;
     if (!pcm || !feats_work || !logits) return fail(ctx, WW_ERR_INVALID, "stream_score: null buffer");
-    if (n_samples <= 0 || n_samples > 0x7fffff00LL) return fail(ctx, WW_ERR_INVALID, "stream_score: bad n_samples");
+    if (pcm_type != WW_PCM_S16 && pcm_type != WW_PCM_F32) return fail(ctx, WW_ERR_INVALID, "stream_score: bad pcm_type");
+    if (stream_len <= 0 || n_samples <= 0 || n_samples > 0x7fffff00LL || first_sample < 0 ||
+        first_sample + n_samples > stream_len)
+        return fail(ctx, WW_ERR_INVALID, "stream_score: bad sample span");
     int rc = check_cnn_args(ctx, cmvn_mode, WW_DECIDE_NONE, cnn_impl);
     if (rc) return rc;
-    const int T = ww_num_frames(WW_FEAT_PY, (int)n_samples);
-    if (T < WW_WINDOW_FRAMES) return fail(ctx, WW_ERR_INVALID, "stream_score: stream shorter than one window");
+    const long long T_all = stream_len < 257 ? 0 : 1 + stream_len / WW_HOP;   // ww_num_frames(PY, .) without the int range
+    if (first_frame < 0 || n_frames < WW_WINDOW_FRAMES || first_frame + n_frames > T_all)
+        return fail(ctx, WW_ERR_INVALID, "stream_score: frame range outside the stream or shorter than one window");
+    const long long lo_tap = WW_HOP * first_frame - 160, hi_tap = WW_HOP * (first_frame + n_frames - 1) + 159;
+    // left side: reflection (taps < 0) needs the stream's first samples; otherwise the tap before the first one
+    if (lo_tap <= 0 ? first_sample != 0 : first_sample > lo_tap - 1)
+        return fail(ctx, WW_ERR_INVALID, "stream_score: segment lacks its left halo");
+    if (hi_tap >= stream_len ? first_sample + n_samples != stream_len : first_sample + n_samples <= hi_tap)
+        return fail(ctx, WW_ERR_INVALID, "stream_score: segment lacks its right halo");
+    const long long origin = WW_HOP * first_frame - 256 - first_sample;
+    if (origin < -0x7fffff00LL || origin > 0x7fffff00LL) return fail(ctx, WW_ERR_INVALID, "stream_score: bad origin");
     cudaStream_t st = (cudaStream_t)stream;
-    rc = launch_mfcc(ctx, pcm, pcm_type, 1, (int)n_samples, n_samples, WW_FEAT_PY, feats_work, (long long)T * WW_N_MFCC,
-                     T, 1, st);
+    const int T = (int)n_frames;
+    {
+        NvtxRange r("ww:frontend(stream)");
+        rc = launch_mfcc_ex(ctx, pcm, pcm_type, 1, (int)n_samples, n_samples, WW_FEAT_PY, (int)origin, /*reflect=*/1, T,
+                            feats_work, (long long)T * WW_N_MFCC, T, 1, st);
+    }
     if (rc) return rc;
+    NvtxRange r("ww:cmvn+cnn(windows)");
     const long long W = T - WW_WINDOW_FRAMES + 1;
     return run_cnn(ctx, feats_work, /*win_stride=*/1, /*coef_stride=*/T, /*frame_stride=*/1, W, cmvn_mode,
                    WW_DECIDE_NONE, 0.f, cnn_impl, logits, nullptr, st);
+}
+
+extern "C" int ww_stream_score(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_samples, int cmvn_mode,
+                               int cnn_impl, float* feats_work, float* logits, ww_stream_t stream) {
+    if (!ctx) return WW_ERR_INVALID;
+    if (n_samples <= 0 || n_samples > 0x7fffff00LL) return fail(ctx, WW_ERR_INVALID, "stream_score: bad n_samples");
+    const int T = ww_num_frames(WW_FEAT_PY, (int)n_samples);
+    if (T < WW_WINDOW_FRAMES) return fail(ctx, WW_ERR_INVALID, "stream_score: stream shorter than one window");
+    return ww_stream_score_segment(ctx, pcm, pcm_type, n_samples, 0, n_samples, 0, T, cmvn_mode, cnn_impl, feats_work,
+                                   logits, stream);
 }
 
 extern "C" long long ww_stream_events(const float* logits_host, long long n_windows, int num_classes,
@@ -1042,6 +1422,7 @@ extern "C" long long ww_stream_events(const float* logits_host, long long n_wind
 struct ww_session {
     ww_ctx* ctx = nullptr;
     int n_streams = 0, max_chunk = 0, cmvn_mode = 0, cnn_impl = 0;
+    int num_classes = 0;       // of the model the logit buffers were sized for (ww_load_weights may not change it)
     float thr = 0.f;
     int warmup = 64, refractory = 313;
     long long n_samples = 0;   // samples received per stream
@@ -1083,6 +1464,7 @@ extern "C" int ww_session_open(ww_ctx* ctx, int n_streams, int max_chunk_samples
     s->max_chunk = max_chunk_samples;
     s->cmvn_mode = cmvn_mode;
     s->cnn_impl = cnn_impl;
+    s->num_classes = ctx->w.num_classes;
     s->thr = threshold_logit;
     s->warmup = warmup_frames;
     s->refractory = refractory_frames;
@@ -1164,12 +1546,15 @@ extern "C" int ww_session_write_tdm(ww_session* s, const int16_t* tdm_host, int 
 // everything after the new chunk is in place: new frames, new windows, hit logic, tails
 static int session_advance(ww_session* s, int chunk_samples) {
     ww_ctx* ctx = s->ctx;
-    const int S = s->n_streams, C = ctx->w.num_classes;
+    const int S = s->n_streams, C = s->num_classes;
+    if (ctx->w.num_classes != C)
+        return fail(ctx, WW_ERR_INVALID, "session: the model's class count changed since ww_session_open");
     int16_t* pcm = s->d_pcm[s->pcm_cur];
     const int L = s->tail_len + chunk_samples;
-    s->n_samples += chunk_samples;
-    // frames whose 320 taps are complete: 256 t + 159 < n_samples
-    const long long t_count = s->n_samples >= 160 ? (s->n_samples - 160) / WW_HOP + 1 : 0;
+    const long long n_samples = s->n_samples + chunk_samples;  // committed once the launches below have succeeded
+    // frames whose 320 taps are complete: 256 t + 159 < n_samples.  Frame 0 is reflect-padded on the left and its tap
+    // -160 is sample +160 (Hamming weight 0.08, not 0): it needs 161 samples
+    const long long t_count = n_samples >= 161 ? (n_samples - 160) / WW_HOP + 1 : 0;
     const int n_new = (int)(t_count - s->t_done);
     float* feat = s->d_feat[s->feat_cur] + s->feat_base;
     const int H = WW_WINDOW_FRAMES - 1;  // 62 frames of history in front of the new ones
@@ -1188,7 +1573,9 @@ static int session_advance(ww_session* s, int chunk_samples) {
         if (n_win > 0) {
             ctx->grp_windows = n_win;
             ctx->grp_stride = (long long)WW_N_MFCC * s->feat_cap;
-            rc = run_cnn(ctx, feat + j_lo, 1, s->feat_cap, 1, (long long)S * n_win, s->cmvn_mode, WW_DECIDE_NONE, 0.f,
+            // no device-side decisions (the hit logic is sequential host work), but the threshold is passed so that the
+            // tensor path re-scores the windows inside its guard band of THIS session's threshold
+            rc = run_cnn(ctx, feat + j_lo, 1, s->feat_cap, 1, (long long)S * n_win, s->cmvn_mode, WW_DECIDE_LOGIT, s->thr,
                          s->cnn_impl, s->d_logits, nullptr, s->st);
             ctx->grp_windows = 0;
             ctx->grp_stride = 0;
@@ -1213,6 +1600,7 @@ static int session_advance(ww_session* s, int chunk_samples) {
                              sizeof(float) * s->feat_cap, sizeof(float) * H, (size_t)S * WW_N_MFCC, cudaMemcpyDeviceToDevice,
                              s->st));
     CK(cudaStreamSynchronize(s->st));
+    s->n_samples = n_samples;
     if (move_pcm) {
         s->pcm_cur ^= 1;
         s->g0 = g0_next;
@@ -1445,18 +1833,12 @@ extern "C" int ww_ctc_loss_bwd(ww_ctx* ctx, const float* log_probs, long long t_
 // tensor-core launch (null disables); also returns how many windows the last launch re-scored in fp32
 extern "C" int ww_debug_tc(ww_ctx* ctx, float* dbg_dev, int* last_rescored) {
     if (!ctx) return WW_ERR_INVALID;
-#ifdef WW_WITH_TC
     ctx->tc_dbg = dbg_dev;
     if (last_rescored) {
         *last_rescored = 0;
         if (ctx->rs_count) CK(cudaMemcpy(last_rescored, ctx->rs_count, sizeof(int), cudaMemcpyDeviceToHost));
     }
     return WW_OK;
-#else
-    (void)dbg_dev;
-    (void)last_rescored;
-    return fail(ctx, WW_ERR_UNSUPPORTED, "tensor-core CNN not built into this library");
-#endif
 }
 
 // host-only: the C-MFCC tables as build_esp_tables() makes them on this machine (tools/gen_tables.py --esp turns them
@@ -1672,6 +2054,7 @@ extern "C" int ww_wav_load_batch(const char* const* paths, int n, int clip_sampl
     if (!paths || n < 0 || clip_samples <= 0 || !pcm_host) return WW_ERR_INVALID;
     if (n_threads < 1) n_threads = 1;
     if (n_threads > n) n_threads = n > 0 ? n : 1;
+    NvtxRange range("ww:wav_load_batch");
     std::atomic<int> next(0), failed(0);
     auto worker = [&]() {
         for (;;) {
@@ -1769,11 +2152,12 @@ extern "C" int ww_augment_waveform(ww_ctx* ctx, const float* audio, long long n,
 // ------------------------------------------------------------------------------------------------
 // mfcc.h drop-in
 // ------------------------------------------------------------------------------------------------
-static std::mutex g_shim_mu;
-static ww_ctx* g_shim_ctx = nullptr;
-
-extern "C" float* ww_extract_mfcc(const float* signal, int signal_len, int sampling_rate, int frame_size, int hop_size,
-                                  int n_fft, int n_filters, int n_mfcc) {
+// extract_mfcc() of mfcc.h:10 with the context made explicit (no hidden statics).  The reference keeps
+// static window / DCT caches (mfcc.c:37-38,362-363) and is not thread-safe; here two threads may run the call at the
+// same time provided each has its own context.
+extern "C" float* ww_extract_mfcc_ctx(ww_ctx* ctx, const float* signal, int signal_len, int sampling_rate, int frame_size,
+                                      int hop_size, int n_fft, int n_filters, int n_mfcc) {
+    if (!ctx) return nullptr;
     if (!signal || signal_len < frame_size) {  // mfcc.c:434-437
         fprintf(stderr, "E MFCC: Invalid signal parameters\n");
         return nullptr;
@@ -1783,9 +2167,7 @@ extern "C" float* ww_extract_mfcc(const float* signal, int signal_len, int sampl
         fprintf(stderr, "E MFCC: only (16000, 320, 256, 512, 40, 13) is supported by ww_b200\n");
         return nullptr;
     }
-    std::lock_guard<std::mutex> lk(g_shim_mu);
-    if (!g_shim_ctx && ww_create(&g_shim_ctx, 0) != WW_OK) return nullptr;
-    ww_ctx* ctx = g_shim_ctx;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
     const int T = ww_num_frames(WW_FEAT_ESP, signal_len);
     float* out = (float*)malloc(sizeof(float) * (size_t)T * n_mfcc);
     if (!out) return nullptr;
@@ -1804,6 +2186,24 @@ extern "C" float* ww_extract_mfcc(const float* signal, int signal_len, int sampl
         return nullptr;
     }
     return out;
+}
+
+// The reference's exact signature has no room for a context: this shim keeps ONE process-wide context on device 0,
+// created on first use and serialised by a mutex (documented in include/ww_b200.h; ww_extract_mfcc_ctx is the
+// re-entrant form).
+static std::mutex g_shim_mu;
+static ww_ctx* g_shim_ctx = nullptr;
+
+extern "C" float* ww_extract_mfcc(const float* signal, int signal_len, int sampling_rate, int frame_size, int hop_size,
+                                  int n_fft, int n_filters, int n_mfcc) {
+    std::lock_guard<std::mutex> lk(g_shim_mu);
+    if (!g_shim_ctx && (!signal || signal_len < frame_size)) {  // argument errors need no GPU (mfcc.c:434-437)
+        fprintf(stderr, "E MFCC: Invalid signal parameters\n");
+        return nullptr;
+    }
+    if (!g_shim_ctx && ww_create(&g_shim_ctx, 0) != WW_OK) return nullptr;
+    return ww_extract_mfcc_ctx(g_shim_ctx, signal, signal_len, sampling_rate, frame_size, hop_size, n_fft, n_filters,
+                               n_mfcc);
 }
 
 extern "C" void ww_free_mfcc(float* mfcc) { free(mfcc); }

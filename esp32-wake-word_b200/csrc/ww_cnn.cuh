@@ -40,6 +40,7 @@ struct CnnArgs {
     long long group_stride;    //    lives at feats + group*group_stride + j*win_stride (concurrent streams)
     const long long* index;  // optional: window ids to score (re-score list); nullptr = 0..n_windows-1
     const int* index_count;  // optional device count for `index` (n_windows is then the capacity)
+    unsigned long long* index_total;  // optional running total of re-scored windows (block 0 adds index_count)
     int cmvn_mode;
     int decide_mode;
     float threshold;         // DECIDE_LOGIT: logit > threshold; DECIDE_DEVICE: sigmoid*100 >= threshold
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(CNN_THREADS) cnn_fp32_kernel(const __grid_cons
     if (a.index_count) {
         const long long c = *a.index_count;
         n = c < n ? c : n;
+        if (a.index_total && blockIdx.x == 0 && tid == 0) atomicAdd(a.index_total, (unsigned long long)n);
     }
     const int C = a.w.num_classes;
 

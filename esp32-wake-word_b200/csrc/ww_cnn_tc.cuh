@@ -53,7 +53,8 @@ constexpr int W1_TAP = 2 * W1_LBO, W2_TAP = 4 * W2_LBO, W3_TAP = 8 * W3_LBO;
 // with its own activation tiles, mbarrier and TMEM columns; the weights are shared.
 constexpr int TC_GROUP_THREADS = TC_THREADS / TC_GROUPS;       // 128: one warp per TMEM lane quadrant
 constexpr int TC_OFF_BAR = 0;                                  // mbarrier[TC_GROUPS] + tmem base (4) at +32
-constexpr int TC_OFF_PART = 64;                                // fc2 partial sums [group][2][8][8] floats
+constexpr int TC_OFF_NORM = 64;                                // ||x||_F of the windows in flight [group][octet parity][8] floats
+constexpr int TC_OFF_PART = TC_OFF_NORM + TC_GROUPS * 2 * 8 * 4;  // fc2 partial sums [group][2][8][8] floats
 constexpr int TC_OFF_FC2 = TC_OFF_PART + TC_GROUPS * 2 * 8 * 8 * 4;  // fc2 weights [8][64] floats
 constexpr int TC_OFF_W = TC_OFF_FC2 + TC_MAX_CLASSES * 64 * 4;  // weight blob (same layout as the device blob)
 constexpr int TC_W1 = 0;
@@ -89,8 +90,13 @@ struct TcArgs {
     long long group_windows, group_stride;  // as in CnnArgs
     int cmvn_mode, decide_mode;
     float threshold;        // as in CnnArgs
-    float thr_logit;        // the threshold expressed as a logit
-    float band;             // |logit - thr_logit| < band -> re-score in fp32
+    // Guard band of the fp16-operand path (ww_api.cu:tc_calibrate).  The network is bias-free, so its rounding error is
+    // proportional to the norm of the window it is fed: a window whose class-0 logit lies within
+    //   bw = band + band_rel * ||x||_F      (band_rel != 0 only for CMVN_NONE; the CMVN modes fix ||z||_F)
+    // of thr0 or thr1 (DECIDE_NONE: 0 and ln 4, the two decision rules of the reference; else the rule asked for, twice),
+    // whose two largest class logits are closer than 2 bw, or whose norm exceeds norm_limit (fp16 range) is re-scored.
+    float thr0, thr1;
+    float band, band_rel, norm_limit;
     float* logits;          // [n][C]
     unsigned char* decisions;
     long long* rescore_list;  // may be null
@@ -357,6 +363,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
 
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR) + group;
     float* part = reinterpret_cast<float*>(smem + TC_OFF_PART) + group * (2 * 8 * 8);
+    float* wnorm = reinterpret_cast<float*>(smem + TC_OFF_NORM) + group * (2 * 8);
     unsigned char* act = smem + TC_OFF_ACT + group * TC_ACT_BYTES;
     unsigned char* sA1 = act + TC_ACT_A1;
     unsigned char* sA2 = act + TC_ACT_A2;
@@ -394,13 +401,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
 
     // each warp owns two windows of the octet (slots 2*q4, 2*q4 + 1); the other groups' GEMM stages and epilogues
     // hide the latency of these loads
+    int np = 0;  // parity of this group's octet count: the norm slots are double-buffered (S0 of the next octet
+                 // runs while warp 0 may still be in this octet's last epilogue)
 #pragma unroll 1
-    for (; oct < n_oct; oct += oct_stride) {
+    for (; oct < n_oct; oct += oct_stride, np ^= 1) {
         // ================= S0: CMVN two windows per warp, write A1 (fp16) =================
         {
             TcWin wa, wb;
             tc_load_window(a, oct * TC_CLIPS + 2 * q4, lane, wa);
             tc_load_window(a, oct * TC_CLIPS + 2 * q4 + 1, lane, wb);
+            if (a.cmvn_mode == CMVN_NONE) {
+                // the caller's features are fed as they are: their norm scales the guard band of these two windows
+                float sa = 0.f, sb = 0.f;
+#pragma unroll
+                for (int q = 0; q < WW_N_MFCC; ++q) {
+                    sa = fmaf(wa.x0[q], wa.x0[q], fmaf(wa.x1[q], wa.x1[q], sa));
+                    sb = fmaf(wb.x0[q], wb.x0[q], fmaf(wb.x1[q], wb.x1[q], sb));
+                }
+                sa = warp_sum(sa);
+                sb = warp_sum(sb);
+                if (lane == 0) {
+                    wnorm[8 * np + 2 * q4] = sqrtf(sa);
+                    wnorm[8 * np + 2 * q4 + 1] = sqrtf(sb);
+                }
+            }
             tc_cmvn_store(a, wa, 2 * q4, lane, sA1);
             tc_cmvn_store(a, wb, 2 * q4 + 1, lane, sA1);
         }
@@ -591,7 +615,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
                     if (a.decide_mode == DECIDE_LOGIT) d = s > a.threshold;
                     else if (a.decide_mode == DECIDE_DEVICE) d = (1.f / (1.f + expf(-s)) * 100.f) >= a.threshold;
                     a.decisions[win] = d;
-                    if (a.rescore_list && fabsf(s - a.thr_logit) < a.band) {
+                }
+                if (c == 0 && a.rescore_list) {
+                    float bw = a.band;
+                    if (a.cmvn_mode == CMVN_NONE) {
+                        const float nx = wnorm[8 * np + c8];
+                        bw = nx <= a.norm_limit ? fmaf(a.band_rel, nx, a.band) : __int_as_float(0x7f800000);
+                    }
+                    // negated comparisons: a NaN / Inf logit (fp16 overflow) is re-scored as well
+                    bool near = !(fabsf(s - a.thr0) >= bw) || !(fabsf(s - a.thr1) >= bw);
+                    if (C > 1) {  // the argmax over classes (CTC best path) must not depend on the operand precision
+                        float top = s, second = -__int_as_float(0x7f800000);
+                        for (int cc = 1; cc < C; ++cc) {
+                            const float v = part[(0 * 8 + cc) * 8 + c8] + part[(1 * 8 + cc) * 8 + c8];
+                            if (!(v <= top)) { second = top; top = v; }
+                            else if (v > second) second = v;
+                        }
+                        near = near || !(top - second >= 2.f * bw);
+                    }
+                    if (near) {
                         const int slot = atomicAdd(a.rescore_count, 1);
                         a.rescore_list[slot] = win;
                     }

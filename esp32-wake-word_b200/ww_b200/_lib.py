@@ -24,6 +24,8 @@ DECODE_KEEP_REPEATS, DECODE_COLLAPSE = 0, 1
 CNN_FP32, CNN_TENSOR, CNN_INT8 = 0, 1, 2
 OPT_I8_IMPL = 1
 OPT_GENERIC_FRONTEND = 2
+NORM_STANDARD, NORM_MINMAX = 0, 1
+ERR_BUSY = -6
 
 EXPORTS = [
     "ww_version", "ww_create", "ww_destroy", "ww_last_error", "ww_load_weights", "ww_num_frames",
@@ -32,6 +34,7 @@ EXPORTS = [
     "ww_session_windows", "ww_session_last_logits", "ww_session_close", "ww_ctc_greedy", "ww_ctc_loss_workspace_bytes",
     "ww_ctc_loss_fwd", "ww_ctc_loss_bwd", "ww_debug_tc", "ww_debug_esp_tables", "ww_extract_mfcc", "ww_free_mfcc", "ww_analyze_mfcc_range", "ww_ring_create", "ww_ring_delete", "ww_ring_write", "ww_ring_read", "ww_ring_count",
     "ww_set_option", "ww_wav_parse", "ww_wav_load_batch", "ww_wav_write", "ww_tdm_downmix", "ww_augment_waveform",
+    "ww_tc_band_info", "ww_tc_rescored_total", "ww_normalize_rows", "ww_stream_score_segment", "ww_extract_mfcc_ctx",
 ]
 
 
@@ -125,6 +128,14 @@ def load_library():
         lib.ww_wav_write.argtypes = [C.c_char_p, vp, C.c_size_t, i32, i32]
         lib.ww_tdm_downmix.argtypes = [vp, vp, i64, i64, i64, vp, i64, vp]
         lib.ww_augment_waveform.argtypes = [vp, vp, i64, i32, vp, vp]
+        fp = C.POINTER(C.c_float)
+        lib.ww_tc_band_info.argtypes = [vp, fp, fp, fp, fp]
+        lib.ww_tc_rescored_total.argtypes = [vp, i32]
+        lib.ww_tc_rescored_total.restype = i64
+        lib.ww_normalize_rows.argtypes = [vp, vp, i64, i32, i64, i32, vp, vp]
+        lib.ww_stream_score_segment.argtypes = [vp, vp, i32, i64, i64, i64, i64, i64, i32, i32, vp, vp, vp]
+        lib.ww_extract_mfcc_ctx.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32]
+        lib.ww_extract_mfcc_ctx.restype = C.POINTER(C.c_float)
         _lib = lib
         return lib
 
@@ -147,6 +158,17 @@ class Context:
         if rc != WW_OK:
             msg = self.lib.ww_last_error(self.h)
             raise WWError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def tc_band_info(self):
+        """Guard band of the tcgen05 CNN for the weights loaded last (ww_tc_band_info): |tensor logit - fp32 logit| <=
+        beta * ||window||_F.  `enabled` False: cnn_impl='tensor' runs the fp32 kernel for every window."""
+        v = [C.c_float() for _ in range(4)]
+        rc = self.lib.ww_tc_band_info(self.h, *[C.byref(x) for x in v])
+        if rc < 0:
+            raise WWError(f"ww_tc_band_info failed ({rc})")
+        return {"enabled": bool(rc), "beta": v[0].value, "beta_calibrated": v[1].value, "beta_rigorous": v[2].value,
+                "norm_limit": v[3].value, "band_python_cmvn": v[0].value * 28.3901391,
+                "band_device_cmvn": v[0].value * 42.9243521}
 
     def close(self):
         if getattr(self, "h", None):

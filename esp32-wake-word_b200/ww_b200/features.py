@@ -144,27 +144,36 @@ def analyze_mfcc_range(mfcc, label=None):
 
 
 def normalize_mfcc(mfcc, method="standardization"):
-    """Reference signature: mfcc [13, T] (or [B, 13, T]) -> normalised tensor of the same shape.
+    """Reference signature (extract_mfcc.py:47): mfcc [13, T] (or [..., T]) -> normalised tensor of the same shape,
+    statistics over the last (time) axis.
 
-    'cmvn' and 'standardization' (identical arithmetic in the reference) on 63-frame CUDA
-    features run in the CMVN kernel; other shapes/methods are evaluated with device tensor ops
-    of the same formula.
+    'cmvn' and 'standardization' are the same arithmetic in the reference (unbiased std, std == 0 -> 1, + 1e-8);
+    'minmax' is (x - min) / (max - min + 1e-8); any other method returns the input, as the reference does.
+    All of it runs in libwwb200.so: [.., 13, 63] windows in the CMVN kernel of the hot path, every other shape in
+    the generic row kernel (ww_normalize_rows).  A CPU tensor is copied to the GPU and the result copied back (the
+    reference is CPU code); without a GPU the call raises -- there is no CPU fallback.
     """
-    if method in ("cmvn", "standardization") and mfcc.is_cuda and mfcc.shape[-1] == WINDOW_FRAMES \
-            and mfcc.shape[-2] == N_MFCC:
-        squeeze = mfcc.dim() == 2
-        out = cmvn_batch(mfcc[None] if squeeze else mfcc)
-        return out[0] if squeeze else out
-    if method in ("cmvn", "standardization"):
-        mean = mfcc.mean(dim=-1, keepdim=True)
-        std = mfcc.std(dim=-1, keepdim=True)
-        std = torch.where(std == 0, torch.ones_like(std), std)
-        return (mfcc - mean) / (std + 1e-8)
-    if method == "minmax":
-        lo = mfcc.min(dim=-1, keepdim=True)[0]
-        hi = mfcc.max(dim=-1, keepdim=True)[0]
-        return (mfcc - lo) / (hi - lo + 1e-8)
-    return mfcc
+    if method not in ("cmvn", "standardization", "minmax"):
+        return mfcc
+    if not isinstance(mfcc, torch.Tensor):
+        mfcc = torch.as_tensor(mfcc)
+    if mfcc.dim() < 1:
+        raise ValueError("normalize_mfcc expects at least one axis (time)")
+    on_cpu = not mfcc.is_cuda
+    if on_cpu and not torch.cuda.is_available():
+        raise L.WWError("CUDA is not available; ww_b200 has no CPU fallback")
+    x = (mfcc.cuda() if on_cpu else mfcc).to(torch.float32).contiguous()
+    if method != "minmax" and x.dim() >= 2 and x.shape[-1] == WINDOW_FRAMES and x.shape[-2] == N_MFCC:
+        out = cmvn_batch(x.reshape(-1, N_MFCC, WINDOW_FRAMES)).reshape(x.shape)
+    else:
+        T = x.shape[-1]
+        rows = x.numel() // T if T else 0
+        out = torch.empty_like(x)
+        ctx = L.get_context(x.device.index)
+        ctx.check(ctx.lib.ww_normalize_rows(ctx.h, L.ptr(x), rows, T, T, L.NORM_MINMAX if method == "minmax"
+                                            else L.NORM_STANDARD, L.ptr(out), L.cur_stream(x.device)),
+                  "ww_normalize_rows")
+    return out.cpu() if on_cpu else out
 
 
 def _load_clip_batch(paths):

@@ -72,7 +72,10 @@ class LightweightKWS(nn.Module):
         self.global_pool = nn.AdaptiveAvgPool1d(1)
         self.classifier = nn.Sequential(
             nn.Linear(128, 64, bias=False), nn.ReLU(), nn.Linear(64, num_classes, bias=False))
-        self.cnn_impl = "fp32"
+        # 'tensor': tcgen05 fp16-operand kernel; every window whose logit lies inside the calibrated guard band of a
+        # decision threshold (0 = sigmoid > 0.5, ln 4 = sigmoid*100 >= 80) is re-scored by the exact fp32 kernel, so
+        # thresholding the returned logits gives the fp32 path's decisions.  'fp32': the exact kernel for every window.
+        self.cnn_impl = "tensor"
         self._ww_token = next(_tokens)
 
     @classmethod
@@ -157,9 +160,10 @@ class WakeWordScorer:
     (esp_wake_word_detector.cpp:179-211,226-245).
     """
 
-    def __init__(self, state_dict, device=None, cmvn="python", decision="python", cnn_impl="fp32",
+    def __init__(self, state_dict, device=None, cmvn="python", decision="python", cnn_impl="tensor",
                  int8_exponents=XIAOA_EXPONENTS):
-        """cnn_impl: 'fp32' (exact, CUDA cores), 'tensor' (tcgen05 fp16 + fp32 re-score near the threshold) or
+        """cnn_impl: 'tensor' (default: tcgen05 fp16 operands, windows inside the calibrated guard band of the threshold
+        re-scored by the fp32 kernel -- decisions are the fp32 path's), 'fp32' (exact, CUDA cores) or
         'int8' (the device model: int8 power-of-two twin on tcgen05 kind::i8; needs cmvn='device')."""
         self.ctx = L.get_context(device)
         self.sd = state_dict
@@ -183,6 +187,11 @@ class WakeWordScorer:
 
     def _prep(self):
         _push_weights(self.ctx, self.sd, self._key, self._i8)
+
+    def tc_band_info(self):
+        """The tensor path's guard band for this scorer's weights (see Context.tc_band_info)."""
+        self._prep()
+        return self.ctx.tc_band_info()
 
     def score(self, pcm):
         """pcm: CUDA [B, 16000] int16 or float32 -> (logits [B, C], decisions uint8 [B])."""

@@ -42,19 +42,28 @@ def gather_scores(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor
 def stream_segments(n_samples: int, world: int):
     """Split a stream's WINDOWS into `world` contiguous ranges and give each the sample span it needs.
 
-    Returns a list of (sample_start, sample_stop, first_window, n_windows).  Window w covers frames w..w+62 and
-    frame t needs samples 256 t - 256 .. 256 t + 255 (reflect padding only at the true stream ends), plus one
-    earlier sample for the pre-emphasis; so a segment of windows [w0, w1) needs samples
-    [256 w0 - 257, 256 (w1 + 61) + 256) clipped to the stream.  The halo is 62 frames + 513 samples and no
+    Returns a list of (sample_start, sample_stop, first_window, n_windows).  Window w covers frames w..w+62 of the
+    stream's frame grid; frame t is centred on sample 256 t and reads the 320 taps 256 t - 160 .. 256 t + 159 plus
+    one earlier sample for the pre-emphasis (reflect padding exists only at the two true ends of the stream).  A
+    segment of windows [w0, w1) therefore needs samples [256 w0 - 161, 256 (w1 + 61) + 160) clipped to the stream;
+    sample_start is rounded DOWN to a multiple of 8 so that the frontend keeps its TMA staging path.  The halo
+    shared by neighbours is the span of 62 frames, 61 * 256 + 321 = 15 937 samples (+ < 8 of alignment), and no
     segment ever needs data from another rank.
+
+    A segment is consumed by `StreamScorer.score_segment(pcm[s0:s1], s0, n_samples, w0, nw)`
+    (ww_stream_score_segment): it enters the frontend with the frame phase of the whole stream, so the stitched
+    per-window logits are bit for bit those of `StreamScorer.score` over the whole stream.
     """
     n_frames = 1 + n_samples // HOP
     n_windows = n_frames - WINDOW + 1
     out = []
     for r in range(world):
         w0, w1 = shard_range(max(n_windows, 0), r, world)
-        s0 = max(0, HOP * w0 - 257)
-        s1 = min(n_samples, HOP * (w1 + WINDOW - 2) + 256) if w1 > w0 else s0
+        if w1 <= w0:
+            out.append((0, 0, w0, 0))
+            continue
+        s0 = max(0, HOP * w0 - 161) // 8 * 8
+        s1 = min(n_samples, HOP * (w1 + WINDOW - 2) + 160)
         out.append((s0, s1, w0, w1 - w0))
     return out
 

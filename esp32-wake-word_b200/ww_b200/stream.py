@@ -26,8 +26,9 @@ def refractory_frames(seconds=5.0, hop=256, sr=16000):
 
 
 class StreamScorer:
-    def __init__(self, state_dict, device=None, cmvn="device", cnn_impl="fp32", int8_exponents=XIAOA_EXPONENTS):
-        """cnn_impl 'int8' = the firmware's own model (int8 power-of-two twin, needs cmvn='device')."""
+    def __init__(self, state_dict, device=None, cmvn="device", cnn_impl="tensor", int8_exponents=XIAOA_EXPONENTS):
+        """cnn_impl: 'tensor' (default; windows inside the guard band of logit 0 / ln 4 re-scored in fp32), 'fp32', or
+        'int8' = the firmware's own model (int8 power-of-two twin, needs cmvn='device')."""
         self.ctx = L.get_context(device)
         self.sd = state_dict
         self.cmvn = {"none": L.CMVN_NONE, "python": L.CMVN_PY, "device": L.CMVN_DEVICE}[cmvn]
@@ -53,6 +54,27 @@ class StreamScorer:
         self.ctx.check(self.ctx.lib.ww_stream_score(self.ctx.h, L.ptr(pcm), pcm_type, N, self.cmvn, self.cnn_impl,
                                                     L.ptr(feats), L.ptr(logits), L.cur_stream(pcm.device)),
                        "ww_stream_score")
+        return feats, logits
+
+    def score_segment(self, pcm, first_sample, stream_len, first_window, n_windows):
+        """One time segment of a long stream (`shard.stream_segments`): pcm = CUDA samples
+        [first_sample, first_sample + len(pcm)) of a stream of `stream_len` samples.  Returns
+        (features [13, n_windows + 62], logits [n_windows, C]) of windows first_window .. first_window + n_windows - 1
+        of the WHOLE stream -- the same bits `score` produces for them (ww_stream_score_segment)."""
+        _push_weights(self.ctx, self.sd, self._key, self._i8)
+        if not pcm.is_cuda or pcm.dim() != 1:
+            raise ValueError("StreamScorer.score_segment expects a 1-D CUDA tensor")
+        pcm = pcm.contiguous()
+        pcm_type = L.PCM_S16 if pcm.dtype == torch.int16 else L.PCM_F32
+        if pcm_type == L.PCM_F32:
+            pcm = pcm.to(torch.float32)
+        n_frames = int(n_windows) + WINDOW - 1
+        feats = torch.empty((13, n_frames), dtype=torch.float32, device=pcm.device)
+        logits = torch.empty((int(n_windows), self.ctx.num_classes), dtype=torch.float32, device=pcm.device)
+        self.ctx.check(self.ctx.lib.ww_stream_score_segment(
+            self.ctx.h, L.ptr(pcm), pcm_type, pcm.numel(), int(first_sample), int(stream_len), int(first_window),
+            n_frames, self.cmvn, self.cnn_impl, L.ptr(feats), L.ptr(logits), L.cur_stream(pcm.device)),
+            "ww_stream_score_segment")
         return feats, logits
 
 
@@ -87,7 +109,7 @@ class StreamSession:
     concatenated stream.
     """
 
-    def __init__(self, state_dict, n_streams, max_chunk_samples=16000, device=None, cmvn="device", cnn_impl="fp32",
+    def __init__(self, state_dict, n_streams, max_chunk_samples=16000, device=None, cmvn="device", cnn_impl="tensor",
                  threshold_logit=LN4, warmup=64, refractory=None, int8_exponents=XIAOA_EXPONENTS):
         self.ctx = L.get_context(device)
         self._key = ("session", next(_tokens))

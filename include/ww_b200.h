@@ -31,7 +31,8 @@ enum {
     WW_ERR_CUDA = -2,        /* CUDA runtime error, see ww_last_error() */
     WW_ERR_NO_WEIGHTS = -3,  /* ww_load_weights() has not been called */
     WW_ERR_UNSUPPORTED = -4,
-    WW_ERR_NOMEM = -5
+    WW_ERR_NOMEM = -5,
+    WW_ERR_BUSY = -6         /* another thread is inside a fused call on this context (one at a time per context) */
 };
 
 /* feature definition */
@@ -58,7 +59,8 @@ enum {
 };
 enum {
     WW_CNN_FP32 = 0,   /* exact fp32, CUDA cores */
-    WW_CNN_TENSOR = 1, /* tcgen05 kind::f16 + fp32 re-score near the threshold */
+    WW_CNN_TENSOR = 1, /* tcgen05 kind::f16; every window inside the calibrated guard band of a decision threshold is
+                          re-scored by the fp32 kernel (ww_tc_band_info), so decisions are those of WW_CNN_FP32 */
     WW_CNN_INT8 = 2    /* the DEVICE model: int8 power-of-two twin on tcgen05 kind::i8 fed by int8 rounding + device CMVN
                           (requires WW_CMVN_DEVICE and ww_quantize_weights_i8); logits are out_q * 2^exp_out, exactly */
 };
@@ -92,6 +94,12 @@ int ww_mfcc_batch(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_signal
 /* normalize_mfcc / device CMVN over 63-frame windows [n][13][63] -> [n][13][63] */
 int ww_cmvn(ww_ctx* ctx, const float* feats, long long n_windows, int cmvn_mode, float* out,
             ww_stream_t stream);
+/* normalize_mfcc(mfcc[n_mfcc, T], method) for rows of ANY length (extract_mfcc.py:47-88): x, out device fp32
+ * [n_rows][row_stride] with T valid values per row (in place allowed).  WW_NORM_STANDARD = 'standardization' and
+ * 'cmvn' (same arithmetic in the reference: unbiased std, std == 0 -> 1, + 1e-8), WW_NORM_MINMAX = 'minmax'. */
+enum { WW_NORM_STANDARD = 0, WW_NORM_MINMAX = 1 };
+int ww_normalize_rows(ww_ctx* ctx, const float* x, long long n_rows, int T, long long row_stride, int method,
+                      float* out, ww_stream_t stream);
 
 /* ---- model forward: LightweightKWS.forward (ml_models/src/wakeModel.py:29-34) ------------------ */
 /* feats[win*win_stride + coef*coef_stride + frame*frame_stride], 63 frames per window.
@@ -117,8 +125,23 @@ int ww_cnn_forward_i8(ww_ctx* ctx, const int8_t* x, long long n_windows, int8_t*
 enum { WW_OPT_I8_IMPL = 1, WW_OPT_GENERIC_FRONTEND = 2 };
 int ww_set_option(ww_ctx* ctx, int option, int value);
 
+/* Guard band of WW_CNN_TENSOR for the weights loaded last.  ww_load_weights runs 4096 calibration windows (noise,
+ * hot frames, square waves, full-scale signs, the CMVN extreme point, raw-MFCC-like rows) through both kernels:
+ *   |tensor logit - fp32 logit| <= beta * ||window||_F,  beta = min(8 x the largest ratio observed, rigorous bound);
+ * the rigorous bound (operator norms of the layers, worst alignment everywhere) is reported for reference, it is
+ * 2-3 orders of magnitude above what fp16 operands actually do.  norm_limit: a window with a larger norm could leave
+ * the fp16 range in some layer and is always re-scored.  Any pointer may be NULL.  Returns 1 when the tensor kernel
+ * is in use for these weights, 0 when WW_CNN_TENSOR falls back to the fp32 kernel for every window (non-finite
+ * calibration logits, more than 8 classes), negative on error. */
+int ww_tc_band_info(const ww_ctx* ctx, float* beta, float* beta_calibrated, float* beta_rigorous, float* norm_limit);
+/* How many windows WW_CNN_TENSOR calls on this context have handed to the fp32 kernel since the counter was last
+ * reset (reset != 0 clears it).  Synchronises the device: a reporting call, not a hot-path one. */
+long long ww_tc_rescored_total(ww_ctx* ctx, int reset);
+
 /* ---- fused clip scoring: PCM -> MFCC -> CMVN -> CNN -> decision -------------------------------- */
-/* pcm: device [n_clips][16000].  The feature intermediate stays in an L2-sized context scratch. */
+/* pcm: device [n_clips][16000].  The features pass from the frontend to the CNN through a context-owned scratch that
+ * is sized to stay in L2 (chunks of clips).  One fused call at a time per context: a second host
+ * thread gets WW_ERR_BUSY; consecutive calls on different streams are ordered on the device. */
 int ww_score_clips(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_clips, int cmvn_mode,
                    int decide_mode, float threshold, int cnn_impl, float* logits, uint8_t* decisions,
                    ww_stream_t stream);
@@ -132,6 +155,17 @@ int ww_score_clips_host(ww_ctx* ctx, const void* pcm_host, int pcm_type, long lo
  * logits: device [T-62][num_classes].  Window w = frames w..w+62, CMVN recomputed per window. */
 int ww_stream_score(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_samples, int cmvn_mode,
                     int cnn_impl, float* feats_work, float* logits, ww_stream_t stream);
+/* One time segment of a stream (a long stream split over the GPUs of a box, no exchange).
+ * pcm: device buffer with samples [first_sample, first_sample + n_samples) of a stream of stream_len samples;
+ * computes frames [first_frame, first_frame + n_frames) of the WHOLE stream's frame grid (frame t is centred on
+ * sample 256 t; reflect padding only at the true stream ends) into feats_work [13][n_frames] and scores the
+ * n_frames - 62 windows made of them into logits.  The buffer must contain every tap of those frames plus one sample
+ * before the first (pre-emphasis): 256 first_frame - 161 .. 256 (first_frame + n_frames - 1) + 159, clipped to the
+ * stream; WW_ERR_INVALID otherwise.  Stitching the segments ww_b200.shard.stream_segments() describes gives
+ * bit for bit what ww_stream_score gives for the whole stream.  first_sample % 8 == 0 keeps the TMA path. */
+int ww_stream_score_segment(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_samples, long long first_sample,
+                            long long stream_len, long long first_frame, long long n_frames, int cmvn_mode,
+                            int cnn_impl, float* feats_work, float* logits, ww_stream_t stream);
 /* Host-side hit logic over per-window logits (class 0 column of [n_windows][num_classes]): first score
  * after `warmup` (64) frames, threshold on the logit, `refractory` frames of lock-out then ring reset
  * (esp_wake_word_detector.cpp:38-44,245-258).  Returns the number of hits (<= max_hits written). */
@@ -245,9 +279,13 @@ unsigned int ww_debug_esp_tables(float* window320, float* fb_dense, float* bias4
 /* Same signature and ownership as the reference's extract_mfcc(): returns a malloc'd
  * float[num_frames * n_mfcc] (frame-major) that the caller releases with ww_free_mfcc(); NULL on bad
  * arguments (mfcc.c:434-437) or when no GPU is available.  Only the reference's fixed parameter set
- * (16000, 320, 256, 512, 40, 13; hello_world_main.cpp:227) is accepted.  Uses a process-wide context. */
+ * (16000, 320, 256, 512, 40, 13; hello_world_main.cpp:227) is accepted.  The reference's signature has no room for a
+ * context, so THIS entry point (and only this one) keeps a process-wide context on device 0 behind a mutex. */
 float* ww_extract_mfcc(const float* signal, int signal_len, int sampling_rate, int frame_size, int hop_size,
                        int n_fft, int n_filters, int n_mfcc);
+/* the same call with the context explicit: re-entrant across contexts, any device (release with ww_free_mfcc) */
+float* ww_extract_mfcc_ctx(ww_ctx* ctx, const float* signal, int signal_len, int sampling_rate, int frame_size,
+                           int hop_size, int n_fft, int n_filters, int n_mfcc);
 void ww_free_mfcc(float* mfcc);
 
 /* analyze_mfcc_range() of main/esp_mfcc/mfcc.h:16 (mfcc.c:530-553): minimum, maximum and mean over the finite

@@ -61,11 +61,17 @@ def test_stream_segments_cover_windows_with_halo():
     n_frames = 1 + n // 256
     assert sum(s[3] for s in segs) == n_frames - 62 == 224939
     for s0, s1, w0, nw in segs:
-        # every frame of every window of the segment has its 512-sample support (or the true stream edge)
-        first, last = 256 * w0 - 256, 256 * (w0 + nw - 1 + 62) + 255
-        assert s0 <= max(first - 1, 0) and s1 >= min(last + 1, n)
-    # halo: consecutive segments overlap by 62 frames plus context
-    assert segs[0][1] - segs[1][0] == 62 * 256 + 513 - 256 or segs[0][1] > segs[1][0]
+        # every frame of every window of the segment has its 320 taps and the pre-emphasis sample in front of them
+        # (or the true stream edge, where the frontend reflects); the start keeps the TMA staging alignment
+        first, last = 256 * w0 - 161, 256 * (w0 + nw - 1 + 62) + 159
+        assert s0 <= max(first, 0) and s1 > min(last, n - 1) and s0 % 8 == 0
+        assert s0 >= max(first, 0) - 7 and s1 <= min(last + 1, n)          # and nothing more than that
+    # halo: consecutive segments share 62 frames = 61 hops + 320 taps + the pre-emphasis sample (+ < 8 of alignment)
+    for a, b in zip(segs, segs[1:]):
+        assert 61 * 256 + 321 <= a[1] - b[0] < 61 * 256 + 321 + 8
+    # degenerate splits: more ranks than windows
+    tiny = shard.stream_segments(63 * 256, 8)
+    assert sum(s[3] for s in tiny) == 2 and [s[3] for s in tiny].count(0) == 6
 
 
 def _ctc_worker(rank, world, port, ret):

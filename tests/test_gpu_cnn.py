@@ -11,11 +11,13 @@ from oracle import mfcc as om
 pytestmark = pytest.mark.gpu
 
 
-def _model(sd, dev, num_classes=None):
+def _model(sd, dev, impl="fp32"):
+    """The tests of this file pin the exact fp32 kernel; the tcgen05 default is covered by test_gpu_tc.py."""
     import ww_b200
 
     m = ww_b200.LightweightKWS(num_classes=sd["classifier.2.weight"].shape[0])
     m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    m.cnn_impl = impl
     return m.to(dev)
 
 
@@ -92,8 +94,9 @@ def test_empty_batch(cuda_device, xiaoa_sd):
     assert out.shape == (0, 1)
 
 
+@pytest.mark.parametrize("impl", ["fp32", "tensor"])
 @pytest.mark.parametrize("cmvn,decision", [("python", "python"), ("device", "device")])
-def test_fused_scorer_vs_oracle_chain(cuda_device, xiaoa_sd, cmvn, decision):
+def test_fused_scorer_vs_oracle_chain(cuda_device, xiaoa_sd, cmvn, decision, impl):
     """PCM -> MFCC -> CMVN -> CNN -> decision.  Logits within 2e-3; decisions EXACT for every clip whose
     oracle margin exceeds the fp32 noise floor (|logit - thr| > 1e-3); the others are counted."""
     import ww_b200
@@ -110,17 +113,20 @@ def test_fused_scorer_vs_oracle_chain(cuda_device, xiaoa_sd, cmvn, decision):
         thr = np.log(4.0)
         decide = ocnn.decide_device
     want = ocnn.forward_torch(z, xiaoa_sd)[:, 0]
-    sc = ww_b200.WakeWordScorer(xiaoa_sd, device=0, cmvn=cmvn, decision=decision)
+    sc = ww_b200.WakeWordScorer(xiaoa_sd, device=0, cmvn=cmvn, decision=decision, cnn_impl=impl)
     logits, dec = sc.score(torch.from_numpy(pcm).to(cuda_device))
     torch.cuda.synchronize()
     got = logits.cpu().numpy()[:, 0]
     d = dec.cpu().numpy().astype(bool)
+    tol = 2e-3 if impl == "fp32" else 1e-2   # fp16 operands away from the threshold (inside the band: fp32 logits)
     if cmvn == "python":
-        assert np.abs(got - want).max() < 2e-3
+        assert np.abs(got - want).max() < tol
     else:
         # device CMVN rounds features to int8: a feature within float noise of x.5 flips one int8 step;
         # such clips are rare and bounded
-        assert np.mean(np.abs(got - want) > 2e-3) < 0.02
+        flips = int((np.abs(got - want) > tol).sum())
+        print(f"device CMVN, {impl}: {flips}/{n} clips differ by more than {tol} (int8 rounding flips)")
+        assert flips < 0.02 * n
     clear = np.abs(want - thr) > 1e-3
     near = int((~clear).sum())
     print(f"{cmvn}: positives {int(decide(want).sum())}/{n}, near-threshold clips excluded: {near}")
@@ -142,7 +148,7 @@ def test_fused_scorer_float_input_and_chunking(cuda_device, xiaoa_sd):
     n = 16384 + 300  # crosses the L2-sized scratch chunk
     pcm = om.synth_clips_int16(512, seed=77)
     pcm = np.tile(pcm, (n // 512 + 1, 1))[:n]
-    sc = ww_b200.WakeWordScorer(xiaoa_sd, device=0)
+    sc = ww_b200.WakeWordScorer(xiaoa_sd, device=0)   # default implementation: tcgen05 + guard-band re-score
     l16, d16 = sc.score(torch.from_numpy(pcm).to(cuda_device))
     torch.cuda.synchronize()
     # periodic input -> periodic output, across the chunk boundary too

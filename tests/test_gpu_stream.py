@@ -25,7 +25,7 @@ def test_stream_windows_vs_oracle(cuda_device, xiaoa_sd, cmvn):
 
     pcm = _stream(20.0, seed=4321)
     feats_o, logits_o = ostream.window_logits(om.pcm16_to_float(pcm), xiaoa_sd, cmvn=cmvn)
-    sc = ww_b200.StreamScorer(xiaoa_sd, device=0, cmvn=cmvn)
+    sc = ww_b200.StreamScorer(xiaoa_sd, device=0, cmvn=cmvn, cnn_impl="fp32")
     feats, logits = sc.score(torch.from_numpy(pcm).to(cuda_device))
     torch.cuda.synchronize()
     T = 1 + len(pcm) // 256
@@ -50,12 +50,13 @@ def test_stream_equals_clip_scoring_on_aligned_windows(cuda_device, xiaoa_sd):
     from ww_b200 import _lib as L
 
     pcm = _stream(6.0, seed=1)
-    sc = ww_b200.StreamScorer(xiaoa_sd, device=0, cmvn="python")
+    sc = ww_b200.StreamScorer(xiaoa_sd, device=0, cmvn="python", cnn_impl="fp32")
     feats, logits = sc.score(torch.from_numpy(pcm).to(cuda_device))
     W = logits.shape[0]
     win = torch.stack([feats[:, w:w + 63] for w in range(0, W, 7)])  # explicit [n,13,63] copies
     m = ww_b200.LightweightKWS(1)
     m.load_state_dict({k: torch.from_numpy(v) for k, v in xiaoa_sd.items()})
+    m.cnn_impl = "fp32"
     out = m(ww_b200.cmvn_batch(win))
     torch.cuda.synchronize()
     assert torch.allclose(out[:, 0], logits[0:W:7, 0], atol=1e-5)
