@@ -124,17 +124,27 @@ __global__ void __launch_bounds__(CNN_THREADS) cnn_fp32_kernel(const __grid_cons
                 v1 = has1 ? lround_clamp_i8(v1) : 0.f;
             }
             float z0 = v0, z1 = v1;
-            if (a.cmvn_mode != CMVN_NONE) {
+            if (a.cmvn_mode == CMVN_PY) {
+                // Operation for operation the arithmetic of the tensor-core kernel's CMVN (tc_cmvn_store: same reduction
+                // tree, mean and 1/(std + eps) as multiplications by correctly rounded reciprocals), so that both kernels
+                // feed the network the SAME z bit for bit.  That matters for rows that are constant up to rounding
+                // (digital silence: c0 = -87.377 in every frame): there (x - mean) / (std + eps) is rounding noise over
+                // rounding noise, a last-bit difference in the mean changes z by O(1), and only identical arithmetic
+                // keeps the tensor path inside its guard band of this kernel.  Within 1 ulp of the reference's
+                // (x - mean) / (std + 1e-8) everywhere else (normalize_mfcc itself is cmvn_rows_kernel: true divisions).
+                const float mean = warp_sum(v0 + v1) * (1.f / (float)WW_WINDOW_FRAMES);
+                const float d0 = v0 - mean, d1 = has1 ? v1 - mean : 0.f;
+                const float ss = warp_sum(fmaf(d0, d0, d1 * d1));
+                float sd = sqrtf(ss * (1.f / (float)(WW_WINDOW_FRAMES - 1)));
+                if (sd == 0.f) sd = 1.f;
+                const float inv = __frcp_rn(sd + 1e-8f);
+                z0 = d0 * inv;
+                z1 = d1 * inv;
+            } else if (a.cmvn_mode != CMVN_NONE) {
                 const float mean = warp_sum(v0 + v1) / (float)WW_WINDOW_FRAMES;
                 const float d0 = v0 - mean, d1 = has1 ? v1 - mean : 0.f;
                 const float ss = warp_sum(d0 * d0 + d1 * d1);
-                if (a.cmvn_mode == CMVN_PY) {
-                    float sd = sqrtf(ss / (float)(WW_WINDOW_FRAMES - 1));
-                    if (sd == 0.f) sd = 1.f;
-                    const float den = sd + 1e-8f;
-                    z0 = d0 / den;
-                    z1 = d1 / den;
-                } else {
+                {
                     const float den = sqrtf(ss / (float)WW_WINDOW_FRAMES) + 1e-8f;
                     // int8 at exponent 0 -> model input at exponent -4: saturates at 127/16
                     z0 = fminf(fmaxf(lround_clamp_i8(d0 / den) * 16.f, -128.f), 127.f) * 0.0625f;

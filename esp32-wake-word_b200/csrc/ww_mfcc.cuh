@@ -41,6 +41,17 @@
 #ifndef WW_TW1_HALF
 #define WW_TW1_HALF 0
 #endif
+// Round-2 switches (A/B on B200, profiles/experiments/README.md):
+//   WW_IPRE     pre-emphasis in exact integer arithmetic, 100 x[i] - 97 x[i-1] by one IDP.2A per sample (|.| < 2^23, exact
+//               in fp32), ONE int -> float conversion per sample on the ALU side (I2FP.F32.S32) instead of three
+//               quarter-rate XU conversions (I2F.S16) per complex point; the 1/100 rides in the window taps
+//   WW_PRESEL   the lane-0 special case of the real-FFT split is resolved on the SOURCE side of the shuffles
+#ifndef WW_IPRE
+#define WW_IPRE 1   // 31.47 -> 32.46 M clips/s (262 144 clips, alternating runs, gpurun_out/r2_ab_ipre.txt)
+#endif
+#ifndef WW_PRESEL
+#define WW_PRESEL 0
+#endif
 
 namespace ww {
 
@@ -342,6 +353,13 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
 #pragma unroll
     for (int i = 0; i < 10; ++i)
         wreg[i].v = __ldg(reinterpret_cast<const unsigned long long*>(a.tables) + TB_WIN_OFF / 8 + 16 * i + l16);
+    // WW_IPRE (int16 PCM): samples reach the window as 100 x[i] - 97 x[i-1]; the taps carry the 1/100
+    constexpr bool IPRE = WW_IPRE && sizeof(TIN) == 2;
+    constexpr float emph_scale = IPRE ? 100.f : 1.f;
+    if constexpr (IPRE) {
+#pragma unroll
+        for (int i = 0; i < 10; ++i) wreg[i] = p_mul(wreg[i], cpk(0.01f, 0.01f));
+    }
 #if WW_TW2_COMPUTE
     const float2 tw2_0 = s_tw2[l16];
 #endif
@@ -480,7 +498,7 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
                     const TIN* sp = reinterpret_cast<const TIN*>(pcm_buf + hh * SM::HALF_STRIDE);
                     const int s0 = WW_HOP * te + origin_off + 96, lo_h = hh ? org1 : org0;
                     for (int j = tid; j < WW_WIN; j += MFCC_THREADS)
-                        edge[slot * WW_WIN + j] = emph_sample<TIN>(sp, lo_h, s0 + j, L, reflect, pre);
+                        edge[slot * WW_WIN + j] = emph_scale * emph_sample<TIN>(sp, lo_h, s0 + j, L, reflect, pre);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars[3]);
@@ -567,6 +585,14 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
                 for (int n1 = 3; n1 <= 12; ++n1) {
                     const cpx w = wreg[n1 - 3];
                     float x0, x1, xm1;
+                    if constexpr (sizeof(TIN) == 2 && WW_IPRE) {
+                        const uint32_t cur = p32b[16 * n1], prv = p32b[16 * n1 - 1];
+                        // {x[2m-1], x[2m]} and {x[2m], x[2m+1]} as int16 pairs . {-97, 100}
+                        const int y0 = __dp2a_lo((int)__byte_perm(prv, cur, 0x5432), 0x649f, 0);
+                        const int y1 = __dp2a_lo((int)cur, 0x649f, 0);
+                        v[n1] = p_mul(w, cpk(__int2float_rn(y0), __int2float_rn(y1)));   // w carries the 1/100
+                        continue;
+                    }
                     if constexpr (sizeof(TIN) == 2) {
                         const uint32_t cur = p32b[16 * n1], prv = p32b[16 * n1 - 1];
 #if WW_I2FP
@@ -601,7 +627,7 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
                 for (int n1 = 3; n1 <= 12; ++n1) {
                     const cpx w = wreg[n1 - 3];
                     const cpx y = *reinterpret_cast<const cpx*>(ep + 32 * (n1 - 3));
-                    v[n1] = p_mul(w, y);
+                    v[n1] = p_mul(w, y);   // WW_IPRE: the edge taps were stored x 100 (emph_scale)
                 }
             }
 
@@ -650,9 +676,15 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
             for (int i = 0; i < 8; ++i) {
                 const int k = l16 + 16 * i;
                 const cpx za = v[i];
+#if WW_PRESEL
+                // lane 0 pairs with itself (register 16 - i, Z[256] = Z[0]): it offers that register to its own shuffle
+                const float2 src = cunpk(l16 == 0 ? v[(16 - i) & 15] : v[15 - i]);
+                const cpx zb = cpk(__shfl_sync(0xffffffffu, src.x, partner, 16), __shfl_sync(0xffffffffu, src.y, partner, 16));
+#else
                 const float2 src = cunpk(v[15 - i]);
                 cpx zb = cpk(__shfl_sync(0xffffffffu, src.x, partner, 16), __shfl_sync(0xffffffffu, src.y, partner, 16));
                 if (l16 == 0) zb = (i == 0) ? v[0] : v[(16 - i) & 15];
+#endif
 #if WW_TW2_COMPUTE
                 // W512^(l16 + 16 i) = W512^l16 * W32^i
                 constexpr float W32C[8] = {1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,

