@@ -383,6 +383,8 @@ def workload_config(args, n):
             "cnn_impl": args.cnn + (" (tcgen05 kind::f16, fp32 accumulate in TMEM; clips inside the guard band calibrated "
                                     "for the loaded weights are re-scored by the fp32 kernel)" if args.cnn == "tensor" else ""),
             "parallelism": f"dp{n} (clip shards, no hot-path collective)",
+            "rank_to_gpu": "rank i -> GPU i * (visible GPUs // ranks): ranks spread over the box's host bridges (e2e leg); "
+                           "identity when ranks == visible GPUs",
             "l2_policy": "inputs (32 KB/clip x clips) exceed L2; no flush needed"}
 
 
@@ -401,6 +403,17 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU (ww_b200 has no CPU fallback)")
+    # Which GPU a rank takes when the box shows more GPUs than ranks: spread the ranks over the box (stride
+    # n_visible / world) instead of packing them onto GPUs 0..N-1.  Measured on this pool (profiles/r2_h2d_ceiling.md):
+    # the eight GPUs hang off TWO host bridges whose aggregate host->device rates saturate at ~115 and ~140 GB/s, so
+    # four ranks packed onto GPUs 0-3 share one of them (28.8 GB/s each) while GPUs 0,2,4,6 get a full link each.
+    # Device-side numbers do not depend on the choice; WW_NO_SPREAD=1 restores rank i -> GPU i.
+    n_vis = torch.cuda.device_count()
+    gpu = local
+    if world > 1 and n_vis > world and n_vis % world == 0 and not os.environ.get("WW_NO_SPREAD") \
+            and int(os.environ.get("LOCAL_WORLD_SIZE", world)) == world:
+        gpu = local * (n_vis // world)
+    local_rank, local = local, gpu
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     host_numa = bind_host_to_gpu_node(local) if world > 1 and not os.environ.get("WW_NO_NUMA_BIND") else None
@@ -411,8 +424,8 @@ def run_ours(args):
     os.dup2(2, 1)
     if world > 1:
         # the communicator's own account of itself (ranks, transport, NVLS) goes to stderr so that it can be checked
-        os.environ.setdefault("NCCL_DEBUG", os.environ.get("WW_NCCL_DEBUG", "INFO"))
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ["NCCL_DEBUG"] = os.environ.get("WW_NCCL_DEBUG", "INFO")
+        os.environ["NCCL_DEBUG_SUBSYS"] = os.environ.get("WW_NCCL_DEBUG_SUBSYS", "INIT")
         dist.init_process_group("nccl", device_id=dev)
         warm = torch.zeros(1, device=dev)
         dist.all_reduce(warm)  # creates the communicator
