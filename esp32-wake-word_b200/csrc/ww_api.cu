@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <thread>
 #include <string>
@@ -64,6 +65,7 @@ struct ww_ctx {
     float tc_band_override = -1.f;  // WW_TC_BAND (absolute, experiments only)
     float* tc_dbg = nullptr;
     long long chunk_clips = 0;      // clips per frontend + CNN pair of the fused path (WW_CHUNK_CLIPS)
+    long long host_chunk_clips = 0; // clips per H2D / compute / D2H stage of the host-buffer paths (WW_HOST_CHUNK_CLIPS)
     std::atomic<int> busy{0};       // ww_score_clips* share one feature scratch per context: one call at a time
     std::vector<float> host_w[5];      // fp32 weights as loaded (for the int8 twin's quantisation)
     signed char* i8blob = nullptr;
@@ -369,6 +371,11 @@ extern "C" int ww_create(ww_ctx** out, int device) {
     if ((e = cudaFuncSetAttribute(cnn_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8T_SMEM)) != cudaSuccess)
         return bail(e, "cudaFuncSetAttribute(cnn_i8_tc_kernel)");
     if (const char* b = getenv("WW_TC_BAND")) ctx->tc_band_override = (float)atof(b);
+    ctx->host_chunk_clips = kHostChunkClips;
+    if (const char* c = getenv("WW_HOST_CHUNK_CLIPS")) {
+        const long long v = atoll(c);
+        if (v >= 8 && v <= (1LL << 20)) ctx->host_chunk_clips = v;
+    }
     ctx->chunk_clips = kScratchClips;
     if (const char* c = getenv("WW_CHUNK_CLIPS")) {
         const long long v = atoll(c);
@@ -1243,7 +1250,7 @@ static void free_host_path(ww_ctx* ctx) {
 // both sides.  Everything is sized for (chunk, sample width, class count); a change of any of them (ww_load_weights
 // with another num_classes frees the set) rebuilds it.
 static int ensure_host_path(ww_ctx* ctx, size_t esz) {
-    const long long chunk = kHostChunkClips;
+    const long long chunk = ctx->host_chunk_clips;
     const size_t bytes = (size_t)chunk * WW_CLIP_SAMPLES * esz;
     const int C = ctx->w.num_classes;
     if (ctx->host_chunk == chunk && ctx->host_chunk_bytes >= bytes && ctx->host_classes == C) return WW_OK;
@@ -2069,6 +2076,94 @@ extern "C" int ww_wav_load_batch(const char* const* paths, int n, int clip_sampl
     for (int t = 1; t < n_threads; ++t) pool.emplace_back(worker);
     worker();
     for (auto& t : pool) t.join();
+    return failed.load();
+}
+
+// files -> decisions as a two-buffer pipeline (the reference's real entry point walks a directory of WAV files:
+// ml_models/src/extract_mfcc.py:151-176; the firmware's offline check does the same over /flash/*.wav,
+// hello_world_main.cpp:186-278).  While the GPU copies in and scores batch k (H2D, frontend, CNN, D2H on the batch's own
+// stream), the reader threads fill the OTHER pinned staging buffer with batch k + 1; a batch is retired (results
+// copied out) right before its buffer is needed again.  stats (may be NULL): [0] seconds spent reading files,
+// [1] seconds blocked waiting for the GPU, [2] total seconds.
+extern "C" long long ww_score_wav_files(ww_ctx* ctx, const char* const* paths, long long n, int n_threads, int cmvn_mode,
+                                        int decide_mode, float threshold, int cnn_impl, float* logits_host,
+                                        uint8_t* decisions_host, ww_wav_info* infos, int* status, double* stats) {
+    if (!ctx) return WW_ERR_INVALID;
+    if (n == 0) return 0;
+    if (!paths || !logits_host || n < 0 || n > 0x7fffffffLL) return fail(ctx, WW_ERR_INVALID, "score_wav_files: bad arguments");
+    int rc = check_cnn_args(ctx, cmvn_mode, decide_mode, cnn_impl);
+    if (rc) return rc;
+    BusyGuard guard(ctx);
+    if (!guard.ok) return WW_ERR_BUSY;
+    NvtxRange whole("ww_score_wav_files");
+    CK(cudaSetDevice(ctx->device));
+    rc = ensure_host_path(ctx, sizeof(int16_t));
+    if (rc) return rc;
+    rc = ensure_scratch(ctx);
+    if (rc) return rc;
+    if (n_threads < 1) n_threads = 1;
+    const int C = ctx->w.num_classes;
+    const long long chunk = ctx->host_chunk;
+    const long long n_chunks = (n + chunk - 1) / chunk;
+    std::atomic<long long> failed(0);
+    double t_load = 0.0, t_wait = 0.0;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    for (long long k = 0; k < n_chunks + 2; ++k) {
+        if (k >= 2) {  // retire batch k - 2: its staging buffer and result buffers are about to be reused
+            const long long kk = k - 2;
+            const int b = (int)(kk & 1);
+            const long long c0 = kk * chunk, nc = (n - c0) < chunk ? (n - c0) : chunk;
+            NvtxRange r("ww:retire(d2h wait + copy out)");
+            const double t0 = now();
+            CK(cudaStreamSynchronize(ctx->hs[b]));
+            t_wait += now() - t0;
+            memcpy(logits_host + c0 * C, ctx->h_logits[b], (size_t)nc * C * sizeof(float));
+            if (decisions_host) memcpy(decisions_host + c0, ctx->h_dec[b], (size_t)nc);
+        }
+        if (k < n_chunks) {
+            const int b = (int)(k & 1);
+            const long long c0 = k * chunk, nc = (n - c0) < chunk ? (n - c0) : chunk;
+            int16_t* stage = static_cast<int16_t*>(ctx->h_pin[b]);
+            {
+                NvtxRange r("ww:load(wav -> pinned batch)");
+                const double t0 = now();
+                std::atomic<long long> next(0);
+                auto worker = [&]() {
+                    for (;;) {
+                        const long long i = next.fetch_add(1);
+                        if (i >= nc) break;
+                        const int st = wav_load_one(paths[c0 + i], WW_CLIP_SAMPLES, stage + (size_t)i * WW_CLIP_SAMPLES,
+                                                    infos ? infos + c0 + i : nullptr);
+                        if (status) status[c0 + i] = st;
+                        if (st != WW_OK) failed.fetch_add(1);
+                    }
+                };
+                const int nt = (long long)n_threads > nc ? (int)nc : n_threads;
+                std::vector<std::thread> pool;
+                for (int t = 1; t < nt; ++t) pool.emplace_back(worker);
+                worker();
+                for (auto& t : pool) t.join();
+                t_load += now() - t0;
+            }
+            NvtxRange r("ww:h2d+enqueue");
+            CK(cudaMemcpyAsync(ctx->d_pcm[b], stage, (size_t)nc * WW_CLIP_SAMPLES * sizeof(int16_t), cudaMemcpyHostToDevice,
+                               ctx->hs[b]));
+            if (k >= 1) CK(cudaStreamWaitEvent(ctx->hs[b], ctx->hev[(k - 1) & 1], 0));
+            rc = score_clips_dev(ctx, ctx->d_pcm[b], WW_PCM_S16, nc, cmvn_mode, decide_mode, threshold, cnn_impl,
+                                 ctx->d_logits[b], ctx->d_dec[b], ctx->hs[b]);
+            if (rc) return rc;
+            CK(cudaEventRecord(ctx->hev[b], ctx->hs[b]));
+            CK(cudaMemcpyAsync(ctx->h_logits[b], ctx->d_logits[b], (size_t)nc * C * sizeof(float), cudaMemcpyDeviceToHost,
+                               ctx->hs[b]));
+            CK(cudaMemcpyAsync(ctx->h_dec[b], ctx->d_dec[b], (size_t)nc, cudaMemcpyDeviceToHost, ctx->hs[b]));
+        }
+    }
+    if (stats) {
+        stats[0] = t_load;
+        stats[1] = t_wait;
+        stats[2] = now() - t_begin;
+    }
     return failed.load();
 }
 

@@ -169,8 +169,17 @@ __global__ void __launch_bounds__(I8T_THREADS, 1) cnn_i8_tc_kernel(const __grid_
 
     const long long n_oct = (a.n_windows + I8T_CLIPS - 1) / I8T_CLIPS;
     const long long oct_stride = (long long)gridDim.x * I8T_GROUPS;
+    // as in cnn_tc_kernel: the next octet of a flat [n][13][63] float batch is pulled into L2 while this one is computed
+    const bool flat = a.feats && a.group_windows == 0 && a.frame_stride == 1 && a.coef_stride == WW_WINDOW_FRAMES &&
+                      a.win_stride == WW_N_MFCC * WW_WINDOW_FRAMES && (reinterpret_cast<uintptr_t>(a.feats) & 15) == 0;
 #pragma unroll 1
     for (long long oct = (long long)blockIdx.x * I8T_GROUPS + group; oct < n_oct; oct += oct_stride) {
+        if (WW_TC_PREFETCH && flat && tig == 0 && oct + oct_stride < n_oct) {
+            long long wins = a.n_windows - (oct + oct_stride) * I8T_CLIPS;
+            wins = wins < I8T_CLIPS ? wins : I8T_CLIPS;
+            const uint32_t bytes = (uint32_t)(wins * WW_N_MFCC * WW_WINDOW_FRAMES * 4) & ~15u;
+            if (bytes) bulk_prefetch_l2(a.feats + (oct + oct_stride) * (long long)(I8T_CLIPS * WW_N_MFCC * WW_WINDOW_FRAMES), bytes);
+        }
         // ================= S0: model input -> A1 rows (lane <-> frame), two windows per warp =================
         if (a.feats) {
             // float features: int8 rounding + device-style CMVN here, so the device path is one launch
@@ -232,7 +241,7 @@ __global__ void __launch_bounds__(I8T_THREADS, 1) cnn_i8_tc_kernel(const __grid_
                     }
             umma_commit(bar);
         }
-        mbar_wait(bar, phase);
+        tc_wait_mma(bar, phase, q4, group);
         phase ^= 1;
         tc_fence_after();
 #pragma unroll 1
@@ -269,7 +278,7 @@ __global__ void __launch_bounds__(I8T_THREADS, 1) cnn_i8_tc_kernel(const __grid_
                 }
             umma_commit(bar);
         }
-        mbar_wait(bar, phase);
+        tc_wait_mma(bar, phase, q4, group);
         phase ^= 1;
         tc_fence_after();
         {
@@ -303,7 +312,7 @@ __global__ void __launch_bounds__(I8T_THREADS, 1) cnn_i8_tc_kernel(const __grid_
                             umma_desc_kmajor(sX3a + r * 16 + ks * 2 * I8_X3_LBO, I8_X3_LBO), idesc, (r | ks) > 0);
             umma_commit(bar);
         }
-        mbar_wait(bar, phase);
+        tc_wait_mma(bar, phase, q4, group);
         phase ^= 1;
         tc_fence_after();
         // thread = channel o: per window ReLU + requantise + MaxPool + exact mean of the 7 pooled steps -> G (int8)
@@ -345,7 +354,7 @@ __global__ void __launch_bounds__(I8T_THREADS, 1) cnn_i8_tc_kernel(const __grid_
                         umma_desc_kmajor(sGa + ks * 2 * I8_G_LBO, I8_G_LBO), idesc, ks > 0);
             umma_commit(bar);
         }
-        mbar_wait(bar, phase);
+        tc_wait_mma(bar, phase, q4, group);
         phase ^= 1;
         tc_fence_after();
         if (q4 < 2) {

@@ -243,6 +243,24 @@ __device__ __forceinline__ void group_sync(int group) {
     asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(TC_GROUP_THREADS) : "memory");
 }
 
+// MMA completion: only the group's first warp polls the mbarrier (try_wait parks the warp for a while per attempt),
+// the other three sleep in the group's hardware barrier instead of spinning -- a quarter of the polling instructions
+// (SYNCS + BRA + YIELD were 16 % of everything the kernel executed).
+#ifndef WW_TC_WAIT1
+#define WW_TC_WAIT1 1
+#endif
+#ifndef WW_TC_PREFETCH
+#define WW_TC_PREFETCH 1
+#endif
+__device__ __forceinline__ void tc_wait_mma(uint64_t* bar, uint32_t phase, int q4, int group) {
+#if WW_TC_WAIT1
+    if (q4 == 0) mbar_wait(bar, phase);
+    group_sync(group);
+#else
+    mbar_wait(bar, phase);
+#endif
+}
+
 // raw features of one window held by a warp: lane <-> frame (t = lane and t = lane + 32)
 struct TcWin {
     float x0[WW_N_MFCC], x1[WW_N_MFCC];
@@ -403,8 +421,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
     // hide the latency of these loads
     int np = 0;  // parity of this group's octet count: the norm slots are double-buffered (S0 of the next octet
                  // runs while warp 0 may still be in this octet's last epilogue)
+    // [n][13][63] batches (one octet = 26 208 contiguous bytes, a multiple of 16 from a 16-byte aligned base): the
+    // group's NEXT octet is pulled into L2 by one asynchronous bulk prefetch while this one is computed, so that the
+    // feature loads of S0 wait for an L2 hit instead of HBM (stall_long_sb was 37 % of the samples, issue slots 39 %
+    // busy: the kernel waits, it does not starve).  Sliding stream windows overlap 62/63 and are L2/L1-hot anyway.
+    const bool flat = a.group_windows == 0 && a.frame_stride == 1 && a.coef_stride == WW_WINDOW_FRAMES &&
+                      a.win_stride == WW_N_MFCC * WW_WINDOW_FRAMES && (reinterpret_cast<uintptr_t>(a.feats) & 15) == 0;
+    auto prefetch_octet = [&](long long o) {
+        if (!WW_TC_PREFETCH || !flat || o >= n_oct) return;
+        long long wins = a.n_windows - o * TC_CLIPS;
+        wins = wins < TC_CLIPS ? wins : TC_CLIPS;
+        const uint32_t bytes = (uint32_t)(wins * WW_N_MFCC * WW_WINDOW_FRAMES * 4) & ~15u;
+        if (bytes) bulk_prefetch_l2(a.feats + o * (long long)(TC_CLIPS * WW_N_MFCC * WW_WINDOW_FRAMES), bytes);
+    };
 #pragma unroll 1
     for (; oct < n_oct; oct += oct_stride, np ^= 1) {
+        if (tig == 0) prefetch_octet(oct + oct_stride);   // one octet (~12 us of work) ahead; the first one is a cold load
         // ================= S0: CMVN two windows per warp, write A1 (fp16) =================
         {
             TcWin wa, wb;
@@ -452,7 +484,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
                     }
             umma_commit(bar);
         }
-        mbar_wait(bar, phase);
+        tc_wait_mma(bar, phase, q4, group);
         phase ^= 1;
         tc_fence_after();
         // ---- epilogue 1: lane = pooled position (w, j): max(even, odd, 0) over 32 channels -> conv2 operand ----
@@ -499,7 +531,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
                     }
             umma_commit(bar);
         }
-        mbar_wait(bar, phase);
+        tc_wait_mma(bar, phase, q4, group);
         phase ^= 1;
         tc_fence_after();
         // ---- epilogue 2: lane = pooled position (w, m): 64 channels -> X3 row 1 + 16 w + m (natural order) ----
@@ -543,7 +575,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
                              umma_desc_kmajor(sX3a + r * 16 + ks * 2 * X3_LBO, X3_LBO), idesc, (r | ks) > 0);
             umma_commit(bar);
         }
-        mbar_wait(bar, phase);
+        tc_wait_mma(bar, phase, q4, group);
         phase ^= 1;
         tc_fence_after();
         // ---- epilogue 3: thread = channel o; per window ReLU + MaxPool + mean over the 7 pooled steps -> G ----
@@ -579,7 +611,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
                          umma_desc_kmajor(sGa + ks * 2 * G_LBO, G_LBO), idesc, ks > 0);
             umma_commit(bar);
         }
-        mbar_wait(bar, phase);
+        tc_wait_mma(bar, phase, q4, group);
         phase ^= 1;
         tc_fence_after();
         // ---- epilogue 4: ReLU, fc2 as a warp reduction (rows 0-63 = the warps of lane quadrants 0 and 1) ----

@@ -11,5 +11,5 @@ from .ctc import (CTCKeywordDetector, CTCLoss, ctc_greedy_decode, ctc_loss, deco
                   greedy_batch)
 from .stream import RingBuffer, StreamScorer, StreamSession, events, refractory_frames  # noqa: F401
 from .onnx_reader import load_kws_state_dict, read_initializers  # noqa: F401
-from .wav import load_wav_batch, parse_wav, read_wav, score_wav_dir, write_wav  # noqa: F401
+from .wav import load_wav_batch, parse_wav, read_wav, score_wav_dir, score_wav_files, write_wav  # noqa: F401
 from .frontdsp import augment_batch, tdm_downmix  # noqa: F401

@@ -34,7 +34,7 @@ EXPORTS = [
     "ww_session_windows", "ww_session_last_logits", "ww_session_close", "ww_ctc_greedy", "ww_ctc_loss_workspace_bytes",
     "ww_ctc_loss_fwd", "ww_ctc_loss_bwd", "ww_debug_tc", "ww_debug_esp_tables", "ww_extract_mfcc", "ww_free_mfcc", "ww_analyze_mfcc_range", "ww_ring_create", "ww_ring_delete", "ww_ring_write", "ww_ring_read", "ww_ring_count",
     "ww_set_option", "ww_wav_parse", "ww_wav_load_batch", "ww_wav_write", "ww_tdm_downmix", "ww_augment_waveform",
-    "ww_tc_band_info", "ww_tc_rescored_total", "ww_normalize_rows", "ww_stream_score_segment", "ww_extract_mfcc_ctx",
+    "ww_score_wav_files", "ww_tc_band_info", "ww_tc_rescored_total", "ww_normalize_rows", "ww_stream_score_segment", "ww_extract_mfcc_ctx",
 ]
 
 
@@ -125,6 +125,9 @@ def load_library():
         lib.ww_set_option.argtypes = [vp, i32, i32]
         lib.ww_wav_parse.argtypes = [vp, C.c_size_t, i32, C.POINTER(WavInfo)]
         lib.ww_wav_load_batch.argtypes = [C.POINTER(C.c_char_p), i32, i32, i32, vp, C.POINTER(WavInfo), C.POINTER(i32)]
+        lib.ww_score_wav_files.argtypes = [vp, C.POINTER(C.c_char_p), i64, i32, i32, i32, f32, i32, vp, vp,
+                                           C.POINTER(WavInfo), C.POINTER(i32), C.POINTER(C.c_double)]
+        lib.ww_score_wav_files.restype = i64
         lib.ww_wav_write.argtypes = [C.c_char_p, vp, C.c_size_t, i32, i32]
         lib.ww_tdm_downmix.argtypes = [vp, vp, i64, i64, i64, vp, i64, vp]
         lib.ww_augment_waveform.argtypes = [vp, vp, i64, i32, vp, vp]

@@ -119,6 +119,38 @@ def write_wav(path: str, pcm, sample_rate: int = 16000, num_channels: int = 1) -
         raise L.WWError(f"ww_wav_write({path}) failed ({rc})")
 
 
+def score_wav_files(paths, scorer, threads: int | None = None, strict: bool = True):
+    """files -> decisions through `scorer` (a WakeWordScorer) as a two-buffer pipeline inside the library
+    (ww_score_wav_files): reader threads fill one pinned batch while the GPU copies in and scores the other.
+
+    Returns (logits [n, C] float32, decisions uint8 [n], infos, status, stats) with stats = {"load_s", "gpu_wait_s",
+    "total_s", "files_per_s"}.  A file that cannot be read raises with strict=True, else it is scored as silence."""
+    paths = [os.fspath(p) for p in paths]
+    n = len(paths)
+    scorer._prep()
+    ctx = scorer.ctx
+    logits = np.empty((n, ctx.num_classes), np.float32)
+    dec = np.empty((n,), np.uint8)
+    infos = (L.WavInfo * max(n, 1))()
+    status = (C.c_int * max(n, 1))()
+    arr = (C.c_char_p * max(n, 1))(*[p.encode() for p in paths])
+    if threads is None:
+        threads = min(32, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    stats = (C.c_double * 3)()
+    failed = ctx.lib.ww_score_wav_files(ctx.h, arr, n, int(threads), scorer.cmvn, scorer.decide, scorer.threshold,
+                                        scorer.cnn_impl, logits.ctypes.data_as(C.c_void_p),
+                                        dec.ctypes.data_as(C.c_void_p), infos, status, stats)
+    if failed < 0:
+        ctx.check(int(failed), "ww_score_wav_files")
+    st = np.array(status[:n], dtype=np.int32)
+    if strict and failed:
+        bad = [paths[i] for i in range(n) if st[i] != 0]
+        raise L.WWError(f"{failed} WAV file(s) could not be loaded: {bad[:5]}")
+    out_stats = {"load_s": stats[0], "gpu_wait_s": stats[1], "total_s": stats[2],
+                 "files_per_s": n / stats[2] if stats[2] > 0 else float("inf")}
+    return logits, dec, WavInfos(infos, n), st, out_stats
+
+
 def score_wav_dir(path, state_dict, device_path=False, threads=None):
     """Score every *.wav of a directory -- the offline check the firmware runs over /flash/*.wav
     (main/hello_world_main.cpp:168-280: load, 63-frame MFCC, model, tally).
@@ -126,16 +158,15 @@ def score_wav_dir(path, state_dict, device_path=False, threads=None):
     device_path=False: float model, python CMVN, sigmoid(out) > 0.5 (ml_models/main.py:53);
     device_path=True:  int8 rounding + device CMVN + int8 esp-dl model + sigmoid*100 >= 80
                        (esp_wake_word_detector.cpp:128-131,179-258).
-    Returns (names, logits [n, C], decisions uint8 [n], number of positives)."""
+    Reading and scoring overlap (score_wav_files).  Returns (names, logits [n, C], decisions uint8 [n], positives)."""
     from .model import WakeWordScorer
 
     names = sorted(n for n in os.listdir(path) if n.endswith(".wav"))
     if not names:
         return [], np.zeros((0, 1), np.float32), np.zeros((0,), np.uint8), 0
-    pcm, _, _ = load_wav_batch([os.path.join(path, n) for n in names], threads=threads)
     if device_path:
         sc = WakeWordScorer(state_dict, cmvn="device", decision="device", cnn_impl="int8")
     else:
         sc = WakeWordScorer(state_dict, cmvn="python", decision="python", cnn_impl="tensor")
-    logits, dec = sc.score_host(pcm)
+    logits, dec, _, _, _ = score_wav_files([os.path.join(path, n) for n in names], sc, threads=threads)
     return names, logits, dec, int(dec.sum())

@@ -139,9 +139,11 @@ int ww_tc_band_info(const ww_ctx* ctx, float* beta, float* beta_calibrated, floa
 long long ww_tc_rescored_total(ww_ctx* ctx, int reset);
 
 /* ---- fused clip scoring: PCM -> MFCC -> CMVN -> CNN -> decision -------------------------------- */
-/* pcm: device [n_clips][16000].  The features pass from the frontend to the CNN through a context-owned scratch that
- * is sized to stay in L2 (chunks of clips).  One fused call at a time per context: a second host
- * thread gets WW_ERR_BUSY; consecutive calls on different streams are ordered on the device. */
+/* pcm: device [n_clips][16000].  The features pass from the frontend to the CNN through a context-owned scratch of
+ * 131 072 clips (429 MB: it round-trips HBM, 6.5 KB per clip on top of the 32 KB of PCM -- measured, DESIGN.md 4.6
+ * says why smaller, L2-sized chunks lose); per chunk: frontend launch, tcgen05 CNN launch, fp32 re-score launch.
+ * One fused call at a time per context: a second host thread gets WW_ERR_BUSY; consecutive calls on different
+ * streams are ordered on the device. */
 int ww_score_clips(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_clips, int cmvn_mode,
                    int decide_mode, float threshold, int cnn_impl, float* logits, uint8_t* decisions,
                    ww_stream_t stream);
@@ -249,6 +251,16 @@ int ww_wav_parse(const void* bytes, size_t n_bytes, int max_samples, ww_wav_info
  * infos[n] and status[n] (WW_OK / WW_ERR_*) may be NULL.  Returns the number of files that failed. */
 int ww_wav_load_batch(const char* const* paths, int n, int clip_samples, int n_threads, int16_t* pcm_host,
                       ww_wav_info* infos, int* status);
+/* files -> decisions: the reference's entry points walk a directory of WAV files (ml_models/src/extract_mfcc.py:151-176;
+ * hello_world_main.cpp:186-278 over /flash/*.wav).  Reads `n` files with `n_threads` reader threads and scores them as a
+ * two-buffer pipeline: while the GPU copies in and scores one batch of 16 384 files, the readers fill the other pinned
+ * staging buffer with the next.  logits_host [n][num_classes], decisions_host [n] (may be NULL), infos / status as in
+ * ww_wav_load_batch; a file that cannot be read is scored as silence and counted.  stats (may be NULL) receives
+ * {seconds reading files, seconds blocked on the GPU, total seconds}.  Returns the number of files that failed
+ * (>= 0) or a negative WW_ERR_*. */
+long long ww_score_wav_files(ww_ctx* ctx, const char* const* paths, long long n, int n_threads, int cmvn_mode,
+                             int decide_mode, float threshold, int cnn_impl, float* logits_host,
+                             uint8_t* decisions_host, ww_wav_info* infos, int* status, double* stats);
 /* Writer side of wav::WavHeader (esp_wav.hpp:41-75,121-213: initialize + write_info_to_file + write_data_to_file +
  * finalize_wav_file): canonical 44-byte header, riff_length = 36 + data bytes. */
 int ww_wav_write(const char* path, const int16_t* pcm, size_t n_samples, int num_channels, int sample_rate);

@@ -196,3 +196,47 @@ def test_score_wav_dir_float_and_device_paths(cuda_device, xiaoa_sd, tmp_path):
     out_q, dec_ref = ww_b200.score_clips_int8(xiaoa_sd, torch.from_numpy(g["pcm"]).to(cuda_device))
     np.testing.assert_array_equal(lq * 8.0, out_q.cpu().numpy().astype(np.float32))
     np.testing.assert_array_equal(dec2, dec_ref.cpu().numpy())
+
+
+def test_files_to_decisions_pipeline_equals_load_then_score(cuda_device, xiaoa_sd, tmp_path, monkeypatch):
+    """ww_score_wav_files (reader threads fill one pinned batch while the GPU scores the other) over several batches,
+    odd batch count, a short file, a file with extra chunks and a missing file: the same logits / decisions as
+    load_wav_batch followed by score_host (ml_models/src/extract_mfcc.py:151-176 walks a directory the same way)."""
+    import ww_b200
+    from ww_b200 import _lib as L
+    from ww_b200.model import WakeWordScorer
+
+    rng = np.random.default_rng(21)
+    n = 333
+    pcm = np.clip(np.round(rng.normal(0, 0.1, (n, 16000)) * 32767), -32768, 32767).astype(np.int16)
+    paths = []
+    for i in range(n):
+        p = tmp_path / f"f{i:04d}.wav"
+        ww_b200.write_wav(str(p), pcm[i, : (9000 if i % 50 == 7 else 16000)])
+        if i % 40 == 3:   # a LIST chunk in front of "data"
+            body = p.read_bytes()
+            p.write_bytes(body[:36] + b"LIST" + (6).to_bytes(4, "little") + bytes(6) + body[36:])
+        paths.append(str(p))
+    monkeypatch.setenv("WW_HOST_CHUNK_CLIPS", "64")      # 6 batches of 64: the two staging buffers rotate three times
+    ctx = L.Context(0)
+    try:
+        sc = WakeWordScorer(xiaoa_sd, device=0)
+        sc.ctx = ctx                                      # a context of its own with the small batch size
+        sc._key = ("pipeline-test", 0)
+        logits, dec, infos, st, stats = ww_b200.score_wav_files(paths, sc, threads=4)
+        assert (st == 0).all() and len(infos) == n and stats["total_s"] > 0
+        batch, _, _ = ww_b200.load_wav_batch(paths)
+        want_l, want_d = sc.score_host(batch)
+        np.testing.assert_array_equal(logits, want_l)
+        np.testing.assert_array_equal(dec, want_d)
+        # a missing file: counted, scored as silence, the others unaffected
+        bad = paths[:100] + [str(tmp_path / "nope.wav")] + paths[100:200]
+        with pytest.raises(ww_b200.WWError):
+            ww_b200.score_wav_files(bad, sc, threads=3)
+        l2, d2, _, st2, _ = ww_b200.score_wav_files(bad, sc, threads=3, strict=False)
+        assert st2[100] != 0 and (np.delete(st2, 100) == 0).all()
+        np.testing.assert_array_equal(np.delete(l2, 100, axis=0), want_l[:200])
+        silence = sc.score_host(np.zeros((1, 16000), np.int16))[0]
+        np.testing.assert_array_equal(l2[100], silence[0])
+    finally:
+        ctx.close()
