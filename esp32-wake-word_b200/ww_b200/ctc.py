@@ -73,14 +73,25 @@ def decode_predictions(log_probs, idx_to_char):
 class CTCKeywordDetector:
     """Keyword scoring on log-probabilities (ml_models/test.py:158-235).
 
-    char_to_idx maps characters to class indices; a keyword hit is a substring match on the greedy
-    decode and its confidence is the reference's constant 0.9, compared with `threshold` (0.8).
+    Reference signature `CTCKeywordDetector(model, char_to_idx, keywords, threshold=0.8)`; the model-less form
+    `CTCKeywordDetector(char_to_idx, keywords, threshold)` scores log-probabilities the caller already has.
+    char_to_idx maps characters to class indices; a keyword hit is a substring match on the greedy decode (GPU
+    kernel, repeats kept, index 0 dropped -- the reference's decoder) and its confidence is the reference's constant
+    0.9, compared with `threshold` (0.8).
     """
 
-    def __init__(self, char_to_idx, keywords, threshold=0.8):
-        self.char_to_idx = char_to_idx
-        self.idx_to_char = {v: k for k, v in char_to_idx.items()}
-        self.keywords = keywords
+    def __init__(self, *args, threshold=0.8, **kwargs):
+        args = list(args)
+        self.model = kwargs.pop("model", None)
+        if args and not isinstance(args[0], dict):
+            self.model = args.pop(0)                       # the reference's first positional argument
+        self.char_to_idx = kwargs.pop("char_to_idx", None) if not args else args.pop(0)
+        self.keywords = kwargs.pop("keywords", None) if not args else args.pop(0)
+        if args:
+            threshold = args.pop(0)
+        if kwargs or args or self.char_to_idx is None or self.keywords is None:
+            raise TypeError("CTCKeywordDetector([model,] char_to_idx, keywords, threshold=0.8)")
+        self.idx_to_char = {v: k for k, v in self.char_to_idx.items()}
         self.threshold = threshold
 
     def ctc_greedy_decode(self, log_probs, char_list=None):
@@ -89,6 +100,42 @@ class CTCKeywordDetector:
     @staticmethod
     def calculate_confidence(decoded_text, keyword, log_probs=None):
         return 0.9 if keyword in decoded_text else 0.0
+
+    def extract_mfcc_features(self, waveform, n_mfcc=13):
+        """test.py:218-229 takes `waveform[0]` of the chunk buffer and returns [T, 13] features.  The reference calls
+        librosa there (a third feature definition, absent here and out of scope); this drop-in uses the
+        engine's own frontend with the same frame geometry (n_fft 512, hop 256, 40 mels, 13 cepstra)."""
+        from .features import mfcc_batch
+
+        x = waveform[0]
+        x = torch.as_tensor(x)
+        if x.dim() == 2:
+            x = x[0]
+        return mfcc_batch(x[None])[0].transpose(0, 1).contiguous()
+
+    def detect_keywords(self, audio_stream):
+        """The reference's streaming loop (test.py:168-200): every chunk is appended to a buffer, the model scores the
+        features of the buffer's OLDEST chunk (sic, :220), the greedy decode is searched for every keyword, and the
+        buffer slides by five chunks.  Needs the `model` ([1, T, 13] -> log-probs [1, T, C])."""
+        if self.model is None:
+            raise ValueError("detect_keywords needs the model (CTCKeywordDetector(model, char_to_idx, keywords))")
+        if hasattr(self.model, "eval"):
+            self.model.eval()
+        buffer, detected = [], []
+        for chunk in audio_stream:
+            buffer.append(chunk)
+            if len(buffer):
+                feats = self.extract_mfcc_features(buffer)
+                with torch.no_grad():
+                    log_probs = self.model(feats.unsqueeze(0))
+                text = self.ctc_greedy_decode(log_probs.squeeze(0), self.idx_to_char)
+                for kw in self.keywords:
+                    if kw in text:
+                        conf = self.calculate_confidence(text, kw, log_probs)
+                        if conf > self.threshold:
+                            detected.append((kw, conf))
+                buffer = buffer[5:]
+        return detected
 
     def detect_batch(self, log_probs):
         """log_probs [B, T, C] -> list (per utterance) of [(keyword, confidence), ...]."""

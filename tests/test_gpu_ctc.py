@@ -85,6 +85,42 @@ def test_keyword_detector(cuda_device):
     assert det.calculate_confidence("xxa", "xa") == 0.9 and det.calculate_confidence("xx", "xa") == 0.0
 
 
+def test_keyword_detector_reference_signature_and_streaming_loop(cuda_device):
+    """CTCKeywordDetector(model, char_to_idx, keywords) and detect_keywords(stream) as in ml_models/test.py:158-200:
+    the oracle is the reference loop restated on the CPU with the same stand-in model and the same features."""
+    import ww_b200
+    from oracle import ctc as octc
+
+    c2i = {"_": 0, "x": 1, "a": 2}
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(13, 3).to(cuda_device)
+
+    class Model(torch.nn.Module):
+        def forward(self, feats):                      # [1, T, 13] -> log-probs [1, T, 3]
+            return torch.log_softmax(lin(feats) * 0.5, dim=-1)
+
+    det = ww_b200.CTCKeywordDetector(Model(), c2i, ["xa", "ax", "a"], threshold=0.8)
+    assert det.model is not None and det.keywords == ["xa", "ax", "a"]
+    g = torch.Generator().manual_seed(1)
+    stream = [torch.randn(1, 4000, generator=g) * 0.1 for _ in range(12)]
+    got = det.detect_keywords(stream)
+    # the reference loop, chunk by chunk (features of buffer[0], slide by five)
+    want, buffer = [], []
+    i2c = {v: k for k, v in c2i.items()}
+    for chunk in stream:
+        buffer.append(chunk)
+        feats = ww_b200.mfcc_batch(buffer[0][0][None].to(cuda_device))[0].T
+        lp = torch.log_softmax(lin(feats) * 0.5, dim=-1).detach().cpu().numpy()
+        text = "".join(i2c[i] for i in octc.greedy_labels(lp, octc.MODE_KEEP_REPEATS))
+        want += [(kw, 0.9) for kw in ["xa", "ax", "a"] if kw in text]
+        buffer = buffer[5:]
+    assert got == want and len(got) > 0
+    with pytest.raises(ValueError):
+        ww_b200.CTCKeywordDetector(c2i, ["xa"]).detect_keywords(stream)
+    with pytest.raises(TypeError):
+        ww_b200.CTCKeywordDetector(c2i)
+
+
 def _rand_problem(T, B, C, S, seed, full_len=False):
     rng = np.random.default_rng(seed)
     x = rng.normal(size=(T, B, C)).astype(np.float32)

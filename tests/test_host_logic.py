@@ -87,6 +87,23 @@ def test_normalize_mfcc_has_no_cpu_path():
                 ww_b200.normalize_mfcc(x, method)
 
 
+def test_keyword_detector_accepts_the_reference_constructor():
+    """ml_models/test.py:158-166: CTCKeywordDetector(model, char_to_idx, keywords, threshold=0.8); the model-less form
+    scores log-probabilities the caller already has."""
+    c2i = {"_": 0, "x": 1, "a": 2}
+    model = torch.nn.Identity()
+    a = ww_b200.CTCKeywordDetector(model, c2i, ["xa"])
+    b = ww_b200.CTCKeywordDetector(c2i, ["xa"], 0.5)
+    c = ww_b200.CTCKeywordDetector(model, c2i, ["xa"], threshold=0.7)
+    assert a.model is model and a.threshold == 0.8 and a.idx_to_char == {0: "_", 1: "x", 2: "a"}
+    assert b.model is None and b.threshold == 0.5 and c.threshold == 0.7
+    assert a.calculate_confidence("xxa", "xa") == 0.9 and a.calculate_confidence("x", "xa") == 0.0
+    with pytest.raises(TypeError):
+        ww_b200.CTCKeywordDetector(c2i)
+    with pytest.raises(ValueError):
+        b.detect_keywords([])
+
+
 def test_load_wav(tmp_path):
     import wave
 
