@@ -41,6 +41,7 @@ struct CnnArgs {
     const long long* index;  // optional: window ids to score (re-score list); nullptr = 0..n_windows-1
     const int* index_count;  // optional device count for `index` (n_windows is then the capacity)
     unsigned long long* index_total;  // optional running total of re-scored windows (block 0 adds index_count)
+    int index_compact;       // 1: the features of index[k] are window k of `feats` (the fused clip kernel's compact copy)
     int cmvn_mode;
     int decide_mode;
     float threshold;         // DECIDE_LOGIT: logit > threshold; DECIDE_DEVICE: sigmoid*100 >= threshold
@@ -109,7 +110,8 @@ __global__ void __launch_bounds__(CNN_THREADS) cnn_fp32_kernel(const __grid_cons
 
     for (long long it = blockIdx.x; it < n; it += gridDim.x) {
         const long long win = a.index ? a.index[it] : it;
-        const float* src = a.group_windows
+        const float* src = a.index_compact ? a.feats + it * a.win_stride
+                           : a.group_windows
                                ? a.feats + (win / a.group_windows) * a.group_stride + (win % a.group_windows) * a.win_stride
                                : a.feats + win * a.win_stride;
 

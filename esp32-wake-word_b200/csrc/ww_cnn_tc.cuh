@@ -101,6 +101,12 @@ struct TcArgs {
     unsigned char* decisions;
     long long* rescore_list;  // may be null
     int* rescore_count;
+    // Compact hand-over to the exact kernel (flat [n][13][63] batches and the fused clip kernel): a listed window's
+    // features are copied to rescore_feat[position in the list] and the list entry is win + rescore_base, so that one
+    // re-score launch can serve many CNN launches whose feature buffer has been recycled in between.  null: the list
+    // indexes `feats` itself and the re-score follows this launch.
+    float* rescore_feat;
+    long long rescore_base;
     const uint4* wblob;     // TC_W_BYTES
     const float* fc2;       // [C][64]
     int num_classes;
@@ -266,6 +272,29 @@ struct TcWin {
     float x0[WW_N_MFCC], x1[WW_N_MFCC];
 };
 
+// Where the CNN role runs.  Stand-alone: one CTA per SM over a feature batch in HBM.  FUSED (ww_fused.cuh): a few CTAs
+// of the clip kernel, fed by the frontend pipelines of the same launch through an L2-resident ring of [13][63] windows
+// (wait_ready / window / release), and the windows inside the guard band are copied out of the ring for the exact kernel.
+struct TcSolo {
+    static constexpr bool FUSED = false;
+    __device__ __forceinline__ long long cta() const { return blockIdx.x; }
+    __device__ __forceinline__ long long n_cta() const { return gridDim.x; }
+    __device__ __forceinline__ void wait_ready(long long, long long, int) const {}
+    __device__ __forceinline__ void release(long long) const {}
+    __device__ __forceinline__ const float* window(long long) const { return nullptr; }
+};
+
+// ring windows: contiguous [13][63], written by other SMs during this launch -> L2 loads only (L1 is not coherent)
+__device__ __forceinline__ void tc_load_window_ring(const float* wbase, bool live, int lane, TcWin& w) {
+    const bool has1 = lane + 32 < WW_WINDOW_FRAMES;
+    const float* p0 = wbase + lane;
+#pragma unroll
+    for (int q = 0; q < WW_N_MFCC; ++q) {
+        w.x0[q] = live ? __ldcg(p0 + q * WW_WINDOW_FRAMES) : 0.f;
+        w.x1[q] = (live && has1) ? __ldcg(p0 + q * WW_WINDOW_FRAMES + 32) : 0.f;
+    }
+}
+
 template <class ARGS>
 __device__ __forceinline__ void tc_load_window(const ARGS& a, long long win, int lane, TcWin& w) {
     const bool live = win < a.n_windows;
@@ -367,8 +396,8 @@ __device__ __forceinline__ void tc_cmvn_store(const TcArgs& a, TcWin& w, int slo
     }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_constant__ TcArgs a) {
-    extern __shared__ __align__(128) unsigned char smem[];
+template <class ROLE>
+__device__ __forceinline__ void cnn_tc_body(const TcArgs& a, unsigned char* smem, const ROLE role) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TC_OFF_BAR + 32);
     float* sfc2 = reinterpret_cast<float*>(smem + TC_OFF_FC2);
     unsigned char* sW = smem + TC_OFF_W;
@@ -407,6 +436,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // programmatic dependent launch: everything above (tiles, weights, TMEM) ran while the frontend launch that produces
+    // the features was finishing
+    if constexpr (!ROLE::FUSED) pdl_wait();
     const uint32_t tmem = *tmem_slot + (uint32_t)(group * TC_GROUP_COLS);
     const uint32_t sA1a = smem_u32(sA1), sA2a = smem_u32(sA2), sX3a = smem_u32(sX3), sGa = smem_u32(sG);
     const uint32_t sWa = smem_u32(sW);
@@ -414,8 +446,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
     const uint32_t tlane = (uint32_t)(32 * q4) << 16;
 
     const long long n_oct = (a.n_windows + TC_CLIPS - 1) / TC_CLIPS;
-    const long long oct_stride = (long long)gridDim.x * TC_GROUPS;
-    long long oct = (long long)blockIdx.x * TC_GROUPS + group;
+    const long long oct_stride = role.n_cta() * TC_GROUPS;
+    long long oct = role.cta() * TC_GROUPS + group;
+    long long oct_held = -1;   // FUSED: octet whose ring slot this group still holds
 
     // each warp owns two windows of the octet (slots 2*q4, 2*q4 + 1); the other groups' GEMM stages and epilogues
     // hide the latency of these loads
@@ -428,7 +461,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
     const bool flat = a.group_windows == 0 && a.frame_stride == 1 && a.coef_stride == WW_WINDOW_FRAMES &&
                       a.win_stride == WW_N_MFCC * WW_WINDOW_FRAMES && (reinterpret_cast<uintptr_t>(a.feats) & 15) == 0;
     auto prefetch_octet = [&](long long o) {
-        if (!WW_TC_PREFETCH || !flat || o >= n_oct) return;
+        if (!WW_TC_PREFETCH || ROLE::FUSED || !flat || o >= n_oct) return;
         long long wins = a.n_windows - o * TC_CLIPS;
         wins = wins < TC_CLIPS ? wins : TC_CLIPS;
         const uint32_t bytes = (uint32_t)(wins * WW_N_MFCC * WW_WINDOW_FRAMES * 4) & ~15u;
@@ -440,8 +473,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
         // ================= S0: CMVN two windows per warp, write A1 (fp16) =================
         {
             TcWin wa, wb;
-            tc_load_window(a, oct * TC_CLIPS + 2 * q4, lane, wa);
-            tc_load_window(a, oct * TC_CLIPS + 2 * q4 + 1, lane, wb);
+            if constexpr (ROLE::FUSED) {
+                role.wait_ready(oct, a.n_windows, lane);   // both blocks of all clips of the octet are in the ring
+                const long long w0 = oct * TC_CLIPS + 2 * q4;
+                tc_load_window_ring(role.window(w0), w0 < a.n_windows, lane, wa);
+                tc_load_window_ring(role.window(w0 + 1), w0 + 1 < a.n_windows, lane, wb);
+            } else {
+                tc_load_window(a, oct * TC_CLIPS + 2 * q4, lane, wa);
+                tc_load_window(a, oct * TC_CLIPS + 2 * q4 + 1, lane, wb);
+            }
             if (a.cmvn_mode == CMVN_NONE) {
                 // the caller's features are fed as they are: their norm scales the guard band of these two windows
                 float sa = 0.f, sb = 0.f;
@@ -463,6 +503,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
         fence_async_smem();
         tc_fence_before();
         group_sync(group);
+        if constexpr (ROLE::FUSED) {
+            // every warp of the group has passed the previous octet's last ring reads (S0 loads, re-score copy)
+            if (tig == 0 && oct_held >= 0) role.release(oct_held);
+            oct_held = oct;
+        }
 
         // ================= conv1: 2 row tiles x {even, odd outputs} x 3 taps (K = 16) =================
         // even output 2j = W0.x[2j-1] + W1.x[2j] + W2.x[2j+1] -> taps (odd, R-1), (even, R), (odd, R)
@@ -636,6 +681,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
         }
         tc_fence_before();
         group_sync(group);
+        int resc_slot = -1;   // FUSED: position of this thread's window (tig = window-in-octet) in the re-score list
         if (tig < 8 * C) {
             const int c8 = tig & 7, c = tig >> 3;
             const long long win = oct * TC_CLIPS + c8;
@@ -667,12 +713,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
                     }
                     if (near) {
                         const int slot = atomicAdd(a.rescore_count, 1);
-                        a.rescore_list[slot] = win;
+                        a.rescore_list[slot] = win + (a.rescore_feat ? a.rescore_base : 0);
+                        resc_slot = slot;
                     }
                 }
             }
         }
+        if (a.rescore_feat) {
+            // the feature buffer is recycled before the re-score runs: the group's first warp copies the windows it just
+            // listed (lanes 0..7 hold their list positions) into the compact buffer that the exact kernel reads
+            if (q4 == 0) {
+                unsigned m = __ballot_sync(0xffffffffu, resc_slot >= 0);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int sl = __shfl_sync(0xffffffffu, resc_slot, src);
+                    const long long w = oct * TC_CLIPS + src;
+                    const float* from = ROLE::FUSED ? role.window(w) : a.feats + w * (long long)(WW_N_MFCC * WW_WINDOW_FRAMES);
+                    float* to = a.rescore_feat + (long long)sl * (WW_N_MFCC * WW_WINDOW_FRAMES);
+                    for (int i = lane; i < WW_N_MFCC * WW_WINDOW_FRAMES; i += 32) to[i] = __ldcg(from + i);
+                }
+            }
+        }
         // `part` is rewritten only after the next octet's four group barriers
+    }
+    if constexpr (ROLE::FUSED) {
+        group_sync(group);
+        if (tig == 0 && oct_held >= 0) role.release(oct_held);
     }
 
     tc_fence_before();
@@ -681,6 +748,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_cons
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"((uint32_t)TC_TMEM_COLS)
                      : "memory");
     }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) cnn_tc_kernel(const __grid_constant__ TcArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    pdl_launch_dependents();
+    cnn_tc_body<TcSolo>(a, smem, TcSolo{});
 }
 
 // ---- stand-alone CMVN (normalize_mfcc / device CMVN over [n][13][63] windows) ------------------------------

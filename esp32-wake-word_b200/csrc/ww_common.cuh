@@ -125,10 +125,37 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
         : "memory");
 }
 
+// the same copy with an L2 cache policy (createpolicy): evict-first for data that is read exactly once
+__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                              uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
 // asynchronous prefetch of a global range into L2 (16-byte aligned address, size a multiple of 16)
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
+
+// Programmatic dependent launch (cudaLaunchAttributeProgrammaticStreamSerialization): a kernel lets the next launch of
+// its stream start early with launch_dependents; the next kernel may run its prologue (tables, weights, TMEM, its first
+// input block) and calls pdl_wait before it touches anything the previous kernel writes or still reads -- the wait
+// returns when that kernel has completed and its memory is visible.  Both are no-ops in an ordinary launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -265,18 +265,40 @@ struct DctDispatch<G, G> {
 // both instantiations produce identical bits; the host picks CLIP when the launch arguments match (launch_mfcc_ex).
 constexpr int CLIP_SAMPLES = 16000, CLIP_FRAMES = 63, CLIP_ORIGIN = -256;
 
-template <typename TIN, int MEL, bool CLIP = false>
-__global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_constant__ MfccArgs a) {
+// Where one frontend pipeline (256 threads, MfccSmem bytes of shared memory) runs.  The stand-alone kernel runs one per
+// CTA (two CTAs per SM); the fused clip kernel (ww_fused.cuh) runs two per 512-thread CTA, each with its own named
+// barrier, and hands the features to the CNN role of the same launch through an L2-resident ring (FUSED: out_slot /
+// free_probe / wait_free / publish).
+// WW_PCM_EVICT_FIRST: the TMA loads of the PCM carry an evict-first L2 policy (every sample is read exactly once; without
+// the hint the 32 KB/clip input stream pushes the tables, the output lines and the next kernel's input out of L2)
+#ifndef WW_PCM_EVICT_FIRST
+#define WW_PCM_EVICT_FIRST 1
+#endif
+struct MfccSolo {
+    static constexpr bool FUSED = false;
+    uint64_t pol_ = 0;
+    __device__ __forceinline__ int tid() const { return threadIdx.x; }
+    __device__ __forceinline__ long long first() const { return blockIdx.x; }
+    __device__ __forceinline__ long long stride() const { return gridDim.x; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ long long out_slot(long long sig) const { return sig; }
+    __device__ __forceinline__ int free_probe(long long) const { return 0; }
+    __device__ __forceinline__ void wait_free(long long, int) const {}
+    __device__ __forceinline__ void publish(long long) const {}
+    __device__ __forceinline__ uint64_t pcm_policy() const { return pol_; }
+};
+
+template <typename TIN, int MEL, bool CLIP, class PIPE>
+__device__ __forceinline__ void mfcc_body(const MfccArgs& a, unsigned char* smem, const PIPE pipe) {
     using SM = MfccSmem<TIN, MEL>;
     constexpr int FRAMES = MFCC_FRAMES;
-    extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
     using ROWS = MfccRows<MEL>;
     const unsigned char* tab = smem + SM::OFF_TAB - SM::TAB_SKIP;  // tab + TB_x_OFF for x = TW1, TW2, MELW, MELM
     float* pw = reinterpret_cast<float*>(smem + SM::OFF_P);
     float* lm = reinterpret_cast<float*>(smem + SM::OFF_LM);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = pipe.tid(), warp = tid >> 5, lane = tid & 31;
     const int half = lane >> 4, l16 = lane & 15;
 
     const int L = CLIP ? CLIP_SAMPLES : a.n_samples;
@@ -308,9 +330,13 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
         mbar_expect_tx(&bars[buf], (uint32_t)((n[0] + n[1]) * (int)sizeof(TIN)));
         for (int h = 0; h < 2; ++h) {
             const int org = WW_HOP * (bt0 + 16 * h) + origin_off + 88;
-            if (n[h])
-                bulk_g2s(smem + SM::OFF_PCM + buf * SM::PCM_BYTES + h * SM::HALF_STRIDE + (lo[h] - org) * (int)sizeof(TIN),
-                         gs + lo[h], (uint32_t)(n[h] * (int)sizeof(TIN)), &bars[buf]);
+            if (n[h]) {
+                unsigned char* dst = smem + SM::OFF_PCM + buf * SM::PCM_BYTES + h * SM::HALF_STRIDE + (lo[h] - org) * (int)sizeof(TIN);
+                if ((PIPE::FUSED || WW_PCM_EVICT_FIRST) && pipe.pcm_policy() != 0)   // the PCM is read once
+                    bulk_g2s_hint(dst, gs + lo[h], (uint32_t)(n[h] * (int)sizeof(TIN)), &bars[buf], pipe.pcm_policy());
+                else
+                    bulk_g2s(dst, gs + lo[h], (uint32_t)(n[h] * (int)sizeof(TIN)), &bars[buf]);
+            }
         }
     };
 
@@ -326,11 +352,11 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
         uint4* dst = reinterpret_cast<uint4*>(smem + SM::OFF_TAB);
         for (int i = tid; i < SM::TAB_BYTES / 16; i += MFCC_THREADS) dst[i] = __ldg(a.tables + SM::TAB_SKIP / 16 + i);
     }
-    __syncthreads();
-    const long long first = blockIdx.x, stride = gridDim.x;
+    pipe.sync();
+    const long long first = pipe.first(), stride = pipe.stride();
     // (signal, block-in-signal) of the current block, advanced incrementally: no 64-bit division in the loop
     const int bps = CLIP ? (CLIP_FRAMES + FRAMES - 1) / FRAMES : a.blocks_per_sig;
-    const int stride_q = (int)gridDim.x / bps, stride_r = (int)gridDim.x % bps;
+    const int stride_q = (int)stride / bps, stride_r = (int)stride % bps;
     long long sig_cur = first / bps;
     int bi_cur = (int)(first - sig_cur * bps);
     if (use_bulk && tid == 0 && first < a.n_blocks) stage_block(sig_cur, bi_cur, 0);
@@ -378,9 +404,20 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
     // written, "every warp has written its log-mel rows" before the DCT, "edge taps are in place" -- are mbarriers
     // that are normally already complete when they are tested.
     //   bars[0..1] PCM buffers (TMA), bars[2] mel done (8 warps), bars[3] edge taps done (8 warps)
+    constexpr unsigned kDctWarps = MEL == MEL_PY ? WW_DCT_PY_WARP_MASK : MEL == MEL_ESP ? WW_DCT_ESP_WARP_MASK : 0xffu;
     long long iter = 0;
     bool prev_valid = false;
     long long prev_sig = 0;
+    bool pub_valid = false;      // FUSED: the block before the previous one has its features stored
+    // FUSED: the hand-over (publish / free_probe / wait_free) is done by single lanes from inline asm.  Fed from sig_cur /
+    // prev_sig it dragged the whole block -> clip bookkeeping off the uniform datapath (+12 % instructions); it gets its
+    // own per-thread copy of the clip index instead (clip of iteration k = v_sig, advanced by stride_q: the fused grid
+    // has an even stride, so stride_r = 0), hidden from the optimiser so that the two chains are not merged again.
+    long long v_sig = 0;
+    if constexpr (PIPE::FUSED) {
+        v_sig = sig_cur;
+        asm volatile("" : "+l"(v_sig));
+    }
     int prev_t0 = 0;
     uint32_t mel_uses = 0, edge_uses = 0;
 #pragma unroll 1
@@ -388,6 +425,21 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
         const bool have = blk_id < a.n_blocks;
         if (!have && !prev_valid) break;
         bool mel_pending = false;
+        // programmatic dependent launch: the first block was staged and transformed while the previous kernel of the
+        // stream (the CNN launch that still reads the feature buffer this launch overwrites) was finishing; the first
+        // output store happens in this iteration's DCT
+        if (!PIPE::FUSED && iter == 1) pdl_wait();
+        // FUSED: the block stored by the previous iteration's DCT is complete (the CTA barrier ordered its stores before
+        // this point): one thread hands it to the CNN role.  The probe of the ring slot this iteration's DCT will write
+        // is issued here, long before its result is needed.
+        int free_seen = 0;
+        if constexpr (PIPE::FUSED) {
+            if (pub_valid && tid == MFCC_THREADS - 32) pipe.publish(v_sig - 2 * stride_q);
+            // every lane of every warp reads the same word (one broadcast transaction per warp): a probe by the DCT
+            // warps' lane 0 alone put a divergent definition in front of the mel stage and cost the kernel its
+            // uniform datapath
+            if (prev_valid) free_seen = pipe.free_probe(v_sig - stride_q);
+        }
 
         // ---- mel + log of the previous block -> LM
         if (prev_valid) {
@@ -479,7 +531,7 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
                     TIN* dst = reinterpret_cast<TIN*>(pcm_buf + h * SM::HALF_STRIDE) + (lo_h - org);
                     for (int i = tid; i < hi_h - lo_h; i += MFCC_THREADS) dst[i] = gsig[lo_h + i];
                 }
-                __syncthreads();
+                pipe.sync();
             }
 
             // Edge frames (t = 0: reflected / no previous sample; the last frame: reflected tail) cannot use the
@@ -518,11 +570,12 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
                 }
                 // DCT: lane <-> frame, four of the warps <-> three or four coefficients each (the generated code's
                 // WW_DCT_*_WARP_MASK; every DCT warp reads the whole log-mel row); stores coalesced along time
-                constexpr unsigned dct_warps = MEL == MEL_PY ? WW_DCT_PY_WARP_MASK : MEL == MEL_ESP ? WW_DCT_ESP_WARP_MASK : 0xffu;
+                constexpr unsigned dct_warps = kDctWarps;
                 if ((dct_warps >> warp) & 1u) {
+                    if constexpr (PIPE::FUSED) pipe.wait_free(v_sig - stride_q, free_seen);
                     const int t = prev_t0 + lane;
                     if (t < n_frames) {
-                        float* outp = a.out + prev_sig * out_sig_stride + (long long)t * out_frame_stride;
+                        float* outp = a.out + pipe.out_slot(prev_sig) * out_sig_stride + (long long)t * out_frame_stride;
                         const float* lrow = lm + lane * ROWS::LM_STRIDE;
                         if constexpr (MEL == MEL_PY) {
                             const long long cs = out_coef_stride;
@@ -716,13 +769,29 @@ __global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_cons
         if (prev_valid) ++mel_uses;
         if (block_has_edge) ++edge_uses;
         // one CTA barrier per block: P(k) is complete; LM(k-1), the edge taps and PCM(k) are free again
-        __syncthreads();
+        pipe.sync();
+        pub_valid = prev_valid;
+        if constexpr (PIPE::FUSED) v_sig += stride_q;
         prev_valid = have;
         prev_sig = sig;
         prev_t0 = t0;
         sig_cur = sig_nxt;
         bi_cur = bi_nxt;
     }
+    if constexpr (PIPE::FUSED) {
+        if (pub_valid && tid == MFCC_THREADS - 32) pipe.publish(v_sig - 2 * stride_q);
+    }
+}
+
+template <typename TIN, int MEL, bool CLIP = false>
+__global__ void __launch_bounds__(MFCC_THREADS, 2) mfcc_kernel(const __grid_constant__ MfccArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    pdl_launch_dependents();
+    MfccSolo pipe;
+#if WW_PCM_EVICT_FIRST
+    pipe.pol_ = l2_policy_evict_first();
+#endif
+    mfcc_body<TIN, MEL, CLIP, MfccSolo>(a, smem, pipe);
 }
 
 }  // namespace ww

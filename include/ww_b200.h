@@ -121,8 +121,16 @@ int ww_cnn_forward_i8(ww_ctx* ctx, const int8_t* x, long long n_windows, int8_t*
  * kind::i8, int32 accumulators in TMEM) or WW_CNN_FP32 (here: the CUDA-core integer kernel).  Both are integer-exact
  * and give identical results.
  * WW_OPT_GENERIC_FRONTEND: 1 makes whole-clip launches use the run-time-shaped frontend kernel instead of the
- * instantiation with the 1 s clip shape frozen at compile time (identical results; for A/B timing and tests). */
-enum { WW_OPT_I8_IMPL = 1, WW_OPT_GENERIC_FRONTEND = 2 };
+ * instantiation with the 1 s clip shape frozen at compile time (identical results; for A/B timing and tests).
+ * WW_OPT_FUSED: how ww_score_clips* run with WW_CNN_TENSOR -- 0 (default): chunked launches (frontend, tcgen05 CNN,
+ * exact re-score per chunk); 2: ONE persistent kernel per <= 131 072 clips (frontend pipelines and tcgen05 CNN groups on
+ * disjoint SMs of the same launch, features handed over through an L2-resident ring: DRAM traffic = the PCM alone,
+ * 0.99 x the algorithmic bytes against 1.21 x, at 26.9 against 30.0 M clips/s on one B200); 1: one kernel from 2048
+ * clips on.  Results are bit-identical either way.  WW_OPT_FUSED_CNN_SMS: SMs given to the CNN role (0 = default by CMVN mode).
+ * WW_OPT_L2_CHUNK_CLIPS: clips per frontend + CNN launch pair of the chunked tensor path when the features are to stay
+ * in L2 (0 = off, default: 131 072-clip chunks through a 429 MB scratch in HBM; 16 384 = 53.7 MB of features that the
+ * next chunk overwrites while still in L2, one exact re-score launch per 131 072 clips instead of one per chunk). */
+enum { WW_OPT_I8_IMPL = 1, WW_OPT_GENERIC_FRONTEND = 2, WW_OPT_FUSED = 3, WW_OPT_FUSED_CNN_SMS = 4, WW_OPT_L2_CHUNK_CLIPS = 5 };
 int ww_set_option(ww_ctx* ctx, int option, int value);
 
 /* Guard band of WW_CNN_TENSOR for the weights loaded last.  ww_load_weights runs 4096 calibration windows (noise,
