@@ -84,6 +84,7 @@ struct ww_ctx {
     cudaStream_t scratch_stream = nullptr;
     bool scratch_used = false;
     // L2-resident feature hand-over of the chunked tensor path: [l2_chunk_clips][13][63], re-used by every chunk
+    int opt_ctc_tiny = 1;              // WW_CTC_TINY=0: the 8-lanes-per-utterance kernels for S <= 3 (A/B)
     int opt_pdl = 1;                   // WW_PDL=0: ordinary launches in that path (A/B)
     float* l2_feats = nullptr;
     long long l2_chunk_clips = 0;      // WW_L2_CHUNK_CLIPS (0 = off: 131 072-clip chunks through `scratch`)
@@ -398,6 +399,7 @@ extern "C" int ww_create(ww_ctx** out, int device) {
         if (v == 0 || (v >= 1024 && v <= 131072)) ctx->l2_chunk_clips = v;
     }
     if (const char* f = getenv("WW_PDL")) ctx->opt_pdl = atoi(f);
+    if (const char* f = getenv("WW_CTC_TINY")) ctx->opt_ctc_tiny = atoi(f);
     if (const char* f = getenv("WW_FUSED")) ctx->opt_fused = atoi(f);
     if (const char* f = getenv("WW_FUSED_CNN_SMS")) ctx->opt_fused_cnn_sms = atoi(f);
     if (const char* b = getenv("WW_TC_BAND")) ctx->tc_band_override = (float)atof(b);
@@ -2019,6 +2021,11 @@ extern "C" int ww_ctc_loss_fwd(ww_ctx* ctx, const float* log_probs, long long t_
     if (B == 0) return WW_OK;
     a.nll = nll;
     a.alpha = (float*)workspace;
+    if (S <= 3 && C <= CTC_TINY_MAX_C && ctx->opt_ctc_tiny) {  // keyword shapes: one thread per utterance, time-major alpha
+        ctc_tiny_fwd_kernel<<<(B + CTC_TINY_THREADS - 1) / CTC_TINY_THREADS, CTC_TINY_THREADS, 0, (cudaStream_t)stream>>>(a);
+        CK(cudaGetLastError());
+        return WW_OK;
+    }
     if (S <= 3) {  // short targets: 8 lanes per utterance, 4 utterances per warp
         ctc_small_fwd_kernel<<<(B + CTC_WARPS * 4 - 1) / (CTC_WARPS * 4), CTC_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
         CK(cudaGetLastError());
@@ -2062,6 +2069,12 @@ extern "C" int ww_ctc_loss_bwd(ww_ctx* ctx, const float* log_probs, long long t_
     a.grad = grad;
     a.gt_stride = gt_stride;
     a.gb_stride = gb_stride;
+    if (S <= 3 && C <= CTC_TINY_MAX_C && ctx->opt_ctc_tiny) {  // must mirror the forward's choice (alpha layout)
+        a.skip_fill = 0;
+        ctc_tiny_bwd_kernel<<<(B + CTC_TINY_THREADS - 1) / CTC_TINY_THREADS, CTC_TINY_THREADS, 0, (cudaStream_t)stream>>>(a);
+        CK(cudaGetLastError());
+        return WW_OK;
+    }
     if (S <= 3 && C <= 64) {
         a.skip_fill = 0;
         ctc_small_bwd_kernel<<<(B + CTC_WARPS * 4 - 1) / (CTC_WARPS * 4), CTC_WARPS * 32, 0, (cudaStream_t)stream>>>(a);

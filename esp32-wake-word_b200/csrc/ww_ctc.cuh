@@ -866,6 +866,186 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_small_bwd_kernel(const Ctc
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Keyword shapes proper (S <= 3, C <= 8: T ~ 63, C = 3, S = 1..2 of ml_models/test.py:99-119): ONE THREAD per utterance.
+// All 2S+1 <= 7 states, the <= 3 labels and the skip flags live in registers, so a time step is straight-line code with
+// no shuffles and no idle lanes (the 8-lanes-per-utterance kernels above spend 8 lanes on <= 7 states and 16 shuffles
+// per class on the gradient: ~2.2 k warp instructions per utterance against ~0.4 k here).  Consecutive threads take
+// consecutive utterances, so the log-prob rows [T][B][C] are read and the gradient written as contiguous 4C-byte pieces,
+// and alpha is kept TIME-MAJOR in the workspace, al[(t (2S+1) + s) B + b], so that a warp's alpha traffic is coalesced
+// (the workspace layout is private to the forward / backward pair; both pick this kernel from (S, C) alone).
+// log-sum-exp through MUFU ex2 / lg2 as in the prefetching kernels.
+// ------------------------------------------------------------------------------------------------
+constexpr int CTC_TINY_THREADS = 128;
+constexpr int CTC_TINY_MAX_C = 8;
+
+struct CtcTinyUtt {
+    int Tb, Sb, L;
+    int tg0, tg1, tg2;     // labels (blank where the target is shorter)
+    bool sk3, sk5;         // state 3 / 5 may be entered from two states back
+};
+
+__device__ __forceinline__ CtcTinyUtt ctc_tiny_utt(const CtcLossArgs& a, long long b) {
+    CtcTinyUtt u;
+    u.Tb = min(max(a.in_len[b], 0), a.T);
+    u.Sb = min(max(a.tgt_len[b], 0), a.S);
+    u.L = 2 * u.Sb + 1;
+    const int* tgt = a.targets + b * (long long)a.S;
+    u.tg0 = u.Sb > 0 ? tgt[0] : a.blank;
+    u.tg1 = u.Sb > 1 ? tgt[1] : a.blank;
+    u.tg2 = u.Sb > 2 ? tgt[2] : a.blank;
+    u.sk3 = u.Sb > 1 && u.tg1 != u.tg0;
+    u.sk5 = u.Sb > 2 && u.tg2 != u.tg1;
+    return u;
+}
+
+__global__ void __launch_bounds__(CTC_TINY_THREADS) ctc_tiny_fwd_kernel(const CtcLossArgs a) {
+    const long long b = (long long)blockIdx.x * CTC_TINY_THREADS + threadIdx.x;
+    if (b >= a.B) return;
+    const CtcTinyUtt u = ctc_tiny_utt(a, b);
+    const int Lw = 2 * a.S + 1;
+    const float NEG = -CUDART_INF_F;
+    const float* base = a.lp + b * a.b_stride;
+    float* al = a.alpha + b;
+    const long long B = a.B;
+    float a0 = NEG, a1 = NEG, a2 = NEG, a3 = NEG, a4 = NEG, a5 = NEG, a6 = NEG;
+    auto store = [&](int t) {
+        float* row = al + (long long)t * Lw * B;
+        row[0] = a0;
+        if (Lw > 1) { row[B] = a1; row[2 * B] = a2; }
+        if (Lw > 3) { row[3 * B] = a3; row[4 * B] = a4; }
+        if (Lw > 5) { row[5 * B] = a5; row[6 * B] = a6; }
+    };
+    if (u.Tb > 0) {
+        a0 = base[a.blank];
+        if (u.L > 1) a1 = base[u.tg0];
+        store(0);
+    }
+    for (int t = 1; t < u.Tb; ++t) {
+        const float* row = base + (long long)t * a.t_stride;
+        const float lb = row[a.blank];
+        const float n0 = a0 + lb;
+        float n1 = NEG, n2 = NEG, n3 = NEG, n4 = NEG, n5 = NEG, n6 = NEG;
+        if (u.L > 1) {
+            n1 = lse2f(a1, a0) + row[u.tg0];
+            n2 = lse2f(a2, a1) + lb;
+        }
+        if (u.L > 3) {
+            n3 = lse3f(a3, a2, u.sk3 ? a1 : NEG) + row[u.tg1];
+            n4 = lse2f(a4, a3) + lb;
+        }
+        if (u.L > 5) {
+            n5 = lse3f(a5, a4, u.sk5 ? a3 : NEG) + row[u.tg2];
+            n6 = lse2f(a6, a5) + lb;
+        }
+        a0 = n0; a1 = n1; a2 = n2; a3 = n3; a4 = n4; a5 = n5; a6 = n6;
+        store(t);
+    }
+    float v;
+    if (u.Tb == 0) v = u.Sb == 0 ? 0.f : CUDART_INF_F;
+    else if (u.L == 1) v = -a0;
+    else if (u.L == 3) v = -lse2f(a2, a1);
+    else if (u.L == 5) v = -lse2f(a4, a3);
+    else v = -lse2f(a6, a5);
+    if (a.zero_infinity && v == CUDART_INF_F) v = 0.f;
+    a.nll[b] = v;
+}
+
+__global__ void __launch_bounds__(CTC_TINY_THREADS) ctc_tiny_bwd_kernel(const CtcLossArgs a) {
+    const long long b = (long long)blockIdx.x * CTC_TINY_THREADS + threadIdx.x;
+    if (b >= a.B) return;
+    const CtcTinyUtt u = ctc_tiny_utt(a, b);
+    const int Lw = 2 * a.S + 1, C = a.C;
+    const float NEG = -CUDART_INF_F;
+    const float* base = a.lp + b * a.b_stride;
+    const float* al = a.alpha + b;
+    float* gbase = a.grad + b * a.gb_stride;
+    const long long B = a.B;
+
+    float nll;
+    {
+        float ll = NEG;
+        if (u.Tb > 0) {
+            const float* row = al + (long long)(u.Tb - 1) * Lw * B;
+            ll = row[(long long)(u.L - 1) * B];
+            if (u.L > 1) ll = lse2f(ll, row[(long long)(u.L - 2) * B]);
+        } else if (u.Sb == 0) {
+            ll = 0.f;
+        }
+        nll = -ll;
+    }
+    const float go = a.grad_out ? a.grad_out[b] : 1.f;
+    const bool dead = a.zero_infinity && nll == CUDART_INF_F;
+    const int Tl = dead ? 0 : u.Tb;   // rows that carry a gradient
+    for (int t = Tl; t < a.T; ++t) {
+        float* g = gbase + (long long)t * a.gt_stride;
+#pragma unroll
+        for (int c = 0; c < CTC_TINY_MAX_C; ++c)
+            if (c < C) g[c] = 0.f;
+    }
+    float b0 = NEG, b1 = NEG, b2 = NEG, b3 = NEG, b4 = NEG, b5 = NEG, b6 = NEG;
+    for (int t = Tl - 1; t >= 0; --t) {
+        const float* row = base + (long long)t * a.t_stride;
+        float lpc[CTC_TINY_MAX_C];
+#pragma unroll
+        for (int c = 0; c < CTC_TINY_MAX_C; ++c) lpc[c] = c < C ? row[c] : 0.f;
+        const float lb = row[a.blank], l0 = row[u.tg0], l1 = row[u.tg1], l2 = row[u.tg2];
+        if (t == u.Tb - 1) {
+            // only the last two states may end the path
+            b0 = u.L == 1 ? lb : NEG;
+            b1 = u.L == 3 ? l0 : NEG;
+            b2 = u.L == 3 ? lb : NEG;
+            b3 = u.L == 5 ? l1 : NEG;
+            b4 = u.L == 5 ? lb : NEG;
+            b5 = u.L == 7 ? l2 : NEG;
+            b6 = u.L == 7 ? lb : NEG;
+        } else {
+            // beta[s] = lse(beta[s], beta[s+1], skip ? beta[s+2]) + lp[label(s)], states >= L stay -inf
+            const float m0 = (u.L > 1 ? lse2f(b0, b1) : b0) + lb;
+            float m1 = NEG, m2 = NEG, m3 = NEG, m4 = NEG, m5 = NEG, m6 = NEG;
+            if (u.L > 1) {
+                m1 = lse3f(b1, b2, u.sk3 ? b3 : NEG) + l0;
+                m2 = (u.L > 3 ? lse2f(b2, b3) : b2) + lb;
+            }
+            if (u.L > 3) {
+                m3 = lse3f(b3, b4, u.sk5 ? b5 : NEG) + l1;
+                m4 = (u.L > 5 ? lse2f(b4, b5) : b4) + lb;
+            }
+            if (u.L > 5) {
+                m5 = lse2f(b5, b6) + l2;
+                m6 = b6 + lb;
+            }
+            b0 = m0; b1 = m1; b2 = m2; b3 = m3; b4 = m4; b5 = m5; b6 = m6;
+        }
+        // posterior mass of every state relative to its own class: exp(alpha + beta + nll - lp[label]) <= 1
+        const float* arow = al + (long long)t * Lw * B;
+        float eb = __expf(arow[0] + b0 + nll - lb), e1 = 0.f, e3 = 0.f, e5 = 0.f;
+        if (u.L > 1) {
+            e1 = __expf(arow[B] + b1 + nll - l0);
+            eb += __expf(arow[2 * B] + b2 + nll - lb);
+        }
+        if (u.L > 3) {
+            e3 = __expf(arow[3 * B] + b3 + nll - l1);
+            eb += __expf(arow[4 * B] + b4 + nll - lb);
+        }
+        if (u.L > 5) {
+            e5 = __expf(arow[5 * B] + b5 + nll - l2);
+            eb += __expf(arow[6 * B] + b6 + nll - lb);
+        }
+        float* g = gbase + (long long)t * a.gt_stride;
+#pragma unroll
+        for (int c = 0; c < CTC_TINY_MAX_C; ++c) {
+            if (c < C) {
+                float res = c == a.blank ? eb : 0.f;
+                if (u.Sb > 0 && c == u.tg0) res += e1;
+                if (u.Sb > 1 && c == u.tg1) res += e3;
+                if (u.Sb > 2 && c == u.tg2) res += e5;
+                g[c] = (__expf(lpc[c]) - res) * go;
+            }
+        }
+    }
+}
+
 // Wide-vocabulary backward, step 1: every (t, b) row gets exp(lp) * grad_out (or 0 past the input length / for
 // an infinite loss under zero_infinity) from a fully parallel, bandwidth-bound pass -- one warp per row, grid
 // stride.  ctc_loss_bwd_kernel (skip_fill = 1) then only patches the <= S+1 target classes of each row.
