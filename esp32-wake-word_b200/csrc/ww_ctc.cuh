@@ -33,8 +33,10 @@ constexpr int CTC_WARPS = 4;
 
 __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_greedy_kernel(const GreedyArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long b = (long long)blockIdx.x * CTC_WARPS + warp;
-    if (b >= a.B) return;
+    // grid stride over the utterances (64 CTAs per SM): measured neutral to slightly better than one CTA per four
+    // utterances at the keyword shape (2.95 against 2.82 G utterances/s, 2^20 x T = 63 x C = 3)
+    const long long warps_total = (long long)gridDim.x * CTC_WARPS;
+    for (long long b = (long long)blockIdx.x * CTC_WARPS + warp; b < a.B; b += warps_total) {
     const int Tb = a.lengths ? min(max(a.lengths[b], 0), a.T) : a.T;
     const float* base = a.lp + b * a.b_stride;
     int* lab = a.labels + b * (long long)a.T;
@@ -102,6 +104,7 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_greedy_kernel(const Greedy
         }
         hit = __any_sync(0xffffffffu, hit);
         if (lane == 0) a.hits[b] = hit ? 1 : 0;
+    }
     }
 }
 

@@ -147,9 +147,10 @@ int ww_tc_band_info(const ww_ctx* ctx, float* beta, float* beta_calibrated, floa
 long long ww_tc_rescored_total(ww_ctx* ctx, int reset);
 
 /* ---- fused clip scoring: PCM -> MFCC -> CMVN -> CNN -> decision -------------------------------- */
-/* pcm: device [n_clips][16000].  The features pass from the frontend to the CNN through a context-owned scratch of
- * 131 072 clips (429 MB: it round-trips HBM, 6.5 KB per clip on top of the 32 KB of PCM -- measured, DESIGN.md 4.6
- * says why smaller, L2-sized chunks lose); per chunk: frontend launch, tcgen05 CNN launch, fp32 re-score launch.
+/* pcm: device [n_clips][16000].  By default the features pass from the frontend to the CNN through a context-owned
+ * scratch of 131 072 clips (429 MB: it round-trips HBM, 6.5 KB per clip on top of the 32 KB of PCM); per chunk:
+ * frontend launch, tcgen05 CNN launch, fp32 re-score launch.  That is the fastest of three hand-overs; the other two
+ * keep the features in L2 (WW_OPT_L2_CHUNK_CLIPS, WW_OPT_FUSED above; measured side by side in DESIGN.md 4.6).
  * One fused call at a time per context: a second host thread gets WW_ERR_BUSY; consecutive calls on different
  * streams are ordered on the device. */
 int ww_score_clips(ww_ctx* ctx, const void* pcm, int pcm_type, long long n_clips, int cmvn_mode,

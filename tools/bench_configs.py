@@ -277,6 +277,10 @@ def main():
         for r in cmvn_bench(dev) + greedy_bench(dev) + int8_bench(dev, sd) + device_path_bench(dev, sd) + session_bench(sd) + frontdsp_bench(dev):
             print(json.dumps(r), flush=True)
         return
+    if "--greedy" in sys.argv:
+        for r in greedy_bench(dev):
+            print(json.dumps(r), flush=True)
+        return
     if "--ctc" in sys.argv:
         for r in (ctc_bench(dev, 63, 1 << 18, 3, 2), ctc_bench(dev, 63, 1 << 18, 3, 1), ctc_bench(dev, 63, 1 << 20, 3, 2),
                   ctc_bench(dev, 801, 256, 4096, 32)):
