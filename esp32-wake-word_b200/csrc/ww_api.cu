@@ -85,6 +85,7 @@ struct ww_ctx {
     bool scratch_used = false;
     // L2-resident feature hand-over of the chunked tensor path: [l2_chunk_clips][13][63], re-used by every chunk
     int opt_greedy_blocks_per_sm = 0;  // WW_GREEDY_BLOCKS_PER_SM (A/B; 0 = 64; measured 8 / 16 / 32 / 64 / unbounded: 2.08 / 2.26 / 2.77 / 2.95 / 2.82 G utt/s)
+    int opt_ctc_split = 1;             // WW_CTC_SPLIT=0: wide-vocabulary backward as fill + one recursion kernel (A/B)
     int opt_ctc_tiny = 1;              // WW_CTC_TINY=0: the 8-lanes-per-utterance kernels for S <= 3 (A/B)
     int opt_pdl = 1;                   // WW_PDL=0: ordinary launches in that path (A/B)
     float* l2_feats = nullptr;
@@ -401,6 +402,7 @@ extern "C" int ww_create(ww_ctx** out, int device) {
     }
     if (const char* f = getenv("WW_PDL")) ctx->opt_pdl = atoi(f);
     if (const char* f = getenv("WW_CTC_TINY")) ctx->opt_ctc_tiny = atoi(f);
+    if (const char* f = getenv("WW_CTC_SPLIT")) ctx->opt_ctc_split = atoi(f);
     if (const char* f = getenv("WW_GREEDY_BLOCKS_PER_SM")) ctx->opt_greedy_blocks_per_sm = atoi(f);
     if (const char* f = getenv("WW_FUSED")) ctx->opt_fused = atoi(f);
     if (const char* f = getenv("WW_FUSED_CNN_SMS")) ctx->opt_fused_cnn_sms = atoi(f);
@@ -1990,7 +1992,10 @@ extern "C" int ww_ctc_greedy(ww_ctx* ctx, const float* log_probs, long long t_st
 
 extern "C" size_t ww_ctc_loss_workspace_bytes(int T, int B, int S) {
     if (T < 0 || B < 0 || S < 0) return 0;
-    return (size_t)B * (size_t)T * (size_t)(2 * S + 1) * sizeof(float) + 16;
+    // alpha [B][T][2S+1] (+ 16 bytes of slack); behind it, for the split wide-vocabulary backward pass, four floats per
+    // utterance and alpha + beta [B][T][2S+1]
+    const size_t al = (size_t)B * (size_t)T * (size_t)(2 * S + 1) * sizeof(float);
+    return al + 16 + (size_t)B * 16 + al;
 }
 
 static int ctc_common(ww_ctx* ctx, CtcLossArgs& a, const float* log_probs, long long t_stride, long long b_stride, int T,
@@ -2062,7 +2067,7 @@ extern "C" int ww_ctc_loss_fwd(ww_ctx* ctx, const float* log_probs, long long t_
 extern "C" int ww_ctc_loss_bwd(ww_ctx* ctx, const float* log_probs, long long t_stride, long long b_stride, int T, int B,
                                int C, const int32_t* targets, int S, const int32_t* input_lengths,
                                const int32_t* target_lengths, int blank, int zero_infinity, const float* grad_out,
-                               const void* workspace, float* grad, long long gt_stride, long long gb_stride,
+                               void* workspace, float* grad, long long gt_stride, long long gb_stride,
                                ww_stream_t stream) {
     if (!ctx) return WW_ERR_INVALID;
     CtcLossArgs a{};
@@ -2103,6 +2108,35 @@ extern "C" int ww_ctc_loss_bwd(ww_ctx* ctx, const float* log_probs, long long t_
         CK(cudaGetLastError());
         return WW_OK;
     };
+    if (a.skip_fill && K <= 4 && ctx->opt_ctc_split) {
+        // wide vocabulary: beta recursion alone (alpha + beta in place), then every row independently
+        const size_t al_bytes = ((size_t)B * T * (2 * S + 1) * sizeof(float) + 15) / 16 * 16;
+        a.meta = reinterpret_cast<float*>((char*)workspace + al_bytes);
+        a.ab = a.meta + 4 * (size_t)B;
+        a.fill_vec = (C % 4 == 0) && ((uintptr_t)log_probs % 16 == 0) && ((uintptr_t)grad % 16 == 0) && (t_stride % 4 == 0) &&
+                     (b_stride % 4 == 0) && (gt_stride % 4 == 0) && (gb_stride % 4 == 0);
+        const size_t smem_b = (size_t)CTC_WARPS * (2 * (32 * K + 2) + 2 * CTC_PF * 32 * K) * sizeof(float);
+        switch (K) {
+            case 1: ctc_beta_pf_kernel<1><<<grid, CTC_WARPS * 32, smem_b, (cudaStream_t)stream>>>(a); break;
+            case 2: ctc_beta_pf_kernel<2><<<grid, CTC_WARPS * 32, smem_b, (cudaStream_t)stream>>>(a); break;
+            case 3: ctc_beta_pf_kernel<3><<<grid, CTC_WARPS * 32, smem_b, (cudaStream_t)stream>>>(a); break;
+            default: ctc_beta_pf_kernel<4><<<grid, CTC_WARPS * 32, smem_b, (cudaStream_t)stream>>>(a); break;
+        }
+        CK(cudaGetLastError());
+        long long rows = (long long)T * B;
+        long long blocks = (rows + CTC_ROWS_WARPS - 1) / CTC_ROWS_WARPS;
+        const long long cap = (long long)ctx->sm_count * 8;
+        if (blocks > cap) blocks = cap;
+        if (ctx->opt_ctc_split == 2) {   // A/B: the stream-only fill kernel, then the patches alone (1.27 + 0.41 ms against 1.57)
+            rc = launch_fill();
+            if (rc) return rc;
+            ctc_grad_rows_kernel<false><<<(unsigned)blocks, CTC_ROWS_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+        } else {
+            ctc_grad_rows_kernel<true><<<(unsigned)blocks, CTC_ROWS_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+        }
+        CK(cudaGetLastError());
+        return WW_OK;
+    }
     if (a.skip_fill) {
         rc = launch_fill();
         if (rc) return rc;

@@ -227,11 +227,13 @@ int ww_ctc_loss_fwd(ww_ctx* ctx, const float* log_probs, long long t_stride, lon
                     int C, const int32_t* targets, int S, const int32_t* input_lengths,
                     const int32_t* target_lengths, int blank, int zero_infinity, float* nll, void* workspace,
                     ww_stream_t stream);
-/* grad[t*gt_stride + b*gb_stride + c] = d(sum_b grad_out[b]*nll[b]) / d(activations), PyTorch convention */
+/* grad[t*gt_stride + b*gb_stride + c] = d(sum_b grad_out[b]*nll[b]) / d(activations), PyTorch convention.
+ * workspace: the one ww_ctc_loss_fwd filled (alpha stays intact, so the call may be repeated); the wide-vocabulary
+ * path keeps alpha + beta and per-utterance scalars in the rest of it. */
 int ww_ctc_loss_bwd(ww_ctx* ctx, const float* log_probs, long long t_stride, long long b_stride, int T, int B,
                     int C, const int32_t* targets, int S, const int32_t* input_lengths,
                     const int32_t* target_lengths, int blank, int zero_infinity, const float* grad_out,
-                    const void* workspace, float* grad, long long gt_stride, long long gb_stride,
+                    void* workspace, float* grad, long long gt_stride, long long gb_stride,
                     ww_stream_t stream);
 
 /* ---- WAV ingestion: main/esp_wav/esp_wav.cpp:8-139, esp_wav.hpp:24-213 ---------------- */

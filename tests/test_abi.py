@@ -58,7 +58,7 @@ def test_create_fails_loudly_without_gpu(lib):
 
 
 def test_workspace_bytes(lib):
-    assert lib.ww_ctc_loss_workspace_bytes(63, 8, 2) == 8 * 63 * 5 * 4 + 16
+    assert lib.ww_ctc_loss_workspace_bytes(63, 8, 2) == 2 * 8 * 63 * 5 * 4 + 16 + 8 * 16
 
 
 def test_extract_mfcc_shim_rejects_bad_args(lib):

@@ -199,6 +199,44 @@ def test_ctc_loss_keyword_shapes_one_thread_per_utterance(cuda_device, T, B, C, 
     assert err_mine <= max(2e-5, 3.0 * err_torch32)
 
 
+@pytest.mark.parametrize("T,B,C,S", [(120, 9, 64, 20), (200, 5, 256, 40), (90, 7, 100, 63), (150, 4, 1000, 31)])
+def test_ctc_loss_wide_vocabulary_split_backward(cuda_device, T, B, C, S):
+    """C >= 64, 2S+1 <= 128: beta recursion + row-parallel gradient.  Targets with many repeated labels (adjacent and
+    not), a label equal to the blank index... is not legal for torch, so the blank-index fold is covered by repeated
+    labels only; ragged lengths, an infeasible utterance, zero-length targets; a second backward through the same graph
+    (the workspace's alpha must survive the first)."""
+    import ww_b200
+
+    rng = np.random.default_rng(T + B + C + S)
+    x = rng.normal(size=(T, B, C)).astype(np.float32)
+    lp = (x - np.log(np.exp(x).sum(-1, keepdims=True))).astype(np.float32)
+    tg = rng.integers(1, min(C, 6), size=(B, S)).astype(np.int64)       # five labels only: repeats everywhere
+    tg[1] = rng.integers(1, C, size=S)                                  # one utterance without repeats (fast path)
+    tl = rng.integers(1, S + 1, size=B)
+    tl[0] = S
+    tl[-1] = 0
+    il = np.full(B, T)
+    il[2] = T // 2
+    il[3] = 3                                                           # infeasible for its target
+    tl[3] = S
+    want_loss, want_grad = octc.ctc_loss_torch(lp, tg, il, tl, reduction="none", zero_infinity=True)
+    _, g64 = octc.ctc_loss_torch(lp, tg, il, tl, reduction="none", zero_infinity=True, dtype="float64")
+    xg = torch.from_numpy(lp).to(cuda_device).requires_grad_(True)
+    loss = ww_b200.ctc_loss(xg, torch.from_numpy(tg), torch.from_numpy(il), torch.from_numpy(tl), reduction="none",
+                            zero_infinity=True)
+    loss.sum().backward(retain_graph=True)
+    g1 = xg.grad.clone()
+    xg.grad = None
+    loss.sum().backward()
+    torch.cuda.synchronize()
+    assert torch.equal(g1, xg.grad)                                     # deterministic, and alpha was not consumed
+    np.testing.assert_allclose(loss.detach().cpu().numpy(), want_loss, rtol=1e-5, atol=1e-5)
+    err_mine = np.abs(g1.cpu().numpy() - g64).max()
+    err_torch32 = np.abs(want_grad - g64).max()
+    print(f"grad err vs fp64: kernel {err_mine:.2e}, torch fp32 {err_torch32:.2e}")
+    assert err_mine <= max(1e-5, 3.0 * err_torch32)
+
+
 def test_ctc_loss_zero_infinity_and_blank_index(cuda_device):
     import ww_b200
 
