@@ -55,9 +55,41 @@ constexpr int CNN_THREADS = 256;
 constexpr int X0_STRIDE = 68, A1_STRIDE = 36, A2_STRIDE = 20;
 constexpr int CNN_SMEM_FLOATS = 13 * X0_STRIDE + 32 * A1_STRIDE + 64 * A2_STRIDE + 2 * 128 + 64;
 
+// lroundf (half away from zero) + saturation to int8.  rintf is one instruction (half to even); only an exact tie needs
+// the other neighbour, and v - rintf(v) is exact, so the test is exact too (checked against round-half-away on 5 M values,
+// every half-integer in +-300, +-inf and the 0.49999997 case: identical)
 __device__ __forceinline__ float lround_clamp_i8(float v) {
-    float r = roundf(v);  // half away from zero == lroundf
+    float r = rintf(v);
+    if (fabsf(v - r) == 0.5f) r = v + copysignf(0.5f, v);
     return fminf(fmaxf(r, -128.f), 127.f);
+}
+
+// The device-style CMVN (esp_wake_word_detector.cpp:179-211) divides: mean = sum / 63 and (v - mean) / (std + 1e-8),
+// each followed by a rounding to int8.  Both kernels must reproduce the IEEE quotients bit for bit (the int8 step turns
+// a last-bit difference into a whole unit), but they need not execute a division to do so:
+//  * x / 63: r = x c with c = RN(1/63), corrected once with the exact residual fma(-r, 63, x), is the correctly rounded
+//    quotient (Markstein's division step: c is the correctly rounded reciprocal and 63's significand is not all ones;
+//    checked for every integer sum in [-8064, 8064] and 2e8 random significands over 53 binades: no mismatch);
+//  * lround(d / den): q = d * rcp(den) (MUFU, 1 ulp) is within 2^-22 |q| of the correctly rounded quotient, so for
+//    |q| <= 256 the two round to the same integer unless q lies within 1e-4 of k + 1/2 -- only then (2 in 10 000) the
+//    division is done.
+__device__ __forceinline__ float div63_exact(float x) {
+    const float c = 1.f / 63.f;
+    const float r = x * c;
+    return fmaf(fmaf(-r, 63.f, x), c, r);
+}
+__device__ __forceinline__ float rcp_approx(float x) {   // 1 ulp, one MUFU
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float div_lround_clamp_i8(float d, float den, float rinv) {
+    const float q = d * rinv;
+    const float r = rintf(q);
+    float out = fminf(fmaxf(r, -128.f), 127.f);
+    // negated comparisons: a NaN quotient takes the exact path as well
+    if (!(fabsf(q) > 256.f) && !(fabsf(fabsf(q - r) - 0.5f) > 1.0e-4f)) out = lround_clamp_i8(d / den);
+    return out;
 }
 
 // conv(k=3, pad=1, no bias) + ReLU + MaxPool(2) for 8 consecutive output steps of one channel.
@@ -143,14 +175,15 @@ __global__ void __launch_bounds__(CNN_THREADS) cnn_fp32_kernel(const __grid_cons
                 z0 = d0 * inv;
                 z1 = d1 * inv;
             } else if (a.cmvn_mode != CMVN_NONE) {
-                const float mean = warp_sum(v0 + v1) / (float)WW_WINDOW_FRAMES;
+                const float mean = div63_exact(warp_sum(v0 + v1));   // the sum of 63 int8 values is exact in any order
                 const float d0 = v0 - mean, d1 = has1 ? v1 - mean : 0.f;
                 const float ss = warp_sum(d0 * d0 + d1 * d1);
                 {
-                    const float den = sqrtf(ss / (float)WW_WINDOW_FRAMES) + 1e-8f;
+                    const float den = sqrtf(div63_exact(ss)) + 1e-8f;
+                    const float rinv = rcp_approx(den);
                     // int8 at exponent 0 -> model input at exponent -4: saturates at 127/16
-                    z0 = fminf(fmaxf(lround_clamp_i8(d0 / den) * 16.f, -128.f), 127.f) * 0.0625f;
-                    z1 = fminf(fmaxf(lround_clamp_i8(d1 / den) * 16.f, -128.f), 127.f) * 0.0625f;
+                    z0 = fminf(fmaxf(div_lround_clamp_i8(d0, den, rinv) * 16.f, -128.f), 127.f) * 0.0625f;
+                    z1 = fminf(fmaxf(div_lround_clamp_i8(d1, den, rinv) * 16.f, -128.f), 127.f) * 0.0625f;
                 }
             }
             x0[q * X0_STRIDE + 1 + lane] = z0;

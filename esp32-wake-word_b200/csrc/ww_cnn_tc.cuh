@@ -325,12 +325,13 @@ __device__ __forceinline__ void tc_cmvn_device(TcWin& w, int lane) {
         const float v1 = has1 ? lround_clamp_i8(w.x1[q]) : 0.f;
         // v0, v1 are integers in [-128, 127]: their sum over the window is exact in any order, so the integer
         // warp reduction (one REDUX) gives the same float as cnn_fp32_kernel's shuffle tree
-        const float mean = (float)__reduce_add_sync(0xffffffffu, (int)v0 + (int)v1) / (float)WW_WINDOW_FRAMES;
+        const float mean = div63_exact((float)__reduce_add_sync(0xffffffffu, (int)v0 + (int)v1));
         const float d0 = v0 - mean, d1 = has1 ? v1 - mean : 0.f;
         const float ss = warp_sum(d0 * d0 + d1 * d1);   // float: keep the shuffle-tree order of cnn_fp32_kernel
-        const float den = sqrtf(ss / (float)WW_WINDOW_FRAMES) + 1e-8f;
-        w.x0[q] = fminf(fmaxf(lround_clamp_i8(d0 / den) * 16.f, -128.f), 127.f) * 0.0625f;
-        w.x1[q] = fminf(fmaxf(lround_clamp_i8(d1 / den) * 16.f, -128.f), 127.f) * 0.0625f;
+        const float den = sqrtf(div63_exact(ss)) + 1e-8f;
+        const float rinv = rcp_approx(den);
+        w.x0[q] = fminf(fmaxf(div_lround_clamp_i8(d0, den, rinv) * 16.f, -128.f), 127.f) * 0.0625f;
+        w.x1[q] = fminf(fmaxf(div_lround_clamp_i8(d1, den, rinv) * 16.f, -128.f), 127.f) * 0.0625f;
     }
 }
 
