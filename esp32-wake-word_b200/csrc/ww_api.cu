@@ -1609,7 +1609,7 @@ extern "C" int ww_score_clips_host(ww_ctx* ctx, const void* pcm_host, int pcm_ty
             CK(cudaMemcpyAsync(ctx->h_dec[b], ctx->d_dec[b], (size_t)nc, cudaMemcpyDeviceToHost, ctx->hs[b]));
         }
     }
-    return WW_OK;
+    return fused_check(ctx);   // every chunk has been retired: a one-kernel launch that gave up a wait is known by now
 }
 
 // ------------------------------------------------------------------------------------------------
