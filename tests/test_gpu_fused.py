@@ -119,6 +119,18 @@ def test_l2_resident_chunks_equal_default_chunks(cuda_device, xiaoa_sd, chunk):
         assert torch.equal(l0, l1) and torch.equal(d0, d1) and r0 == r1, (n, same, r0, r1)
         if same:
             assert r1 == n
+    if chunk == 16384:
+        # more clips than one exact re-score launch covers (131 072): the compact list is flushed and restarted mid-call
+        n = 131072 + 16384 + 9
+        pcm = _clips(n, 17, cuda_device)
+        sc.threshold = 0.0
+        l0, d0, r0 = _score(sc, pcm, 0)
+        sc.ctx.check(sc.ctx.lib.ww_set_option(sc.ctx.h, L.OPT_L2_CHUNK_CLIPS, chunk), "ww_set_option")
+        try:
+            l1, d1, r1 = _score(sc, pcm, 0)
+        finally:
+            sc.ctx.check(sc.ctx.lib.ww_set_option(sc.ctx.h, L.OPT_L2_CHUNK_CLIPS, 0), "ww_set_option")
+        assert torch.equal(l0, l1) and torch.equal(d0, d1) and r0 == r1
 
 
 def test_fused_three_classes_and_cnn_sm_count(cuda_device):
