@@ -544,8 +544,8 @@ def run_ours(args):
         del feats
 
     # ---- the three feature hand-overs of ww_score_clips, same clips, same bits (rank 0 of a 1-GPU run) --------------
-    # default: 131 072-clip chunks through a scratch in HBM; l2_chunks: 16 384-clip frontend + CNN launch pairs whose
-    # features stay in L2 (programmatic dependent launch, one exact re-score launch per 131 072 clips); one_kernel: a single
+    # default: 131 072-clip chunks through a scratch in HBM; l2_chunks: 14 208-clip frontend + CNN launch pairs (a whole
+    # number of waves for both kernels) whose features stay in L2 (programmatic dependent launch, one exact re-score launch per 131 072 clips); one_kernel: a single
     # persistent launch, frontend pipelines and tcgen05 CNN groups on disjoint SMs, L2-resident ring (csrc/ww_fused.cuh)
     handoff = None
     if rank == 0 and world == 1 and cnn_impl == "tensor" and not args.no_handoff:
@@ -558,7 +558,7 @@ def run_ours(args):
                                              L.ptr(lg), L.ptr(dc), sp), "ww_score_clips")
 
         modes = [("default", [(L.OPT_FUSED, 0), (L.OPT_L2_CHUNK_CLIPS, 0)], 38758.6, "profiles/r2_fused_dram_by_chunk.txt", 3 * 131072),
-                 ("l2_chunks", [(L.OPT_FUSED, 0), (L.OPT_L2_CHUNK_CLIPS, 16384)], 32213.3, "profiles/r2_handoff_dram_modes.txt", None),
+                 ("l2_chunks", [(L.OPT_FUSED, 0), (L.OPT_L2_CHUNK_CLIPS, 14208)], 32123.8, "profiles/r2_handoff_dram_modes.txt", None),
                  ("one_kernel", [(L.OPT_FUSED, 2), (L.OPT_L2_CHUNK_CLIPS, 0)], 31951.2, "profiles/r2_handoff_dram_modes.txt", None)]
         handoff = {"clips": hb, "algorithmic_bytes_per_clip": FUSED_BYTES_PER_CLIP, "modes": {}}
         ref_out = None
@@ -577,7 +577,7 @@ def run_ours(args):
             hms = h0.elapsed_time(h1) / 3
             if ref_out is None:
                 ref_out = (lg2.clone(), dc2.clone())
-            launches_1m = {"default": 8 * 3, "l2_chunks": 64 * 2 + 8, "one_kernel": 8 * 2}[name]
+            launches_1m = {"default": 8 * 3, "l2_chunks": 74 * 2 + 8, "one_kernel": 8 * 2}[name]
             handoff["modes"][name] = {"clips_per_s": hb / (hms * 1e-3), "dram_bytes_per_clip_ncu": dram,
                                       "dram_over_algorithmic": dram / FUSED_BYTES_PER_CLIP, "dram_source": src,
                                       "kernel_launches_per_2^20_clips": launches_1m,

@@ -128,8 +128,9 @@ int ww_cnn_forward_i8(ww_ctx* ctx, const int8_t* x, long long n_windows, int8_t*
  * 0.99 x the algorithmic bytes against 1.21 x, at 26.9 against 30.0 M clips/s on one B200); 1: one kernel from 2048
  * clips on.  Results are bit-identical either way.  WW_OPT_FUSED_CNN_SMS: SMs given to the CNN role (0 = default by CMVN mode).
  * WW_OPT_L2_CHUNK_CLIPS: clips per frontend + CNN launch pair of the chunked tensor path when the features are to stay
- * in L2 (0 = off, default: 131 072-clip chunks through a 429 MB scratch in HBM; 16 384 = 53.7 MB of features that the
- * next chunk overwrites while still in L2, one exact re-score launch per 131 072 clips instead of one per chunk). */
+ * in L2 (0 = off, default: 131 072-clip chunks through a 429 MB scratch in HBM; 14 208 = 46.5 MB of features that the
+ * next chunk overwrites while still in L2 and a whole number of waves for both kernels: DRAM traffic 1.004 x the
+ * algorithmic bytes at -1.1 % throughput; one exact re-score launch per 131 072 clips instead of one per chunk). */
 enum { WW_OPT_I8_IMPL = 1, WW_OPT_GENERIC_FRONTEND = 2, WW_OPT_FUSED = 3, WW_OPT_FUSED_CNN_SMS = 4, WW_OPT_L2_CHUNK_CLIPS = 5 };
 int ww_set_option(ww_ctx* ctx, int option, int value);
 
