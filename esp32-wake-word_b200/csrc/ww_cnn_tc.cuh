@@ -797,11 +797,16 @@ __global__ void __launch_bounds__(256) cmvn_rows_kernel(const CmvnArgs a) {
             float sd = sqrtf(ss / (float)(WW_WINDOW_FRAMES - 1));
             if (sd == 0.f) sd = 1.f;
             const float den = sd + 1e-8f;
+            const float rden = __frcp_rn(den);   // one correctly rounded reciprocal per row ...
 #pragma unroll
             for (int q = 0; q < WW_N_MFCC; ++q) {
-                const float dq = __shfl_sync(0xffffffffu, den, 2 * q);
-                w.x0[q] = w.x0[q] / dq;
-                w.x1[q] = w.x1[q] / dq;
+                // ... and one Markstein step per element: q0 = x r, q1 = q0 + fma(-q0, d, x) r is the correctly rounded
+                // x / d (up to the rare double-rounding cases of the method: a last-bit matter inside the 2e-5 of this
+                // call's parity bar; the CNN kernels do not use this path)
+                const float dq = __shfl_sync(0xffffffffu, den, 2 * q), rq = __shfl_sync(0xffffffffu, rden, 2 * q);
+                const float a0 = w.x0[q] * rq, a1 = w.x1[q] * rq;
+                w.x0[q] = fmaf(fmaf(-a0, dq, w.x0[q]), rq, a0);
+                w.x1[q] = fmaf(fmaf(-a1, dq, w.x1[q]), rq, a1);
             }
         } else if (a.cmvn_mode == CMVN_DEVICE) {
             tc_cmvn_device(w, lane);

@@ -122,6 +122,58 @@ __global__ void __launch_bounds__(256) ctc_argmax_rows_kernel(const GreedyArgs a
     const int sub = lane / lpr, l = lane % lpr;
     const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
     const long long rows = (long long)a.B * a.T;
+    if constexpr (LPR < 32) {
+        // short rows (one 16-byte element per lane at most): a warp iteration is 2-4 rows = 256-512 bytes, and with one
+        // iteration in flight per warp the kernel waited for HBM latency, not bandwidth (0.37 of the peak at C = 64).
+        // Four iterations' loads are issued before the first reduction; row -> (b, t) by 32-bit division when it fits.
+        if (a.vec_ok && rows < (1LL << 31)) {
+            constexpr int U = 4;
+            const int n4 = a.C >> 2;
+            const unsigned T = (unsigned)a.T;
+            for (long long r0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (rpw * U); r0 < rows;
+                 r0 += warps * (rpw * U)) {
+                float4 v[U];
+                unsigned bb[U], tt[U];
+                bool live[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const long long r = r0 + u * rpw + sub;
+                    const bool in = r < rows;
+                    const unsigned ru = in ? (unsigned)r : 0u;
+                    bb[u] = ru / T;
+                    tt[u] = ru - bb[u] * T;
+                    live[u] = in && l < n4 && !(a.lengths && (int)tt[u] >= min(max(a.lengths[bb[u]], 0), a.T));
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (live[u])
+                        v[u] = __ldcs(reinterpret_cast<const float4*>(a.lp + (long long)bb[u] * a.b_stride + (long long)tt[u] * a.t_stride) + l);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    float best = -CUDART_INF_F;
+                    int bi = 0x7fffffff;
+                    if (live[u]) {
+                        const int c = 4 * l;
+                        best = v[u].x; bi = c;
+                        if (v[u].y > best) { best = v[u].y; bi = c + 1; }
+                        if (v[u].z > best) { best = v[u].z; bi = c + 2; }
+                        if (v[u].w > best) { best = v[u].w; bi = c + 3; }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        if (o < lpr) {
+                            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+                        }
+                    }
+                    const long long r = r0 + u * rpw + sub;
+                    const bool rowlive = r < rows && !(a.lengths && (int)tt[u] >= min(max(a.lengths[bb[u]], 0), a.T));
+                    if (rowlive && l == 0) a.labels[(long long)bb[u] * a.T + tt[u]] = bi;
+                }
+            }
+            return;
+        }
+    }
     for (long long r0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * rpw; r0 < rows; r0 += warps * rpw) {
         const long long r = r0 + sub;
         const bool in = r < rows;
