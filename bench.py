@@ -39,8 +39,8 @@ UNIT = "clips/s"
 FRONTEND_BYTES_PER_CLIP = 16000 * 2 + 13 * 63 * 4  # 35 276
 FUSED_BYTES_PER_CLIP = 16000 * 2 + 5
 # dram__bytes_read.sum + dram__bytes_write.sum of mfcc_kernel<int16, PY> per clip, from the `ncu --set full` capture
-# profiles/r1_ncu_mfcc_kernel.txt (2.0977 GB + 211.0 MB over a 65 536-clip launch): traffic == algorithmic bytes
-FRONTEND_DRAM_BYTES_PER_CLIP_NCU = (2.097739e9 + 210.983680e6) / 65536
+# profiles/r2_ncu_mfcc_kernel.txt (2.0974 GB + 209.5 MB over a 65 536-clip launch): traffic == algorithmic bytes
+FRONTEND_DRAM_BYTES_PER_CLIP_NCU = (2.097394e9 + 209.455104e6) / 65536
 # executed warp instructions and shared-memory wavefronts per clip of the same kernel (ncu, same capture family;
 # profiles/r2_ncu_mfcc_kernel.txt when present, else round 1's): the issue ports (4 warp-instructions/clk/SM) and the
 # shared-memory pipe (1 wavefront/clk/SM) are what the kernel is actually limited by, so their fractions are reported
@@ -524,7 +524,7 @@ def run_ours(args):
         n_sm = torch.cuda.get_device_properties(local).multi_processor_count
         roof = {"bound": "hbm", "kernel": "mfcc_kernel<int16, PY> (frontend alone, 1 persistent launch over %d clips)" % rb,
                 "achieved": ach, "peak": peak, "peak_source": how, "unit": "GB/s", "frac": ach / peak,
-                "traffic": FRONTEND_DRAM_BYTES_PER_CLIP_NCU * rb, "traffic_source": "profiles/r1_ncu_mfcc_kernel.txt "
+                "traffic": FRONTEND_DRAM_BYTES_PER_CLIP_NCU * rb, "traffic_source": "profiles/r2_ncu_mfcc_kernel.txt "
                 "(ncu --set full, per-clip DRAM bytes x clips of this launch)", "algorithmic_bytes": rb * FRONTEND_BYTES_PER_CLIP,
                 "ms_per_launch": fms, "clips_per_s": rb / (fms * 1e-3),
                 "algorithmic_bytes_per_clip": FRONTEND_BYTES_PER_CLIP,
