@@ -163,7 +163,8 @@ def test_ctc_loss_fwd_bwd_vs_torch(cuda_device, T, B, C, S, reduction):
         assert err_mine <= max(1e-5, 3.0 * err_torch32)
 
 
-@pytest.mark.parametrize("T,B,C,S", [(63, 1000, 3, 3), (40, 333, 8, 3), (63, 257, 5, 2), (17, 129, 2, 1), (63, 4097, 3, 2)])
+@pytest.mark.parametrize("T,B,C,S", [(63, 1000, 3, 3), (40, 333, 8, 3), (63, 257, 5, 2), (17, 129, 2, 1), (63, 4097, 3, 2),
+                                     (801, 33, 5, 3)])
 @pytest.mark.parametrize("blank", [0, 1])
 def test_ctc_loss_keyword_shapes_one_thread_per_utterance(cuda_device, T, B, C, S, blank):
     """The S <= 3, C <= 8 kernels (one thread per utterance, time-major alpha): ragged input lengths down to 0, target
