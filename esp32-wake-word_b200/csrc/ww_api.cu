@@ -2108,7 +2108,7 @@ extern "C" int ww_ctc_loss_bwd(ww_ctx* ctx, const float* log_probs, long long t_
         CK(cudaGetLastError());
         return WW_OK;
     };
-    if (a.skip_fill && K <= 4 && ctx->opt_ctc_split) {
+    if (a.skip_fill && K <= 4 && ctx->opt_ctc_split && ((uintptr_t)workspace % 16) == 0) {
         // wide vocabulary: beta recursion alone (alpha + beta in place), then every row independently
         const size_t al_bytes = ((size_t)B * T * (2 * S + 1) * sizeof(float) + 15) / 16 * 16;
         a.meta = reinterpret_cast<float*>((char*)workspace + al_bytes);
