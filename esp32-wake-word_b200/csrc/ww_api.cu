@@ -84,6 +84,7 @@ struct ww_ctx {
     cudaStream_t scratch_stream = nullptr;
     bool scratch_used = false;
     // L2-resident feature hand-over of the chunked tensor path: [l2_chunk_clips][13][63], re-used by every chunk
+    int opt_greedy_generic = 0;        // WW_GREEDY_GENERIC=1 (A/B): keyword shapes (T <= 64, C <= 4) through ctc_greedy_kernel too
     int opt_greedy_blocks_per_sm = 0;  // WW_GREEDY_BLOCKS_PER_SM (A/B; 0 = 64; measured 8 / 16 / 32 / 64 / unbounded: 2.08 / 2.26 / 2.77 / 2.95 / 2.82 G utt/s)
     int opt_ctc_split = 1;             // WW_CTC_SPLIT=0: wide-vocabulary backward as fill + one recursion kernel (A/B)
     int opt_ctc_tiny = 1;              // WW_CTC_TINY=0: the 8-lanes-per-utterance kernels for S <= 3 (A/B)
@@ -404,6 +405,7 @@ extern "C" int ww_create(ww_ctx** out, int device) {
     if (const char* f = getenv("WW_CTC_TINY")) ctx->opt_ctc_tiny = atoi(f);
     if (const char* f = getenv("WW_CTC_SPLIT")) ctx->opt_ctc_split = atoi(f);
     if (const char* f = getenv("WW_GREEDY_BLOCKS_PER_SM")) ctx->opt_greedy_blocks_per_sm = atoi(f);
+    if (const char* f = getenv("WW_GREEDY_GENERIC")) ctx->opt_greedy_generic = atoi(f);
     if (const char* f = getenv("WW_FUSED")) ctx->opt_fused = atoi(f);
     if (const char* f = getenv("WW_FUSED_CNN_SMS")) ctx->opt_fused_cnn_sms = atoi(f);
     if (const char* b = getenv("WW_TC_BAND")) ctx->tc_band_override = (float)atof(b);
@@ -1980,7 +1982,19 @@ extern "C" int ww_ctc_greedy(ww_ctx* ctx, const float* log_probs, long long t_st
         CK(cudaGetLastError());
         a.pre_argmax = 1;
     }
-    {
+    if (T <= CTC_SHORT_T && C <= 4 && !ctx->opt_greedy_generic) {
+        // keyword shapes: two frames per lane, the next utterance's rows in flight, labels compacted in shared memory
+        long long blocks = ((long long)B + CTC_WARPS - 1) / CTC_WARPS;
+        const long long cap = (long long)ctx->sm_count * (ctx->opt_greedy_blocks_per_sm > 0 ? ctx->opt_greedy_blocks_per_sm : 16);
+        if (blocks > cap) blocks = cap;   // all CTAs resident (16 x 128 threads per SM); the warps stride over the utterances
+        const unsigned g = (unsigned)blocks, t = CTC_WARPS * 32;
+        switch (C) {
+            case 1: ctc_greedy_short_kernel<1><<<g, t, 0, (cudaStream_t)stream>>>(a); break;
+            case 2: ctc_greedy_short_kernel<2><<<g, t, 0, (cudaStream_t)stream>>>(a); break;
+            case 3: ctc_greedy_short_kernel<3><<<g, t, 0, (cudaStream_t)stream>>>(a); break;
+            default: ctc_greedy_short_kernel<4><<<g, t, 0, (cudaStream_t)stream>>>(a); break;
+        }
+    } else {
         long long blocks = ((long long)B + CTC_WARPS - 1) / CTC_WARPS;
         const long long cap = (long long)ctx->sm_count * (ctx->opt_greedy_blocks_per_sm > 0 ? ctx->opt_greedy_blocks_per_sm : 64);
         if (blocks > cap) blocks = cap;   // persistent: the warps stride over the utterances

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(CNN_THREADS) cnn_fp32_kernel(const __grid_cons
     float* gp = a2 + 64 * A2_STRIDE;       // [2][128]
     float* h1 = gp + 2 * 128;              // [64]
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = warp_index_uniform(tid), lane = tid & 31;
     for (int i = tid; i < CNN_SMEM_FLOATS; i += CNN_THREADS) sm[i] = 0.f;
     __syncthreads();
 
@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(CNN_THREADS) cnn_fp32_kernel(const __grid_cons
         if (a.index_total && blockIdx.x == 0 && tid == 0) atomicAdd(a.index_total, (unsigned long long)n);
     }
     const int C = a.w.num_classes;
+    n = __shfl_sync(0xffffffffu, n, 0);   // a loaded loop bound: tell the compiler it is warp-uniform (see warp_index_uniform)
 
     for (long long it = blockIdx.x; it < n; it += gridDim.x) {
         const long long win = a.index ? a.index[it] : it;

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(CNN_THREADS) cnn_i8_kernel(const I8Args a) {
     int* a2 = a1 + 32 * A1_STRIDE;      // [64][20]
     int* gp = a2 + 64 * A2_STRIDE;      // [2][128]
     int* h1 = gp + 2 * 128;             // [64]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = warp_index_uniform(tid), lane = tid & 31;
     for (int i = tid; i < CNN_SMEM_FLOATS; i += CNN_THREADS) sm[i] = 0;
     __syncthreads();
     const int C = a.w.num_classes;

@@ -130,7 +130,10 @@ __global__ void __launch_bounds__(I8T_THREADS, 1) cnn_i8_tc_kernel(const __grid_
     int* sfc2 = reinterpret_cast<int*>(smem + I8T_OFF_FC2);
     unsigned char* sW = smem + I8T_OFF_W;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // warp index through a shuffle: known warp-uniform to the compiler, so the UMMA descriptors are built on the uniform
+    // datapath (see cnn_tc_body)
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = warp_index_uniform(tid);
     const int group = warp >> 2, q4 = warp & 3, tig = tid & 127;
     const int C = a.num_classes;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + I8T_OFF_BAR) + group;
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(I8T_THREADS, 1) cnn_i8_tc_kernel(const __grid_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot + (uint32_t)(group * I8T_GROUP_COLS);
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0) + (uint32_t)(group * I8T_GROUP_COLS);
     const uint32_t sA1a = smem_u32(sA1), sA2a = smem_u32(sA2), sX3a = smem_u32(sX3), sGa = smem_u32(sG), sWa = smem_u32(sW);
     const uint32_t tlane = (uint32_t)(32 * q4) << 16;
     uint32_t phase = 0;

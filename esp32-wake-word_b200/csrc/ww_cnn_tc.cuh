@@ -403,7 +403,11 @@ __device__ __forceinline__ void cnn_tc_body(const TcArgs& a, unsigned char* smem
     float* sfc2 = reinterpret_cast<float*>(smem + TC_OFF_FC2);
     unsigned char* sW = smem + TC_OFF_W;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // the warp index comes out of a shuffle so that the compiler knows it (and the group, the tile addresses and the TMEM
+    // columns derived from it) to be warp-uniform: the UMMA descriptors are then built on the uniform datapath instead of
+    // being moved there one MMA at a time (an ELECT / R2UR / BRA.U.ANY loop around each of the 44 MMAs of an octet)
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = warp_index_uniform(tid);
     const int group = warp >> 2;     // independent 4-warp group (own octet stream, tiles, mbarrier, TMEM columns)
     const int q4 = warp & 3;         // TMEM lane quadrant this warp may read (= warp % 4)
     const int tig = tid & (TC_GROUP_THREADS - 1);
@@ -440,7 +444,7 @@ __device__ __forceinline__ void cnn_tc_body(const TcArgs& a, unsigned char* smem
     // programmatic dependent launch: everything above (tiles, weights, TMEM) ran while the frontend launch that produces
     // the features was finishing
     if constexpr (!ROLE::FUSED) pdl_wait();
-    const uint32_t tmem = *tmem_slot + (uint32_t)(group * TC_GROUP_COLS);
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0) + (uint32_t)(group * TC_GROUP_COLS);
     const uint32_t sA1a = smem_u32(sA1), sA2a = smem_u32(sA2), sX3a = smem_u32(sX3), sGa = smem_u32(sG);
     const uint32_t sWa = smem_u32(sW);
     uint32_t phase = 0;
@@ -774,7 +778,7 @@ __global__ void __launch_bounds__(256) cmvn_rows_kernel(const CmvnArgs a) {
     const int lane = threadIdx.x & 31;
     const bool has1 = lane + 32 < WW_WINDOW_FRAMES;
     const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
-    for (long long win = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); win < a.n_windows; win += warps) {
+    for (long long win = (long long)blockIdx.x * (blockDim.x >> 5) + warp_index_uniform(); win < a.n_windows; win += warps) {
         TcWin w;
         tc_load_window(a, win, lane, w);
         if (a.cmvn_mode == CMVN_PY) {

@@ -157,6 +157,14 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Warp index of a thread, taken out of a shuffle: to the compiler threadIdx.x >> 5 is a per-thread value, so every loop
+// bound, branch and address derived from it counts as divergent -- each __shfl_sync / __ballot_sync inside such a loop is
+// then compiled with a WARPSYNC + ENDCOLLECTIVE slow path, and operands that must live in uniform registers (UMMA
+// descriptors) are moved there one instruction at a time.  A value that comes out of a shuffle with a constant source
+// lane is known to be warp-uniform.
+__device__ __forceinline__ int warp_index_uniform(int tid) { return __shfl_sync(0xffffffffu, tid >> 5, 0); }
+__device__ __forceinline__ int warp_index_uniform() { return warp_index_uniform((int)threadIdx.x); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

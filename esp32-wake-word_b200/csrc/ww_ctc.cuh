@@ -32,7 +32,7 @@ struct GreedyArgs {
 constexpr int CTC_WARPS = 4;
 
 __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_greedy_kernel(const GreedyArgs a) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
     // grid stride over the utterances (64 CTAs per SM): measured neutral to slightly better than one CTA per four
     // utterances at the keyword shape (2.95 against 2.82 G utterances/s, 2^20 x T = 63 x C = 3)
     const long long warps_total = (long long)gridDim.x * CTC_WARPS;
@@ -108,6 +108,118 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_greedy_kernel(const Greedy
     }
 }
 
+// Keyword shapes (T <= 64, C <= 4: the reference's test.py decoder sees T = 63 frames of 3 classes, the clip path feeds
+// 63-window utterances of one binary logit).  ctc_greedy_kernel walks such an utterance as a chain of dependent global
+// round trips (lengths -> frames 0..31 -> frames 32..63 -> labels written and re-read for the keyword match), one
+// utterance per warp at a time: latency-bound at a third of the HBM peak.  Here a lane takes frames `lane` and
+// `lane + 32` at once, the rows of the warp's NEXT utterance are in flight while this one is compacted, and the labels
+// are compacted in shared memory: stored once, coalesced, and matched against the keyword without touching HBM again.
+constexpr int CTC_SHORT_T = 64;
+constexpr int CTC_SHORT_KW = 8;   // keyword labels held in registers; longer keywords are read through L1
+
+template <int C>
+struct GreedyRows {
+    float v0[C], v1[C];
+    int Tb;
+};
+
+template <int C>
+__device__ __forceinline__ void greedy_short_load(const GreedyArgs& a, long long b, int lane, GreedyRows<C>& r) {
+    r.Tb = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) r.v0[c] = r.v1[c] = 0.f;
+    if (b >= a.B) return;
+    r.Tb = a.lengths ? min(max(__ldg(a.lengths + b), 0), a.T) : a.T;
+    const float* base = a.lp + b * a.b_stride;
+    // the length is only needed to MASK: the loads are bounded by T so that they do not wait for it
+    if (lane < a.T) {
+        const float* row = base + (long long)lane * a.t_stride;
+#pragma unroll
+        for (int c = 0; c < C; ++c) r.v0[c] = __ldcs(row + c);
+    }
+    if (lane + 32 < a.T) {
+        const float* row = base + (long long)(lane + 32) * a.t_stride;
+#pragma unroll
+        for (int c = 0; c < C; ++c) r.v1[c] = __ldcs(row + c);
+    }
+}
+
+template <int C>
+__device__ __forceinline__ int greedy_short_argmax(const float (&v)[C]) {
+    if (C == 1) return v[0] > 0.f ? 1 : 0;   // binary posterior in logit form (as in ctc_greedy_kernel)
+    float best = v[0];
+    int idx = 0;
+#pragma unroll
+    for (int c = 1; c < C; ++c)
+        if (v[c] > best) { best = v[c]; idx = c; }
+    return idx;
+}
+
+template <int C>
+__global__ void __launch_bounds__(CTC_WARPS * 32) ctc_greedy_short_kernel(const GreedyArgs a) {
+    __shared__ int s_lab[CTC_WARPS][CTC_SHORT_T + CTC_SHORT_KW];
+    const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
+    int* sl = s_lab[warp];
+    int kw[CTC_SHORT_KW];
+#pragma unroll
+    for (int k = 0; k < CTC_SHORT_KW; ++k) kw[k] = (a.hits && k < a.K) ? __ldg(a.keyword + k) : 0;
+    const long long warps_total = (long long)gridDim.x * CTC_WARPS;
+    long long b = (long long)blockIdx.x * CTC_WARPS + warp;
+    GreedyRows<C> cur, nxt;
+    greedy_short_load<C>(a, b, lane, cur);
+    for (; b < a.B; b += warps_total) {
+        greedy_short_load<C>(a, b + warps_total, lane, nxt);
+        const int Tb = cur.Tb;
+        const int i0 = lane < Tb ? greedy_short_argmax<C>(cur.v0) : 0;
+        const int i1 = lane + 32 < Tb ? greedy_short_argmax<C>(cur.v1) : 0;
+        bool k0 = lane < Tb && i0 != 0, k1 = lane + 32 < Tb && i1 != 0;
+        if (a.mode == DECODE_COLLAPSE) {
+            int p0 = __shfl_up_sync(0xffffffffu, i0, 1), p1 = __shfl_up_sync(0xffffffffu, i1, 1);
+            const int c31 = __shfl_sync(0xffffffffu, i0, 31);
+            if (lane == 0) { p0 = 0; p1 = c31; }
+            k0 = k0 && i0 != p0;
+            k1 = k1 && i1 != p1;
+        }
+        const unsigned m0 = __ballot_sync(0xffffffffu, k0), m1 = __ballot_sync(0xffffffffu, k1);
+        const unsigned lt = (1u << lane) - 1u;
+        const int n0 = __popc(m0), pos = n0 + __popc(m1);
+        sl[lane] = 0;
+        sl[lane + 32] = 0;
+        if (lane < CTC_SHORT_KW) sl[CTC_SHORT_T + lane] = 0;
+        __syncwarp();
+        if (k0) sl[__popc(m0 & lt)] = i0;
+        if (k1) sl[n0 + __popc(m1 & lt)] = i1;
+        __syncwarp();
+        int* lab = a.labels + b * (long long)a.T;
+        if (lane < a.T) lab[lane] = sl[lane];
+        if (lane + 32 < a.T) lab[lane + 32] = sl[lane + 32];
+        if (lane == 0) a.out_len[b] = pos;
+        if (a.hits) {
+            bool hit = (a.K == 0);
+            if (a.K > 0 && a.K <= CTC_SHORT_KW) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int s = lane + 32 * h;
+                    bool eq = s + a.K <= pos;
+#pragma unroll
+                    for (int k = 0; k < CTC_SHORT_KW; ++k) eq = eq && (k >= a.K || sl[s + k] == kw[k]);
+                    hit = hit || eq;
+                }
+            } else if (a.K > 0) {
+                for (int s = lane; s + a.K <= pos; s += 32) {
+                    bool eq = true;
+                    for (int k = 0; k < a.K; ++k) eq = eq && (sl[s + k] == __ldg(a.keyword + k));
+                    hit = hit || eq;
+                }
+            }
+            hit = __any_sync(0xffffffffu, hit);
+            if (lane == 0) a.hits[b] = hit ? 1 : 0;
+        }
+        __syncwarp();   // s_lab is rewritten by the next utterance
+        cur = nxt;
+    }
+}
+
 // Wide-vocabulary best path, step 1: argmax of every (b, t) row -- one warp per row, grid stride over all B*T rows,
 // 16-byte streaming loads; first index wins ties (torch.argmax).  T*C*4 bytes per utterance, HBM-bound.  A warp per
 // UTTERANCE (ctc_greedy_kernel alone) walks its T rows one after the other and reaches 3.5 % of HBM bandwidth at
@@ -130,7 +242,7 @@ __global__ void __launch_bounds__(256) ctc_argmax_rows_kernel(const GreedyArgs a
             constexpr int U = 4;
             const int n4 = a.C >> 2;
             const unsigned T = (unsigned)a.T;
-            for (long long r0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (rpw * U); r0 < rows;
+            for (long long r0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp_index_uniform()) * (rpw * U); r0 < rows;
                  r0 += warps * (rpw * U)) {
                 float4 v[U];
                 unsigned bb[U], tt[U];
@@ -174,7 +286,7 @@ __global__ void __launch_bounds__(256) ctc_argmax_rows_kernel(const GreedyArgs a
             return;
         }
     }
-    for (long long r0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * rpw; r0 < rows; r0 += warps * rpw) {
+    for (long long r0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp_index_uniform()) * rpw; r0 < rows; r0 += warps * rpw) {
         const long long r = r0 + sub;
         const bool in = r < rows;
         const long long b = in ? r / a.T : 0;
@@ -267,7 +379,7 @@ __host__ __device__ inline int ctc_lp(int S) { return ((2 * S + 1 + 31) / 32) * 
 
 __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_fwd_kernel(const CtcLossArgs a) {
     extern __shared__ float ctc_sm[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
     const long long b = (long long)blockIdx.x * CTC_WARPS + warp;
     if (b >= a.B) return;
     const int Lp = ctc_lp(a.S);
@@ -331,7 +443,7 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_fwd_kernel(const CtcL
 
 __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_bwd_kernel(const CtcLossArgs a) {
     extern __shared__ float ctc_sm[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
     const long long b = (long long)blockIdx.x * CTC_WARPS + warp;
     if (b >= a.B) return;
     const int Lp = ctc_lp(a.S);
@@ -490,7 +602,7 @@ __device__ __forceinline__ void cp_async_wait() {
 template <int K>
 __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_fwd_pf_kernel(const CtcLossArgs a) {
     extern __shared__ float ctc_sm[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
     const long long b = (long long)blockIdx.x * CTC_WARPS + warp;
     if (b >= a.B) return;
     constexpr int Lp = 32 * K;
@@ -599,7 +711,7 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_fwd_pf_kernel(const C
 template <int K>
 __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_bwd_pf_kernel(const CtcLossArgs a) {
     extern __shared__ float ctc_sm[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
     const long long b = (long long)blockIdx.x * CTC_WARPS + warp;
     if (b >= a.B) return;
     constexpr int Lp = 32 * K;
@@ -801,7 +913,7 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_bwd_pf_kernel(const C
 template <int K>
 __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_beta_pf_kernel(const CtcLossArgs a) {
     extern __shared__ float ctc_sm[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
     const long long b = (long long)blockIdx.x * CTC_WARPS + warp;
     if (b >= a.B) return;
     constexpr int Lp = 32 * K;
@@ -930,7 +1042,7 @@ constexpr int CTC_ROWS_WARPS = 8;
 template <bool FILL>
 __global__ void __launch_bounds__(CTC_ROWS_WARPS * 32) ctc_grad_rows_kernel(const CtcLossArgs a) {
     __shared__ float se_all[CTC_ROWS_WARPS][64];   // repeated labels only: per-state posterior mass of the odd states
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = warp_index_uniform();
     float* se = se_all[warp];
     const long long warps = (long long)gridDim.x * CTC_ROWS_WARPS;
     const long long rows = (long long)a.T * a.B;
@@ -1046,7 +1158,7 @@ __device__ __forceinline__ int group_max(int v) {
 }
 
 __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_small_fwd_kernel(const CtcLossArgs a) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
     const int s = lane & 7;
     long long b = ((long long)blockIdx.x * CTC_WARPS + warp) * 4 + (lane >> 3);
     const bool live = b < a.B;
@@ -1092,7 +1204,7 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_small_fwd_kernel(const Ctc
 }
 
 __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_small_bwd_kernel(const CtcLossArgs a) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
     const int s = lane & 7;
     long long b = ((long long)blockIdx.x * CTC_WARPS + warp) * 4 + (lane >> 3);
     const bool live = b < a.B;
@@ -1359,7 +1471,7 @@ __global__ void __launch_bounds__(256) ctc_grad_fill_kernel(const CtcLossArgs a)
     const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
     const long long rows = (long long)a.T * a.B;
     const int Lw = 2 * a.S + 1;
-    for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
+    for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + warp_index_uniform(); r < rows; r += warps) {
         const int t = (int)(r / a.B);
         const long long b = r - (long long)t * a.B;
         const int Tb = min(max(a.in_len[b], 0), a.T);

@@ -298,7 +298,8 @@ __device__ __forceinline__ void mfcc_body(const MfccArgs& a, unsigned char* smem
     float* pw = reinterpret_cast<float*>(smem + SM::OFF_P);
     float* lm = reinterpret_cast<float*>(smem + SM::OFF_LM);
 
-    const int tid = pipe.tid(), warp = tid >> 5, lane = tid & 31;
+    // warp index out of a shuffle (known warp-uniform to the compiler, ww_common.cuh): 32.36 -> 32.49 M clips/s, same bits
+    const int tid = pipe.tid(), warp = warp_index_uniform(tid), lane = tid & 31;
     const int half = lane >> 4, l16 = lane & 15;
 
     const int L = CLIP ? CLIP_SAMPLES : a.n_samples;

@@ -26,7 +26,7 @@ template <int G>
 __device__ __forceinline__ float group_sum(float v, float* red) {
     v = warp_sum(v);
     if constexpr (G > 32) {
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
         __syncthreads();  // red is reused between reductions
         if (lane == 0) red[warp] = v;
         __syncthreads();
@@ -44,7 +44,7 @@ __device__ __forceinline__ float group_ext(float v, float* red) {
         v = MAX ? fmaxf(v, w) : fminf(v, w);
     }
     if constexpr (G > 32) {
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
         __syncthreads();
         if (lane == 0) red[warp] = v;
         __syncthreads();
@@ -60,7 +60,7 @@ template <int G>
 __global__ void __launch_bounds__(256) normalize_rows_kernel(const NormArgs a) {
     __shared__ float red[8];
     const int rows_per_cta = 256 / G;
-    const int sub = G == 32 ? (threadIdx.x >> 5) : 0;
+    const int sub = G == 32 ? warp_index_uniform() : 0;
     const int li = G == 32 ? (threadIdx.x & 31) : threadIdx.x;
     // G = 256 uses __syncthreads in the reductions: every thread of the CTA walks the same rows
     for (long long row = (long long)blockIdx.x * rows_per_cta + sub; row < a.n_rows; row += (long long)gridDim.x * rows_per_cta) {

@@ -53,6 +53,62 @@ def test_greedy_batch_vs_oracle(cuda_device, B, T, C, mode):
     assert np.array_equal(l2.cpu().numpy(), labels) and np.array_equal(n2.cpu().numpy(), n)
 
 
+def _greedy_raw(ctx, lp, mode, lengths, kw):
+    """ww_ctc_greedy through an explicit context (the A/B switch WW_GREEDY_GENERIC is read by ww_create)."""
+    from ww_b200 import _lib as L
+
+    B, T, C = lp.shape
+    labels = torch.full((B, T), -7, dtype=torch.int32, device=lp.device)
+    n = torch.full((B,), -7, dtype=torch.int32, device=lp.device)
+    hits = torch.full((B,), 9, dtype=torch.uint8, device=lp.device)
+    kwt = torch.as_tensor(kw, dtype=torch.int32, device=lp.device)
+    dm = L.DECODE_COLLAPSE if mode == "collapse" else L.DECODE_KEEP_REPEATS
+    ctx.check(ctx.lib.ww_ctc_greedy(ctx.h, L.ptr(lp), lp.stride(1), lp.stride(0), T, B, C, L.ptr(lengths), dm, L.ptr(labels),
+                                    L.ptr(n), L.ptr(kwt), len(kw), L.ptr(hits), L.cur_stream(lp.device)), "ww_ctc_greedy")
+    torch.cuda.synchronize()
+    return labels.cpu().numpy(), n.cpu().numpy(), hits.cpu().numpy()
+
+
+@pytest.mark.parametrize("B,T,C,kw", [(1000, 63, 1, [1, 1, 1]), (513, 63, 3, [1, 2]), (77, 64, 4, [3]), (129, 40, 2, [1] * 9),
+                                      (64, 7, 3, [2, 1]), (5, 1, 1, [1]), (4099, 33, 3, [])])
+@pytest.mark.parametrize("mode", ["collapse", "keep_repeats"])
+def test_greedy_keyword_shapes(cuda_device, B, T, C, kw, mode):
+    """T <= 64, C <= 4 run ctc_greedy_short_kernel: same labels, lengths and keyword hits as the generic kernel
+    (WW_GREEDY_GENERIC=1 context) and as the oracle; C = 1 is the binary posterior in logit form (label 1 iff x > 0)."""
+    from ww_b200 import _lib as L
+
+    rng = np.random.default_rng(B * 131 + T * 7 + C)
+    x = rng.normal(size=(B, T, C)).astype(np.float32)
+    if C > 1:
+        x[..., 0] += 0.5
+    x = np.ascontiguousarray(np.repeat(x[:, ::2], 2, axis=1)[:, :T])  # runs of equal argmax
+    x[B // 2] = 0.0                                                   # ties / exact zeros
+    lengths = rng.integers(0, T + 1, size=B).astype(np.int32)
+    lengths[0] = T
+    lp = torch.from_numpy(x).to(cuda_device)
+    ln = torch.from_numpy(lengths).to(cuda_device)
+    os.environ["WW_GREEDY_GENERIC"] = "1"
+    try:
+        generic = L.Context(cuda_device.index or 0)
+    finally:
+        del os.environ["WW_GREEDY_GENERIC"]
+    try:
+        for lens in (ln, None):
+            got = _greedy_raw(L.get_context(cuda_device.index or 0), lp, mode, lens, kw)
+            ref = _greedy_raw(generic, lp, mode, lens, kw)
+            for g, r in zip(got, ref):
+                assert np.array_equal(g, r)
+            labels, n, hits = got
+            m = octc.MODE_COLLAPSE if mode == "collapse" else octc.MODE_KEEP_REPEATS
+            x2 = x if C > 1 else np.concatenate([np.zeros_like(x), x], axis=-1)
+            for b in range(0, B, max(1, B // 97)):
+                want = octc.greedy_labels(x2[b], m, length=int(lengths[b]) if lens is not None else T)
+                assert n[b] == len(want) and labels[b, : n[b]].tolist() == want and (labels[b, n[b]:] == 0).all()
+                assert bool(hits[b]) == octc.keyword_hit(want, kw)
+    finally:
+        generic.close()
+
+
 def test_argmax_ties_take_first_index(cuda_device):
     import ww_b200
 

@@ -127,8 +127,10 @@ def greedy_bench(dev):
         torch.cuda.synchronize()
         dt_t = timed(lambda: torch.argmax(lp, dim=-1))
         gb = B * T * C * 4 / 1e9
+        gbo = gb + B * (T * 4 + 4) / 1e9      # + the int32 [B, T] label matrix and the lengths it has to write
         out.append({"config": f"a12 CTC greedy decode B={B} T={T} C={C}", "seq_per_s": B / dt, "algorithmic_GBps": gb / dt,
-                    "hbm_frac": gb / dt / peak, "torch_argmax_only_GBps": gb / dt_t})
+                    "hbm_frac": gb / dt / peak, "with_outputs_GBps": gbo / dt, "hbm_frac_with_outputs": gbo / dt / peak,
+                    "torch_argmax_only_GBps": gb / dt_t})
         del lp
     return out
 
