@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(CNN_THREADS) cnn_fp32_kernel(const __grid_cons
             }
             float z0 = v0, z1 = v1;
             if (a.cmvn_mode == CMVN_PY) {
-                // Operation for operation the arithmetic of the tensor-core kernel's CMVN (tc_cmvn_store: same reduction
+                // Operation for operation the arithmetic of the tensor-core kernel's CMVN (tc_cmvn_py: same reduction
                 // tree, mean and 1/(std + eps) as multiplications by correctly rounded reciprocals), so that both kernels
                 // feed the network the SAME z bit for bit.  That matters for rows that are constant up to rounding
                 // (digital silence: c0 = -87.377 in every frame): there (x - mean) / (std + eps) is rounding noise over

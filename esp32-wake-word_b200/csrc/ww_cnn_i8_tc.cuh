@@ -187,8 +187,15 @@ __global__ void __launch_bounds__(I8T_THREADS, 1) cnn_i8_tc_kernel(const __grid_
         if (a.feats) {
             // float features: int8 rounding + device-style CMVN here, so the device path is one launch
             TcWin w2[2];
-            tc_load_window(a, oct * I8T_CLIPS + 2 * q4, lane, w2[0]);       // both windows' loads in flight
-            tc_load_window(a, oct * I8T_CLIPS + 2 * q4 + 1, lane, w2[1]);
+            if (flat) {   // immediate-offset loads, as in cnn_tc_body
+                const long long w0 = oct * I8T_CLIPS + 2 * q4;
+                const float* wbase = a.feats + w0 * (long long)(WW_N_MFCC * WW_WINDOW_FRAMES);
+                tc_load_window_flat(wbase, w0 < a.n_windows, lane, w2[0]);
+                tc_load_window_flat(wbase + WW_N_MFCC * WW_WINDOW_FRAMES, w0 + 1 < a.n_windows, lane, w2[1]);
+            } else {
+                tc_load_window(a, oct * I8T_CLIPS + 2 * q4, lane, w2[0]);       // both windows' loads in flight
+                tc_load_window(a, oct * I8T_CLIPS + 2 * q4 + 1, lane, w2[1]);
+            }
 #pragma unroll
             for (int ww_ = 0; ww_ < 2; ++ww_) {
                 const int slot = 2 * q4 + ww_;

@@ -42,8 +42,17 @@ constexpr int A1P_ROWS = 32 * TC_CLIPS + 2;  // 258 rows per parity tile (63 fra
 constexpr int A2P_ROWS = 16 * TC_CLIPS + 2;  // 130 (31 positions -> 16 even + 15 odd)
 constexpr int X3_ROWS = 16 * TC_CLIPS + 2;   // 130: natural order (conv3 pools along TMEM columns)
 constexpr int G_ROWS = 16;                   // fc1 B operand: 8 windows + 8 zero rows (N must be a multiple of 16)
-constexpr int A1_LBO = A1P_ROWS * 16, A2_LBO = A2P_ROWS * 16, X3_LBO = X3_ROWS * 16, G_LBO = G_ROWS * 16;
-constexpr int A1_PAR = 2 * A1_LBO, A2_PAR = 4 * A2_LBO;  // bytes per parity tile
+// Bank staggers (ncu: 31 % of the kernel's shared-memory wavefronts were bank-conflict replays).  The conv1 epilogue
+// writes one 16-byte row per lane, even lanes into the even-position tile of A2 and odd lanes into the odd one: with
+// A2_PAR a multiple of 128 both halves of a quarter-warp hit the same banks (2-way), so the odd tile starts 64 bytes
+// later (A1_PAR = 8256 already is 64 mod 128).  The conv3 epilogue writes G two bytes per lane, eight lanes per
+// 16-byte row, the next eight lanes one K chunk further: a chunk stride of 256 puts all four on the same banks
+// (4-way), 272 spreads them.  UMMA only needs 16-byte multiples for tile bases and the K-chunk stride (LBO).
+#ifndef WW_TC_STAGGER
+#define WW_TC_STAGGER 1
+#endif
+constexpr int A1_LBO = A1P_ROWS * 16, A2_LBO = A2P_ROWS * 16, X3_LBO = X3_ROWS * 16, G_LBO = G_ROWS * 16 + (WW_TC_STAGGER ? 16 : 0);
+constexpr int A1_PAR = 2 * A1_LBO, A2_PAR = 4 * A2_LBO + (WW_TC_STAGGER ? 64 : 0);  // bytes per parity tile
 // fc1's A operand stores only its 64 real rows per K chunk: rows 64..127 of the M = 128 tile read the next chunk
 // (finite weights; one zero chunk follows the last) and produce accumulator rows nobody reads
 constexpr int W1_LBO = 32 * 16, W2_LBO = 64 * 16, W3_LBO = 128 * 16, WF1_LBO = 64 * 16;
@@ -72,7 +81,7 @@ constexpr int TC_ACT_A1 = 0;
 constexpr int TC_ACT_X3 = 0;
 constexpr int TC_ACT_A2 = (2 * A1_PAR > 8 * X3_LBO ? 2 * A1_PAR : 8 * X3_LBO);
 constexpr int TC_ACT_G = TC_ACT_A2;
-constexpr int TC_ACT_BYTES = TC_ACT_A2 + 2 * A2_PAR;           // 33 280
+constexpr int TC_ACT_BYTES = TC_ACT_A2 + 2 * A2_PAR;           // 33 408
 static_assert(16 * G_LBO <= A2_PAR, "G must stay inside A2's even-position tile");
 constexpr int TC_SMEM = TC_OFF_ACT + TC_GROUPS * TC_ACT_BYTES;
 static_assert(TC_OFF_W % 16 == 0 && TC_OFF_ACT % 16 == 0 && TC_ACT_A2 % 16 == 0 && TC_ACT_X3 % 16 == 0 &&
@@ -245,6 +254,48 @@ __device__ __forceinline__ float reduce16(const float (&v)[16], int lane) {
     return a1;
 }
 
+// reduce16 of two value sets in lock-step (the same operations per set, interleaved level by level)
+__device__ __forceinline__ void reduce16x2(const float (&va)[16], const float (&vb)[16], int lane, float& ra, float& rb) {
+    float a8[8], b8[8], a4[4], b4[4], a2[2], b2[2];
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float sa = up ? va[i] : va[i + 8], ka = up ? va[i + 8] : va[i];
+            const float sb = up ? vb[i] : vb[i + 8], kb = up ? vb[i + 8] : vb[i];
+            a8[i] = ka + __shfl_xor_sync(0xffffffffu, sa, 16);
+            b8[i] = kb + __shfl_xor_sync(0xffffffffu, sb, 16);
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float sa = up ? a8[i] : a8[i + 4], ka = up ? a8[i + 4] : a8[i];
+            const float sb = up ? b8[i] : b8[i + 4], kb = up ? b8[i + 4] : b8[i];
+            a4[i] = ka + __shfl_xor_sync(0xffffffffu, sa, 8);
+            b4[i] = kb + __shfl_xor_sync(0xffffffffu, sb, 8);
+        }
+    }
+    {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float sa = up ? a4[i] : a4[i + 2], ka = up ? a4[i + 2] : a4[i];
+            const float sb = up ? b4[i] : b4[i + 2], kb = up ? b4[i + 2] : b4[i];
+            a2[i] = ka + __shfl_xor_sync(0xffffffffu, sa, 4);
+            b2[i] = kb + __shfl_xor_sync(0xffffffffu, sb, 4);
+        }
+    }
+    const bool up = lane & 2;
+    const float sa = up ? a2[0] : a2[1], ka = up ? a2[1] : a2[0];
+    const float sb = up ? b2[0] : b2[1], kb = up ? b2[1] : b2[0];
+    ra = ka + __shfl_xor_sync(0xffffffffu, sa, 2);
+    rb = kb + __shfl_xor_sync(0xffffffffu, sb, 2);
+    ra += __shfl_xor_sync(0xffffffffu, ra, 1);
+    rb += __shfl_xor_sync(0xffffffffu, rb, 1);
+}
+
 __device__ __forceinline__ void group_sync(int group) {
     asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(TC_GROUP_THREADS) : "memory");
 }
@@ -257,6 +308,9 @@ __device__ __forceinline__ void group_sync(int group) {
 #endif
 #ifndef WW_TC_PREFETCH
 #define WW_TC_PREFETCH 1
+#endif
+#ifndef WW_TC_CMVN2
+#define WW_TC_CMVN2 1   // python CMVN of a warp's two windows in lock-step (tc_cmvn_py2)
 #endif
 __device__ __forceinline__ void tc_wait_mma(uint64_t* bar, uint32_t phase, int q4, int group) {
 #if WW_TC_WAIT1
@@ -292,6 +346,24 @@ __device__ __forceinline__ void tc_load_window_ring(const float* wbase, bool liv
     for (int q = 0; q < WW_N_MFCC; ++q) {
         w.x0[q] = live ? __ldcg(p0 + q * WW_WINDOW_FRAMES) : 0.f;
         w.x1[q] = (live && has1) ? __ldcg(p0 + q * WW_WINDOW_FRAMES + 32) : 0.f;
+    }
+}
+
+// flat [n][13][63] batches: the 26 loads of a lane are `base + lane + constant`, i.e. immediate offsets of one address
+// (the strided form below spends two IADD3 per load on its 64-bit pointers: 52 of S0's ~480 instructions per window),
+// and a window past the end is skipped by a warp-uniform branch instead of 26 predicated selects
+__device__ __forceinline__ void tc_load_window_flat(const float* wbase, bool live, int lane, TcWin& w) {
+    const bool has1 = lane + 32 < WW_WINDOW_FRAMES;
+    if (live) {
+        const float* p = wbase + lane;
+#pragma unroll
+        for (int q = 0; q < WW_N_MFCC; ++q) {
+            w.x0[q] = p[q * WW_WINDOW_FRAMES];
+            w.x1[q] = has1 ? p[q * WW_WINDOW_FRAMES + 32] : 0.f;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < WW_N_MFCC; ++q) w.x0[q] = w.x1[q] = 0.f;
     }
 }
 
@@ -335,45 +407,94 @@ __device__ __forceinline__ void tc_cmvn_device(TcWin& w, int lane) {
     }
 }
 
-// CMVN of one window (python or device style) and fp16 store into the conv1 operand rows 64*slot + t + 1
-__device__ __forceinline__ void tc_cmvn_store(const TcArgs& a, TcWin& w, int slot, int lane, unsigned char* sA1) {
+// python-style CMVN of one window in place: two transposed warp reductions (16 shuffles each) instead of 26 butterflies
+__device__ __forceinline__ void tc_cmvn_py(TcWin& w, int lane) {
     float(&x0)[WW_N_MFCC] = w.x0;
     float(&x1)[WW_N_MFCC] = w.x1;
-    const bool has1 = lane + 32 < WW_WINDOW_FRAMES;
-    if (a.cmvn_mode == CMVN_PY) {
-        // python-style CMVN: two transposed warp reductions (16 shuffles each) instead of 26 butterflies
-        float v[16];
+    const float m1 = lane + 32 < WW_WINDOW_FRAMES ? 1.f : 0.f;
+    float v[16];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = q < WW_N_MFCC ? x0[q] + x1[q] : 0.f;
-        // lane 2q holds sum_t x[q][t]; the mean is a multiply here (the operand is rounded to fp16 anyway; the exact
-        // division lives in cnn_fp32_kernel, which re-scores every window near the threshold)
-        const float tot = reduce16(v, lane) * (1.f / (float)WW_WINDOW_FRAMES);
-        float mean[WW_N_MFCC];
+    for (int q = 0; q < 16; ++q) v[q] = q < WW_N_MFCC ? x0[q] + x1[q] : 0.f;
+    // lane 2q holds sum_t x[q][t]; the mean is a multiply here (the operand is rounded to fp16 anyway; the exact
+    // division lives in cnn_fp32_kernel, which re-scores every window near the threshold)
+    const float tot = reduce16(v, lane) * (1.f / (float)WW_WINDOW_FRAMES);
+    float mean[WW_N_MFCC];
 #pragma unroll
-        for (int q = 0; q < WW_N_MFCC; ++q) mean[q] = __shfl_sync(0xffffffffu, tot, 2 * q);
+    for (int q = 0; q < WW_N_MFCC; ++q) mean[q] = __shfl_sync(0xffffffffu, tot, 2 * q);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            if (q < WW_N_MFCC) {
-                x0[q] -= mean[q];
-                x1[q] = has1 ? x1[q] - mean[q] : 0.f;
-                v[q] = fmaf(x0[q], x0[q], x1[q] * x1[q]);
-            } else {
-                v[q] = 0.f;
-            }
+    for (int q = 0; q < 16; ++q) {
+        if (q < WW_N_MFCC) {
+            x0[q] -= mean[q];
+            x1[q] = fmaf(-mean[q], m1, x1[q]);   // = has1 ? x1 - mean : 0 (x1 is 0 in lane 31): no select
+            v[q] = fmaf(x0[q], x0[q], x1[q] * x1[q]);
+        } else {
+            v[q] = 0.f;
         }
-        const float ss = reduce16(v, lane);
-        float sd = sqrtf(ss * (1.f / (float)(WW_WINDOW_FRAMES - 1)));
-        if (sd == 0.f) sd = 1.f;
-        const float inv = __frcp_rn(sd + 1e-8f);
-#pragma unroll
-        for (int q = 0; q < WW_N_MFCC; ++q) {
-            const float iq = __shfl_sync(0xffffffffu, inv, 2 * q);
-            x0[q] *= iq;
-            x1[q] *= iq;
-        }
-    } else if (a.cmvn_mode == CMVN_DEVICE) {
-        tc_cmvn_device(w, lane);
     }
+    const float ss = reduce16(v, lane);
+    float sd = sqrtf(ss * (1.f / (float)(WW_WINDOW_FRAMES - 1)));
+    if (sd == 0.f) sd = 1.f;
+    const float inv = __frcp_rn(sd + 1e-8f);
+#pragma unroll
+    for (int q = 0; q < WW_N_MFCC; ++q) {
+        const float iq = __shfl_sync(0xffffffffu, inv, 2 * q);
+        x0[q] *= iq;
+        x1[q] *= iq;
+    }
+}
+
+// The same for the warp's TWO windows in lock-step.  One window's CMVN is a chain of dependent shuffle levels (two
+// reductions of five levels, two broadcasts: ~1000 cycles of latency with four warps per scheduler to hide it); written
+// as two calls the compiler keeps the windows one after the other (each call branches on the CMVN mode).  Here every
+// step is issued for both windows before the next one, so the two chains overlap.  Same operations in the same order
+// per window: the bits do not change.
+__device__ __forceinline__ void tc_cmvn_py2(TcWin& wa, TcWin& wb, int lane) {
+    const float m1 = lane + 32 < WW_WINDOW_FRAMES ? 1.f : 0.f;
+    float va[16], vb[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        va[q] = q < WW_N_MFCC ? wa.x0[q] + wa.x1[q] : 0.f;
+        vb[q] = q < WW_N_MFCC ? wb.x0[q] + wb.x1[q] : 0.f;
+    }
+    float ta, tb;
+    reduce16x2(va, vb, lane, ta, tb);
+    ta *= (1.f / (float)WW_WINDOW_FRAMES);
+    tb *= (1.f / (float)WW_WINDOW_FRAMES);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        if (q < WW_N_MFCC) {
+            const float ma = __shfl_sync(0xffffffffu, ta, 2 * q), mb = __shfl_sync(0xffffffffu, tb, 2 * q);
+            wa.x0[q] -= ma;
+            wb.x0[q] -= mb;
+            wa.x1[q] = fmaf(-ma, m1, wa.x1[q]);   // = has1 ? x1 - mean : 0 (x1 is 0 in lane 31): no select
+            wb.x1[q] = fmaf(-mb, m1, wb.x1[q]);
+            va[q] = fmaf(wa.x0[q], wa.x0[q], wa.x1[q] * wa.x1[q]);
+            vb[q] = fmaf(wb.x0[q], wb.x0[q], wb.x1[q] * wb.x1[q]);
+        } else {
+            va[q] = 0.f;
+            vb[q] = 0.f;
+        }
+    }
+    float sa, sb;
+    reduce16x2(va, vb, lane, sa, sb);
+    float da = sqrtf(sa * (1.f / (float)(WW_WINDOW_FRAMES - 1))), db = sqrtf(sb * (1.f / (float)(WW_WINDOW_FRAMES - 1)));
+    if (da == 0.f) da = 1.f;
+    if (db == 0.f) db = 1.f;
+    const float ia = __frcp_rn(da + 1e-8f), ib = __frcp_rn(db + 1e-8f);
+#pragma unroll
+    for (int q = 0; q < WW_N_MFCC; ++q) {
+        const float qa = __shfl_sync(0xffffffffu, ia, 2 * q), qb = __shfl_sync(0xffffffffu, ib, 2 * q);
+        wa.x0[q] *= qa;
+        wa.x1[q] *= qa;
+        wb.x0[q] *= qb;
+        wb.x1[q] *= qb;
+    }
+}
+
+// fp16 store of one normalised window into the conv1 operand rows 64*slot + t + 1
+__device__ __forceinline__ void tc_store_a1(const TcWin& w, int slot, int lane, unsigned char* sA1) {
+    const float(&x0)[WW_N_MFCC] = w.x0;
+    const float(&x1)[WW_N_MFCC] = w.x1;
     // frame t -> parity tile t & 1, row 1 + 32*slot + (t >> 1); channels 0-7 -> chunk 0, 8-12 (+3 zeros) -> chunk 1
     {
         const float lo8[8] = {x0[0], x0[1], x0[2], x0[3], x0[4], x0[5], x0[6], x0[7]};
@@ -395,6 +516,23 @@ __device__ __forceinline__ void tc_cmvn_store(const TcArgs& a, TcWin& w, int slo
         *reinterpret_cast<uint4*>(sA1 + A1_PAR) = make_uint4(0, 0, 0, 0);
         *reinterpret_cast<uint4*>(sA1 + A1_PAR + A1_LBO) = make_uint4(0, 0, 0, 0);
     }
+}
+
+// CMVN (python or device style) of the warp's two windows and their fp16 store (slots `slot`, `slot + 1`)
+__device__ __forceinline__ void tc_cmvn_store2(const TcArgs& a, TcWin& wa, TcWin& wb, int slot, int lane, unsigned char* sA1) {
+    if (a.cmvn_mode == CMVN_PY) {
+#if WW_TC_CMVN2
+        tc_cmvn_py2(wa, wb, lane);
+#else
+        tc_cmvn_py(wa, lane);
+        tc_cmvn_py(wb, lane);
+#endif
+    } else if (a.cmvn_mode == CMVN_DEVICE) {
+        tc_cmvn_device(wa, lane);
+        tc_cmvn_device(wb, lane);
+    }
+    tc_store_a1(wa, slot, lane, sA1);
+    tc_store_a1(wb, slot + 1, lane, sA1);
 }
 
 template <class ROLE>
@@ -483,6 +621,11 @@ __device__ __forceinline__ void cnn_tc_body(const TcArgs& a, unsigned char* smem
                 const long long w0 = oct * TC_CLIPS + 2 * q4;
                 tc_load_window_ring(role.window(w0), w0 < a.n_windows, lane, wa);
                 tc_load_window_ring(role.window(w0 + 1), w0 + 1 < a.n_windows, lane, wb);
+            } else if (flat) {
+                const long long w0 = oct * TC_CLIPS + 2 * q4;
+                const float* wbase = a.feats + w0 * (long long)(WW_N_MFCC * WW_WINDOW_FRAMES);
+                tc_load_window_flat(wbase, w0 < a.n_windows, lane, wa);
+                tc_load_window_flat(wbase + WW_N_MFCC * WW_WINDOW_FRAMES, w0 + 1 < a.n_windows, lane, wb);
             } else {
                 tc_load_window(a, oct * TC_CLIPS + 2 * q4, lane, wa);
                 tc_load_window(a, oct * TC_CLIPS + 2 * q4 + 1, lane, wb);
@@ -502,8 +645,7 @@ __device__ __forceinline__ void cnn_tc_body(const TcArgs& a, unsigned char* smem
                     wnorm[8 * np + 2 * q4 + 1] = sqrtf(sb);
                 }
             }
-            tc_cmvn_store(a, wa, 2 * q4, lane, sA1);
-            tc_cmvn_store(a, wb, 2 * q4 + 1, lane, sA1);
+            tc_cmvn_store2(a, wa, wb, 2 * q4, lane, sA1);
         }
         fence_async_smem();
         tc_fence_before();
