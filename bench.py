@@ -577,7 +577,7 @@ def run_ours(args):
             hms = h0.elapsed_time(h1) / 3
             if ref_out is None:
                 ref_out = (lg2.clone(), dc2.clone())
-            launches_1m = {"default": 8 * 3, "l2_chunks": 74 * 2 + 8, "one_kernel": 8 * 2}[name]
+            launches_1m = {"default": 8 * 2 + 1, "l2_chunks": 74 * 2 + 8, "one_kernel": 8 * 2}[name]
             handoff["modes"][name] = {"clips_per_s": hb / (hms * 1e-3), "dram_bytes_per_clip_ncu": dram,
                                       "dram_over_algorithmic": dram / FUSED_BYTES_PER_CLIP, "dram_source": src,
                                       "kernel_launches_per_2^20_clips": launches_1m,
@@ -682,8 +682,13 @@ def run_ours(args):
     if rank == 0:
         chunk = int(os.environ.get("WW_CHUNK_CLIPS", "131072"))  # ww_api.cu kScratchClips: clips per fused frontend + CNN pair
         chunks = (B + chunk - 1) // chunk
-        per_chunk = 3 if cnn_impl == "tensor" else 2  # frontend + CNN (+ fp32 re-score of borderline clips)
-        launches = args.steps * (chunks * per_chunk + (1 if n_utt else 0))
+        # frontend + CNN per chunk; tensor path: + the fp32 re-score of the borderline clips, ONE launch per 2^20 clips when the
+        # call spans several chunks (ww_api.cu kRescoreWindowClips, WW_RESCORE_WINDOW_CLIPS=0: one per chunk)
+        window = int(os.environ.get("WW_RESCORE_WINDOW_CLIPS", str(1 << 20)))
+        rescores = 0
+        if cnn_impl == "tensor":
+            rescores = chunks if (chunks == 1 or window == 0) else (B + max(window, chunk) - 1) // max(window, chunk)
+        launches = args.steps * (chunks * 2 + rescores + (1 if n_utt else 0))
         cpu = None
         if world == 1 and not args.no_cpu:
             v, dt, cores = time_cpu(args.cpu_clips, 5, 1)

@@ -91,6 +91,11 @@ struct ww_ctx {
     int opt_pdl = 1;                   // WW_PDL=0: ordinary launches in that path (A/B)
     float* l2_feats = nullptr;
     long long l2_chunk_clips = 0;      // WW_L2_CHUNK_CLIPS (0 = off: 131 072-clip chunks through `scratch`)
+    // deferred exact re-score of the default (HBM scratch) hand-over: compact copies of the listed windows, one exact
+    // launch per rescore_window_clips clips (WW_OPT_RESCORE_WINDOW_CLIPS; 0 = one re-score launch per chunk)
+    float* rs_feats = nullptr;         // [rs_feats_cap][13][63]
+    long long rs_feats_cap = 0;
+    long long rescore_window_clips = 0;
     // one-kernel clip path (ww_fused.cuh): L2-resident feature ring + its counters, err flag mirrored to pinned memory
     int opt_fused = 0;                 // ww_set_option(WW_OPT_FUSED): 0 chunked launches (default), 1 one kernel from 2048 clips on, 2 always
     int opt_fused_cnn_sms = 0;         // ww_set_option(WW_OPT_FUSED_CNN_SMS): SMs given to the CNN role, 0 = by CMVN mode
@@ -311,6 +316,11 @@ extern "C" const char* ww_last_error(const ww_ctx* ctx) { return ctx ? ctx->err.
 // 32768 -> 18.3, 65536 -> 18.5 M clips/s; the host-buffer pipeline keeps 16384-clip chunks for copy overlap.
 static const long long kScratchClips = 131072;  // WW_CHUNK_CLIPS overrides (sweep: 65536 -> 25.25, 131072 -> 25.49, 262144 -> 25.35 M clips/s)
 static const long long kHostChunkClips = 16384;
+// Default hand-over of ww_score_clips (chunks through the HBM scratch), calls of more than one chunk: the windows inside
+// the guard band are copied to a compact buffer by the tcgen05 kernel and ONE exact launch re-scores them per this many
+// clips (a ~50 us launch however short its list; per chunk it was 1.3 % of the step), and the launch pairs are chained
+// with programmatic dependent launch.  The compact buffer is sized for the worst case (every window listed).
+static const long long kRescoreWindowClips = 1LL << 20;
 // Tensor path of ww_score_clips: clips per frontend + CNN launch pair.  16 384 clips = 53.7 MB of features: written by
 // the frontend, read back by the CNN kernel and overwritten by the next chunk while still in the 126 MB L2 (the PCM
 // stream carries an evict-first policy), so they never reach HBM; the windows inside the guard band are copied to a
@@ -401,6 +411,11 @@ extern "C" int ww_create(ww_ctx** out, int device) {
         const long long v = atoll(c);
         if (v == 0 || (v >= 1024 && v <= 131072)) ctx->l2_chunk_clips = v;
     }
+    ctx->rescore_window_clips = kRescoreWindowClips;
+    if (const char* c = getenv("WW_RESCORE_WINDOW_CLIPS")) {
+        const long long v = atoll(c);
+        if (v == 0 || (v >= 1024 && v <= (1LL << 22))) ctx->rescore_window_clips = v;
+    }
     if (const char* f = getenv("WW_PDL")) ctx->opt_pdl = atoi(f);
     if (const char* f = getenv("WW_CTC_TINY")) ctx->opt_ctc_tiny = atoi(f);
     if (const char* f = getenv("WW_CTC_SPLIT")) ctx->opt_ctc_split = atoi(f);
@@ -438,6 +453,7 @@ extern "C" void ww_destroy(ww_ctx* ctx) {
     }
     free_host_path(ctx);
     cudaFree(ctx->l2_feats);
+    cudaFree(ctx->rs_feats);
     cudaFree(ctx->fused_ring);
     cudaFree(ctx->fused_sync);
     if (ctx->fused_err_host) cudaFreeHost(ctx->fused_err_host);
@@ -471,6 +487,11 @@ extern "C" int ww_set_option(ww_ctx* ctx, int option, int value) {
                 ctx->l2_feats = nullptr;
                 ctx->l2_chunk_clips = value;
             }
+            return WW_OK;
+        case WW_OPT_RESCORE_WINDOW_CLIPS:
+            if (value != 0 && (value < 1024 || value > (1 << 22)))
+                return fail(ctx, WW_ERR_INVALID, "WW_OPT_RESCORE_WINDOW_CLIPS: 0 (one exact launch per chunk) or 1024 .. 4194304");
+            ctx->rescore_window_clips = value;
             return WW_OK;
         case WW_OPT_FUSED_CNN_SMS:
             if (value < 0 || value >= ctx->sm_count) return fail(ctx, WW_ERR_INVALID, "WW_OPT_FUSED_CNN_SMS: 0 (default) .. SM count - 1");
@@ -1412,19 +1433,44 @@ static int score_clips_dev(ww_ctx* ctx, const void* pcm, int pcm_type, long long
             }
         }
     } mark{ctx, st};
-    // ---- tensor path with the L2-resident hand-over: small chunks, compact re-score list, deferred exact launch ----
-    if (!fused && cnn_impl == WW_CNN_TENSOR && ctx->l2_chunk_clips > 0 && ctx->tc_ok && C <= TC_MAX_CLASSES &&
-        tc_norm_mode(cmvn_mode) <= ctx->tc_norm_limit) {
-        const long long chunk = ctx->l2_chunk_clips;
-        if (!ctx->l2_feats) CK(cudaMalloc(&ctx->l2_feats, sizeof(float) * (size_t)chunk * WW_N_MFCC * WW_WINDOW_FRAMES));
-        rc = ensure_rescore(ctx, ctx->scratch_clips);
+    // ---- tensor path, compact re-score list and deferred exact launch: small chunks whose features stay in L2
+    //      (WW_OPT_L2_CHUNK_CLIPS), or the default scratch-sized chunks through HBM when the call spans several of them ----
+    const bool l2_mode = ctx->l2_chunk_clips > 0;
+    if (!fused && cnn_impl == WW_CNN_TENSOR && ctx->tc_ok && C <= TC_MAX_CLASSES &&
+        tc_norm_mode(cmvn_mode) <= ctx->tc_norm_limit &&
+        (l2_mode || (ctx->rescore_window_clips > 0 && n_clips > ctx->scratch_clips))) {
+        const long long chunk = l2_mode ? ctx->l2_chunk_clips : ctx->scratch_clips;
+        // features of the chunk in flight / compact copies of the listed windows / clips per exact launch
+        float* feat_buf;
+        float* compact;
+        long long window;
+        if (l2_mode) {
+            if (!ctx->l2_feats) CK(cudaMalloc(&ctx->l2_feats, sizeof(float) * (size_t)chunk * WW_N_MFCC * WW_WINDOW_FRAMES));
+            feat_buf = ctx->l2_feats;
+            compact = ctx->scratch;
+            window = ctx->scratch_clips;
+        } else {
+            window = n_clips < ctx->rescore_window_clips ? n_clips : ctx->rescore_window_clips;
+            if (window < chunk) window = chunk;
+            if (ctx->rs_feats_cap < window) {
+                CK(cudaDeviceSynchronize());   // an earlier call's exact launch may still read the old buffer
+                cudaFree(ctx->rs_feats);
+                ctx->rs_feats = nullptr;
+                ctx->rs_feats_cap = 0;
+                CK(cudaMalloc(&ctx->rs_feats, sizeof(float) * (size_t)window * WW_N_MFCC * WW_WINDOW_FRAMES));
+                ctx->rs_feats_cap = window;
+            }
+            feat_buf = ctx->scratch;
+            compact = ctx->rs_feats;
+        }
+        rc = ensure_rescore(ctx, window);
         if (rc) return rc;
         const TcBand b = tc_band(ctx, cmvn_mode, decide_mode, threshold);
         long long base = 0;  // first clip of the current re-score window (<= scratch_clips clips share one exact launch)
         auto flush = [&](long long end) -> int {
             long long g = (long long)ctx->sm_count * 2;
             NvtxRange r("ww:exact re-score");
-            return launch_cnn_fp32(ctx, ctx->scratch, WW_N_MFCC * WW_WINDOW_FRAMES, WW_WINDOW_FRAMES, 1, end - base /* capacity */,
+            return launch_cnn_fp32(ctx, compact, WW_N_MFCC * WW_WINDOW_FRAMES, WW_WINDOW_FRAMES, 1, end - base /* capacity */,
                                    ctx->rs_list, ctx->rs_count, cmvn_mode, decide_mode, threshold, logits + base * C,
                                    decisions ? decisions + base : nullptr, nullptr, st, (unsigned)(g < end - base ? g : end - base),
                                    /*index_compact=*/true);
@@ -1432,7 +1478,7 @@ static int score_clips_dev(ww_ctx* ctx, const void* pcm, int pcm_type, long long
         CK(cudaMemsetAsync(ctx->rs_count, 0, sizeof(int), st));
         for (long long c0 = 0; c0 < n_clips; c0 += chunk) {
             const long long nc = (n_clips - c0) < chunk ? (n_clips - c0) : chunk;
-            if (c0 + nc - base > ctx->scratch_clips) {
+            if (c0 + nc - base > window) {
                 rc = flush(c0);
                 if (rc) return rc;
                 base = c0;
@@ -1443,19 +1489,19 @@ static int score_clips_dev(ww_ctx* ctx, const void* pcm, int pcm_type, long long
                 NvtxRange r("ww:frontend");
                 // chunk k + 1's frontend starts while chunk k's CNN launch drains (it overwrites the features that launch
                 // reads only after its pdl_wait); not across a flush, whose memset sits between the kernels
-                rc = launch_mfcc(ctx, p, pcm_type, nc, WW_CLIP_SAMPLES, WW_CLIP_SAMPLES, WW_FEAT_PY, ctx->l2_feats,
+                rc = launch_mfcc(ctx, p, pcm_type, nc, WW_CLIP_SAMPLES, WW_CLIP_SAMPLES, WW_FEAT_PY, feat_buf,
                                  WW_N_MFCC * WW_WINDOW_FRAMES, WW_WINDOW_FRAMES, 1, st, /*pdl=*/ctx->opt_pdl && c0 > base);
             }
             if (rc) return rc;
             NvtxRange r("ww:cmvn+cnn+decision");
             TcArgs a;
-            tc_fill_args(ctx, a, ctx->l2_feats, WW_N_MFCC * WW_WINDOW_FRAMES, WW_WINDOW_FRAMES, 1, nc, cmvn_mode, decide_mode,
+            tc_fill_args(ctx, a, feat_buf, WW_N_MFCC * WW_WINDOW_FRAMES, WW_WINDOW_FRAMES, 1, nc, cmvn_mode, decide_mode,
                          threshold, b.thr0, b.thr1, b.band, b.band_rel, logits + c0 * C, decisions ? decisions + c0 : nullptr,
                          ctx->rs_list);
             a.group_windows = 0;
             a.group_stride = 0;
             a.dbg = nullptr;
-            a.rescore_feat = ctx->scratch;
+            a.rescore_feat = compact;
             a.rescore_base = c0 - base;
             const long long n_cta = ((nc + TC_CLIPS - 1) / TC_CLIPS + TC_GROUPS - 1) / TC_GROUPS;
             CK(launch_kernel(cnn_tc_kernel, (unsigned)(n_cta < ctx->sm_count ? n_cta : ctx->sm_count), TC_THREADS, TC_SMEM, st,

@@ -27,6 +27,7 @@ OPT_GENERIC_FRONTEND = 2
 OPT_FUSED = 3            # 0 chunked launches (default), 1 one persistent kernel from 2048 clips on, 2 always one kernel
 OPT_FUSED_CNN_SMS = 4    # SMs given to the CNN role of the one-kernel path (0 = default)
 OPT_L2_CHUNK_CLIPS = 5    # chunked tensor path with the features kept in L2: clips per launch pair (0 = off)
+OPT_RESCORE_WINDOW_CLIPS = 6  # default hand-over over several chunks: clips per exact re-score launch (0 = per chunk)
 NORM_STANDARD, NORM_MINMAX = 0, 1
 ERR_BUSY = -6
 

@@ -130,8 +130,13 @@ int ww_cnn_forward_i8(ww_ctx* ctx, const int8_t* x, long long n_windows, int8_t*
  * WW_OPT_L2_CHUNK_CLIPS: clips per frontend + CNN launch pair of the chunked tensor path when the features are to stay
  * in L2 (0 = off, default: 131 072-clip chunks through a 429 MB scratch in HBM; 14 208 = 46.5 MB of features that the
  * next chunk overwrites while still in L2 and a whole number of waves for both kernels: DRAM traffic 1.004 x the
- * algorithmic bytes at -1.1 % throughput; one exact re-score launch per 131 072 clips instead of one per chunk). */
-enum { WW_OPT_I8_IMPL = 1, WW_OPT_GENERIC_FRONTEND = 2, WW_OPT_FUSED = 3, WW_OPT_FUSED_CNN_SMS = 4, WW_OPT_L2_CHUNK_CLIPS = 5 };
+ * algorithmic bytes at -1.1 % throughput; one exact re-score launch per 131 072 clips instead of one per chunk).
+ * WW_OPT_RESCORE_WINDOW_CLIPS: default hand-over, calls that span more than one 131 072-clip chunk -- clips per exact
+ * re-score launch (default 1 048 576: the tcgen05 kernel copies the windows inside the guard band to a compact buffer,
+ * sized for the worst case of every window listed, 3.3 KB per clip of the window, allocated at the first such call;
+ * the chunks' launch pairs are chained with programmatic dependent launch).  0 = one exact launch per chunk. */
+enum { WW_OPT_I8_IMPL = 1, WW_OPT_GENERIC_FRONTEND = 2, WW_OPT_FUSED = 3, WW_OPT_FUSED_CNN_SMS = 4, WW_OPT_L2_CHUNK_CLIPS = 5,
+       WW_OPT_RESCORE_WINDOW_CLIPS = 6 };
 int ww_set_option(ww_ctx* ctx, int option, int value);
 
 /* Guard band of WW_CNN_TENSOR for the weights loaded last.  ww_load_weights runs 4096 calibration windows (noise,
@@ -150,7 +155,8 @@ long long ww_tc_rescored_total(ww_ctx* ctx, int reset);
 /* ---- fused clip scoring: PCM -> MFCC -> CMVN -> CNN -> decision -------------------------------- */
 /* pcm: device [n_clips][16000].  By default the features pass from the frontend to the CNN through a context-owned
  * scratch of 131 072 clips (429 MB: it round-trips HBM, 6.5 KB per clip on top of the 32 KB of PCM); per chunk:
- * frontend launch, tcgen05 CNN launch, fp32 re-score launch.  That is the fastest of three hand-overs; the other two
+ * frontend launch, tcgen05 CNN launch, and one fp32 re-score launch (per call of up to 2^20 clips when the call spans
+ * several chunks, WW_OPT_RESCORE_WINDOW_CLIPS).  That is the fastest of three hand-overs; the other two
  * keep the features in L2 (WW_OPT_L2_CHUNK_CLIPS, WW_OPT_FUSED above; measured side by side in DESIGN.md 4.6).
  * One fused call at a time per context: a second host thread gets WW_ERR_BUSY; consecutive calls on different
  * streams are ordered on the device. */

@@ -133,6 +133,43 @@ def test_l2_resident_chunks_equal_default_chunks(cuda_device, xiaoa_sd, chunk):
         assert torch.equal(l0, l1) and torch.equal(d0, d1) and r0 == r1
 
 
+@pytest.mark.parametrize("cmvn,decision", [("python", "python"), ("device", "device")])
+def test_deferred_rescore_of_the_default_handover_equals_per_chunk_rescore(cuda_device, xiaoa_sd, cmvn, decision):
+    """WW_OPT_RESCORE_WINDOW_CLIPS: a call that spans several 131 072-clip chunks copies the windows inside the guard band
+    to a compact buffer and re-scores them with ONE exact launch (per window of clips) -- same bits and the same re-score
+    count as one exact launch per chunk, for a window that covers the call, a window of one chunk (flush between the
+    chunks), and when EVERY window is listed (the compact buffer's worst case)."""
+    import ww_b200
+    from ww_b200 import _lib as L
+
+    sc = ww_b200.WakeWordScorer(xiaoa_sd, device=0, cmvn=cmvn, decision=decision)
+    n = 2 * 131072 + 4099
+    for same in (False, True):
+        if same:
+            if cmvn != "python":
+                continue
+            pcm = torch.from_numpy(om.synth_clips_int16(1, seed=78)).to(cuda_device).repeat(n, 1).contiguous()
+            sc.threshold = float(ww_b200.WakeWordScorer(xiaoa_sd, device=0, cnn_impl="fp32").score(pcm[:1])[0][0, 0].item())
+        else:
+            pcm = _clips(n, 23, cuda_device)
+        out = {}
+        try:
+            for window in (0, 1 << 20, 1024):
+                sc._prep()
+                sc.ctx.check(sc.ctx.lib.ww_set_option(sc.ctx.h, L.OPT_RESCORE_WINDOW_CLIPS, window), "ww_set_option")
+                out[window] = _score(sc, pcm, 0)
+        finally:
+            sc.ctx.check(sc.ctx.lib.ww_set_option(sc.ctx.h, L.OPT_RESCORE_WINDOW_CLIPS, 1 << 20), "ww_set_option")
+        l0, d0, r0 = out[0]
+        for window in (1 << 20, 1024):
+            l1, d1, r1 = out[window]
+            assert torch.equal(l0, l1) and torch.equal(d0, d1) and r0 == r1, (cmvn, same, window, r0, r1)
+        if same:
+            assert r0 == n
+        else:
+            assert 0 < r0 < n // 20
+
+
 def test_fused_three_classes_and_cnn_sm_count(cuda_device):
     """random 3-class weights (the CTC keyword shape) and a non-default split of the SMs between the two roles"""
     import ww_b200
