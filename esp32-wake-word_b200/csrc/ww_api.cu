@@ -86,7 +86,14 @@ struct ww_ctx {
     // L2-resident feature hand-over of the chunked tensor path: [l2_chunk_clips][13][63], re-used by every chunk
     int opt_greedy_generic = 0;        // WW_GREEDY_GENERIC=1 (A/B): keyword shapes (T <= 64, C <= 4) through ctc_greedy_kernel too
     int opt_greedy_blocks_per_sm = 0;  // WW_GREEDY_BLOCKS_PER_SM (A/B; 0 = 64; measured 8 / 16 / 32 / 64 / unbounded: 2.08 / 2.26 / 2.77 / 2.95 / 2.82 G utt/s)
-    int opt_ctc_split = 1;             // WW_CTC_SPLIT=0: wide-vocabulary backward as fill + one recursion kernel (A/B)
+    // wide-vocabulary CTC backward (WW_OPT_CTC_SPLIT / WW_CTC_SPLIT).  1 (default): beta recursion, then fill + patches in
+    // one pass over the rows; 2: beta, fill, patches one after the other; 3: beta on a side stream WHILE the fill streams
+    // on the caller's, then the patches -- measured and rejected: under the fill's HBM load every gather of the recursion
+    // queues behind the stream, 5.1 ms against 2.5 ms at T = 801, C = 4096 (profiles/r2e_ab_ctc_split.jsonl); 0: fill +
+    // one recursion kernel that also patches
+    int opt_ctc_split = 1;
+    cudaStream_t ctc_side = nullptr;   // high-priority side stream of the split backward pass
+    cudaEvent_t ctc_fork = nullptr, ctc_join = nullptr;
     int opt_ctc_tiny = 1;              // WW_CTC_TINY=0: the 8-lanes-per-utterance kernels for S <= 3 (A/B)
     int opt_pdl = 1;                   // WW_PDL=0: ordinary launches in that path (A/B)
     float* l2_feats = nullptr;
@@ -452,6 +459,9 @@ extern "C" void ww_destroy(ww_ctx* ctx) {
         if (ctx->hev[i]) cudaEventDestroy(ctx->hev[i]);
     }
     free_host_path(ctx);
+    if (ctx->ctc_side) cudaStreamDestroy(ctx->ctc_side);
+    if (ctx->ctc_fork) cudaEventDestroy(ctx->ctc_fork);
+    if (ctx->ctc_join) cudaEventDestroy(ctx->ctc_join);
     cudaFree(ctx->l2_feats);
     cudaFree(ctx->rs_feats);
     cudaFree(ctx->fused_ring);
@@ -487,6 +497,10 @@ extern "C" int ww_set_option(ww_ctx* ctx, int option, int value) {
                 ctx->l2_feats = nullptr;
                 ctx->l2_chunk_clips = value;
             }
+            return WW_OK;
+        case WW_OPT_CTC_SPLIT:
+            if (value < 0 || value > 3) return fail(ctx, WW_ERR_INVALID, "WW_OPT_CTC_SPLIT: 0 .. 3");
+            ctx->opt_ctc_split = value;
             return WW_OK;
         case WW_OPT_RESCORE_WINDOW_CLIPS:
             if (value != 0 && (value < 1024 || value > (1 << 22)))
@@ -2156,11 +2170,11 @@ extern "C" int ww_ctc_loss_bwd(ww_ctx* ctx, const float* log_probs, long long t_
     a.skip_fill = C >= 64 ? 1 : 0;
     const int K = ctc_lp(S) / 32;
     const unsigned grid = (unsigned)((B + CTC_WARPS - 1) / CTC_WARPS);
-    auto launch_fill = [&]() -> int {
+    auto launch_fill = [&](int ctas_per_sm) -> int {
         // wide vocabulary: the exp(lp) fill is a bandwidth-bound pass over all T*B rows, not warp-per-utterance work
         long long rows = (long long)T * B;
         long long blocks = (rows + 7) / 8;
-        const long long cap = (long long)ctx->sm_count * 8;
+        const long long cap = (long long)ctx->sm_count * ctas_per_sm;
         if (blocks > cap) blocks = cap;
         a.fill_vec = (C % 4 == 0) && ((uintptr_t)log_probs % 16 == 0) && ((uintptr_t)grad % 16 == 0) && (t_stride % 4 == 0) &&
                      (b_stride % 4 == 0) && (gt_stride % 4 == 0) && (gb_stride % 4 == 0);
@@ -2169,26 +2183,49 @@ extern "C" int ww_ctc_loss_bwd(ww_ctx* ctx, const float* log_probs, long long t_
         return WW_OK;
     };
     if (a.skip_fill && K <= 4 && ctx->opt_ctc_split && ((uintptr_t)workspace % 16) == 0) {
-        // wide vocabulary: beta recursion alone (alpha + beta in place), then every row independently
+        // wide vocabulary: beta recursion alone (alpha + beta in a second block), then every row independently
         const size_t al_bytes = ((size_t)B * T * (2 * S + 1) * sizeof(float) + 15) / 16 * 16;
         a.meta = reinterpret_cast<float*>((char*)workspace + al_bytes);
         a.ab = a.meta + 4 * (size_t)B;
         a.fill_vec = (C % 4 == 0) && ((uintptr_t)log_probs % 16 == 0) && ((uintptr_t)grad % 16 == 0) && (t_stride % 4 == 0) &&
                      (b_stride % 4 == 0) && (gt_stride % 4 == 0) && (gb_stride % 4 == 0);
         const size_t smem_b = (size_t)CTC_WARPS * (2 * (32 * K + 2) + 2 * CTC_PF * 32 * K) * sizeof(float);
+        // Mode 3 (A/B, rejected): the recursion is a latency chain on B / 8 CTAs, the fill a stream over every SM, and they do
+        // not depend on each other (the fill reads alpha's last row only) -- recursion on a high-priority side stream,
+        // submitted first, the fill leaving it two CTA slots per SM.  It loses 2x: the chain's gathers wait behind the stream.
+        const bool overlap = ctx->opt_ctc_split == 3;
+        cudaStream_t rs = (cudaStream_t)stream;
+        if (overlap) {
+            if (!ctx->ctc_side) {
+                int lo = 0, hi = 0;
+                CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                CK(cudaStreamCreateWithPriority(&ctx->ctc_side, cudaStreamNonBlocking, hi));
+                CK(cudaEventCreateWithFlags(&ctx->ctc_fork, cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&ctx->ctc_join, cudaEventDisableTiming));
+            }
+            CK(cudaEventRecord(ctx->ctc_fork, (cudaStream_t)stream));
+            CK(cudaStreamWaitEvent(ctx->ctc_side, ctx->ctc_fork, 0));
+            rs = ctx->ctc_side;
+        }
         switch (K) {
-            case 1: ctc_beta_pf_kernel<1><<<grid, CTC_WARPS * 32, smem_b, (cudaStream_t)stream>>>(a); break;
-            case 2: ctc_beta_pf_kernel<2><<<grid, CTC_WARPS * 32, smem_b, (cudaStream_t)stream>>>(a); break;
-            case 3: ctc_beta_pf_kernel<3><<<grid, CTC_WARPS * 32, smem_b, (cudaStream_t)stream>>>(a); break;
-            default: ctc_beta_pf_kernel<4><<<grid, CTC_WARPS * 32, smem_b, (cudaStream_t)stream>>>(a); break;
+            case 1: ctc_beta_pf_kernel<1><<<grid, CTC_WARPS * 32, smem_b, rs>>>(a); break;
+            case 2: ctc_beta_pf_kernel<2><<<grid, CTC_WARPS * 32, smem_b, rs>>>(a); break;
+            case 3: ctc_beta_pf_kernel<3><<<grid, CTC_WARPS * 32, smem_b, rs>>>(a); break;
+            default: ctc_beta_pf_kernel<4><<<grid, CTC_WARPS * 32, smem_b, rs>>>(a); break;
         }
         CK(cudaGetLastError());
         long long rows = (long long)T * B;
         long long blocks = (rows + CTC_ROWS_WARPS - 1) / CTC_ROWS_WARPS;
         const long long cap = (long long)ctx->sm_count * 8;
         if (blocks > cap) blocks = cap;
-        if (ctx->opt_ctc_split == 2) {   // A/B: the stream-only fill kernel, then the patches alone (1.27 + 0.41 ms against 1.57)
-            rc = launch_fill();
+        if (overlap) {
+            CK(cudaEventRecord(ctx->ctc_join, ctx->ctc_side));
+            rc = launch_fill(6);
+            if (rc) return rc;
+            CK(cudaStreamWaitEvent((cudaStream_t)stream, ctx->ctc_join, 0));
+            ctc_grad_rows_kernel<false><<<(unsigned)blocks, CTC_ROWS_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+        } else if (ctx->opt_ctc_split == 2) {   // A/B: the stream-only fill kernel, then the patches alone (1.27 + 0.41 ms against 1.57)
+            rc = launch_fill(8);
             if (rc) return rc;
             ctc_grad_rows_kernel<false><<<(unsigned)blocks, CTC_ROWS_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
         } else {
@@ -2198,7 +2235,7 @@ extern "C" int ww_ctc_loss_bwd(ww_ctx* ctx, const float* log_probs, long long t_
         return WW_OK;
     }
     if (a.skip_fill) {
-        rc = launch_fill();
+        rc = launch_fill(8);
         if (rc) return rc;
     }
     if (K <= 4) {

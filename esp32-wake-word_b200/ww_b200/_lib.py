@@ -28,6 +28,7 @@ OPT_FUSED = 3            # 0 chunked launches (default), 1 one persistent kernel
 OPT_FUSED_CNN_SMS = 4    # SMs given to the CNN role of the one-kernel path (0 = default)
 OPT_L2_CHUNK_CLIPS = 5    # chunked tensor path with the features kept in L2: clips per launch pair (0 = off)
 OPT_RESCORE_WINDOW_CLIPS = 6  # default hand-over over several chunks: clips per exact re-score launch (0 = per chunk)
+OPT_CTC_SPLIT = 7         # wide-vocabulary CTC backward: 1 beta, rows (default); 2 beta, fill, patches; 3 beta || fill (rejected); 0 fill, recursion
 NORM_STANDARD, NORM_MINMAX = 0, 1
 ERR_BUSY = -6
 

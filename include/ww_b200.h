@@ -134,9 +134,14 @@ int ww_cnn_forward_i8(ww_ctx* ctx, const int8_t* x, long long n_windows, int8_t*
  * WW_OPT_RESCORE_WINDOW_CLIPS: default hand-over, calls that span more than one 131 072-clip chunk -- clips per exact
  * re-score launch (default 1 048 576: the tcgen05 kernel copies the windows inside the guard band to a compact buffer,
  * sized for the worst case of every window listed, 3.3 KB per clip of the window, allocated at the first such call;
- * the chunks' launch pairs are chained with programmatic dependent launch).  0 = one exact launch per chunk. */
+ * the chunks' launch pairs are chained with programmatic dependent launch).  0 = one exact launch per chunk.
+ * WW_OPT_CTC_SPLIT: backward pass of ww_ctc_loss_bwd for wide vocabularies (C >= 64, 2S+1 <= 128) -- 1 (default): beta
+ * recursion, then fill + patches in one pass over the rows; 2: beta, fill, patches as three launches; 3: beta on a
+ * context-owned side stream while the fill streams on the caller's (forked and joined with events), then the patches:
+ * measured 2x slower (the recursion's gathers queue behind the fill), kept for A/B; 0: fill, then one recursion kernel
+ * that also patches.  Identical results. */
 enum { WW_OPT_I8_IMPL = 1, WW_OPT_GENERIC_FRONTEND = 2, WW_OPT_FUSED = 3, WW_OPT_FUSED_CNN_SMS = 4, WW_OPT_L2_CHUNK_CLIPS = 5,
-       WW_OPT_RESCORE_WINDOW_CLIPS = 6 };
+       WW_OPT_RESCORE_WINDOW_CLIPS = 6, WW_OPT_CTC_SPLIT = 7 };
 int ww_set_option(ww_ctx* ctx, int option, int value);
 
 /* Guard band of WW_CNN_TENSOR for the weights loaded last.  ww_load_weights runs 4096 calibration windows (noise,

@@ -256,8 +256,20 @@ def test_ctc_loss_keyword_shapes_one_thread_per_utterance(cuda_device, T, B, C, 
     assert err_mine <= max(2e-5, 3.0 * err_torch32)
 
 
+@pytest.fixture
+def ctc_split_mode(request, cuda_device):
+    """WW_OPT_CTC_SPLIT for the duration of a test (1 is the default: beta recursion, then fill + patches per row)"""
+    from ww_b200 import _lib as L
+
+    ctx = L.get_context(0)
+    ctx.check(ctx.lib.ww_set_option(ctx.h, L.OPT_CTC_SPLIT, request.param), "ww_set_option")
+    yield request.param
+    ctx.check(ctx.lib.ww_set_option(ctx.h, L.OPT_CTC_SPLIT, 1), "ww_set_option")
+
+
+@pytest.mark.parametrize("ctc_split_mode", [1, 2, 3, 0], indirect=True)
 @pytest.mark.parametrize("T,B,C,S", [(120, 9, 64, 20), (200, 5, 256, 40), (90, 7, 100, 63), (150, 4, 1000, 31)])
-def test_ctc_loss_wide_vocabulary_split_backward(cuda_device, T, B, C, S):
+def test_ctc_loss_wide_vocabulary_split_backward(cuda_device, T, B, C, S, ctc_split_mode):
     """C >= 64, 2S+1 <= 128: beta recursion + row-parallel gradient.  Targets with many repeated labels (adjacent and
     not), a label equal to the blank index... is not legal for torch, so the blank-index fold is covered by repeated
     labels only; ragged lengths, an infeasible utterance, zero-length targets; a second backward through the same graph

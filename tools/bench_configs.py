@@ -55,7 +55,7 @@ def stream_bench(dev, sd, seconds=3600, impl="tensor"):
     return out
 
 
-def ctc_bench(dev, T, B, C, S, seed=777):
+def ctc_bench(dev, T, B, C, S, seed=777, compare=True):
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
     lp = torch.log_softmax(torch.randn((T, B, C), generator=g, device=dev), dim=-1)
@@ -74,6 +74,9 @@ def ctc_bench(dev, T, B, C, S, seed=777):
         ref(x, tg, il.long(), tl.long()).backward()
 
     d_ours = timed(ours)
+    if not compare:
+        return {"config": f"configs[4] CTC loss fwd+bwd T={T} B={B} C={C} S={S}", "seq_per_s": B / d_ours,
+                "ms": d_ours * 1e3, "algorithmic_GBps": 2 * T * C * 4 * B / d_ours / 1e9}
     try:
         d_torch = timed(torch_gpu)
     except Exception:   # torch's CUDA kernel rejects very large batches (grid limit)
@@ -287,6 +290,22 @@ def main():
         for r in (ctc_bench(dev, 63, 1 << 18, 3, 2), ctc_bench(dev, 63, 1 << 18, 3, 1), ctc_bench(dev, 63, 1 << 20, 3, 2),
                   ctc_bench(dev, 801, 256, 4096, 32)):
             print(json.dumps(r), flush=True)
+        return
+    if "--ctc-split" in sys.argv:
+        # wide-vocabulary backward, the four ways (WW_OPT_CTC_SPLIT), alternating twice
+        from ww_b200 import _lib as L
+
+        ctx = L.get_context(0)
+        names = {1: "beta, rows (fill + patches)", 2: "beta, fill, patches", 3: "beta || fill, patches", 0: "fill, recursion with patches"}
+        for _ in range(2):
+            for mode in (1, 2, 3, 0):
+                ctx.check(ctx.lib.ww_set_option(ctx.h, L.OPT_CTC_SPLIT, mode), "opt")
+                for shape in ((801, 256, 4096, 32), (801, 64, 4096, 32), (200, 1024, 512, 20)):
+                    r = ctc_bench(dev, *shape, compare=False)
+                    r["ctc_split"] = mode
+                    r["how"] = names[mode]
+                    print(json.dumps(r), flush=True)
+        ctx.check(ctx.lib.ww_set_option(ctx.h, L.OPT_CTC_SPLIT, 1), "opt")
         return
     res += batch_sweep(dev, sd)
     res += stream_bench(dev, sd)
