@@ -52,6 +52,15 @@
 #ifndef WW_PRESEL
 #define WW_PRESEL 0
 #endif
+// WW_LANE_INTERLEAVE: the two frames of a warp take the EVEN and the ODD lanes (frame = lane & 1, point index = lane >> 1)
+// instead of the two half-warps.  Both frames read the same twiddles, and a 64-/128-bit shared load is served per
+// half-warp: lanes i and i + 16 reading the same 16 bytes cost 4 wavefronts (the half-warps are not merged), lanes 2j and
+// 2j + 1 reading the same 16 bytes cost 2 (tools/ubench/lds_dup.cu, profiles/r2e_ubench_lds_dup.txt: 4.00 against 2.11
+// clocks per LDS.128, 1.75 against 0.98 per LDS.64).  The twiddle loads were 24.5 % of the kernel's shared-memory
+// wavefronts; the two frames' exchange tiles are staggered by 64 B so that the transposition stays conflict-free.
+#ifndef WW_LANE_INTERLEAVE
+#define WW_LANE_INTERLEAVE 1
+#endif
 
 namespace ww {
 
@@ -69,6 +78,9 @@ constexpr int MFCC_THREADS = 256;
 constexpr int MFCC_WARPS = MFCC_THREADS / 32;
 constexpr int EXCH_ROW_BYTES = 144;                    // 16 complex + 16 B pad: conflict-free LDS.128
 constexpr int EXCH_FRAME_BYTES = 16 * EXCH_ROW_BYTES;  // 2304 (>= 257 complex for the natural-order pass)
+// a warp's two exchange tiles: with interleaved lanes a half-warp touches both, so the second one sits 16 banks further
+constexpr int EXCH_STAGGER = WW_LANE_INTERLEAVE ? 64 : 0;
+constexpr int EXCH_WARP_BYTES = 2 * EXCH_FRAME_BYTES + EXCH_STAGGER;
 // Rows of the power-spectrum and log-mel buffers (lane <-> frame in the mel / DCT stages).  The generated mel / DCT
 // code reads its row with 16-byte loads: rows are 16-byte aligned with a stride of 4 (mod 32) words, which makes the
 // eight lanes of a quarter-warp hit disjoint banks, and the rows of frames 16..31 are shifted by another 16 words so
@@ -216,7 +228,7 @@ struct MfccSmem {
     static constexpr int OFF_TAB = 32;
     static constexpr int OFF_PCM = OFF_TAB + TAB_BYTES;
     static constexpr int OFF_EXCH = OFF_PCM + PCM_BUFS * PCM_BYTES;
-    static constexpr int OFF_P = OFF_EXCH + MFCC_WARPS * 2 * EXCH_FRAME_BYTES;
+    static constexpr int OFF_P = OFF_EXCH + MFCC_WARPS * EXCH_WARP_BYTES;
     static constexpr int OFF_LM = OFF_P + MfccRows<MEL>::P_FLOATS * 4;
     static constexpr int OFF_EDGE = OFF_LM + FRAMES * MfccRows<MEL>::LM_STRIDE * 4;   // 2 x 320 pre-emphasised edge-frame samples
     static constexpr int TOTAL = OFF_EDGE + 2 * WW_WIN * 4;
@@ -300,7 +312,8 @@ __device__ __forceinline__ void mfcc_body(const MfccArgs& a, unsigned char* smem
 
     // warp index out of a shuffle (known warp-uniform to the compiler, ww_common.cuh): 32.36 -> 32.49 M clips/s, same bits
     const int tid = pipe.tid(), warp = warp_index_uniform(tid), lane = tid & 31;
-    const int half = lane >> 4, l16 = lane & 15;
+    // which of the warp's two frames this lane works on, and its point index inside the frame
+    const int half = WW_LANE_INTERLEAVE ? (lane & 1) : (lane >> 4), l16 = WW_LANE_INTERLEAVE ? (lane >> 1) : (lane & 15);
 
     const int L = CLIP ? CLIP_SAMPLES : a.n_samples;
     const int n_frames = CLIP ? CLIP_FRAMES : a.n_frames;
@@ -368,7 +381,7 @@ __device__ __forceinline__ void mfcc_body(const MfccArgs& a, unsigned char* smem
     const float4* s_tw1 = reinterpret_cast<const float4*>(tab + TB_TW1_OFF);
     const float2* s_tw2 = reinterpret_cast<const float2*>(tab + TB_TW2_OFF);
 
-    unsigned char* exch = smem + SM::OFF_EXCH + (warp * 2 + half) * EXCH_FRAME_BYTES;
+    unsigned char* exch = smem + SM::OFF_EXCH + warp * EXCH_WARP_BYTES + half * (EXCH_FRAME_BYTES + EXCH_STAGGER);
 
     // Per-thread constants that depend on l16 only can live in registers for the whole kernel.  Both half-warps of a
     // warp need the same table entries, and 64/128-bit shared loads are served per half/quarter warp, so every
@@ -726,6 +739,8 @@ __device__ __forceinline__ void mfcc_body(const MfccArgs& a, unsigned char* smem
             // real-FFT split: pair (k, 256-k), k = l16 + 16*i -> 4*|X[k]|^2 and 4*|X[256-k]|^2.  Z[256-k] lives in lane
             // 16-l16, register 15-i (lane 0 pairs with itself: register 16-i, and Z[256] = Z[0])
             const int partner = (16 - l16) & 15;
+            // lane that holds the partner row of the SAME frame
+            const int plane = WW_LANE_INTERLEAVE ? 2 * partner + half : 16 * half + partner;
     #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int k = l16 + 16 * i;
@@ -733,10 +748,10 @@ __device__ __forceinline__ void mfcc_body(const MfccArgs& a, unsigned char* smem
 #if WW_PRESEL
                 // lane 0 pairs with itself (register 16 - i, Z[256] = Z[0]): it offers that register to its own shuffle
                 const float2 src = cunpk(l16 == 0 ? v[(16 - i) & 15] : v[15 - i]);
-                const cpx zb = cpk(__shfl_sync(0xffffffffu, src.x, partner, 16), __shfl_sync(0xffffffffu, src.y, partner, 16));
+                const cpx zb = cpk(__shfl_sync(0xffffffffu, src.x, plane), __shfl_sync(0xffffffffu, src.y, plane));
 #else
                 const float2 src = cunpk(v[15 - i]);
-                cpx zb = cpk(__shfl_sync(0xffffffffu, src.x, partner, 16), __shfl_sync(0xffffffffu, src.y, partner, 16));
+                cpx zb = cpk(__shfl_sync(0xffffffffu, src.x, plane), __shfl_sync(0xffffffffu, src.y, plane));
                 if (l16 == 0) zb = (i == 0) ? v[0] : v[(16 - i) & 15];
 #endif
 #if WW_TW2_COMPUTE
