@@ -61,6 +61,14 @@
 #ifndef WW_LANE_INTERLEAVE
 #define WW_LANE_INTERLEAVE 1
 #endif
+// WW_SPLIT_BARRIER (clip-shape instantiation): the CTA barrier at the end of a block becomes arrive ... wait on an
+// mbarrier, and the edge-frame taps of the NEXT block (every block of a 1 s clip has one edge frame: 320 reflected,
+// pre-emphasised taps, ~70 instructions per warp) are materialised between the two, i.e. while the warp would
+// otherwise idle until the slowest warp of the CTA arrives (6 % of the stall samples).  The two tap slots alternate per
+// iteration instead of per edge kind.
+#ifndef WW_SPLIT_BARRIER
+#define WW_SPLIT_BARRIER 1
+#endif
 
 namespace ww {
 
@@ -224,8 +232,8 @@ struct MfccSmem {
     // the window taps (head of the blob) live in registers and are never staged: smem holds blob[TB_TW1_OFF ..)
     static constexpr int TAB_SKIP = TB_TW1_OFF;
     static constexpr int TAB_BYTES = (MEL != MEL_TABLE ? TB_BYTES_PY : TB_BYTES) - TAB_SKIP;
-    static constexpr int OFF_BAR = 0;
-    static constexpr int OFF_TAB = 32;
+    static constexpr int OFF_BAR = 0;   // five mbarriers
+    static constexpr int OFF_TAB = 48;
     static constexpr int OFF_PCM = OFF_TAB + TAB_BYTES;
     static constexpr int OFF_EXCH = OFF_PCM + PCM_BUFS * PCM_BYTES;
     static constexpr int OFF_P = OFF_EXCH + MFCC_WARPS * EXCH_WARP_BYTES;
@@ -359,6 +367,7 @@ __device__ __forceinline__ void mfcc_body(const MfccArgs& a, unsigned char* smem
         mbar_init(&bars[1], 1);
         mbar_init(&bars[2], MFCC_WARPS);  // every warp has finished its mel stage (P free, LM complete)
         mbar_init(&bars[3], MFCC_WARPS);  // every warp has written its share of the edge taps
+        mbar_init(&bars[4], MFCC_WARPS);  // WW_SPLIT_BARRIER: every warp has finished the block
         mbar_fence_init();
     }
     // tables -> smem (once per persistent CTA)
@@ -377,6 +386,26 @@ __device__ __forceinline__ void mfcc_body(const MfccArgs& a, unsigned char* smem
 
     float* edge = reinterpret_cast<float*>(smem + SM::OFF_EDGE);
     const int t_tail = (L - origin_off - 416) / WW_HOP + 1;  // first frame whose taps run past the signal end
+    // WW_SPLIT_BARRIER: the one edge frame of a clip block (frame 0 of block 0, the tail frame of block 1), filled a block
+    // ahead into tap slot `slot` from the PCM buffer the block was staged into
+    constexpr bool EARLY_EDGE = WW_SPLIT_BARRIER && CLIP && NBUF == 2;   // needs the next block's PCM staged ahead
+    auto fill_edge_ahead = [&](int bi, const unsigned char* pcm_b, int slot) {
+        const int bt0 = bi * MFCC_FRAMES;
+        const int te = bi == 0 ? 0 : t_tail;
+        const int hh = (te - bt0) >> 4;
+        const TIN* sp = reinterpret_cast<const TIN*>(pcm_b + hh * SM::HALF_STRIDE);
+        const int s0 = WW_HOP * te + origin_off + 96, lo_h = WW_HOP * (bt0 + 16 * hh) + origin_off + 88;
+        constexpr float es = (WW_IPRE && sizeof(TIN) == 2) ? 100.f : 1.f;
+        for (int j = tid; j < WW_WIN; j += MFCC_THREADS)
+            edge[slot * WW_WIN + j] = es * emph_sample<TIN>(sp, lo_h, s0 + j, L, reflect, a.preemph);
+    };
+    if constexpr (EARLY_EDGE) {
+        if (first < a.n_blocks) {
+            mbar_wait(&bars[0], 0);
+            fill_edge_ahead(bi_cur, smem + SM::OFF_PCM, 0);
+        }
+        pipe.sync();
+    }
 
     const float4* s_tw1 = reinterpret_cast<const float4*>(tab + TB_TW1_OFF);
     const float2* s_tw2 = reinterpret_cast<const float2*>(tab + TB_TW2_OFF);
@@ -555,7 +584,10 @@ __device__ __forceinline__ void mfcc_body(const MfccArgs& a, unsigned char* smem
             const bool has0 = (t0 == 0) && (origin_off + 95 < 0);
             const bool has1 = (t_tail >= t0) && (t_tail < t0 + FRAMES) && (t_tail < n_frames) && (t_tail > 0 || !has0);
             block_has_edge = has0 || has1;
-            if (block_has_edge) {
+            if (block_has_edge && EARLY_EDGE) {
+                const int it_edge = has0 ? 0 : (((t_tail - t0) & 15) >> 3);
+                it_first = it_edge ^ 1;
+            } else if (block_has_edge) {
                 const float pre = a.preemph;
     #pragma unroll 1
                 for (int slot = has0 ? 0 : 1; slot <= (has1 ? 1 : 0); ++slot) {
@@ -637,7 +669,7 @@ __device__ __forceinline__ void mfcc_body(const MfccArgs& a, unsigned char* smem
             cpx v[16];
     #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = cpk(0.f, 0.f);
-            if (block_has_edge && __any_sync(0xffffffffu, valid && !interior)) mbar_wait(&bars[3], edge_uses & 1);
+            if (!EARLY_EDGE && block_has_edge && __any_sync(0xffffffffu, valid && !interior)) mbar_wait(&bars[3], edge_uses & 1);
 
             // this half-warp's staging half: frames 16*half.. live in half `half` (fl = 16*half + ...)
             const TIN* spcm = reinterpret_cast<const TIN*>(pcm_buf + half * SM::HALF_STRIDE);
@@ -689,7 +721,7 @@ __device__ __forceinline__ void mfcc_body(const MfccArgs& a, unsigned char* smem
                 }
             } else if (valid) {
                 // edge frame: taps were pre-emphasised into `edge` (slot 0: frame 0, slot 1: the tail frame)
-                const float* ep = edge + (t == 0 ? 0 : WW_WIN) + 2 * l16;
+                const float* ep = edge + ((EARLY_EDGE ? (int)(iter & 1) != 0 : t != 0) ? WW_WIN : 0) + 2 * l16;
     #pragma unroll
                 for (int n1 = 3; n1 <= 12; ++n1) {
                     const cpx w = wreg[n1 - 3];
@@ -783,9 +815,22 @@ __device__ __forceinline__ void mfcc_body(const MfccArgs& a, unsigned char* smem
             __syncwarp();
         }
         if (prev_valid) ++mel_uses;
-        if (block_has_edge) ++edge_uses;
+        if (block_has_edge && !EARLY_EDGE) ++edge_uses;
         // one CTA barrier per block: P(k) is complete; LM(k-1), the edge taps and PCM(k) are free again
-        pipe.sync();
+        if constexpr (EARLY_EDGE) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[4]);
+            // while the slower warps finish: the edge taps of the next block (its PCM was staged an iteration ago) go to
+            // the tap slot this block did not use
+            if (blk_id + stride < a.n_blocks) {
+                const int nb = (int)((iter + 1) & 1);
+                mbar_wait(&bars[nb], (uint32_t)(((iter + 1) >> 1) & 1));
+                fill_edge_ahead(bi_nxt, smem + SM::OFF_PCM + nb * SM::PCM_BYTES, nb);
+            }
+            mbar_wait(&bars[4], (uint32_t)(iter & 1));
+        } else {
+            pipe.sync();
+        }
         pub_valid = prev_valid;
         if constexpr (PIPE::FUSED) v_sig += stride_q;
         prev_valid = have;
