@@ -10,14 +10,15 @@
 // block with TMA while it transforms the current one.
 //   * the PCM span of the block is staged once into shared memory with a 1-D TMA bulk copy
 //     (cp.async.bulk + mbarrier); int16 PCM is kept as int16 in smem (16.5 KB per block)
-//   * a warp transforms TWO frames at a time, one per half-warp: the 512-point real FFT is a 256-point
+//   * a warp transforms TWO frames at a time, 16 lanes each (the even lanes one frame, the odd lanes the other:
+//     WW_LANE_INTERLEAVE below): the 512-point real FFT is a 256-point
 //     complex FFT of the packed frame (z[m] = x[2m] + i x[2m+1]) done as radix-16 (registers) x
 //     radix-16 (registers) with one transposition through a per-warp smem tile, followed by the
 //     real-FFT split that yields two power bins per butterfly
 //   * pre-emphasis and the window are folded into the load (w*(x[i] - 0.97*x[i-1])); only the 160 complex
 //     points under the 320-tap window are loaded.  The block's PCM is staged as two halves whose smem
-//     bases differ by 64 B mod 128, so the two half-warps of a warp (frames t and t+16) hit disjoint banks
-//   * the real-FFT split takes its partner values Z[256-k] with 16 width-16 shuffles instead of parking Z in
+//     bases differ by 64 B mod 128, so the two frames of a warp (t and t+16) hit disjoint banks
+//   * the real-FFT split takes its partner values Z[256-k] with 16 shuffles inside the frame's 16 lanes instead of parking Z in
 //     shared memory: the kernel is co-limited by issue slots and shared-memory wavefronts, not by HBM
 //   * the 32 power spectra of the block are parked in shared memory (33 KB); after a CTA barrier the mel
 //     filterbank runs with lane <-> frame and warp <-> filter range as generated straight-line code
