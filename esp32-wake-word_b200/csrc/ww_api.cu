@@ -2090,7 +2090,33 @@ static int ctc_common(ww_ctx* ctx, CtcLossArgs& a, const float* log_probs, long 
     a.in_len = il;
     a.tgt_len = tl;
     a.blank = blank;
-    a.zero_infinity = zero_infinity;
+    a.zero_infinity = zero_infinity & 1;   // bit 1 = WW_CTC_BETA_IN_FWD, handled by the callers
+    return WW_OK;
+}
+
+// Would ww_ctc_loss_bwd take the split wide-vocabulary path (beta recursion, then the rows pass) for this problem?
+// ww_ctc_loss_fwd asks the same question when WW_CTC_BETA_IN_FWD is set, so the two calls agree on who ran the recursion.
+static bool ctc_split_applies(const ww_ctx* ctx, int C, int S, const void* workspace) {
+    if (S <= 3 && C <= CTC_TINY_MAX_C && ctx->opt_ctc_tiny) return false;
+    if (S <= 3 && C <= 64) return false;
+    return C >= 64 && ctc_lp(S) / 32 <= 4 && ctx->opt_ctc_split == 1 && ((uintptr_t)workspace % 16) == 0;
+}
+
+// ... and is it worth running the beta recursion beside the alpha recursion?  Only when the two chains are long and
+// leave most of the GPU idle (B / 8 CTAs each): measured at T = 801, C = 4096: B = 256 2.51 -> 2.22 ms, B = 64
+// 1.30 -> 0.91 ms; at T = 200, B = 1024, C = 512 the two kernels fill the GPU by themselves and the pair loses
+// (0.42 -> 0.65 ms) -- profiles/r2f_ab_ctc_beta_in_fwd.jsonl.
+static bool ctc_beta_in_fwd_applies(const ww_ctx* ctx, int T, int B, int C, int S, const void* workspace) {
+    return ctc_split_applies(ctx, C, S, workspace) && T >= 256 && (B + CTC_WARPS - 1) / CTC_WARPS <= ctx->sm_count / 2;
+}
+
+static int ctc_side_stream(ww_ctx* ctx) {
+    if (ctx->ctc_side) return WW_OK;
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&ctx->ctc_side, cudaStreamNonBlocking, hi));
+    CK(cudaEventCreateWithFlags(&ctx->ctc_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ctc_join, cudaEventDisableTiming));
     return WW_OK;
 }
 
@@ -2121,6 +2147,29 @@ extern "C" int ww_ctc_loss_fwd(ww_ctx* ctx, const float* log_probs, long long t_
     const unsigned grid = (unsigned)((B + CTC_WARPS - 1) / CTC_WARPS);
     if (K <= 4) {  // states and labels in registers, gathers prefetched CTC_PF steps ahead
         const size_t smem_pf = (size_t)CTC_WARPS * (2 * (32 * K + 2) + CTC_PF * 32 * K) * sizeof(float);
+        // WW_CTC_BETA_IN_FWD: the caller will ask for the gradient.  The beta recursion does not depend on alpha (only the
+        // sum alpha + beta does, and the rows pass can form it), and both recursions are latency chains on B / 8 CTAs that
+        // leave the GPU idle: run them side by side, beta on the context's side stream, joined before this call returns
+        // control of the stream (0.32 + 0.53 ms -> 0.53 ms at T = 801, B = 256, C = 4096).
+        const bool beta_too = (zero_infinity & WW_CTC_BETA_IN_FWD) && ctc_beta_in_fwd_applies(ctx, T, B, C, S, workspace);
+        if (beta_too) {
+            rc = ctc_side_stream(ctx);
+            if (rc) return rc;
+            const size_t al_bytes = ((size_t)B * T * (2 * S + 1) * sizeof(float) + 15) / 16 * 16;
+            a.meta = reinterpret_cast<float*>((char*)workspace + al_bytes);
+            a.ab = a.meta + 4 * (size_t)B;
+            const size_t smem_b = (size_t)CTC_WARPS * (2 * (32 * K + 2) + 2 * CTC_PF * 32 * K) * sizeof(float);
+            CK(cudaEventRecord(ctx->ctc_fork, (cudaStream_t)stream));
+            CK(cudaStreamWaitEvent(ctx->ctc_side, ctx->ctc_fork, 0));
+            switch (K) {
+                case 1: ctc_beta_pf_kernel<1, true><<<grid, CTC_WARPS * 32, smem_b, ctx->ctc_side>>>(a); break;
+                case 2: ctc_beta_pf_kernel<2, true><<<grid, CTC_WARPS * 32, smem_b, ctx->ctc_side>>>(a); break;
+                case 3: ctc_beta_pf_kernel<3, true><<<grid, CTC_WARPS * 32, smem_b, ctx->ctc_side>>>(a); break;
+                default: ctc_beta_pf_kernel<4, true><<<grid, CTC_WARPS * 32, smem_b, ctx->ctc_side>>>(a); break;
+            }
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(ctx->ctc_join, ctx->ctc_side));
+        }
         switch (K) {
             case 1: ctc_loss_fwd_pf_kernel<1><<<grid, CTC_WARPS * 32, smem_pf, (cudaStream_t)stream>>>(a); break;
             case 2: ctc_loss_fwd_pf_kernel<2><<<grid, CTC_WARPS * 32, smem_pf, (cudaStream_t)stream>>>(a); break;
@@ -2128,6 +2177,7 @@ extern "C" int ww_ctc_loss_fwd(ww_ctx* ctx, const float* log_probs, long long t_
             default: ctc_loss_fwd_pf_kernel<4><<<grid, CTC_WARPS * 32, smem_pf, (cudaStream_t)stream>>>(a); break;
         }
         CK(cudaGetLastError());
+        if (beta_too) CK(cudaStreamWaitEvent((cudaStream_t)stream, ctx->ctc_join, 0));
         return WW_OK;
     }
     const size_t smem = (size_t)CTC_WARPS * 2 * ctc_lp(S) * sizeof(float);
@@ -2195,14 +2245,19 @@ extern "C" int ww_ctc_loss_bwd(ww_ctx* ctx, const float* log_probs, long long t_
         // submitted first, the fill leaving it two CTA slots per SM.  It loses 2x: the chain's gathers wait behind the stream.
         const bool overlap = ctx->opt_ctc_split == 3;
         cudaStream_t rs = (cudaStream_t)stream;
+        long long rows_n = (long long)T * B;
+        long long rblocks = (rows_n + CTC_ROWS_WARPS - 1) / CTC_ROWS_WARPS;
+        if (rblocks > (long long)ctx->sm_count * 8) rblocks = (long long)ctx->sm_count * 8;
+        if ((zero_infinity & WW_CTC_BETA_IN_FWD) && ctc_beta_in_fwd_applies(ctx, T, B, C, S, workspace)) {
+            // ww_ctc_loss_fwd ran the beta recursion beside alpha (the second block holds beta, `meta` the repeated-label
+            // flags): only the rows pass is left
+            ctc_grad_rows_kernel<true, true><<<(unsigned)rblocks, CTC_ROWS_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+            CK(cudaGetLastError());
+            return WW_OK;
+        }
         if (overlap) {
-            if (!ctx->ctc_side) {
-                int lo = 0, hi = 0;
-                CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-                CK(cudaStreamCreateWithPriority(&ctx->ctc_side, cudaStreamNonBlocking, hi));
-                CK(cudaEventCreateWithFlags(&ctx->ctc_fork, cudaEventDisableTiming));
-                CK(cudaEventCreateWithFlags(&ctx->ctc_join, cudaEventDisableTiming));
-            }
+            rc = ctc_side_stream(ctx);
+            if (rc) return rc;
             CK(cudaEventRecord(ctx->ctc_fork, (cudaStream_t)stream));
             CK(cudaStreamWaitEvent(ctx->ctc_side, ctx->ctc_fork, 0));
             rs = ctx->ctc_side;

@@ -910,7 +910,10 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_loss_bwd_pf_kernel(const C
 // fill 1.09-1.27 + recursion-with-patches 1.2 ms: 104 k against 90.5 k seq/s in the same harness (+15 %).  The rows pass
 // runs at 4.5 TB/s; the stream-only fill followed by a patches-only pass is slower (1.27 + 0.41 ms).
 // ------------------------------------------------------------------------------------------------
-template <int K>
+// ALONE = true: the recursion runs BESIDE the forward pass (ww_ctc_loss_fwd with WW_CTC_BETA_IN_FWD, on a side stream), so
+// it may not read alpha: it stores beta itself, leaves only the repeated-label flag in `meta`, and the rows kernel adds
+// alpha + beta and derives nll / the live rows from alpha's last row.
+template <int K, bool ALONE = false>
 __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_beta_pf_kernel(const CtcLossArgs a) {
     extern __shared__ float ctc_sm[];
     const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
@@ -931,8 +934,8 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_beta_pf_kernel(const CtcLo
     float* abw = a.ab + b * (long long)a.T * Lw;
     const float NEG = -CUDART_INF_F;
 
-    float nll;
-    {
+    float nll = 0.f;
+    if constexpr (!ALONE) {
         float ll = NEG;
         if (Tb > 0) {
             ll = al[(long long)(Tb - 1) * Lw + L - 1];
@@ -942,7 +945,7 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_beta_pf_kernel(const CtcLo
         }
         nll = -ll;
     }
-    const bool dead = (a.zero_infinity && nll == CUDART_INF_F);
+    const bool dead = !ALONE && (a.zero_infinity && nll == CUDART_INF_F);
     const int t_live = dead ? 0 : Tb;
     bool dup = false;
     for (int i0 = 0; i0 < Sb; i0 += 32) {
@@ -957,8 +960,10 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_beta_pf_kernel(const CtcLo
     }
     if (lane == 0) {
         float* m = a.meta + 4 * b;
-        m[0] = nll;
-        m[1] = __int_as_float(t_live);
+        if constexpr (!ALONE) {
+            m[0] = nll;
+            m[1] = __int_as_float(t_live);
+        }
         m[2] = __int_as_float(dup ? 1 : 0);
     }
     if (t_live == 0) return;
@@ -987,7 +992,7 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_beta_pf_kernel(const CtcLo
         for (int k = 0; k < K; ++k)
             if (t >= 0 && ((flags >> k) & 1u)) {
                 cp_async4(ring_lp + p * Lp + lane + 32 * k, base + (long long)t * a.t_stride + lab[k]);
-                cp_async4(ring_al + p * Lp + lane + 32 * k, al + (long long)t * Lw + lane + 32 * k);
+                if constexpr (!ALONE) cp_async4(ring_al + p * Lp + lane + 32 * k, al + (long long)t * Lw + lane + 32 * k);
             }
         cp_async_commit();
     }
@@ -1002,14 +1007,14 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_beta_pf_kernel(const CtcLo
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             lpv[k] = ((flags >> k) & 1u) ? ring_lp[p * Lp + lane + 32 * k] : 0.f;
-            alv[k] = ((flags >> k) & 1u) ? ring_al[p * Lp + lane + 32 * k] : 0.f;
+            alv[k] = (!ALONE && ((flags >> k) & 1u)) ? ring_al[p * Lp + lane + 32 * k] : 0.f;
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int tn = t - CTC_PF;   // rows >= 8 steps away from the one written below
             if (tn >= 0 && ((flags >> k) & 1u)) {
                 cp_async4(ring_lp + p * Lp + lane + 32 * k, base + (long long)tn * a.t_stride + lab[k]);
-                cp_async4(ring_al + p * Lp + lane + 32 * k, al + (long long)tn * Lw + lane + 32 * k);
+                if constexpr (!ALONE) cp_async4(ring_al + p * Lp + lane + 32 * k, al + (long long)tn * Lw + lane + 32 * k);
             }
         }
         cp_async_commit();
@@ -1026,7 +1031,7 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_beta_pf_kernel(const CtcLo
                     const float c2 = ((flags >> (8 + k)) & 1u) ? nxt[s + 2] : NEG;
                     v = lse3f(c0, c1, c2) + lpv[k];
                 }
-                abw[(long long)t * Lw + s] = alv[k] + v;   // alpha + beta
+                abw[(long long)t * Lw + s] = alv[k] + v;   // alpha + beta (ALONE: beta, alv is 0)
             }
             now[s] = v;
         }
@@ -1039,7 +1044,7 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_beta_pf_kernel(const CtcLo
 constexpr int CTC_ROWS_WARPS = 8;
 
 // FILL = false: the rows were filled by ctc_grad_fill_kernel (a pure stream at 6.2 TB/s); this kernel only patches.
-template <bool FILL>
+template <bool FILL, bool ALONE = false>
 __global__ void __launch_bounds__(CTC_ROWS_WARPS * 32) ctc_grad_rows_kernel(const CtcLossArgs a) {
     __shared__ float se_all[CTC_ROWS_WARPS][64];   // repeated labels only: per-state posterior mass of the odd states
     const int lane = threadIdx.x & 31, warp = warp_index_uniform();
@@ -1051,9 +1056,26 @@ __global__ void __launch_bounds__(CTC_ROWS_WARPS * 32) ctc_grad_rows_kernel(cons
         const int t = (int)(r / a.B);
         const long long b = r - (long long)t * a.B;
         const float4 m = *reinterpret_cast<const float4*>(a.meta + 4 * b);
-        const float nll = m.x;
-        const int t_live = __float_as_int(m.y);
+        float nll = m.x;
+        int t_live = __float_as_int(m.y);
         const bool dup = __float_as_int(m.z) != 0;
+        if constexpr (ALONE) {
+            // the beta recursion ran beside the forward pass and knew nothing of alpha: nll and the live rows from
+            // alpha's last row, exactly as ctc_beta_pf_kernel derives them
+            const int Tb0 = min(max(a.in_len[b], 0), a.T);
+            const int Sb0 = min(max(a.tgt_len[b], 0), a.S);
+            const int L0 = 2 * Sb0 + 1;
+            float ll = -CUDART_INF_F;
+            if (Tb0 > 0) {
+                const float* al_last = a.alpha + (b * (long long)a.T + (Tb0 - 1)) * Lw;
+                ll = al_last[L0 - 1];
+                if (L0 > 1) ll = lse2(ll, al_last[L0 - 2]);
+            } else if (Sb0 == 0) {
+                ll = 0.f;
+            }
+            nll = -ll;
+            t_live = (a.zero_infinity && nll == CUDART_INF_F) ? 0 : Tb0;
+        }
         const float* row = a.lp + b * a.b_stride + (long long)t * a.t_stride;
         float* grow = a.grad + b * a.gb_stride + (long long)t * a.gt_stride;
         const bool live = t < t_live;
@@ -1084,6 +1106,7 @@ __global__ void __launch_bounds__(CTC_ROWS_WARPS * 32) ctc_grad_rows_kernel(cons
             lab[k] = a.blank;
             if (s < L) {
                 vab[k] = ab[s];
+                if constexpr (ALONE) vab[k] = a.alpha[(b * (long long)a.T + t) * Lw + s] + vab[k];   // alpha + beta
                 if (s & 1) lab[k] = tgt[s >> 1];
             }
             lpl[k] = s < L ? row[lab[k]] : 0.f;

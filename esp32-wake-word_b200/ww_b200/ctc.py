@@ -150,6 +150,13 @@ class CTCKeywordDetector:
         return out
 
 
+# WW_CTC_BETA_IN_FWD (include/ww_b200.h): when the log-probs require a gradient the forward call also runs the beta
+# recursion, beside the alpha recursion (wide vocabularies), and the backward call is the row-parallel pass alone.
+# Set to False to keep the two recursions in their own calls (A/B, tests); results are identical.
+BETA_IN_FWD = True
+_FLAG_BETA_IN_FWD = 2
+
+
 class _CTCLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx_, log_probs, targets, input_lengths, target_lengths, blank, zero_infinity):
@@ -167,11 +174,14 @@ class _CTCLossFn(torch.autograd.Function):
         eng = L.get_context(dev.index)
         ws = torch.empty(eng.lib.ww_ctc_loss_workspace_bytes(T, B, S), dtype=torch.uint8, device=dev)
         nll = torch.empty((B,), dtype=torch.float32, device=dev)
+        flags = int(bool(zero_infinity))
+        if BETA_IN_FWD and ctx_.needs_input_grad[0]:
+            flags |= _FLAG_BETA_IN_FWD
         eng.check(eng.lib.ww_ctc_loss_fwd(eng.h, L.ptr(lp), lp.stride(0), lp.stride(1), T, B, C, L.ptr(tg), S,
-                                          L.ptr(il), L.ptr(tl), int(blank), int(bool(zero_infinity)), L.ptr(nll),
+                                          L.ptr(il), L.ptr(tl), int(blank), flags, L.ptr(nll),
                                           L.ptr(ws), L.cur_stream(dev)), "ww_ctc_loss_fwd")
         ctx_.save_for_backward(lp, tg, il, tl, ws)
-        ctx_.blank, ctx_.zero_infinity = int(blank), int(bool(zero_infinity))
+        ctx_.blank, ctx_.zero_infinity = int(blank), flags   # the backward call gets the same flags
         return nll
 
     @staticmethod

@@ -234,7 +234,13 @@ int ww_ctc_greedy(ww_ctx* ctx, const float* log_probs, long long t_stride, long 
 
 /* ---- CTC loss (nn.CTCLoss call shape: ml_models/test.py:89,111-112, ml_models/ctc.py:369,396) -- */
 size_t ww_ctc_loss_workspace_bytes(int T, int B, int S);
-/* nll: [B] per-sample loss before reduction; zero_infinity as in torch. */
+/* nll: [B] per-sample loss before reduction; zero_infinity as in torch (bit 0).  Bit 1, WW_CTC_BETA_IN_FWD: the caller
+ * will also call ww_ctc_loss_bwd with the same flag, the same arguments and unchanged context options -- for wide
+ * vocabularies (C >= 64, 2S+1 <= 128), long inputs (T >= 256) and batches that leave the GPU idle (B / 8 CTAs <= half
+ * the SMs) the forward call then runs the beta recursion beside the alpha recursion (two
+ * latency chains that leave the GPU idle, on a context-owned side stream joined before the call returns the stream)
+ * and the backward call is the row-parallel gradient pass alone.  Same results bit for bit. */
+#define WW_CTC_BETA_IN_FWD 2
 int ww_ctc_loss_fwd(ww_ctx* ctx, const float* log_probs, long long t_stride, long long b_stride, int T, int B,
                     int C, const int32_t* targets, int S, const int32_t* input_lengths,
                     const int32_t* target_lengths, int blank, int zero_infinity, float* nll, void* workspace,

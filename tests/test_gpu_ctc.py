@@ -306,6 +306,52 @@ def test_ctc_loss_wide_vocabulary_split_backward(cuda_device, T, B, C, S, ctc_sp
     assert err_mine <= max(1e-5, 3.0 * err_torch32)
 
 
+@pytest.mark.parametrize("T,B,C,S", [(300, 9, 64, 20), (260, 5, 256, 40), (257, 7, 100, 63), (256, 33, 4096, 32), (120, 9, 64, 20)])
+def test_ctc_beta_recursion_beside_the_forward_pass_gives_the_same_bits(cuda_device, T, B, C, S):
+    """WW_CTC_BETA_IN_FWD: the beta recursion of the wide-vocabulary path runs inside the forward call, beside alpha
+    (it stores beta; the rows pass forms alpha + beta and re-derives nll / the live rows) -- loss and gradient must
+    equal the two-call form bit for bit, with ragged lengths, an infeasible utterance, an empty target, repeated
+    labels, a second backward through the kept graph, and with and without zero_infinity."""
+    import ww_b200
+    from ww_b200 import ctc as wctc
+
+    rng = np.random.default_rng(7 * T + B + C + S)
+    x = rng.normal(size=(T, B, C)).astype(np.float32)
+    lp = torch.log_softmax(torch.from_numpy(x), dim=-1).to(cuda_device)
+    tg = rng.integers(1, min(C, 6), size=(B, S)).astype(np.int64)
+    tg[1] = rng.integers(1, C, size=S)
+    tl = rng.integers(1, S + 1, size=B)
+    tl[0] = S
+    tl[-1] = 0
+    il = np.full(B, T)
+    il[2] = T // 2
+    il[3] = 3
+    tl[3] = S
+    res = {}
+    for zi in (True, False):
+        for beta_in_fwd in (False, True):
+            wctc.BETA_IN_FWD = beta_in_fwd
+            try:
+                xg = lp.clone().requires_grad_(True)
+                loss = ww_b200.ctc_loss(xg, torch.from_numpy(tg), torch.from_numpy(il), torch.from_numpy(tl),
+                                        reduction="none", zero_infinity=zi)
+                w = torch.linspace(0.5, 1.5, B, device=cuda_device)
+                (loss * w)[torch.isfinite(loss)].sum().backward(retain_graph=True)
+                g1 = xg.grad.clone()
+                xg.grad = None
+                (loss * w)[torch.isfinite(loss)].sum().backward()
+                torch.cuda.synchronize()
+                # (without zero_infinity the infeasible utterance's rows are NaN, as torch's are)
+                assert torch.equal(torch.nan_to_num(g1, nan=123.0), torch.nan_to_num(xg.grad, nan=123.0))
+                res[(zi, beta_in_fwd)] = (loss.detach().clone(), g1)
+            finally:
+                wctc.BETA_IN_FWD = True
+        l0, g0 = res[(zi, False)]
+        l1, g1 = res[(zi, True)]
+        assert torch.equal(l0, l1)
+        assert torch.equal(torch.nan_to_num(g0, nan=123.0), torch.nan_to_num(g1, nan=123.0)), (zi, (g0 - g1).abs().max())
+
+
 def test_ctc_loss_zero_infinity_and_blank_index(cuda_device):
     import ww_b200
 

@@ -306,6 +306,17 @@ def main():
                     r["how"] = names[mode]
                     print(json.dumps(r), flush=True)
         ctx.check(ctx.lib.ww_set_option(ctx.h, L.OPT_CTC_SPLIT, 1), "opt")
+        # the beta recursion beside the forward pass (WW_CTC_BETA_IN_FWD, default) against the two-call form
+        from ww_b200 import ctc as wctc
+
+        for _ in range(2):
+            for flag in (False, True):
+                wctc.BETA_IN_FWD = flag
+                for shape in ((801, 256, 4096, 32), (801, 64, 4096, 32), (200, 1024, 512, 20)):
+                    r = ctc_bench(dev, *shape, compare=False)
+                    r["beta_in_fwd"] = flag
+                    print(json.dumps(r), flush=True)
+        wctc.BETA_IN_FWD = True
         return
     res += batch_sweep(dev, sd)
     res += stream_bench(dev, sd)
