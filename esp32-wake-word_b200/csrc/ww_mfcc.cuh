@@ -42,6 +42,12 @@
 #ifndef WW_TW1_HALF
 #define WW_TW1_HALF 0
 #endif
+// WW_TW1_REGS = N: the first N inter-pass twiddle entries of a lane in registers (the launch bound leaves a dozen free).
+// Measured after the lane interleave (profiles/r2f_ab_tw1_regs.txt): N = 0 / 1 / 2 / 3 / 4 / 6 -> 33.70 / 33.25 / 33.19 /
+// 33.50 / 32.51 / 32.58 M clips/s: ptxas pays for the longer live ranges with a worse schedule (off)
+#ifndef WW_TW1_REGS
+#define WW_TW1_REGS 0
+#endif
 // Round-2 switches (A/B on B200, profiles/experiments/README.md):
 //   WW_IPRE     pre-emphasis in exact integer arithmetic, 100 x[i] - 97 x[i-1] by one IDP.2A per sample (|.| < 2^23, exact
 //               in fp32), ONE int -> float conversion per sample on the ALU side (I2FP.F32.S32) instead of three
@@ -440,6 +446,9 @@ __device__ __forceinline__ void mfcc_body(const MfccArgs& a, unsigned char* smem
 #if WW_TW1_HALF
     const cpx tw1_8 = cpk(s_tw1[16 * 4 + l16].x, s_tw1[16 * 4 + l16].y);
 #endif
+    float4 tw1_r[WW_TW1_REGS > 0 ? WW_TW1_REGS : 1];
+#pragma unroll
+    for (int j = 0; j < WW_TW1_REGS; ++j) tw1_r[j] = __ldg(reinterpret_cast<const float4*>(a.tables) + TB_TW1_OFF / 16 + 16 * j + l16);
 
     // Per-CTA software pipeline over this CTA's blocks (one CTA-wide barrier per block):
     //   iteration k:  mel(k-1) | stage PCM(k) + edge taps | FFT(k) first pass | DCT(k-1) | FFT(k) second pass | barrier
@@ -746,7 +755,7 @@ __device__ __forceinline__ void mfcc_body(const MfccArgs& a, unsigned char* smem
 #else
     #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float4 tw = s_tw1[16 * j + l16];
+                const float4 tw = j < WW_TW1_REGS ? tw1_r[j < WW_TW1_REGS ? j : 0] : s_tw1[16 * j + l16];
                 if (j > 0) v[2 * j] = p_cmul(v[2 * j], tw.x, tw.y);
                 v[2 * j + 1] = p_cmul(v[2 * j + 1], tw.z, tw.w);
             }
