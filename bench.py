@@ -48,6 +48,10 @@ FRONTEND_DRAM_BYTES_PER_CLIP_NCU = (2.104546e9 + 160.128256e6) / 65536
 # beside the HBM one
 FRONTEND_WARP_INSTR_PER_CLIP = 1390628285 / 65536
 FRONTEND_SMEM_WAVEFRONTS_PER_CLIP = 391394891 / 65536
+# FP32-pipe cycles per clip of the same capture (profiles/r2f_mfcc_sass_summary.txt): a packed f32x2 instruction
+# (FFMA2 224.4 M + FADD2 184.5 M + FMUL2 120.9 M warp instructions) holds a scheduler's FMA pipe for two cycles, a scalar
+# FFMA / FMUL / FADD (106.0 + 17.3 + 17.0 M) for one; an SM has four such pipes
+FRONTEND_FMA_PIPE_CYCLES_PER_CLIP = (2 * (224395264 + 184549376 + 120872064) + 106037248 + 17301504 + 17039360) / 65536
 UTT = 63  # windows per CTC utterance
 CPU_BATCH = 200
 PARITY_DISTINCT = 65536   # exact-match check on >= 65 536 distinct clips per GPU
@@ -540,7 +544,12 @@ def run_ours(args):
                      "peak": 1.0, "unit": "wavefronts/clk/SM",
                      "frac": FRONTEND_SMEM_WAVEFRONTS_PER_CLIP * rb / (fms * 1e-3) / (n_sm * sm_clk),
                      "per_clip": FRONTEND_SMEM_WAVEFRONTS_PER_CLIP,
-                     "source": "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum / clips (ncu)"}],
+                     "source": "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum / clips (ncu)"},
+                    {"bound": "fp32 pipes", "achieved": FRONTEND_FMA_PIPE_CYCLES_PER_CLIP * rb / (fms * 1e-3) / (n_sm * sm_clk),
+                     "peak": 4.0, "unit": "pipe-cycles/clk/SM",
+                     "frac": FRONTEND_FMA_PIPE_CYCLES_PER_CLIP * rb / (fms * 1e-3) / (n_sm * sm_clk) / 4.0,
+                     "per_clip": FRONTEND_FMA_PIPE_CYCLES_PER_CLIP,
+                     "source": "2 x packed f32x2 + scalar FP32 warp instructions / clips (ncu source view)"}],
                 "sm_clock_hz_used": sm_clk}
         del feats
 
