@@ -2324,6 +2324,17 @@ extern "C" int ww_debug_tc(ww_ctx* ctx, float* dbg_dev, int* last_rescored) {
     return WW_OK;
 }
 
+#ifdef WW_MFCC_STATS
+// diagnostic build only: read (and clear) the per-warp barrier slack of the clip-shape frontend
+extern "C" int ww_debug_mfcc_slack(unsigned long long* out_host, int n) {
+    if (n > 1024 * 8) n = 1024 * 8;
+    if (cudaMemcpyFromSymbol(out_host, g_mfcc_slack, sizeof(unsigned long long) * n) != cudaSuccess) return -1;
+    static unsigned long long zero[1024 * 8];
+    cudaMemcpyToSymbol(g_mfcc_slack, zero, sizeof(zero));
+    return 0;
+}
+#endif
+
 // host-only: the C-MFCC tables as build_esp_tables() makes them on this machine (tools/gen_tables.py --esp turns them
 // into ww_mel_esp.inc).  fb is dense [40][257]; returns the checksum the generated code must carry, 0 on failure.
 extern "C" unsigned int ww_debug_esp_tables(float* window320, float* fb_dense, float* bias40, float* dct_40x13) {

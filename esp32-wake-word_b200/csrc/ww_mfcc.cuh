@@ -76,8 +76,23 @@
 #ifndef WW_SPLIT_BARRIER
 #define WW_SPLIT_BARRIER 1
 #endif
+// WW_STAGE_WARP: the warp whose lane 0 issues the TMA copies of the next block (~60 instructions executed by one lane,
+// a serial chain that costs its warp several hundred clocks per block).  Per-warp arrival at the block barrier, measured
+// with the -DWW_MFCC_STATS build and tools/mfcc_warp_slack.py (profiles/r2f_mfcc_warp_slack.txt): with warp 0 issuing
+// them it arrives ~160 clocks after the mean of the eight and is the warp the CTA waits for.  Measured (1 048 576
+// clips, alternating builds, profiles/r2f_ab_stage_warp.txt): warp 0 / 1 / 2 / 4: 33.74 / 33.93 / 33.93 / 33.80 M clips/s;
+// the two halves issued by two warps (4 + 1, 1 + 2): 33.51 / 33.71 (two arrivals, the address arithmetic twice).
+#ifndef WW_STAGE_WARP
+#define WW_STAGE_WARP 1
+#endif
 
 namespace ww {
+
+#ifdef WW_MFCC_STATS
+// diagnostic build: per (CTA, warp) sum of clocks between a warp's arrival at the block barrier and the barrier's
+// completion as that warp sees it (tools/mfcc_warp_slack.py)
+__device__ unsigned long long g_mfcc_slack[1024 * 8];
+#endif
 
 // ---- table blob (one per feature mode, device memory, copied to smem by every CTA) ----------------
 constexpr int TB_WIN_OFF = 0;                       // float2[160]  {w[2m], w[2m+1]} for packed point m = 48 + i
@@ -340,6 +355,8 @@ __device__ __forceinline__ void mfcc_body(const MfccArgs& a, unsigned char* smem
     const long long out_frame_stride = CLIP ? 1LL : a.out_frame_stride;
     const int reflect = CLIP ? 1 : a.reflect;
     constexpr int NBUF = SM::PCM_BUFS;
+    constexpr int kStageTid = 32 * WW_STAGE_WARP;
+    const bool stager = tid == kStageTid;
     uint64_t* bars = bar;  // one mbarrier per PCM buffer
 
     // half h of a block holds frames 16h..16h+15; smem sample index = s - org[h]
@@ -389,7 +406,7 @@ __device__ __forceinline__ void mfcc_body(const MfccArgs& a, unsigned char* smem
     const int stride_q = (int)stride / bps, stride_r = (int)stride % bps;
     long long sig_cur = first / bps;
     int bi_cur = (int)(first - sig_cur * bps);
-    if (use_bulk && tid == 0 && first < a.n_blocks) stage_block(sig_cur, bi_cur, 0);
+    if (use_bulk && stager && first < a.n_blocks) stage_block(sig_cur, bi_cur, 0);
 
     float* edge = reinterpret_cast<float*>(smem + SM::OFF_EDGE);
     const int t_tail = (L - origin_off - 416) / WW_HOP + 1;  // first frame whose taps run past the signal end
@@ -567,10 +584,10 @@ __device__ __forceinline__ void mfcc_body(const MfccArgs& a, unsigned char* smem
             if (use_bulk) {
                 if (NBUF == 2) {
                     // the other buffer was last read in the FFT passes of the previous block (before its barrier)
-                    if (tid == 0 && blk_id + stride < a.n_blocks) stage_block(sig_nxt, bi_nxt, buf ^ 1);
+                    if (stager && blk_id + stride < a.n_blocks) stage_block(sig_nxt, bi_nxt, buf ^ 1);
                     mbar_wait(&bars[buf], (uint32_t)((iter >> 1) & 1));
                 } else {
-                    if (iter > 0 && tid == 0) stage_block(sig_cur, bi_cur, 0);
+                    if (iter > 0 && stager) stage_block(sig_cur, bi_cur, 0);
                     mbar_wait(&bars[0], (uint32_t)(iter & 1));
                 }
             } else {
@@ -829,6 +846,9 @@ __device__ __forceinline__ void mfcc_body(const MfccArgs& a, unsigned char* smem
         // one CTA barrier per block: P(k) is complete; LM(k-1), the edge taps and PCM(k) are free again
         if constexpr (EARLY_EDGE) {
             __syncwarp();
+#ifdef WW_MFCC_STATS
+            const long long t_arr = clock64();
+#endif
             if (lane == 0) mbar_arrive(&bars[4]);
             // while the slower warps finish: the edge taps of the next block (its PCM was staged an iteration ago) go to
             // the tap slot this block did not use
@@ -838,6 +858,9 @@ __device__ __forceinline__ void mfcc_body(const MfccArgs& a, unsigned char* smem
                 fill_edge_ahead(bi_nxt, smem + SM::OFF_PCM + nb * SM::PCM_BYTES, nb);
             }
             mbar_wait(&bars[4], (uint32_t)(iter & 1));
+#ifdef WW_MFCC_STATS
+            if (lane == 0 && !PIPE::FUSED) g_mfcc_slack[(blockIdx.x & 1023) * 8 + warp] += (unsigned long long)(clock64() - t_arr);
+#endif
         } else {
             pipe.sync();
         }
