@@ -85,6 +85,11 @@
 #ifndef WW_STAGE_WARP
 #define WW_STAGE_WARP 1
 #endif
+// WW_FILL2_WARP: the 64 edge taps that are left over after one tap per thread are filled by this warp and the next one
+// (warps 0 and 1 before: 34.00 M clips/s; 4 and 5: 33.78 M; 5 and 6: 34.05 M, profiles/r2g_ab_fill2.txt)
+#ifndef WW_FILL2_WARP
+#define WW_FILL2_WARP 5
+#endif
 
 namespace ww {
 
@@ -420,8 +425,12 @@ __device__ __forceinline__ void mfcc_body(const MfccArgs& a, unsigned char* smem
         const TIN* sp = reinterpret_cast<const TIN*>(pcm_b + hh * SM::HALF_STRIDE);
         const int s0 = WW_HOP * te + origin_off + 96, lo_h = WW_HOP * (bt0 + 16 * hh) + origin_off + 88;
         constexpr float es = (WW_IPRE && sizeof(TIN) == 2) ? 100.f : 1.f;
-        for (int j = tid; j < WW_WIN; j += MFCC_THREADS)
-            edge[slot * WW_WIN + j] = es * emph_sample<TIN>(sp, lo_h, s0 + j, L, reflect, a.preemph);
+        static_assert(WW_WIN > MFCC_THREADS && WW_WIN - MFCC_THREADS <= 64, "one tap per thread and 64 left over");
+        edge[slot * WW_WIN + tid] = es * emph_sample<TIN>(sp, lo_h, s0 + tid, L, reflect, a.preemph);
+        // the 64 taps left over go to the two warps that reach the barrier first (WW_FILL2_WARP), not to warps 0 and 1
+        const int j2 = MFCC_THREADS + tid - 32 * WW_FILL2_WARP;
+        if (tid >= 32 * WW_FILL2_WARP && j2 < WW_WIN)
+            edge[slot * WW_WIN + j2] = es * emph_sample<TIN>(sp, lo_h, s0 + j2, L, reflect, a.preemph);
     };
     if constexpr (EARLY_EDGE) {
         if (first < a.n_blocks) {
