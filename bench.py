@@ -39,16 +39,16 @@ UNIT = "clips/s"
 FRONTEND_BYTES_PER_CLIP = 16000 * 2 + 13 * 63 * 4  # 35 276
 FUSED_BYTES_PER_CLIP = 16000 * 2 + 5
 # dram__bytes_read.sum + dram__bytes_write.sum of mfcc_kernel<int16, PY> per clip, from the `ncu --set full` capture
-# profiles/r2f_ncu_mfcc_kernel.txt (2.1045 GB + 160.1 MB over a 65 536-clip launch; the last output lines are still in
+# profiles/r2h_ncu_mfcc_kernel.txt (2.1033 GB + 159.5 MB over a 65 536-clip launch; the last output lines are still in
 # L2 when the launch ends -- a capture of the round's first half read 2.0974 GB + 209.5 MB): traffic == algorithmic bytes
-FRONTEND_DRAM_BYTES_PER_CLIP_NCU = (2.104546e9 + 160.128256e6) / 65536
+FRONTEND_DRAM_BYTES_PER_CLIP_NCU = (2.103297e9 + 159.499264e6) / 65536
 # executed warp instructions and shared-memory wavefronts per clip of the same kernel (ncu, same capture family;
-# profiles/r2f_ncu_mfcc_kernel.txt, the final kernel of round 2): the issue ports (4 warp-instructions/clk/SM) and the
+# profiles/r2h_ncu_mfcc_kernel.txt, the final kernel of round 2): the issue ports (4 warp-instructions/clk/SM) and the
 # shared-memory pipe (1 wavefront/clk/SM) are what the kernel is actually limited by, so their fractions are reported
 # beside the HBM one
-FRONTEND_WARP_INSTR_PER_CLIP = 1390628285 / 65536
-FRONTEND_SMEM_WAVEFRONTS_PER_CLIP = 391394891 / 65536
-# FP32-pipe cycles per clip of the same capture (profiles/r2f_mfcc_sass_summary.txt): a packed f32x2 instruction
+FRONTEND_WARP_INSTR_PER_CLIP = 1380660280 / 65536
+FRONTEND_SMEM_WAVEFRONTS_PER_CLIP = 392761723 / 65536
+# FP32-pipe cycles per clip of the same capture (profiles/r2h_mfcc_sass_summary.txt): a packed f32x2 instruction
 # (FFMA2 224.4 M + FADD2 184.5 M + FMUL2 120.9 M warp instructions) holds a scheduler's FMA pipe for two cycles, a scalar
 # FFMA / FMUL / FADD (106.0 + 17.3 + 17.0 M) for one; an SM has four such pipes
 FRONTEND_FMA_PIPE_CYCLES_PER_CLIP = (2 * (224395264 + 184549376 + 120872064) + 106037248 + 17301504 + 17039360) / 65536
@@ -529,7 +529,7 @@ def run_ours(args):
         n_sm = torch.cuda.get_device_properties(local).multi_processor_count
         roof = {"bound": "hbm", "kernel": "mfcc_kernel<int16, PY> (frontend alone, 1 persistent launch over %d clips)" % rb,
                 "achieved": ach, "peak": peak, "peak_source": how, "unit": "GB/s", "frac": ach / peak,
-                "traffic": FRONTEND_DRAM_BYTES_PER_CLIP_NCU * rb, "traffic_source": "profiles/r2f_ncu_mfcc_kernel.txt "
+                "traffic": FRONTEND_DRAM_BYTES_PER_CLIP_NCU * rb, "traffic_source": "profiles/r2h_ncu_mfcc_kernel.txt "
                 "(ncu --set full, per-clip DRAM bytes x clips of this launch)", "algorithmic_bytes": rb * FRONTEND_BYTES_PER_CLIP,
                 "ms_per_launch": fms, "clips_per_s": rb / (fms * 1e-3),
                 "algorithmic_bytes_per_clip": FRONTEND_BYTES_PER_CLIP,
