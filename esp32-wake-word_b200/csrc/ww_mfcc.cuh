@@ -445,9 +445,10 @@ __device__ __forceinline__ void mfcc_body(const MfccArgs& a, unsigned char* smem
 
     unsigned char* exch = smem + SM::OFF_EXCH + warp * EXCH_WARP_BYTES + half * (EXCH_FRAME_BYTES + EXCH_STAGGER);
 
-    // Per-thread constants that depend on l16 only can live in registers for the whole kernel.  Both half-warps of a
-    // warp need the same table entries, and 64/128-bit shared loads are served per half/quarter warp, so every
-    // table read costs a wavefront per frame (the kernel runs the shared-memory pipe at ~2/3 of its peak):
+    // Per-thread constants that depend on l16 only can live in registers for the whole kernel.  Both frames of a warp
+    // need the same table entries; with the frames on adjacent lanes (WW_LANE_INTERLEAVE) a 64-/128-bit table read is
+    // merged inside each half-warp and costs half the wavefronts it cost with a frame per half-warp (the kernel runs
+    // the shared-memory pipe at ~2/3 of its peak):
     //   window: 10 packed taps (20 registers)                                              [on]
     //   tw2:    W512^(l16 + 16 i) = W512^l16 * W32^i with W32^i as immediates              [measured, off]
     //   tw1:    W256^(l16 k1), k1 >= 8, = W256^(8 l16) * W256^(l16 (k1 - 8))               [measured, off]
@@ -707,7 +708,7 @@ __device__ __forceinline__ void mfcc_body(const MfccArgs& a, unsigned char* smem
             for (int i = 0; i < 16; ++i) v[i] = cpk(0.f, 0.f);
             if (!EARLY_EDGE && block_has_edge && __any_sync(0xffffffffu, valid && !interior)) mbar_wait(&bars[3], edge_uses & 1);
 
-            // this half-warp's staging half: frames 16*half.. live in half `half` (fl = 16*half + ...)
+            // this frame's staging half: frames 16*half.. live in half `half` (fl = 16*half + ...)
             const TIN* spcm = reinterpret_cast<const TIN*>(pcm_buf + half * SM::HALF_STRIDE);
             const int org = half ? org1 : org0;
             const float pre = a.preemph;
