@@ -34,6 +34,20 @@ def test_header_symbols_are_exported(lib):
         assert getattr(lib, n) is not None
 
 
+def test_python_constants_follow_the_header():
+    """the option ids and flag bits ww_b200 passes through ctypes are the ones include/ww_b200.h defines"""
+    hdr = open(os.path.join(ROOT, "include", "ww_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    opts = {k: int(v) for k, v in re.findall(r"\bWW_(OPT_[A-Z0-9_]+)\s*=\s*(\d+)", hdr)}
+    assert len(opts) >= 7
+    from ww_b200 import _lib as L
+    from ww_b200 import ctc as wctc
+
+    for name, value in opts.items():
+        assert getattr(L, name) == value, name
+    assert int(re.search(r"#define\s+WW_CTC_BETA_IN_FWD\s+(\d+)", hdr).group(1)) == wctc._FLAG_BETA_IN_FWD
+
+
 def test_num_frames(lib):
     assert lib.ww_num_frames(0, 16000) == 63       # torch.stft center=True
     assert lib.ww_num_frames(1, 16000) == 62       # mfcc.c:448
